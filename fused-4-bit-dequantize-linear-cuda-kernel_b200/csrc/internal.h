@@ -1,0 +1,60 @@
+// Host-side internals shared by the translation units of libb200q.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstddef>
+#include "../../include/b200q.h"
+
+namespace b200q {
+
+// ---- error plumbing (thread-local message, C ABI never throws)
+int set_error(int code, const char* fmt, ...);
+int check_cuda(cudaError_t e, const char* what);
+#define B200Q_CUDA(expr)                                        \
+    do {                                                        \
+        int _rc = ::b200q::check_cuda((expr), #expr);           \
+        if (_rc != 0) return _rc;                               \
+    } while (0)
+
+// ---- immutable per-device cache
+struct DeviceInfo {
+    int device = -1;
+    int sm_count = 0;
+    int cc_major = 0, cc_minor = 0;
+    int max_smem_optin = 0;
+};
+// Fills `out` for the current device; returns 0 or an error code.  Fails with B200Q_EARCH when the
+// device is not compute capability 10.x.
+int current_device(DeviceInfo* out);
+
+// ---- tuning overrides (bench hook, see b200q_tune_set)
+struct Tuning {
+    int gemv_warps = -1;    // consumer warps per CTA (8 or 16)
+    int gemv_cluster = -1;  // 1 or 2 CTAs splitting K
+    int gemv_stages = -1;   // cap on ring depth
+    int gemv_pdl = -1;      // 0 disables programmatic dependent launch
+    int force_path = -1;    // 0 auto, 1 generic SIMT, 2 gemv, 3 tcgen05 gemm
+};
+const Tuning& tuning();
+
+// ---- kernel launchers (each returns 0 / error code, enqueues on stream, no sync)
+int launch_quantize_rows(const float* w, int64_t N, int64_t K, const float* given_scales,
+                         const float* given_zps, uint8_t* packed, float* scales, float* zps,
+                         cudaStream_t st);
+int launch_dequantize_rows(const uint8_t* packed, const float* scales, const float* zps, int64_t N,
+                           int64_t K, float* out, cudaStream_t st);
+int launch_minmax(const float* v, int64_t count, float* out, void* ws, cudaStream_t st);
+
+// generic SIMT fused dequant-linear (any even K); optional grouped mode via offsets/E
+int launch_linear_generic(const void* x, int x_dtype, const uint8_t* packed, const float* scales,
+                          const float* zps, void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
+                          const int32_t* offsets, int E, cudaStream_t st);
+
+// decode GEMV, M <= 16, K % 128 == 0.  Returns B200Q_EINVAL if the shape is not supported so
+// the dispatcher can fall through.
+bool gemv_supported(int64_t M, int64_t N, int64_t K, int x_dtype);
+int launch_gemv(const DeviceInfo& dev, const void* x, int x_dtype, const uint8_t* packed,
+                const float* scales, const float* zps, void* y, int y_dtype, int64_t M, int64_t N,
+                int64_t K, unsigned flags, cudaStream_t st);
+
+}  // namespace b200q

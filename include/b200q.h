@@ -1,0 +1,163 @@
+/*
+ * b200q.h — C ABI of libb200q.so: the B200 (sm_100a) INT4 dequantize-linear / INT4 MoE hot path.
+ *
+ * This is the drop-in boundary.  Every entry point below replaces one piece of the
+ * reference's Python/pybind surface (citations are paths under the reference repo):
+ *
+ *   b200q_linear_fwd        <- fused_quant_linear_cuda.forward      csrc/quantized_linear.cpp:22-28,
+ *                                                                    csrc/quantized_linear_kernel.cu:293-378
+ *   b200q_quantize_rows     <- quantize_weights                     python/quantize.py:38-124
+ *   b200q_quantize_rows_given / b200q_minmax
+ *                           <- quantize_weights_moe                 python/moe_int4_module.py:19-80
+ *   b200q_dequantize_rows   <- dequantize_weights                   python/quantize.py:127-173
+ *   b200q_moe_topk          <- simulate_routing softmax/topk/renorm benchmark/moe_grouped_gemm/routing.py:72-76
+ *   b200q_moe_permute       <- simulate_routing histogram/offsets   routing.py:79-86
+ *                              + create_expert_inputs               routing.py:96-149
+ *   b200q_moe_gather_rows   <- create_expert_inputs row gather      routing.py:137-147
+ *   b200q_moe_grouped_fwd   <- moe_int4_cuda.forward                csrc/moe_int4_kernel.cu:93-141
+ *                              + QuantizedMoE.forward               benchmark/moe_grouped_gemm/moe_int4_module.py:123-125
+ *   b200q_moe_silu_mul      <- (north_star extension: gated MLP, silu(x w1^T) * (x w3^T))
+ *   b200q_moe_combine       <- combine_expert_outputs               routing.py:152-189
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch types.  All pointers are DEVICE pointers unless
+ *     the parameter name starts with `h_`.
+ *   - every function returns 0 on success or a negative B200Q_E* code; it never throws, never
+ *     allocates device memory, never synchronises the device.  Work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*; NULL = legacy default stream).
+ *   - outputs and workspaces are caller-owned.  A workspace must be zero-filled ONCE by the
+ *     caller when it is allocated; the kernels leave it zeroed again on exit.
+ *   - re-entrant / thread-safe: the only global state is an immutable per-device property cache
+ *     and a thread-local last-error string.
+ *   - there is no CPU path.  On a machine without an sm_100 GPU the compute entry points
+ *     return B200Q_EARCH / B200Q_ECUDA.
+ *
+ * Packed layout (identical to python/quantize.py:120-122): packed[n, b] holds column 2b in the
+ * low nibble and column 2b+1 in the high nibble; scales[n], zero_points[n] are fp32 per row and
+ * w[n,k] = (q[n,k] - zero_points[n]) * scales[n].
+ */
+#ifndef B200Q_H_
+#define B200Q_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200Q_VERSION 100 /* major*10000 + minor*100 + patch */
+
+/* error codes */
+#define B200Q_OK 0
+#define B200Q_EINVAL (-1)     /* bad argument (null pointer, negative size, unsupported dtype ...) */
+#define B200Q_EALIGN (-2)     /* pointer or shape violates an alignment rule (see each function)   */
+#define B200Q_EARCH (-3)      /* current device is not compute capability 10.x                     */
+#define B200Q_ECUDA (-4)      /* a CUDA runtime call failed; see b200q_last_error_string()          */
+#define B200Q_EWORKSPACE (-5) /* workspace too small                                                */
+
+/* element types of activations / outputs */
+#define B200Q_F32 0
+#define B200Q_F16 1
+#define B200Q_BF16 2
+
+/* flags for b200q_linear_fwd */
+#define B200Q_FLAG_NONE 0u
+/* The packed weights / scales / zero points are NOT written by the kernel that precedes this call
+ * on `stream` (true for any inference module whose weights are fixed buffers).  Allows the kernel
+ * to be launched with programmatic dependent launch and to start streaming weights into shared
+ * memory while its predecessor drains; activations are only read after the dependency resolves. */
+#define B200Q_FLAG_STATIC_WEIGHTS 1u
+
+int b200q_version(void);
+/* Thread-local description of the last non-zero return value on this thread ("" if none). */
+const char* b200q_last_error_string(void);
+/* 0 if `device` (or the current device when device < 0) can run this library (sm_100). */
+int b200q_device_check(int device);
+/* Number of SMs of the current device (148 on B200); negative error code on failure. */
+int b200q_sm_count(void);
+
+/* ---- quantisation format ------------------------------------------------------------------ */
+
+/* Per-row asymmetric INT4 quantisation, bit-exact with python/quantize.py:38-124.
+ *   w [N,K] f32 row-major (K even, K <= 2^20) -> packed [N,K/2] u8, scales [N] f32, zps [N] f32 */
+int b200q_quantize_rows(const float* w, int64_t N, int64_t K, uint8_t* packed, float* scales,
+                        float* zps, void* stream);
+
+/* Quantise with caller-supplied per-row scale / zero point (python/moe_int4_module.py:56-76:
+ * q = clamp(round(w/scale + zp), 0, 15)); scales/zps are [N] f32 and are only read. */
+int b200q_quantize_rows_given(const float* w, int64_t N, int64_t K, const float* scales,
+                              const float* zps, uint8_t* packed, void* stream);
+
+/* min and max over `count` f32 values -> out_minmax[0], out_minmax[1] (for the per-expert scalar
+ * scale of python/moe_int4_module.py:46-50).  ws: >= b200q_minmax_ws_bytes() bytes. */
+size_t b200q_minmax_ws_bytes(void);
+int b200q_minmax(const float* v, int64_t count, float* out_minmax, void* ws, size_t ws_bytes,
+                 void* stream);
+
+/* python/quantize.py:127-173: out[n,k] = (q[n,k] - zps[n]) * scales[n], fp32, bit-exact. */
+int b200q_dequantize_rows(const uint8_t* packed, const float* scales, const float* zps, int64_t N,
+                          int64_t K, float* out, void* stream);
+
+/* ---- fused dequantize + linear ------------------------------------------------------------ */
+
+/* y[M,N] = x[M,K] @ dequant(packed[N,K/2], scales[N], zps[N])^T
+ *   x_dtype / y_dtype: B200Q_F32 | B200Q_F16 | B200Q_BF16 (the reference API is f32/f32).
+ *   x, y row-major and contiguous; x 16-byte aligned, packed 16-byte aligned, K even.
+ *   M may be any value >= 0.  Shapes with K % 128 == 0 take the TMA-ring tensor-core paths;
+ *   other even K take a generic SIMT kernel.
+ *   ws: >= b200q_linear_ws_bytes(M,N,K) bytes (may be NULL when that is 0). */
+size_t b200q_linear_ws_bytes(int64_t M, int64_t N, int64_t K);
+int b200q_linear_fwd(const void* x, int x_dtype, const uint8_t* packed, const float* scales,
+                     const float* zps, void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
+                     void* ws, size_t ws_bytes, unsigned flags, void* stream);
+
+/* Bench / tuning hook: override a launch heuristic process-wide (key = "gemv_warps" | "gemv_cluster"
+ * | "gemv_stages" | "gemv_pdl" | "force_path"; value < 0 restores the default).  Not needed by callers. */
+int b200q_tune_set(const char* key, int value);
+
+/* ---- MoE ---------------------------------------------------------------------------------- */
+
+/* softmax over E logits -> top-k (ties: lowest expert index first) -> renormalise
+ * (routing.py:72-76).  logits [T,E] f32, E <= 256, k <= 8.  idx [T,k] i32, weights [T,k] f32. */
+int b200q_moe_topk(const float* logits, int64_t T, int E, int k, int32_t* idx, float* weights,
+                   void* stream);
+
+/* Histogram + exclusive offsets + stable counting sort of the T*k (token,slot) assignments by
+ * expert (routing.py:79-86, 121-132).
+ *   idx [T*k] i32 -> counts [E] i32, offsets [E+1] i32 (offsets[E] = T*k),
+ *   sorted_slot [T*k] i32 : flat assignment index (t*k+s) of every sorted position, ascending
+ *                           inside an expert (the stable order; the reference's argsort is
+ *                           unstable, so only the per-expert SET is comparable),
+ *   inv_perm [T*k] i32    : sorted position of flat assignment t*k+s.
+ *   ws: >= b200q_moe_permute_ws_bytes(T,E,k) bytes. */
+size_t b200q_moe_permute_ws_bytes(int64_t T, int E, int k);
+int b200q_moe_permute(const int32_t* idx, int64_t T, int E, int k, int32_t* counts,
+                      int32_t* offsets, int32_t* sorted_slot, int32_t* inv_perm, void* ws,
+                      size_t ws_bytes, void* stream);
+
+/* xs[p,:] = x[sorted_slot[p] / k, :]  (routing.py:137-147).  d % 4 == 0 (f32) / 8 (16-bit). */
+int b200q_moe_gather_rows(const void* x, int dtype, const int32_t* sorted_slot, int64_t rows,
+                          int k, int64_t d, void* xs, void* stream);
+
+/* Grouped fused dequantize-linear over rows already grouped by expert:
+ *   y[p,:] = xs[p,:] @ dequant(packed[e], scales[e], zps[e])^T   for offsets[e] <= p < offsets[e+1]
+ *   packed [E,N,K/2] u8, scales/zps [E,N] f32, xs [R,K], y [R,N]; offsets [E+1] i32 ON DEVICE
+ *   (no host sync).  Rows outside every group are zero-filled (moe_int4_kernel.cu:109).
+ *   ws: >= b200q_moe_grouped_ws_bytes(R,E,N,K). */
+size_t b200q_moe_grouped_ws_bytes(int64_t R, int E, int64_t N, int64_t K);
+int b200q_moe_grouped_fwd(const void* xs, int x_dtype, const uint8_t* packed, const float* scales,
+                          const float* zps, const int32_t* offsets, int E, void* y, int y_dtype,
+                          int64_t R, int64_t N, int64_t K, void* ws, size_t ws_bytes, void* stream);
+
+/* h[p,f] = silu(a[p,f]) * b[p,f] where a = gu[p, 0:F], b = gu[p, F:2F]  (gated-MLP extension). */
+int b200q_moe_silu_mul(const void* gu, int dtype, int64_t R, int64_t F, void* h, void* stream);
+
+/* out[t,:] = sum_s weights[t,s] * y[inv_perm[t*k+s], :]   (routing.py:175-187). */
+int b200q_moe_combine(const void* y, int dtype, const int32_t* inv_perm, const float* weights,
+                      int64_t T, int k, int64_t F, void* out, int out_dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200Q_H_ */
