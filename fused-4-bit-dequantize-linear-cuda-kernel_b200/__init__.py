@@ -1,0 +1,21 @@
+"""B200-native fused INT4 dequantize-linear and INT4 MoE hot path.
+
+Drop-in surface of samy19980109/Fused-4-bit-Dequantize-Linear-CUDA-Kernel (python/__init__.py:14-22
+and benchmark/moe_grouped_gemm): same names, same buffers, same results -- computed by hand-written
+sm_100a kernels in ``libb200q.so`` (C ABI: include/b200q.h).
+"""
+from .quantize import quantize_weights, dequantize_weights, reference_quantized_linear
+from .module import QuantizedLinear
+from .moe import QuantizedMoEExpert, QuantizedMoE, MoEINT4, quantize_weights_moe
+from .routing import (RoutingResult, DeviceRouting, simulate_routing, create_expert_inputs,
+                      combine_expert_outputs, get_expert_sizes_for_benchmark, route, make_logits)
+from .config import MoEConfig, MIXTRAL_8x7B, DEBUG_CONFIG, LLAMA_7B_MLP
+from . import _lib
+
+__all__ = [
+    "quantize_weights", "dequantize_weights", "reference_quantized_linear", "QuantizedLinear",
+    "QuantizedMoEExpert", "QuantizedMoE", "MoEINT4", "quantize_weights_moe",
+    "RoutingResult", "DeviceRouting", "simulate_routing", "create_expert_inputs",
+    "combine_expert_outputs", "get_expert_sizes_for_benchmark", "route", "make_logits",
+    "MoEConfig", "MIXTRAL_8x7B", "DEBUG_CONFIG", "LLAMA_7B_MLP",
+]

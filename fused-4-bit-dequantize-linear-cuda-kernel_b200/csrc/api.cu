@@ -1,0 +1,131 @@
+// C ABI entry points of libb200q.so (declared in include/b200q.h): argument validation and
+// dispatch to the kernel launchers.  Nothing here allocates device memory or synchronises.
+#include "internal.h"
+
+using namespace b200q;
+
+namespace {
+
+inline int elem_size(int dtype) {
+    switch (dtype) {
+        case B200Q_F32: return 4;
+        case B200Q_F16: return 2;
+        case B200Q_BF16: return 2;
+    }
+    return 0;
+}
+
+inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
+
+}  // namespace
+
+extern "C" {
+
+int b200q_quantize_rows(const float* w, int64_t N, int64_t K, uint8_t* packed, float* scales,
+                        float* zps, void* stream) {
+    if (N < 0 || K < 0 || (K & 1)) return set_error(B200Q_EINVAL, "quantize_rows: need N >= 0 and even K >= 0 (N=%lld K=%lld)", (long long)N, (long long)K);
+    if (K > (1 << 20)) return set_error(B200Q_EINVAL, "quantize_rows: K > 2^20");
+    if (N == 0) return 0;
+    if (!scales || !zps || (K > 0 && (!w || !packed))) return set_error(B200Q_EINVAL, "quantize_rows: null pointer");
+    if (!aligned(w, 4) || !aligned(scales, 4) || !aligned(zps, 4)) return set_error(B200Q_EALIGN, "quantize_rows: fp32 pointers must be 4-byte aligned");
+    if (K == 0) return set_error(B200Q_EINVAL, "quantize_rows: K == 0 has no min/max");
+    DeviceInfo d;
+    if (int rc = current_device(&d)) return rc;
+    return launch_quantize_rows(w, N, K, nullptr, nullptr, packed, scales, zps, static_cast<cudaStream_t>(stream));
+}
+
+int b200q_quantize_rows_given(const float* w, int64_t N, int64_t K, const float* scales,
+                              const float* zps, uint8_t* packed, void* stream) {
+    if (N < 0 || K < 0 || (K & 1)) return set_error(B200Q_EINVAL, "quantize_rows_given: need N >= 0 and even K >= 0");
+    if (N == 0 || K == 0) return 0;
+    if (!w || !scales || !zps || !packed) return set_error(B200Q_EINVAL, "quantize_rows_given: null pointer");
+    DeviceInfo d;
+    if (int rc = current_device(&d)) return rc;
+    return launch_quantize_rows(w, N, K, scales, zps, packed, nullptr, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int b200q_minmax(const float* v, int64_t count, float* out_minmax, void* ws, size_t ws_bytes,
+                 void* stream) {
+    if (count <= 0 || !v || !out_minmax) return set_error(B200Q_EINVAL, "minmax: need count > 0 and non-null pointers");
+    if (!ws || ws_bytes < b200q_minmax_ws_bytes()) return set_error(B200Q_EWORKSPACE, "minmax: workspace too small");
+    DeviceInfo d;
+    if (int rc = current_device(&d)) return rc;
+    return launch_minmax(v, count, out_minmax, ws, static_cast<cudaStream_t>(stream));
+}
+
+int b200q_dequantize_rows(const uint8_t* packed, const float* scales, const float* zps, int64_t N,
+                          int64_t K, float* out, void* stream) {
+    if (N < 0 || K < 0 || (K & 1)) return set_error(B200Q_EINVAL, "dequantize_rows: need N >= 0 and even K >= 0");
+    if (N == 0 || K == 0) return 0;
+    if (!packed || !scales || !zps || !out) return set_error(B200Q_EINVAL, "dequantize_rows: null pointer");
+    DeviceInfo d;
+    if (int rc = current_device(&d)) return rc;
+    return launch_dequantize_rows(packed, scales, zps, N, K, out, static_cast<cudaStream_t>(stream));
+}
+
+size_t b200q_linear_ws_bytes(int64_t M, int64_t N, int64_t K) {
+    size_t a = gemv_ws_bytes(M, N, K);
+    size_t b = gemm_tc_ws_bytes(M, N, K);
+    return a > b ? a : b;
+}
+
+int b200q_linear_fwd(const void* x, int x_dtype, const uint8_t* packed, const float* scales,
+                     const float* zps, void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
+                     void* ws, size_t ws_bytes, unsigned flags, void* stream) {
+    if (M < 0 || N < 0 || K < 0 || (K & 1)) return set_error(B200Q_EINVAL, "linear_fwd: need M,N >= 0 and even K >= 0 (M=%lld N=%lld K=%lld)", (long long)M, (long long)N, (long long)K);
+    if (!elem_size(x_dtype) || !elem_size(y_dtype)) return set_error(B200Q_EINVAL, "linear_fwd: unsupported dtype (x=%d y=%d)", x_dtype, y_dtype);
+    if (M == 0 || N == 0) return 0;
+    if (!y || !scales || !zps || (K > 0 && (!x || !packed))) return set_error(B200Q_EINVAL, "linear_fwd: null pointer");
+    if (!aligned(x, elem_size(x_dtype)) || !aligned(y, elem_size(y_dtype))) return set_error(B200Q_EALIGN, "linear_fwd: x / y not aligned to their element size");
+    DeviceInfo d;
+    if (int rc = current_device(&d)) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int force = tuning().force_path;
+    const bool vec_ok = aligned(x, 16) && aligned(packed, 16) && aligned(y, 16);
+    if (force != 1 && force != 3 && vec_ok && gemv_supported(M, N, K, x_dtype))
+        return launch_gemv(d, x, x_dtype, packed, scales, zps, y, y_dtype, M, N, K, ws, ws_bytes, flags, st);
+    if (force != 1 && force != 2 && vec_ok && gemm_tc_supported(M, N, K, x_dtype, y_dtype))
+        return launch_gemm_tc(d, x, x_dtype, packed, scales, zps, y, y_dtype, M, N, K, nullptr, nullptr, 1, ws, ws_bytes, flags, st);
+    if (force == 2 || force == 3) return set_error(B200Q_EINVAL, "linear_fwd: forced path %d does not support this shape / alignment", force);
+    return launch_linear_generic(x, x_dtype, packed, scales, zps, y, y_dtype, M, N, K, nullptr, nullptr, 1, 0, st);
+}
+
+size_t b200q_moe_grouped_ws_bytes(int64_t R, int E, int64_t N, int64_t K) {
+    (void)E;
+    return gemm_tc_ws_bytes(R, N, K);
+}
+
+static int grouped_impl(const void* xs, int x_dtype, const uint8_t* packed, const float* scales,
+                        const float* zps, const int32_t* starts, const int32_t* ends, int E,
+                        int zero_outside, void* y, int y_dtype, int64_t R, int64_t N, int64_t K,
+                        void* ws, size_t ws_bytes, void* stream) {
+    if (R < 0 || N < 0 || K < 0 || (K & 1) || E <= 0) return set_error(B200Q_EINVAL, "moe_grouped_fwd: need R,N >= 0, even K >= 0, E > 0");
+    if (!elem_size(x_dtype) || !elem_size(y_dtype)) return set_error(B200Q_EINVAL, "moe_grouped_fwd: unsupported dtype");
+    if (R == 0 || N == 0) return 0;
+    if (!y || !scales || !zps || !starts || !ends || (K > 0 && (!xs || !packed))) return set_error(B200Q_EINVAL, "moe_grouped_fwd: null pointer");
+    DeviceInfo d;
+    if (int rc = current_device(&d)) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int force = tuning().force_path;
+    const bool vec_ok = aligned(xs, 16) && aligned(packed, 16) && aligned(y, 16);
+    if (force != 1 && vec_ok && gemm_tc_supported(R, N, K, x_dtype, y_dtype))
+        return launch_gemm_tc(d, xs, x_dtype, packed, scales, zps, y, y_dtype, R, N, K, starts, ends, E, ws, ws_bytes, 0u, st);
+    return launch_linear_generic(xs, x_dtype, packed, scales, zps, y, y_dtype, R, N, K, starts, ends, E, zero_outside, st);
+}
+
+int b200q_moe_grouped_fwd(const void* xs, int x_dtype, const uint8_t* packed, const float* scales,
+                          const float* zps, const int32_t* offsets, int E, void* y, int y_dtype,
+                          int64_t R, int64_t N, int64_t K, void* ws, size_t ws_bytes, void* stream) {
+    return grouped_impl(xs, x_dtype, packed, scales, zps, offsets, offsets ? offsets + 1 : nullptr, E, 1,
+                        y, y_dtype, R, N, K, ws, ws_bytes, stream);
+}
+
+int b200q_moe_grouped_fwd_ranges(const void* xs, int x_dtype, const uint8_t* packed,
+                                 const float* scales, const float* zps, const int32_t* starts,
+                                 const int32_t* counts_end, int E, void* y, int y_dtype, int64_t R,
+                                 int64_t N, int64_t K, void* ws, size_t ws_bytes, void* stream) {
+    return grouped_impl(xs, x_dtype, packed, scales, zps, starts, counts_end, E, 0, y, y_dtype, R, N, K,
+                        ws, ws_bytes, stream);
+}
+
+}  // extern "C"

@@ -30,9 +30,10 @@ int current_device(DeviceInfo* out);
 // ---- tuning overrides (bench hook, see b200q_tune_set)
 struct Tuning {
     int gemv_warps = -1;    // consumer warps per CTA (8 or 16)
-    int gemv_cluster = -1;  // 1 or 2 CTAs splitting K
+    int gemv_slabs = -1;    // number of K slabs (CTAs splitting K)
     int gemv_stages = -1;   // cap on ring depth
     int gemv_pdl = -1;      // 0 disables programmatic dependent launch
+    int gemv_ctas = -1;     // cap on the number of CTAs (default: SM count)
     int force_path = -1;    // 0 auto, 1 generic SIMT, 2 gemv, 3 tcgen05 gemm
 };
 const Tuning& tuning();
@@ -45,16 +46,29 @@ int launch_dequantize_rows(const uint8_t* packed, const float* scales, const flo
                            int64_t K, float* out, cudaStream_t st);
 int launch_minmax(const float* v, int64_t count, float* out, void* ws, cudaStream_t st);
 
-// generic SIMT fused dequant-linear (any even K); optional grouped mode via offsets/E
+// generic SIMT fused dequant-linear (any even K).  Grouped mode: rows [starts[e], ends[e]) use
+// expert e of packed [E,N,K/2]; starts == nullptr is the plain linear.  zero_outside: also zero the
+// rows before starts[0] and after ends[E-1] (the offsets[E+1] form of the C ABI).
 int launch_linear_generic(const void* x, int x_dtype, const uint8_t* packed, const float* scales,
                           const float* zps, void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
-                          const int32_t* offsets, int E, cudaStream_t st);
+                          const int32_t* starts, const int32_t* ends, int E, int zero_outside,
+                          cudaStream_t st);
 
 // decode GEMV, M <= 16, K % 128 == 0.  Returns B200Q_EINVAL if the shape is not supported so
 // the dispatcher can fall through.
 bool gemv_supported(int64_t M, int64_t N, int64_t K, int x_dtype);
+size_t gemv_ws_bytes(int64_t M, int64_t N, int64_t K);
 int launch_gemv(const DeviceInfo& dev, const void* x, int x_dtype, const uint8_t* packed,
                 const float* scales, const float* zps, void* y, int y_dtype, int64_t M, int64_t N,
-                int64_t K, unsigned flags, cudaStream_t st);
+                int64_t K, void* ws, size_t ws_bytes, unsigned flags, cudaStream_t st);
+
+// prefill / grouped path on tcgen05 tensor cores (M >= 17 rows, K % 128 == 0, N % 16 == 0).
+// starts == nullptr: plain linear; else grouped over E experts (packed [E,N,K/2]).
+bool gemm_tc_supported(int64_t M, int64_t N, int64_t K, int x_dtype, int y_dtype);
+size_t gemm_tc_ws_bytes(int64_t M, int64_t N, int64_t K);
+int launch_gemm_tc(const DeviceInfo& dev, const void* x, int x_dtype, const uint8_t* packed,
+                   const float* scales, const float* zps, void* y, int y_dtype, int64_t M,
+                   int64_t N, int64_t K, const int32_t* starts, const int32_t* ends, int E,
+                   void* ws, size_t ws_bytes, unsigned flags, cudaStream_t st);
 
 }  // namespace b200q

@@ -1,0 +1,67 @@
+"""QuantizedLinear: drop-in for the reference's python/module.py:33-138 on B200.
+
+Same constructor, ``from_linear`` classmethod, buffer names / shapes / dtypes (so reference
+``state_dict``s load), ``forward`` and ``extra_repr``.  ``forward`` always runs the fused sm_100a
+kernel; a CPU tensor raises instead of silently taking a slow path.
+Superset: any leading dims ``[..., K]``, fp16 / bf16 activations.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .quantize import quantize_weights
+
+
+class QuantizedLinear(nn.Module):
+    def __init__(self, in_features: int, out_features: int):
+        super().__init__()
+        self.in_features = in_features
+        self.out_features = out_features
+        # python/module.py:59-64
+        self.register_buffer("packed_weights",
+                             torch.zeros(out_features, in_features // 2, dtype=torch.uint8))
+        self.register_buffer("scales", torch.zeros(out_features, dtype=torch.float32))
+        self.register_buffer("zero_points", torch.zeros(out_features, dtype=torch.float32))
+        # Weights written by a kernel that may still be running (from_linear) must not be
+        # prefetched ahead of it; the first forward therefore runs without the static-weights flag.
+        self._weights_settled = False
+
+    @classmethod
+    def from_linear(cls, linear: nn.Linear) -> "QuantizedLinear":
+        assert linear.bias is None, "Bias not supported yet"   # python/module.py:84
+        module = cls(linear.in_features, linear.out_features)
+        packed, scales, zp = quantize_weights(linear.weight.data)
+        module.packed_weights = packed
+        module.scales = scales
+        module.zero_points = zp
+        return module
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if not x.is_cuda:
+            raise RuntimeError("QuantizedLinear (b200) runs on CUDA only; move the module and the input to a B200")
+        if self.packed_weights.device != x.device:
+            raise RuntimeError(f"weights are on {self.packed_weights.device}, input on {x.device}")
+        return self._forward_cuda(x)
+
+    def _forward_cuda(self, x: torch.Tensor) -> torch.Tensor:
+        lead = x.shape[:-1]
+        if x.shape[-1] != self.in_features:
+            raise RuntimeError(f"expected last dim {self.in_features}, got {x.shape[-1]}")
+        x2 = x.reshape(-1, self.in_features)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        flags = _lib.FLAG_STATIC_WEIGHTS if self._weights_settled else _lib.FLAG_NONE
+        y = _lib.linear_fwd(x2, self.packed_weights, self.scales, self.zero_points, flags=flags)
+        self._weights_settled = True
+        return y.reshape(*lead, self.out_features)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._weights_settled = False
+        return super()._load_from_state_dict(*args, **kwargs)
+
+    def extra_repr(self) -> str:
+        return (f"in_features={self.in_features}, "
+                f"out_features={self.out_features}, "
+                f"bits=4")

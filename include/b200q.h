@@ -16,6 +16,7 @@
  *   b200q_moe_gather_rows   <- create_expert_inputs row gather      routing.py:137-147
  *   b200q_moe_grouped_fwd   <- moe_int4_cuda.forward                csrc/moe_int4_kernel.cu:93-141
  *                              + QuantizedMoE.forward               benchmark/moe_grouped_gemm/moe_int4_module.py:123-125
+ *   b200q_moe_grouped_fwd_ranges <- moe_int4_cuda.forward (input_offsets, tokens_per_expert)   csrc/moe_int4_kernel.cu:112-123
  *   b200q_moe_silu_mul      <- (north_star extension: gated MLP, silu(x w1^T) * (x w3^T))
  *   b200q_moe_combine       <- combine_expert_outputs               routing.py:152-189
  *
@@ -112,8 +113,8 @@ int b200q_linear_fwd(const void* x, int x_dtype, const uint8_t* packed, const fl
                      const float* zps, void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
                      void* ws, size_t ws_bytes, unsigned flags, void* stream);
 
-/* Bench / tuning hook: override a launch heuristic process-wide (key = "gemv_warps" | "gemv_cluster"
- * | "gemv_stages" | "gemv_pdl" | "force_path"; value < 0 restores the default).  Not needed by callers. */
+/* Bench / tuning hook: override a launch heuristic process-wide (key = "gemv_warps" | "gemv_slabs"
+ * | "gemv_stages" | "gemv_pdl" | "gemv_ctas" | "force_path"; value < 0 restores the default).  Not needed by callers. */
 int b200q_tune_set(const char* key, int value);
 
 /* ---- MoE ---------------------------------------------------------------------------------- */
@@ -149,6 +150,15 @@ size_t b200q_moe_grouped_ws_bytes(int64_t R, int E, int64_t N, int64_t K);
 int b200q_moe_grouped_fwd(const void* xs, int x_dtype, const uint8_t* packed, const float* scales,
                           const float* zps, const int32_t* offsets, int E, void* y, int y_dtype,
                           int64_t R, int64_t N, int64_t K, void* ws, size_t ws_bytes, void* stream);
+
+/* Same, for groups given as explicit ranges [starts[e], ends[e]) (both [E] i32 on device) that
+ * need not be contiguous -- the (input_offsets, tokens_per_expert) form of
+ * csrc/moe_int4_kernel.cu:112-123 with ends = input_offsets + tokens_per_expert.  Rows covered by no
+ * range are NOT written (the caller zero-fills y, as moe_int4_kernel.cu:109 does). */
+int b200q_moe_grouped_fwd_ranges(const void* xs, int x_dtype, const uint8_t* packed,
+                                 const float* scales, const float* zps, const int32_t* starts,
+                                 const int32_t* ends, int E, void* y, int y_dtype, int64_t R,
+                                 int64_t N, int64_t K, void* ws, size_t ws_bytes, void* stream);
 
 /* h[p,f] = silu(a[p,f]) * b[p,f] where a = gu[p, 0:F], b = gu[p, F:2F]  (gated-MLP extension). */
 int b200q_moe_silu_mul(const void* gu, int dtype, int64_t R, int64_t F, void* h, void* stream);

@@ -1,0 +1,179 @@
+"""GPU parity tests for the fused dequantize-linear path, through the reference-facing API
+(fused_quant_linear_cuda.forward / QuantizedLinear) which calls the C ABI of libb200q.so.
+
+Tolerances: the reference's own (tests/test_correctness.py:201-253): atol 1e-3 for K <= 512,
+atol 1e-2 for K = 4096 against the fp32 dequantize+matmul oracle; tighter bounds vs the float64
+oracle are asserted too and documented per test."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+Q = load_golden("quantize")
+L = load_golden("linear")
+
+
+def cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def ext_forward(x, p, s, z):
+    import fused_quant_linear_cuda
+    return fused_quant_linear_cuda.forward(cuda(x), cuda(p), cuda(s), cuda(z)).cpu().numpy()
+
+
+# ---- the reference's three CUDA tests, same seeds / shapes / tolerances -----------------------
+def test_cuda_matches_reference_1d(oracle):
+    torch.manual_seed(42)
+    weight = torch.randn(64, 128)
+    x = torch.randn(128)
+    p, s, z = oracle.quantize_weights(weight.numpy())
+    ref = oracle.reference_quantized_linear(x.numpy(), p, s, z)
+    out = ext_forward(x.numpy(), p, s, z)
+    assert out.shape == (64,)
+    assert np.allclose(ref, out, atol=1e-3), f"Max diff: {np.abs(ref - out).max()}"
+    assert np.allclose(L["t1d_y"], out, atol=1e-3)          # the real reference's output
+
+
+def test_cuda_matches_reference_batched(oracle):
+    torch.manual_seed(42)
+    weight = torch.randn(256, 512)
+    x = torch.randn(4, 512)
+    p, s, z = oracle.quantize_weights(weight.numpy())
+    ref = oracle.reference_quantized_linear(x.numpy(), p, s, z)
+    out = ext_forward(x.numpy(), p, s, z)
+    assert out.shape == (4, 256)
+    assert np.allclose(ref, out, atol=1e-3), f"Max diff: {np.abs(ref - out).max()}"
+    assert np.allclose(L["tb_y"], out, atol=1e-3)
+
+
+def test_cuda_large_dims(oracle):
+    torch.manual_seed(7)
+    weight = torch.randn(4096, 4096)
+    x = torch.randn(4096)
+    p, s, z = oracle.quantize_weights(weight.numpy())
+    ref = oracle.reference_quantized_linear(x.numpy(), p, s, z)
+    out = ext_forward(x.numpy(), p, s, z)
+    assert np.allclose(ref, out, atol=1e-2), f"Max diff: {np.abs(ref - out).max()}"
+    assert np.allclose(Q["s7_4096_y"], out, atol=1e-2)
+    ref64 = oracle.reference_quantized_linear(x.numpy(), p, s, z, acc=np.float64)
+    err = np.abs(ref64 - out).max()
+    print(f"4096x4096 max abs err vs float64 oracle: {err:.3e} (|y|max {np.abs(ref64).max():.1f})")
+    assert err < 2e-3
+
+
+# ---- shape / batch sweep over every kernel path ------------------------------------------------
+@pytest.mark.parametrize("N,K", [(64, 128), (100, 256), (256, 512), (1000, 1024), (37, 90), (8, 2), (129, 384)])
+@pytest.mark.parametrize("M", [1, 2, 3, 4, 5, 8, 13, 16, 17, 40])
+def test_linear_sweep(oracle, N, K, M):
+    rng = np.random.default_rng(N * 131 + K * 7 + M)
+    w = rng.standard_normal((N, K), dtype=np.float32)
+    x = rng.standard_normal((M, K), dtype=np.float32)
+    p, s, z = oracle.quantize_weights(w)
+    ref = oracle.reference_quantized_linear(x, p, s, z, acc=np.float64)
+    out = ext_forward(x, p, s, z)
+    assert out.shape == (M, N)
+    tol = 1e-3 if K <= 512 else 2e-3
+    assert np.abs(ref - out).max() < tol, f"max err {np.abs(ref - out).max()}"
+
+
+@pytest.mark.parametrize("K,N", [(4096, 11008), (11008, 4096), (4096, 14336), (14336, 4096)])
+@pytest.mark.parametrize("M", [1, 4, 16])
+def test_llama_mixtral_decode_shapes(oracle, K, N, M):
+    """BASELINE config 2 shapes at full size: rows sampled against the float64 oracle plus two
+    size-independent properties: linearity in x and exact zero for zero input."""
+    rng = np.random.default_rng(K + N + M)
+    packed = rng.integers(0, 256, size=(N, K // 2), dtype=np.uint8)
+    scales = (rng.random(N, dtype=np.float32) * 0.01 + 0.001).astype(np.float32)
+    zps = rng.integers(0, 16, size=N).astype(np.float32)
+    x = rng.standard_normal((M, K), dtype=np.float32)
+    import fused_quant_linear_cuda as ext
+    P, S, Z = cuda(packed), cuda(scales), cuda(zps)
+    y = ext.forward(cuda(x), P, S, Z).cpu().numpy()
+    rows = rng.choice(N, size=256, replace=False)
+    ref = oracle.reference_quantized_linear(x, packed[rows], scales[rows], zps[rows], acc=np.float64)
+    err = np.abs(ref - y[:, rows]).max()
+    scale = np.abs(ref).max()
+    print(f"K={K} N={N} M={M}: max abs err {err:.3e}, |y|max {scale:.2f}, rel {err / scale:.2e}")
+    assert err < 1e-2 and err / scale < 2e-5
+    # linearity: f(2x) == 2 f(x) exactly (power-of-two scaling commutes with every rounding step)
+    y2 = ext.forward(cuda(2 * x), P, S, Z).cpu().numpy()
+    assert np.array_equal(y2, 2 * y)
+    # determinism: bit-identical on a second run
+    assert np.array_equal(ext.forward(cuda(x), P, S, Z).cpu().numpy(), y)
+    assert not np.any(ext.forward(cuda(np.zeros_like(x)), P, S, Z).cpu().numpy())
+
+
+def test_forced_generic_path_matches(oracle, pkg):
+    """The SIMT path mirrors the reference's arithmetic order (w = (q - zp) * s first)."""
+    rng = np.random.default_rng(0)
+    w = rng.standard_normal((96, 256), dtype=np.float32)
+    x = rng.standard_normal((3, 256), dtype=np.float32)
+    p, s, z = oracle.quantize_weights(w)
+    ref = oracle.reference_quantized_linear(x, p, s, z, acc=np.float64)
+    pkg._lib.tune("force_path", 1)
+    try:
+        out = ext_forward(x, p, s, z)
+    finally:
+        pkg._lib.tune("force_path", -1)
+    assert np.abs(ref - out).max() < 1e-4
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("M", [1, 7, 33])
+def test_half_precision_activations(oracle, pkg, dtype, M):
+    """Superset of the reference API: fp16 / bf16 activations and outputs (what QuantizedMoEExpert
+    feeds, moe_int4_module.py:71-72).  Error bound: output rounding of the 16-bit type."""
+    rng = np.random.default_rng(M)
+    w = (rng.standard_normal((192, 512)) * 0.05).astype(np.float32)
+    p, s, z = oracle.quantize_weights(w)
+    x = torch.from_numpy(rng.standard_normal((M, 512)).astype(np.float32)).to(dtype)
+    ref = oracle.reference_quantized_linear(x.float().numpy(), p, s, z, acc=np.float64)
+    y = pkg._lib.linear_fwd(x.cuda(), cuda(p), cuda(s), cuda(z))
+    assert y.dtype == dtype
+    eps = 2.0 ** -10 if dtype == torch.float16 else 2.0 ** -7
+    assert np.abs(ref - y.float().cpu().numpy()).max() <= eps * np.abs(ref).max() + 1e-4
+
+
+def test_module_forward_and_state_dict(oracle, pkg):
+    torch.manual_seed(42)
+    lin = torch.nn.Linear(512, 256, bias=False)
+    ql = pkg.QuantizedLinear.from_linear(lin.cuda())
+    p, s, z = oracle.quantize_weights(lin.weight.detach().cpu().numpy())
+    assert np.array_equal(ql.packed_weights.cpu().numpy(), p)
+    x = torch.randn(2, 3, 512, device="cuda")
+    y = ql(x)
+    assert y.shape == (2, 3, 256)
+    ref = oracle.reference_quantized_linear(x.reshape(-1, 512).cpu().numpy(), p, s, z, acc=np.float64)
+    assert np.abs(ref - y.reshape(-1, 256).cpu().numpy()).max() < 1e-3
+    y1 = ql(x[0, 0])                      # second call takes the static-weights (PDL) launch
+    assert y1.shape == (256,)
+    assert np.abs(ref[0] - y1.cpu().numpy()).max() < 1e-3
+    ql2 = pkg.QuantizedLinear(512, 256).cuda()
+    ql2.load_state_dict(ql.state_dict())
+    assert torch.equal(ql2(x), y)
+    with pytest.raises(RuntimeError):
+        ql(x.cpu())
+
+
+def test_extension_error_behaviour(pkg):
+    import fused_quant_linear_cuda as ext
+    p = torch.zeros(8, 16, dtype=torch.uint8, device="cuda")
+    s = torch.ones(8, device="cuda")
+    z = torch.zeros(8, device="cuda")
+    x = torch.zeros(32, device="cuda")
+    assert ext.forward(x, p, s, z).shape == (8,)
+    with pytest.raises(RuntimeError, match="input must be float32"):
+        ext.forward(x.half(), p, s, z)
+    with pytest.raises(RuntimeError, match="packed_weights must be uint8"):
+        ext.forward(x, p.float(), s, z)
+    with pytest.raises(RuntimeError, match="packed_weights dim 1 must be input_dim / 2"):
+        ext.forward(torch.zeros(30, device="cuda"), p, s, z)
+    with pytest.raises(RuntimeError, match="input must be contiguous"):
+        ext.forward(torch.zeros(4, 64, device="cuda")[:, ::2], p, s, z)
+    with pytest.raises(RuntimeError, match="packed_weights must be a CUDA tensor"):
+        ext.forward(x, p.cpu(), s, z)
+    assert ext.forward(torch.zeros(0, 32, device="cuda"), p, s, z).shape == (0, 8)
