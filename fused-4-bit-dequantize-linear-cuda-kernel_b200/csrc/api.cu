@@ -66,7 +66,9 @@ int b200q_dequantize_rows(const uint8_t* packed, const float* scales, const floa
 size_t b200q_linear_ws_bytes(int64_t M, int64_t N, int64_t K) {
     size_t a = gemv_ws_bytes(M, N, K);
     size_t b = gemm_tc_ws_bytes(M, N, K);
-    return a > b ? a : b;
+    size_t c = gemv_tc_ws_bytes(M, N, K);
+    if (b > a) a = b;
+    return c > a ? c : a;
 }
 
 int b200q_linear_fwd(const void* x, int x_dtype, const uint8_t* packed, const float* scales,
@@ -82,11 +84,13 @@ int b200q_linear_fwd(const void* x, int x_dtype, const uint8_t* packed, const fl
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int force = tuning().force_path;
     const bool vec_ok = aligned(x, 16) && aligned(packed, 16) && aligned(y, 16);
-    if (force != 1 && force != 3 && vec_ok && gemv_supported(M, N, K, x_dtype))
+    if ((force <= 0 || force == 4) && vec_ok && gemv_tc_supported(M, N, K))
+        return launch_gemv_tc(d, x, x_dtype, packed, scales, zps, y, y_dtype, M, N, K, ws, ws_bytes, flags, st);
+    if (force != 1 && force != 3 && force != 4 && vec_ok && gemv_supported(M, N, K, x_dtype))
         return launch_gemv(d, x, x_dtype, packed, scales, zps, y, y_dtype, M, N, K, ws, ws_bytes, flags, st);
     if (force != 1 && force != 2 && vec_ok && gemm_tc_supported(M, N, K, x_dtype, y_dtype))
         return launch_gemm_tc(d, x, x_dtype, packed, scales, zps, y, y_dtype, M, N, K, nullptr, nullptr, 1, ws, ws_bytes, flags, st);
-    if (force == 2 || force == 3) return set_error(B200Q_EINVAL, "linear_fwd: forced path %d does not support this shape / alignment", force);
+    if (force == 2 || force == 3 || force == 4) return set_error(B200Q_EINVAL, "linear_fwd: forced path %d does not support this shape / alignment", force);
     return launch_linear_generic(x, x_dtype, packed, scales, zps, y, y_dtype, M, N, K, nullptr, nullptr, 1, 0, st);
 }
 

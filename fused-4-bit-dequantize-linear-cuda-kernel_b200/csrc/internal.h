@@ -34,7 +34,8 @@ struct Tuning {
     int gemv_stages = -1;   // cap on ring depth
     int gemv_pdl = -1;      // 0 disables programmatic dependent launch
     int gemv_ctas = -1;     // cap on the number of CTAs (default: SM count)
-    int force_path = -1;    // 0 auto, 1 generic SIMT, 2 gemv, 3 tcgen05 gemm
+    int gemv_debug = -1;    // bench-only ablations: 1 = skip the mma work, 2 = skip the weight loads
+    int force_path = -1;    // 0 auto, 1 generic SIMT, 2 gemv (mma.sync), 3 tcgen05 gemm, 4 gemv (tcgen05)
 };
 const Tuning& tuning();
 
@@ -61,6 +62,13 @@ size_t gemv_ws_bytes(int64_t M, int64_t N, int64_t K);
 int launch_gemv(const DeviceInfo& dev, const void* x, int x_dtype, const uint8_t* packed,
                 const float* scales, const float* zps, void* y, int y_dtype, int64_t M, int64_t N,
                 int64_t K, void* ws, size_t ws_bytes, unsigned flags, cudaStream_t st);
+
+// decode GEMV on tcgen05 (weights -> TMEM A operand), M <= 8, K % 128 == 0
+bool gemv_tc_supported(int64_t M, int64_t N, int64_t K);
+size_t gemv_tc_ws_bytes(int64_t M, int64_t N, int64_t K);
+int launch_gemv_tc(const DeviceInfo& dev, const void* x, int x_dtype, const uint8_t* packed,
+                   const float* scales, const float* zps, void* y, int y_dtype, int64_t M, int64_t N,
+                   int64_t K, void* ws, size_t ws_bytes, unsigned flags, cudaStream_t st);
 
 // prefill / grouped path on tcgen05 tensor cores (M >= 17 rows, K % 128 == 0, N % 16 == 0).
 // starts == nullptr: plain linear; else grouped over E experts (packed [E,N,K/2]).
