@@ -1,20 +1,22 @@
-// Decode path: y[M,N] = x[M,K] @ dequant(W)^T for M <= 16.  HBM-bound: every packed byte is read
+// Decode path: y[M,N] = x[M,K] @ dequant(W)^T for M <= 8.  HBM-bound: every packed byte is read
 // exactly once, by the TMA engine, into shared memory; everything else is on-chip.
 //
 // Decomposition (DESIGN.md "GEMV"):
 //   * K is cut into `nslab` slabs of whole 128-column granules, N into `nrb` row blocks;
 //     CTA (rb, slab) streams rows [r0,r1) x slab bytes.  nslab * nrb ~= SM count, one CTA per SM.
-//   * a stage of the shared-memory ring = 16 weight rows x one chunk of NW granules, filled by 16
-//     cp.async.bulk row copies (UBLKCP) that complete on the stage's mbarrier.  The ring is deep
-//     enough that for the Llama shapes the CTA's whole slab is requested in the first instructions
-//     of the kernel (every warp issues its share; there is no dedicated producer warp).
+//   * a stage of the shared-memory ring = 16 weight rows x one chunk of NW granules.  Warp w issues
+//     the cp.async.bulk (UBLKCP) of row w of every stage, so the whole slab of the Llama shapes is
+//     requested within the first microsecond of the kernel, 16 issuers in parallel.
+//   * arithmetic is EXACT INTEGER: nibbles are widened to u8 with 3 ALU ops per 8 weights
+//     (w & 0x0f0f0f0f, (w >> 4) & 0x0f0f0f0f) and fed to IMMA m16n8k32 (u8 x s8 -> s32); x is a
+//     per-row fixed-point number round(x * 2^e) < 2^30 cut into four signed base-256 limbs, one mma
+//     column per (batch row, limb).  sum_k q*X and sum_k X are exact, so the result differs from the
+//     fp32 reference only by the 2^-30 fixed-point step of x and the final fp32 rounding, and it is
+//     bit-reproducible whatever the summation order.
 //   * warp w owns granules w, w+NW, ... of the slab for the whole kernel, so its x operand (mma B
-//     fragments) is built ONCE in registers; the main loop is LDS.128 -> LOP3 -> HMMA only.
-//     Weights enter the mma as exact fp16 SUBNORMALS (nibble * 2^-24, no arithmetic); x enters as
-//     an fp16 hi/lo split of x * 2^e (per-warp power-of-two e), so the products are exact and the
-//     accumulation is fp32: results match the fp32 reference to ~1e-6 relative.
-//   * per-warp tile partials go to shared memory without a barrier; once per round of `rt` tiles:
-//     one named barrier, fixed-order cross-warp sum, epilogue y = s * (acc - zp * sum(x)); with
+//     fragments) sits in registers; the CTA builds it cooperatively, once, through shared memory.
+//   * per-warp tile partials (s32) go to shared memory without a barrier; once per round of `rt`
+//     tiles: one named barrier, cross-warp sum, epilogue y = s * 2^-e * (sum q*X - zp * sum X); with
 //     nslab > 1 the slab partials go to a workspace and the last CTA of a row block (ticket counter)
 //     adds them in slab order: deterministic.
 //
@@ -36,6 +38,8 @@ constexpr int GRAN_K = 128;          // columns per granule
 constexpr int GRAN_B = GRAN_K / 2;   // packed bytes per granule per row
 constexpr int MAX_SLABS = 16;
 constexpr int MAX_RB = 1024;         // ticket counters at the head of the workspace
+constexpr int MAX_STAGES = 64;
+constexpr int LIMBS = 4;             // signed base-256 digits of round(x * 2^e)
 
 struct GemvParams {
     const void* x;
@@ -47,15 +51,18 @@ struct GemvParams {
     unsigned int* tickets;  // [nrb]
     int x_dtype, y_dtype;
     int M, N, K;
-    int nslab, nrb, G;      // G = K / 128
-    int stages;             // ring depth (stage = 16 rows x one chunk of NW granules)
+    int nslab, nrb;
+    int rows_q, rows_rem;   // N = nrb * rows_q + rows_rem: row block rb has rows_q (+1 if rb < rows_rem) rows
+    int gran_q, gran_rem;   // K / 128 granules split the same way over the slabs
+    int stages;             // ring depth (stage = 16 rows x one chunk of granules)
+    int whole_row;          // 1: a stage holds the whole slab row (all GPW granules of every warp), else NW granules
+    int contig;             // 1 (nslab == 1, whole_row): a tile is ONE contiguous bulk copy, pitch = K/2
     int pitch;              // bytes between rows of a stage
     int rt;                 // tiles per cross-warp reduction round
-    int rg, rg_shift;       // live mma columns per n-tile (2, 4 or 8) and log2 of it
-    int red_off;            // byte offset of the reduction buffer
-    int ring_off;           // byte offset of the ring in dynamic shared memory
+    int rg, rg_shift;       // live mma columns per n-tile (4 or 8) and log2 of it
+    int xf_off, red_off, ring_off;   // byte offsets in dynamic shared memory
     int wait_weights;       // 1: weights may be written by the preceding kernel -> wait first
-    int debug;              // bench-only: 1 = skip the mma work, 2 = skip the weight loads
+    int debug;              // bench-only: low bits 1 = skip the mma work, 2 = skip the weight loads; 8 = timestamps
 };
 
 __device__ __forceinline__ void load4f(const void* x, int dtype, int64_t idx, float (&v)[4]) {
@@ -81,54 +88,41 @@ __device__ __forceinline__ void store_y(void* y, int dtype, int64_t idx, float v
     else static_cast<__nv_bfloat16*>(y)[idx] = __float2bfloat16_rn(v);
 }
 
-// Nibble -> fp16 with NO arithmetic: a nibble left in the low mantissa bits of an fp16 with a zero
-// exponent field is the subnormal n * 2^-24 (bits 0-3) or n * 2^-20 (bits 4-7), exactly.  The tensor
-// core consumes fp16 subnormals at full precision, so one LOP3 (AND) per two weights is the whole
-// dequantisation; the 2^-24 / 2^-20 factors are folded into x (high-nibble columns are pre-scaled
-// by 2^-4) and into the epilogue's power-of-two descale.
-//   r[0] = (n0,n4) * 2^-24   r[1] = (n1,n5) * 2^-20   r[2] = (n2,n6) * 2^-24   r[3] = (n3,n7) * 2^-20
-__device__ __forceinline__ void nibbles_to_subnormal_half2x4(uint32_t w, uint32_t (&r)[4]) {
-    constexpr uint32_t LO = 0x000f000fu, HI = 0x00f000f0u;
-    const uint32_t w2 = w >> 8;
-    r[0] = w & LO;
-    r[1] = w & HI;
-    r[2] = w2 & LO;
-    r[3] = w2 & HI;
-}
-
-__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
-    __half2 h = __halves2half2(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
+// D(16x8,s32) += A(16x32,u8,row) * B(32x8,s8,col)      SASS: IMMA.16832.U8.S8
+__device__ __forceinline__ void mma_m16n8k32_u8s8(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                                  uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
 // Shared memory carve-up (dynamic):
 //   [0, 512) full mbarriers, [512, 1024) empty mbarriers, [1024, 1088) flags
-//   [1088, ..)   rowc[48] f32, pro[NW][16][2] f32 (prologue scratch)
-//   [XF_OFF, ..) xf: mma-B vectors, ng * NT * rg * 256 bytes
-//   [red_off,..) red[rt][NW][NT*4][16] f32
+//   [1088, 1152)  per-warp amax f32 [16], [1280, 1536) limb sums s32 [16][4]
+//   [1536, ..)    ls: limb-sum slots s32, one per (granule, n-tile, column)
+//   [xf_off, ..)  xf: mma-B vectors (8 bytes per (granule, n-tile, column, t, word))
+//   [red_off,..)  red[rt][NW][NT*8 columns][16] s32
 //   [ring_off, ...)  stages x 16 x pitch bytes
-constexpr int BAR_BYTES = 1024;
 constexpr int MISC_OFF = 1024;
-constexpr int MAX_STAGES = 64;
-
-template <int NW, int NT>
-struct SmemLayout {
-    static constexpr int COLS = NT * 4;
-    static constexpr int ROWC_OFF = 1088;
-    static constexpr int PRO_OFF = ROWC_OFF + 48 * 4;
-    static constexpr int XF_OFF = ((PRO_OFF + NW * 16 * 2 * 4 + 127) / 128) * 128;
-    static constexpr int RED_TILE_BYTES = NW * COLS * TILE_ROWS * 4;
-};
+constexpr int AMAX_OFF = 1088;
+constexpr int LSUM_OFF = 1280;
+constexpr int LS_OFF = 1536;
 
 template <int NW, int GPW, int NT>
 __global__ void __launch_bounds__(NW * 32, 1) gemv_kernel(const GemvParams p) {
-    using L = SmemLayout<NW, NT>;
-    constexpr int COLS = NT * 4;
-    constexpr int CH = NT == 1 ? 4 : 2;            // independent mma accumulator chains per n-tile
+    constexpr int COLS = NT * 8;                   // mma columns: (batch row, limb), two batch rows per n-tile
+    constexpr int NTHR = NW * 32;
+    constexpr int RPW = TILE_ROWS / NW;            // stage rows issued per warp (1 or 2)
+    constexpr int CH = NT == 1 ? 4 : 2;            // independent IMMA accumulator chains per n-tile
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t smem_base = smem_u32(smem);
-    float* red = reinterpret_cast<float*>(smem + p.red_off);
+    float* amax_w = reinterpret_cast<float*>(smem + AMAX_OFF);     // one slot per warp
+    int* lsum_s = reinterpret_cast<int*>(smem + LSUM_OFF);          // [batch row][limb] after consolidation
+    int* ls = reinterpret_cast<int*>(smem + LS_OFF);                // per (granule, n-tile, column) partial sums
+    int* red = reinterpret_cast<int*>(smem + p.red_off);
     volatile int* flag = reinterpret_cast<volatile int*>(smem + MISC_OFF);
+    const uint32_t xf = smem_base + p.xf_off;
     const uint32_t ring = smem_base + p.ring_off;
     const int S = p.stages;
     const int dbg = p.debug & 7;
@@ -136,263 +130,402 @@ __global__ void __launch_bounds__(NW * 32, 1) gemv_kernel(const GemvParams p) {
     auto empty_bar = [&](int s) { return smem_base + 512u + 8u * s; };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ctid = threadIdx.x;
     const bool prof = (p.debug & 8) && threadIdx.x == 0 && blockIdx.x < 256;
     auto stamp = [&](int i) { if (prof) g_gemv_prof[blockIdx.x * 16 + i] = clock64(); };
     stamp(0);
-    const int slab = blockIdx.x % p.nslab, rb = blockIdx.x / p.nslab;
-    const int g0 = (int)((int64_t)p.G * slab / p.nslab), g1 = (int)((int64_t)p.G * (slab + 1) / p.nslab);
-    const int ng = g1 - g0;                       // granules in this slab
-    const int r0 = (int)((int64_t)p.N * rb / p.nrb), r1 = (int)((int64_t)p.N * (rb + 1) / p.nrb);
+    const int slab = p.nslab == 1 ? 0 : (int)(blockIdx.x % p.nslab);
+    const int rb = p.nslab == 1 ? (int)blockIdx.x : (int)(blockIdx.x / p.nslab);
+    const int g0 = slab * p.gran_q + min(slab, p.gran_rem);
+    const int ng = p.gran_q + (slab < p.gran_rem ? 1 : 0);        // granules in this slab
+    const int r0 = rb * p.rows_q + min(rb, p.rows_rem);
+    const int r1 = r0 + p.rows_q + (rb < p.rows_rem ? 1 : 0);
     const int ntiles = (r1 - r0 + TILE_ROWS - 1) / TILE_ROWS;
+    const int nq = p.whole_row ? 1 : (ng + NW - 1) / NW;          // chunks (= stages) per tile
+    const int total_stages = ntiles * nq;
     const uint32_t stage_bytes = TILE_ROWS * p.pitch;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
-            mbar_init(full_bar(s), 1);
+            mbar_init(full_bar(s), p.contig ? 1 : NW);
             mbar_init(empty_bar(s), NW);
         }
         fence_mbar_init();
     }
     __syncthreads();
     pdl_launch_dependents();
+    stamp(1);
 
-    // ---- weight streaming.  Stage st = (tile st / nq, chunk st % nq): 16 rows x NW granules, one
-    // cp.async.bulk per row.  Stage st is issued by warp st % NW: the first min(S, total) stages
-    // right here (for the Llama shapes that is the CTA's whole slab), later ones as ring slots
-    // free up (see the refill hook in the main loop).
-    const int nq = (ng + NW - 1) / NW;             // chunks per tile in this slab
-    const int total_stages = ntiles * nq;
+    // ---- weight streaming.  Stage st = (tile, chunk): 16 rows x up to NW granules.  Warp w owns row
+    // w (and w + 8 when NW == 8) of every stage: its lane 0 arms the stage barrier with that row's
+    // byte count and issues the row's bulk copy.  The first min(S, total) stages go out right here
+    // (for the Llama shapes: the CTA's whole slab); later ones as ring slots free up.
     const uint64_t pol = policy_evict_first();
     const uint8_t* src0 = p.packed + (int64_t)g0 * GRAN_B;
-    auto issue_stage = [&](int st, int slot) {
-        const int ti = st / nq, q = st - ti * nq;
+    const int64_t row_bytes = p.K / 2;
+    auto issue_stage = [&](int ti, int q, int slot) {         // call with lane 0 only
         const int row = r0 + ti * TILE_ROWS;
-        const int rows = min(TILE_ROWS, r1 - row);
-        const int cb = min(NW, ng - q * NW) * GRAN_B;
-        if (lane == 0) mbar_arrive_expect_tx(full_bar(slot), (uint32_t)(rows * cb));
-        __syncwarp();
-        if (lane < rows)
-            bulk_g2s_hint(ring + slot * stage_bytes + lane * p.pitch,
-                          src0 + (int64_t)(row + lane) * (p.K / 2) + q * NW * GRAN_B, (uint32_t)cb,
-                          full_bar(slot), pol);
+        const uint32_t cb = (uint32_t)((p.whole_row ? ng : min(NW, ng - q * NW)) * GRAN_B);
+        uint32_t tx = 0;
+#pragma unroll
+        for (int rr = 0; rr < RPW; ++rr)
+            if (row + warp + rr * NW < r1) tx += cb;
+        if (tx) mbar_arrive_expect_tx(full_bar(slot), tx);
+        else mbar_arrive(full_bar(slot));
+#pragma unroll
+        for (int rr = 0; rr < RPW; ++rr) {
+            const int r = warp + rr * NW;
+            if (row + r < r1)
+                bulk_g2s_hint(ring + slot * stage_bytes + r * p.pitch,
+                              src0 + (int64_t)(row + r) * row_bytes + q * NW * GRAN_B, cb, full_bar(slot), pol);
+        }
     };
-    stamp(1);
+    // contiguous mode (one K slab): the rows of a tile are adjacent in memory, so the whole tile is
+    // ONE bulk copy of up to 32 KB issued by warp 0 -- the TMA unit accepts a copy only every ~18 clk,
+    // which made 16 copies per tile the longest part of the prologue (profiles/r01_gemv_notes.md).
+    auto issue_tile = [&](int ti, int slot) {                 // warp 0, lane 0
+        const int row = r0 + ti * TILE_ROWS;
+        const uint32_t bytes = (uint32_t)(min(TILE_ROWS, r1 - row) * row_bytes);
+        mbar_arrive_expect_tx(full_bar(slot), bytes);
+        bulk_g2s_hint(ring + slot * stage_bytes, p.packed + (int64_t)row * row_bytes, bytes, full_bar(slot), pol);
+    };
     if (p.wait_weights) pdl_wait();
-    if (dbg != 2)
-        for (int st = warp; st < min(S, total_stages); st += NW) issue_stage(st, st);
+    if (lane == 0 && dbg != 2) {
+        if (p.contig) {
+            if (warp == 0)
+                for (int ti = 0; ti < ntiles && ti < S; ++ti) issue_tile(ti, ti);
+        } else {
+            int st = 0;
+            for (int ti = 0; ti < ntiles && st < S; ++ti)
+                for (int q = 0; q < nq && st < S; ++q, ++st) issue_stage(ti, q, st);
+        }
+    }
     stamp(2);
 
-    // ---------------------------------------------------------------- consumer warps
     const int g = lane >> 2, t = lane & 3;
-    const int ctid = threadIdx.x;                     // 0 .. NW*32-1
     pdl_wait();   // x (and the output / workspace) belong to the stream-ordered predecessor
     stamp(3);
 
-    // ---- x operand, built cooperatively ONCE per CTA (every CTA needs all of x[:, slab]; doing it
-    // per warp made this prologue the longest phase of the kernel, profiles/r01_gemv_notes.md).
-    //  pass 1: per batch row amax and sum over the slab           -> rowc (2^e, 2^(24-e), sum x)
-    //  pass 2: one 16-byte mma-B vector per item                  -> xf in shared memory
-    //  then every lane loads its own B fragments with LDS.128.
-    // Lane (g,t) feeds mma column g: batch row nt*4 + g/2, part g&1 (0: fp16(x*2^e), 1: the fp16
-    // remainder).  Vector j of a granule covers columns k0 + 32t + 8j + {0..7}, packed in the nibble
-    // order of nibbles_to_subnormal_half2x4; the columns that meet high nibbles carry 2^-4.
-    float* pro = reinterpret_cast<float*>(smem + L::PRO_OFF);     // [NW][16][2] scratch
-    float* rowc = reinterpret_cast<float*>(smem + L::ROWC_OFF);   // descale[16], sumx[16], up[16]
-    const uint32_t xf = smem_base + L::XF_OFF;
-    const int kslab0 = g0 * GRAN_K, kslab = ng * GRAN_K;
-    const int rg = p.rg, rgs = p.rg_shift;                        // live mma columns per n-tile (2, 4 or 8)
-#pragma unroll 1
-    for (int m = 0; m < p.M; ++m) {
-        float am = 0.0f, sm = 0.0f;
-        for (int k = ctid * 4; k < kslab; k += NW * 32 * 4) {
-            float v[4];
-            load4f(p.x, p.x_dtype, (int64_t)m * p.K + kslab0 + k, v);
-            am = fmaxf(am, fmaxf(fmaxf(fabsf(v[0]), fabsf(v[1])), fmaxf(fabsf(v[2]), fabsf(v[3]))));
-            sm += (v[0] + v[1]) + (v[2] + v[3]);
-        }
+    // ---- x operand, built cooperatively ONCE per CTA.
+    // item = (granule gq, n-tile nt, batch row h of the tile, t, word j) -> the 8 columns
+    // k0 + 32t + 8j + {0..7} of batch row m = 2nt + h.  X = round(x * 2^e) is split into four signed
+    // base-256 digits; digit l of the 8 values is stored as the two B registers of IMMA j in mma
+    // column 4h + l: {X0,X2,X4,X6} (meets the low nibbles) and {X1,X3,X5,X7} (high nibbles).
+    const int kslab0 = g0 * GRAN_K;
+    const int rg = p.rg, rgs = p.rg_shift;
+    const int hs = rgs - 2;                                  // log2(batch rows per n-tile that are stored)
+    const int items = ng * NT * 16 << hs;
+    auto decode = [&](int it, int& m, uint32_t& slot, int64_t& base) {
+        const int t_ = it & 3, j = (it >> 2) & 3, h = (it >> 4) & ((1 << hs) - 1);
+        const int rest = it >> (4 + hs);
+        const int nt = rest % NT, gq = rest / NT;
+        m = nt * 2 + h;
+        base = (int64_t)m * p.K + kslab0 + gq * GRAN_K + t_ * 32 + j * 8;
+        // lane (column c, t) of (gq, nt) reads its 4 words (32 bytes) contiguously; c = 4h + limb
+        slot = (uint32_t)((((((gq * NT + nt) << rgs) + 4 * h) * 4 + t_) * 4 + j) * 8);
+    };
+    // ONE power-of-two scale for the CTA's block of x: amax * 2^e in [2^29, 2^30) (e is exact to undo)
+    auto scale_exp = [&]() {
+        float am = 0.0f;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, o));
-            sm += __shfl_xor_sync(0xffffffffu, sm, o);
-        }
-        if (lane == 0) {
-            pro[(warp * 16 + m) * 2] = am;
-            pro[(warp * 16 + m) * 2 + 1] = sm;
-        }
-    }
-    named_bar_sync(1, NW * 32);
-    stamp(4);
-    if (ctid < p.M) {       // per-row scale 2^e with amax * 2^e in [2^13, 2^14); fixed summation order
-        float am = 0.0f, sm = 0.0f;
-#pragma unroll 1
-        for (int w = 0; w < NW; ++w) {
-            am = fmaxf(am, pro[(w * 16 + ctid) * 2]);
-            sm += pro[(w * 16 + ctid) * 2 + 1];
-        }
+        for (int w = 0; w < NW; ++w) am = fmaxf(am, amax_w[w]);
         int ex = 0;
-        if (am > 0.0f && am < INFINITY) {
-            ex = 140 - (int)((__float_as_uint(am) >> 23) & 0xffu);
-            ex = max(-100, min(100, ex));
-        }
-        rowc[ctid] = __uint_as_float((uint32_t)(127 + 24 - ex) << 23);     // descale 2^(24-e)
-        rowc[16 + ctid] = sm;
-        rowc[32 + ctid] = __uint_as_float((uint32_t)(127 + ex) << 23);     // 2^e
-    }
-    named_bar_sync(1, NW * 32);
-    {
-        const int items = ng * NT * 16 * rg;        // (granule, n-tile, j, g, t)
-#pragma unroll 1
-        for (int it = ctid; it < items; it += NW * 32) {
-            const int t_ = it & 3, g_ = (it >> 2) & (rg - 1);
-            int rest = it >> (2 + rgs);
-            const int j = rest & 3;
-            rest >>= 2;
-            const int nt = rest % NT, gq = rest / NT;
-            const int m = nt * 4 + (g_ >> 1), part = g_ & 1;
-            uint4 out = make_uint4(0u, 0u, 0u, 0u);
-            if (m < p.M) {
-                float a[4], b[4];
-                const int64_t base = (int64_t)m * p.K + kslab0 + gq * GRAN_K + t_ * 32 + j * 8;
-                load4f(p.x, p.x_dtype, base, a);
-                load4f(p.x, p.x_dtype, base + 4, b);
-                const float u = rowc[32 + m], u_hi = u * 0.0625f;
-                // (n0,n4) (n1,n5) (n2,n6) (n3,n7): odd columns meet high nibbles (2^-20 instead of 2^-24)
-                const float s0 = a[0] * u, s4 = b[0] * u, s1 = a[1] * u_hi, s5 = b[1] * u_hi;
-                const float s2 = a[2] * u, s6 = b[2] * u, s3 = a[3] * u_hi, s7 = b[3] * u_hi;
-                __half2 h0 = __floats2half2_rn(s0, s4), h1 = __floats2half2_rn(s1, s5);
-                __half2 h2 = __floats2half2_rn(s2, s6), h3 = __floats2half2_rn(s3, s7);
-                if (part) {
-                    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
-                    const float2 f2 = __half22float2(h2), f3 = __half22float2(h3);
-                    h0 = __floats2half2_rn(s0 - f0.x, s4 - f0.y);
-                    h1 = __floats2half2_rn(s1 - f1.x, s5 - f1.y);
-                    h2 = __floats2half2_rn(s2 - f2.x, s6 - f2.y);
-                    h3 = __floats2half2_rn(s3 - f3.x, s7 - f3.y);
+        if (am > 0.0f && am < INFINITY) ex = max(-96, min(126, 156 - (int)(__float_as_uint(am) >> 23)));
+        return ex;
+    };
+    // Items are handled in batches of BATCH per thread so that a batch's global loads are in flight
+    // together.  When the CTA's whole share of x is one batch (M = 1 at K = 4096: one item per
+    // thread) it stays in registers across the amax barrier: x is read exactly once.
+    constexpr int BATCH = 2;
+    const int nbatch = (items + BATCH * NTHR - 1) / (BATCH * NTHR);
+    float v[BATCH][8];
+    auto load_batch = [&](int b, float& am) {
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u) {
+            const int it = (b * BATCH + u) * NTHR + ctid;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[u][i] = 0.0f;
+            if (it < items) {
+                int m;
+                uint32_t slot;
+                int64_t base;
+                decode(it, m, slot, base);
+                if (m < p.M) {
+                    float a[4], b4[4];
+                    load4f(p.x, p.x_dtype, base, a);
+                    load4f(p.x, p.x_dtype, base + 4, b4);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        v[u][i] = a[i]; v[u][4 + i] = b4[i];
+                        am = fmaxf(am, fmaxf(fabsf(a[i]), fabsf(b4[i])));
+                    }
                 }
-                out = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
-                                 *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
             }
-            sts128(xf + it * 16u, out);
+        }
+    };
+    float am = 0.0f;
+    if (nbatch == 1) {
+        load_batch(0, am);
+    } else {
+        for (int k = ctid * 4; k < p.M * ng * GRAN_K; k += NTHR * 4) {      // coalesced sweep of x[:, slab]
+            const int m = k / (ng * GRAN_K), kk = k - m * (ng * GRAN_K);
+            float a[4];
+            load4f(p.x, p.x_dtype, (int64_t)m * p.K + kslab0 + kk, a);
+            am = fmaxf(am, fmaxf(fmaxf(fabsf(a[0]), fabsf(a[1])), fmaxf(fabsf(a[2]), fabsf(a[3]))));
         }
     }
-    named_bar_sync(1, NW * 32);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, o));
+    if (lane == 0) amax_w[warp] = am;
+    named_bar_sync(1, NTHR);
+    stamp(4);
+    const float up = __uint_as_float((uint32_t)(127 + scale_exp()) << 23);
+#pragma unroll 1
+    for (int b = 0; b < nbatch; ++b) {
+        float dummy = 0.0f;
+        if (nbatch > 1) load_batch(b, dummy);
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u) {
+            const int it = (b * BATCH + u) * NTHR + ctid;
+            if (it < items) {                       // warp-uniform: items is a multiple of 64
+                int m;
+                uint32_t slot;
+                int64_t base;
+                decode(it, m, slot, base);
+                uint32_t D[8];
+                int slo = 0, shi = 0;               // sum of X as (X & 0xffff) and (X >> 16): exact in s32
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int X = __float2int_rn(v[u][i] * up);
+                    slo += X & 0xffff;
+                    shi += X >> 16;
+                    D[i] = (uint32_t)(X + 0x00808080) ^ 0x00808080u;     // byte l = signed base-256 digit l
+                }
+                // 4x4 byte transposes: digit l of the even values -> lo[l], of the odd values -> hi[l]
+                const uint32_t e0 = __byte_perm(D[0], D[2], 0x5140), e1 = __byte_perm(D[4], D[6], 0x5140);
+                const uint32_t e2 = __byte_perm(D[0], D[2], 0x7362), e3 = __byte_perm(D[4], D[6], 0x7362);
+                const uint32_t o0 = __byte_perm(D[1], D[3], 0x5140), o1 = __byte_perm(D[5], D[7], 0x5140);
+                const uint32_t o2 = __byte_perm(D[1], D[3], 0x7362), o3 = __byte_perm(D[5], D[7], 0x7362);
+                const uint32_t lo[4] = {__byte_perm(e0, e1, 0x5410), __byte_perm(e0, e1, 0x7632),
+                                        __byte_perm(e2, e3, 0x5410), __byte_perm(e2, e3, 0x7632)};
+                const uint32_t hi[4] = {__byte_perm(o0, o1, 0x5410), __byte_perm(o0, o1, 0x7632),
+                                        __byte_perm(o2, o3, 0x5410), __byte_perm(o2, o3, 0x7632)};
+#pragma unroll
+                for (int l = 0; l < 4; ++l)        // mma column 4h + l is 128 bytes further per limb
+                    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(xf + slot + 128u * l), "r"(lo[l]), "r"(hi[l]) : "memory");
+                // the 16 lanes (t, word) of an item group cover one (granule, n-tile, batch row): their sum
+                // of X goes to that group's slot -- plain stores, no atomics
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) {
+                    slo += __shfl_xor_sync(0xffffffffu, slo, o);
+                    shi += __shfl_xor_sync(0xffffffffu, shi, o);
+                }
+                if ((lane & 15) == 0) { ls[(it >> 4) * 2] = slo; ls[(it >> 4) * 2 + 1] = shi; }
+            }
+        }
+    }
+    stamp(10);
+    if ((p.debug & 8) && threadIdx.x == NTHR - 1 && blockIdx.x < 256) g_gemv_prof[blockIdx.x * 16 + 11] = clock64();
+    named_bar_sync(1, NTHR);
     stamp(5);
-    uint32_t bf[GPW][NT][4][4];
+    if (warp == 0) {                 // sum_k X per batch row (two s32 halves), read by the epilogue after its barrier
+#pragma unroll 1
+        for (int mh = 0; mh < p.M * 2; ++mh) {
+            const int m = mh >> 1, half = mh & 1;
+            const int nt = m >> 1, h = m & 1;
+            int a = 0;
+            for (int gq = lane; gq < ng; gq += 32) a += ls[((((gq * NT + nt) << hs) + h) << 1) + half];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (lane == 0) lsum_s[mh] = a;
+        }
+    }
+    uint32_t bf[GPW][NT][4][2];
 #pragma unroll
     for (int q = 0; q < GPW; ++q) {
         const int gq = warp + q * NW;
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                if (gq < ng && g < rg) v = lds128(xf + (((((gq * NT + nt) * 4 + j) << rgs) + g) * 4 + t) * 16u);
-                bf[q][nt][j][0] = v.x; bf[q][nt][j][1] = v.y; bf[q][nt][j][2] = v.z; bf[q][nt][j][3] = v.w;
+        for (int nt = 0; nt < NT; ++nt) {
+            uint4 v0 = make_uint4(0u, 0u, 0u, 0u), v1 = v0;
+            if (gq < ng && g < rg) {
+                const uint32_t a = xf + (uint32_t)(((((gq * NT + nt) << rgs) + g) * 4 + t) * 32);
+                v0 = lds128(a);
+                v1 = lds128(a + 16);
             }
+            bf[q][nt][0][0] = v0.x; bf[q][nt][0][1] = v0.y; bf[q][nt][1][0] = v0.z; bf[q][nt][1][1] = v0.w;
+            bf[q][nt][2][0] = v1.x; bf[q][nt][2][1] = v1.y; bf[q][nt][3][0] = v1.z; bf[q][nt][3][1] = v1.w;
+        }
     }
-
     stamp(6);
-    // ---- main loop: tiles of 16 rows; per tile GPW stages (one granule of this warp in each)
+
+    // ---- main loop: tiles of 16 rows; per tile nq stages (one granule of this warp in each)
     int s = 0, ph = 0, st = 0;
+    int rti = 0, rtq = 0;          // (tile, chunk) of the next stage to re-issue in recycle mode
+    {   // the first S stages were issued above: advance the refill cursor past them
+        const int adv = min(S, total_stages);
+        rti = adv / nq;
+        rtq = adv - rti * nq;
+    }
     int round_first = 0;           // first tile of the current reduction round
     for (int i = 0; i < ntiles; ++i) {
-        float acc[NT][CH][4];
+        int acc[NT][CH][4];
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
             for (int c = 0; c < CH; ++c)
 #pragma unroll
-                for (int r = 0; r < 4; ++r) acc[nt][c][r] = 0.0f;
+                for (int r = 0; r < 4; ++r) acc[nt][c][r] = 0;
+        if (p.whole_row) {
+            // one stage per tile: wait once, pull this warp's GPW granules (rows g and g+8) into registers
+            // with back-to-back LDS.128, then run the IMMAs over CH independent accumulator chains
+            if (dbg != 2) mbar_wait(full_bar(s), ph);
+            uint4 lo[GPW], hi[GPW];
 #pragma unroll
-        for (int q = 0; q < GPW; ++q) {
-            if (q * NW < ng) {                                   // stage exists (uniform over the CTA)
-                if (dbg != 2) mbar_wait(full_bar(s), ph);
+            for (int q = 0; q < GPW; ++q) {
+                lo[q] = make_uint4(0u, 0u, 0u, 0u);
+                hi[q] = lo[q];
                 if (warp + q * NW < ng && dbg != 1) {
-                    const uint32_t sbase = ring + s * stage_bytes + g * p.pitch + warp * GRAN_B + t * 16;
-                    const uint4 lo = lds128(sbase);
-                    const uint4 hi = lds128(sbase + 8 * p.pitch);
-                    const uint32_t wl[4] = {lo.x, lo.y, lo.z, lo.w};
-                    const uint32_t wh[4] = {hi.x, hi.y, hi.z, hi.w};
+                    const uint32_t sbase = ring + s * stage_bytes + g * p.pitch + (warp + q * NW) * GRAN_B + t * 16;
+                    lo[q] = lds128(sbase);
+                    hi[q] = lds128(sbase + 8 * p.pitch);
+                }
+            }
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint32_t al[4], ah[4];
-                        nibbles_to_subnormal_half2x4(wl[j], al);
-                        nibbles_to_subnormal_half2x4(wh[j], ah);
+            for (int q = 0; q < GPW; ++q) {
+                const uint32_t wl[4] = {lo[q].x, lo[q].y, lo[q].z, lo[q].w};
+                const uint32_t wh[4] = {hi[q].x, hi[q].y, hi[q].z, hi[q].w};
 #pragma unroll
-                        for (int nt = 0; nt < NT; ++nt) {
-                            mma_m16n8k16_f16(acc[nt][(2 * j) % CH], al[0], ah[0], al[1], ah[1], bf[q][nt][j][0], bf[q][nt][j][1]);
-                            mma_m16n8k16_f16(acc[nt][(2 * j + 1) % CH], al[2], ah[2], al[3], ah[3], bf[q][nt][j][2], bf[q][nt][j][3]);
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t a0 = wl[j] & 0x0f0f0f0fu, a2 = (wl[j] >> 4) & 0x0f0f0f0fu;   // row g
+                    const uint32_t a1 = wh[j] & 0x0f0f0f0fu, a3 = (wh[j] >> 4) & 0x0f0f0f0fu;   // row g + 8
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt)
+                        mma_m16n8k32_u8s8(acc[nt][(q * 4 + j) % CH], a0, a1, a2, a3, bf[q][nt][j][0], bf[q][nt][j][1]);
+                }
+            }
+            __syncwarp();
+            if (st + S < total_stages) {                         // ring smaller than the slab: recycle
+                if (lane == 0) {
+                    mbar_arrive(empty_bar(s));
+                    if (dbg != 2 && (!p.contig || warp == 0)) {
+                        mbar_wait(empty_bar(s), ph);             // every warp has read the slot
+                        if (p.contig) issue_tile(rti, s);
+                        else issue_stage(rti, rtq, s);
+                    }
+                }
+                if (++rtq == nq) { rtq = 0; ++rti; }
+                __syncwarp();
+            }
+            ++st;
+            if (++s == S) { s = 0; ph ^= 1; }
+        } else {
+#pragma unroll
+            for (int q = 0; q < GPW; ++q) {
+                if (q < nq) {                                    // stage exists (uniform over the CTA)
+                    if (dbg != 2) mbar_wait(full_bar(s), ph);
+                    if (warp + q * NW < ng && dbg != 1) {
+                        const uint32_t sbase = ring + s * stage_bytes + g * p.pitch + warp * GRAN_B + t * 16;
+                        const uint4 lo = lds128(sbase);
+                        const uint4 hi = lds128(sbase + 8 * p.pitch);
+                        const uint32_t wl[4] = {lo.x, lo.y, lo.z, lo.w};
+                        const uint32_t wh[4] = {hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint32_t a0 = wl[j] & 0x0f0f0f0fu, a2 = (wl[j] >> 4) & 0x0f0f0f0fu;
+                            const uint32_t a1 = wh[j] & 0x0f0f0f0fu, a3 = (wh[j] >> 4) & 0x0f0f0f0fu;
+#pragma unroll
+                            for (int nt = 0; nt < NT; ++nt)
+                                mma_m16n8k32_u8s8(acc[nt][j % CH], a0, a1, a2, a3, bf[q][nt][j][0], bf[q][nt][j][1]);
                         }
                     }
-                }
-                __syncwarp();
-                if (st + S < total_stages) {                     // ring smaller than the slab: recycle
-                    if (lane == 0) mbar_arrive(empty_bar(s));
-                    if (st % NW == warp && dbg != 2) {       // this warp refills the slot
-                        mbar_wait(empty_bar(s), ph);
-                        issue_stage(st + S, s);
+                    __syncwarp();
+                    if (st + S < total_stages) {
+                        if (lane == 0) {
+                            mbar_arrive(empty_bar(s));
+                            if (dbg != 2) {
+                                mbar_wait(empty_bar(s), ph);
+                                issue_stage(rti, rtq, s);
+                            }
+                        }
+                        if (++rtq == nq) { rtq = 0; ++rti; }
+                        __syncwarp();
                     }
+                    ++st;
+                    if (++s == S) { s = 0; ph ^= 1; }
                 }
-                ++st;
-                if (++s == S) { s = 0; ph ^= 1; }
             }
         }
         // this warp's partial of tile i -> red[i - round_first][warp][col][row]   (no barrier here)
-        float* rbuf = red + ((i - round_first) * NW + warp) * (COLS * TILE_ROWS);
+        int* rbuf = red + ((i - round_first) * NW + warp) * (COLS * TILE_ROWS);
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
-            const int col = nt * 4 + t;   // C columns 2t (hi part) and 2t+1 (lo part) of batch row nt*4+t
-            float top = 0.0f, bot = 0.0f;   // rows g and g+8: hi-part column + lo-part column, all chains
+            const int col = nt * 8 + 2 * t;
+            int c4[4] = {0, 0, 0, 0};
 #pragma unroll
-            for (int c = 0; c < CH; ++c) {
-                top += acc[nt][c][0] + acc[nt][c][1];
-                bot += acc[nt][c][2] + acc[nt][c][3];
-            }
-            rbuf[col * TILE_ROWS + g] = top;
-            rbuf[col * TILE_ROWS + g + 8] = bot;
+            for (int c = 0; c < CH; ++c)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) c4[r] += acc[nt][c][r];
+            rbuf[col * TILE_ROWS + g] = c4[0];
+            rbuf[(col + 1) * TILE_ROWS + g] = c4[1];
+            rbuf[col * TILE_ROWS + g + 8] = c4[2];
+            rbuf[(col + 1) * TILE_ROWS + g + 8] = c4[3];
         }
         if (i + 1 - round_first == p.rt || i + 1 == ntiles) {
-            // ---- end of a round: fixed-order cross-warp sum, zero-point term, scale, store
+            // ---- end of a round: cross-warp sum (exact), limbs -> value, zero-point term, scale, store
             if (i + 1 == ntiles) stamp(7);
-            named_bar_sync(1, NW * 32);
+            named_bar_sync(1, NTHR);
             if (i + 1 == ntiles) stamp(8);
+            // one thread per (tile, batch row, row, limb): sum the NW warp partials (exact s32), then the
+            // four limb lanes of a quad combine through shuffles into sum_k q*X (exact s64)
             const int nt_round = i + 1 - round_first;
-            const int total = nt_round * TILE_ROWS * p.M;
-            for (int idx = ctid; idx < total; idx += NW * 32) {
-                const int er = idx & (TILE_ROWS - 1);
-                const int rest = idx >> 4;
+            const int total = nt_round * TILE_ROWS * p.M * LIMBS;
+            const int ex = scale_exp();
+            const double down = __longlong_as_double((long long)(1023 - ex) << 52);   // 2^-e
+            for (int idx0 = 0; idx0 < total; idx0 += NTHR) {
+                const int idx = idx0 + ctid;
+                const int l = idx & 3, er = (idx >> 2) & (TILE_ROWS - 1);
+                const int rest = idx >> 6;
                 const int em = rest % p.M, j = rest / p.M;
                 const int row = r0 + (round_first + j) * TILE_ROWS + er;
-                if (row < r1) {
-                    const float* rr = red + (j * NW) * (COLS * TILE_ROWS) + em * TILE_ROWS + er;
-                    float a = 0.0f;
+                const bool ok = idx < total && row < r1;
+                float sc = 0.0f, zp = 0.0f;
+                if (ok && l == 0) { sc = __ldg(p.scales + row); zp = __ldg(p.zps + row); }
+                long long a = 0;
+                if (ok) {
+                    const int* rr = red + (j * NW) * (COLS * TILE_ROWS) + (em * LIMBS + l) * TILE_ROWS + er;
+                    int a32 = 0;
 #pragma unroll
-                    for (int w = 0; w < NW; ++w) a += rr[w * (COLS * TILE_ROWS)];
-                    const float sc = __ldg(p.scales + row), zp = __ldg(p.zps + row);
-                    const float v = sc * (a * rowc[em] - zp * rowc[16 + em]);
+                    for (int w = 0; w < NW; ++w) a32 += rr[w * (COLS * TILE_ROWS)];
+                    a = (long long)a32 * (1LL << (8 * l));
+                }
+                a += __shfl_xor_sync(0xffffffffu, a, 1);
+                a += __shfl_xor_sync(0xffffffffu, a, 2);
+                if (ok && l == 0) {
+                    const double tx = (double)lsum_s[em * 2] + 65536.0 * (double)lsum_s[em * 2 + 1];   // sum_k X
+                    const float v = sc * (float)(((double)a - (double)zp * tx) * down);
                     if (p.nslab == 1) store_y(p.y, p.y_dtype, (int64_t)em * p.N + row, v);
                     else p.part[((int64_t)slab * p.M + em) * p.N + row] = v;
                 }
             }
             round_first = i + 1;
-            if (i + 1 < ntiles) named_bar_sync(1, NW * 32);    // red is reused by the next round
+            if (i + 1 < ntiles) named_bar_sync(1, NTHR);    // red is reused by the next round
         }
     }
-
     stamp(9);
+
     // ---- cross-slab reduction by the last CTA of the row block (deterministic slab order)
     if (p.nslab > 1) {
         __threadfence();
-        named_bar_sync(1, NW * 32);
+        named_bar_sync(1, NTHR);
         if (ctid == 0) {
             const unsigned int old = atomicAdd(p.tickets + rb, 1u);
             *flag = (old == (unsigned)p.nslab - 1u);
         }
-        named_bar_sync(1, NW * 32);
+        named_bar_sync(1, NTHR);
         if (*flag) {
             __threadfence();
             const int nrows = r1 - r0;
-            for (int idx = ctid; idx < nrows * p.M; idx += NW * 32) {
+            for (int idx = ctid; idx < nrows * p.M; idx += NTHR) {
                 const int m = idx / nrows, row = r0 + idx % nrows;
                 float a = 0.0f;
                 for (int sl = 0; sl < p.nslab; ++sl) a += __ldcg(p.part + ((int64_t)sl * p.M + m) * p.N + row);
@@ -404,27 +537,23 @@ __global__ void __launch_bounds__(NW * 32, 1) gemv_kernel(const GemvParams p) {
 }
 
 struct GemvConfig {
-    int nw, gpw, nt, nslab, nrb, stages, pitch, rt, ring_off, red_off, rg;
+    int nw, gpw, nt, nslab, nrb, stages, whole_row, contig, pitch, rt, xf_off, ring_off, red_off, rg;
     size_t smem;
 };
 
 // kernel instances that exist (NW, GPW, NT); see launch_gemv
 bool has_instance(int nw, int gpw, int nt) {
-    if (nw == 16) return (nt == 1 && gpw <= 3) || (nt == 2 && gpw <= 2) || (nt == 4 && gpw == 1);
-    if (nw == 8) return (nt == 1 && gpw <= 4) || (nt == 2 && gpw <= 2) || (nt == 4 && gpw <= 2);
+    if (nw == 16) return (nt == 1 && gpw <= 3) || (nt == 2 && gpw <= 3) || (nt == 4 && gpw <= 2);
+    if (nw == 8) return (nt == 1 && gpw <= 4) || (nt == 2 && gpw <= 4) || (nt == 4 && gpw <= 2);
     return false;
 }
 
-int xf_off_for(int nw, int nt) {
-    if (nw == 16) return nt == 1 ? SmemLayout<16, 1>::XF_OFF : nt == 2 ? SmemLayout<16, 2>::XF_OFF : SmemLayout<16, 4>::XF_OFF;
-    return nt == 1 ? SmemLayout<8, 1>::XF_OFF : nt == 2 ? SmemLayout<8, 2>::XF_OFF : SmemLayout<8, 4>::XF_OFF;
-}
-
 bool plan(const DeviceInfo& dev, int64_t M, int64_t N, int64_t K, GemvConfig* c) {
-    if (M < 1 || M > 16 || K % GRAN_K != 0 || K <= 0 || N < 1 || N > 0x7fffffff || K > 0x7fffffff) return false;
+    if (M < 1 || M > 8 || K % GRAN_K != 0 || K <= 0 || N < 1 || N > 0x7fffffff || K > 0x7fffffff) return false;
     const Tuning& tu = tuning();
     const int G = (int)(K / GRAN_K);
-    const int nt = M <= 4 ? 1 : (M <= 8 ? 2 : 4);
+    const int nt = M <= 2 ? 1 : (M <= 4 ? 2 : 4);      // two batch rows (x 4 limbs) per n-tile
+    const int rg = M == 1 ? 4 : 8;
     int ctas = dev.sm_count;
     if (tu.gemv_ctas > 0 && tu.gemv_ctas < ctas) ctas = tu.gemv_ctas;
     double best_cost = 1e30;
@@ -442,30 +571,45 @@ bool plan(const DeviceInfo& dev, int64_t M, int64_t N, int64_t K, GemvConfig* c)
             if (nrb > MAX_RB) nrb = MAX_RB;
             const int rows = (int)((N + nrb - 1) / nrb);
             const int ntiles = (rows + TILE_ROWS - 1) / TILE_ROWS;
-            const int pitch = ((ng < nw ? ng : nw) | 1) * GRAN_B;
-            const int stage_bytes = TILE_ROWS * pitch;
-            const int red_tile = nw * nt * 4 * TILE_ROWS * 4;
+            const int red_tile = nw * nt * 8 * TILE_ROWS * 4;
             int rt = 32768 / red_tile;
             if (rt < 1) rt = 1;
             if (rt > ntiles) rt = ntiles;
-            const int rg = nt > 1 ? 8 : (M == 1 ? 2 : (M == 2 ? 4 : 8));
-            const int red_off = ((xf_off_for(nw, nt) + ng * nt * rg * 256 + 127) / 128) * 128;
+            const int xf_bytes = ng * nt * rg * 128;              // 16 (t, word) slots of 8 bytes per column
+            const int xf_off = ((LS_OFF + ng * nt * (rg / 4) * 8 + 127) / 128) * 128;
+            const int red_off = ((xf_off + xf_bytes + 127) / 128) * 128;
             const int ring_off = ((red_off + rt * red_tile + 127) / 128) * 128;
+            // stage = 16 rows x the whole slab row when at least 3 of those fit (fewest, largest bulk
+            // copies: the TMA unit accepts one every ~18 clk), else 16 rows x NW granules
+            int whole_row = 1;
+            const int contig = ns == 1 ? 1 : 0;          // one K slab: a tile's rows are adjacent in memory
+            int pitch = contig ? ng * GRAN_B : (ng | 1) * GRAN_B;
+            int stage_bytes = TILE_ROWS * pitch;
+            int per_tile = 1;
             int stages = (dev.max_smem_optin - ring_off) / stage_bytes;
-            if (stages > ntiles * gpw) stages = ntiles * gpw;
+            if (!contig && stages < (ntiles < 3 ? ntiles : 3)) {
+                whole_row = 0;
+                pitch = ((ng < nw ? ng : nw) | 1) * GRAN_B;
+                stage_bytes = TILE_ROWS * pitch;
+                per_tile = gpw;
+                stages = (dev.max_smem_optin - ring_off) / stage_bytes;
+            }
+            if (stages > ntiles * per_tile) stages = ntiles * per_tile;
             if (stages > MAX_STAGES) stages = MAX_STAGES;
             if (tu.gemv_stages > 0 && tu.gemv_stages < stages) stages = tu.gemv_stages;
             if (stages < 1) continue;
             // cost ~ bytes of the busiest CTA; small charges for the cross-slab reduction, for idle
             // warps in the last chunk, for a ring that cannot hold the whole slab, and for 8 warps
             double cost = (double)rows * ng * (1.0 + 0.03 * (ns - 1)) * (1.0 + 0.1 * ((double)gpw * nw / ng - 1.0));
-            if (stages < ntiles * gpw) cost *= 1.05;
+            if (stages < ntiles * per_tile) cost *= 1.05;
             if (nw == 8) cost *= 1.10;
             if (cost < best_cost) {
                 best_cost = cost;
                 found = true;
                 c->nw = nw; c->gpw = gpw; c->nt = nt; c->nslab = ns; c->nrb = nrb; c->stages = stages;
-                c->pitch = pitch; c->rt = rt; c->ring_off = ring_off; c->red_off = red_off; c->rg = rg;
+                c->whole_row = whole_row; c->contig = contig;
+                c->pitch = pitch; c->rt = rt; c->xf_off = xf_off; c->ring_off = ring_off; c->red_off = red_off;
+                c->rg = rg;
                 c->smem = (size_t)ring_off + (size_t)stages * stage_bytes;
             }
         }
@@ -523,9 +667,13 @@ int launch_gemv(const DeviceInfo& dev, const void* x, int x_dtype, const uint8_t
     p.x = x; p.packed = packed; p.scales = scales; p.zps = zps; p.y = y;
     p.x_dtype = x_dtype; p.y_dtype = y_dtype;
     p.M = (int)M; p.N = (int)N; p.K = (int)K;
-    p.nslab = c.nslab; p.nrb = c.nrb; p.G = (int)(K / GRAN_K);
-    p.stages = c.stages; p.pitch = c.pitch; p.rt = c.rt; p.ring_off = c.ring_off; p.red_off = c.red_off;
-    p.rg = c.rg; p.rg_shift = c.rg == 2 ? 1 : (c.rg == 4 ? 2 : 3);
+    p.nslab = c.nslab; p.nrb = c.nrb;
+    p.rows_q = (int)(N / c.nrb); p.rows_rem = (int)(N % c.nrb);
+    const int G = (int)(K / GRAN_K);
+    p.gran_q = G / c.nslab; p.gran_rem = G % c.nslab;
+    p.stages = c.stages; p.whole_row = c.whole_row; p.contig = c.contig; p.pitch = c.pitch; p.rt = c.rt;
+    p.xf_off = c.xf_off; p.ring_off = c.ring_off; p.red_off = c.red_off;
+    p.rg = c.rg; p.rg_shift = c.rg == 4 ? 2 : 3;
     const bool is_static = (flags & B200Q_FLAG_STATIC_WEIGHTS) != 0;
     const bool pdl = tuning().gemv_pdl != 0;
     p.wait_weights = is_static ? 0 : 1;
@@ -540,9 +688,10 @@ int launch_gemv(const DeviceInfo& dev, const void* x, int x_dtype, const uint8_t
 #define B200Q_GEMV_CASE(NW_, GPW_, NT_) \
     if (c.nw == NW_ && c.gpw == GPW_ && c.nt == NT_) return launch_inst<NW_, GPW_, NT_>(c, p, pdl, st);
     B200Q_GEMV_CASE(16, 1, 1) B200Q_GEMV_CASE(16, 2, 1) B200Q_GEMV_CASE(16, 3, 1)
-    B200Q_GEMV_CASE(16, 1, 2) B200Q_GEMV_CASE(16, 2, 2) B200Q_GEMV_CASE(16, 1, 4)
+    B200Q_GEMV_CASE(16, 1, 2) B200Q_GEMV_CASE(16, 2, 2) B200Q_GEMV_CASE(16, 3, 2)
+    B200Q_GEMV_CASE(16, 1, 4) B200Q_GEMV_CASE(16, 2, 4)
     B200Q_GEMV_CASE(8, 1, 1) B200Q_GEMV_CASE(8, 2, 1) B200Q_GEMV_CASE(8, 3, 1) B200Q_GEMV_CASE(8, 4, 1)
-    B200Q_GEMV_CASE(8, 1, 2) B200Q_GEMV_CASE(8, 2, 2)
+    B200Q_GEMV_CASE(8, 1, 2) B200Q_GEMV_CASE(8, 2, 2) B200Q_GEMV_CASE(8, 3, 2) B200Q_GEMV_CASE(8, 4, 2)
     B200Q_GEMV_CASE(8, 1, 4) B200Q_GEMV_CASE(8, 2, 4)
 #undef B200Q_GEMV_CASE
     return set_error(B200Q_EINVAL, "gemv: no kernel instance for nw=%d gpw=%d nt=%d", c.nw, c.gpw, c.nt);
