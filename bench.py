@@ -120,8 +120,10 @@ def blas_threads():
 
 
 def cpu_reference_gemv(steps, warmup, M=1):
-    """The reference CPU path (dequantize_weights + F.linear, python/quantize.py:127-202) restated in
-    numpy, timed on the host cores; one 4096->11008 layer per step."""
+    """The reference CPU path (dequantize_weights to a full fp32 matrix, then F.linear:
+    python/quantize.py:127-202) timed on the host cores, one 4096->11008 layer per step.  Uses the C
+    restatement (oracle/oracle.c, pthreads over all online cores) when it is built, else the numpy one.
+    Returns (GB/s, seconds per layer, threads, description)."""
     import numpy as np
     oracle = oracle_module()
     rng = np.random.default_rng(42)
@@ -129,23 +131,29 @@ def cpu_reference_gemv(steps, warmup, M=1):
     scales = (rng.random(N_OUT, dtype=np.float32) * 0.004 + 0.002).astype(np.float32)
     zps = rng.integers(0, 16, size=N_OUT).astype(np.float32)
     x = rng.standard_normal((M, K_IN), dtype=np.float32)
+    try:
+        import c_oracle
+        lin = c_oracle.Linear(packed, scales, zps)
+        fn, threads, what = (lambda: lin(x)), c_oracle.max_threads(), "C restatement (oracle/oracle.c, pthreads)"
+    except Exception:
+        fn = lambda: oracle.reference_quantized_linear(x, packed, scales, zps)
+        threads, what = blas_threads(), "numpy restatement (oracle/int4_oracle.py)"
     for _ in range(warmup):
-        oracle.reference_quantized_linear(x, packed, scales, zps)
+        fn()
     t0 = time.perf_counter()
     for _ in range(steps):
-        oracle.reference_quantized_linear(x, packed, scales, zps)
+        fn()
     dt = (time.perf_counter() - t0) / steps
-    return gemv_bytes(M, N_OUT, K_IN) / dt / 1e9, dt
+    return gemv_bytes(M, N_OUT, K_IN) / dt / 1e9, dt, threads, what
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 50))
-    warmup = max(1, min(args.warmup, 3))
-    gbs, dt = cpu_reference_gemv(steps, warmup)
-    cores = blas_threads()
+    steps = max(1, min(args.steps, 200))
+    warmup = max(1, min(args.warmup, 5))
+    gbs, dt, cores, what = cpu_reference_gemv(steps, warmup)
     line = {
         "impl": "reference", "metric": "int4_gemv_hbm_gbps", "value": gbs, "unit": "GB/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -153,8 +161,8 @@ def run_reference(args):
         "config": {"workload": f"Llama-7B MLP INT4 decode GEMV M=1 ({K_IN}->{N_OUT}), CPU dequantize + matmul",
                    "M": 1, "K": K_IN, "N": N_OUT},
         "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": cores, "kind": "port",
-                         "sample": f"{steps} x one {K_IN}->{N_OUT} layer forward (numpy restatement of "
-                                   "python/quantize.py dequantize_weights + F.linear)"},
+                         "sample": f"{steps} x one {K_IN}->{N_OUT} layer forward, M=1: {what} of "
+                                   "python/quantize.py dequantize_weights + F.linear"},
         "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -252,7 +260,7 @@ def run_gemv(args):
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    launches = args.steps * POOL
+    launches = args.steps * POOL            # fused dequantize-linear calls; each is 2 kernels (xprep + gemv)
     per_launch_s = ms * 1e-3 / launches
     bytes_per_launch = gemv_bytes(M, N_OUT, K_IN)
     gbs_per_gpu = bytes_per_launch / per_launch_s / 1e9
@@ -306,7 +314,7 @@ def run_gemv(args):
                 traffic = json.load(f).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    cpu_gbs, cpu_dt = cpu_reference_gemv(steps=5, warmup=1, M=M) if not args.no_cpu else (None, None)
+    cpu_gbs, cpu_dt, cpu_threads, cpu_what = cpu_reference_gemv(steps=20, warmup=2, M=M) if not args.no_cpu else (None, None, None, None)
     line = {
         "metric": "int4_gemv_hbm_gbps", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -326,14 +334,14 @@ def run_gemv(args):
         "e2e": {"value": e2e_gbs, "unit": "GB/s", "h2d_bytes_per_step": POOL * M * K_IN * 4,
                 "d2h_bytes_per_step": POOL * M * N_OUT * 4, "steps": e2e_steps,
                 "api": "QuantizedLinear.forward on pinned host activations (weights resident)"},
-        "gpu_launches": launches,
+        "gpu_launches": 2 * launches,
         "clocks": clocks.summary(),
         "parity": {"max_abs_err_vs_f64_oracle": err},
     }
     if cpu_gbs is not None:
-        line["cpu_baseline"] = {"value": cpu_gbs, "unit": "GB/s", "cores": blas_threads(), "kind": "port",
-                                "sample": f"5 x one {K_IN}->{N_OUT} layer forward, M={M} (numpy restatement of "
-                                          "dequantize_weights + F.linear)", "ms_per_layer": cpu_dt * 1e3}
+        line["cpu_baseline"] = {"value": cpu_gbs, "unit": "GB/s", "cores": cpu_threads, "kind": "port",
+                                "sample": f"20 x one {K_IN}->{N_OUT} layer forward, M={M}: {cpu_what} of "
+                                          "dequantize_weights + F.linear", "ms_per_layer": cpu_dt * 1e3}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -84,7 +84,9 @@ int b200q_linear_fwd(const void* x, int x_dtype, const uint8_t* packed, const fl
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int force = tuning().force_path;
     const bool vec_ok = aligned(x, 16) && aligned(packed, 16) && aligned(y, 16);
-    if ((force <= 0 || force == 4) && vec_ok && gemv_tc_supported(M, N, K))
+    // decode: register-fed IMMA kernel (gemv.cu); the tcgen05 TS-mode variant (gemv_tc.cu) is exact but
+    // slower for M <= 8 (A-from-TMEM feed rate, profiles/r01_gemv_notes.md) and only runs when forced
+    if (force == 4 && vec_ok && gemv_tc_supported(M, N, K))
         return launch_gemv_tc(d, x, x_dtype, packed, scales, zps, y, y_dtype, M, N, K, ws, ws_bytes, flags, st);
     if (force != 1 && force != 3 && force != 4 && vec_ok && gemv_supported(M, N, K, x_dtype))
         return launch_gemv(d, x, x_dtype, packed, scales, zps, y, y_dtype, M, N, K, ws, ws_bytes, flags, st);

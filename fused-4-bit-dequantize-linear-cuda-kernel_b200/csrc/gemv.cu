@@ -40,6 +40,7 @@ constexpr int MAX_SLABS = 16;
 constexpr int MAX_RB = 1024;         // ticket counters at the head of the workspace
 constexpr int MAX_STAGES = 64;
 constexpr int LIMBS = 4;             // signed base-256 digits of round(x * 2^e)
+constexpr int XHDR_INTS = 4 + 2 * MAX_SLABS;   // per batch row: {e, 0, 0, 0}, then {sum lo16, sum hi16} per K slab
 
 struct GemvParams {
     const void* x;
@@ -47,6 +48,8 @@ struct GemvParams {
     const float* scales;
     const float* zps;
     void* y;
+    const uint8_t* ximg;    // B-fragment image of x (xprep_kernel)
+    const int* xhdr;        // per batch row: XHDR_INTS ints (xprep_kernel)
     float* part;            // [nslab][M][N] fp32 slab partials (nslab > 1)
     unsigned int* tickets;  // [nrb]
     int x_dtype, y_dtype;
@@ -60,7 +63,7 @@ struct GemvParams {
     int pitch;              // bytes between rows of a stage
     int rt;                 // tiles per cross-warp reduction round
     int rg, rg_shift;       // live mma columns per n-tile (4 or 8) and log2 of it
-    int xf_off, red_off, ring_off;   // byte offsets in dynamic shared memory
+    int red_off, ring_off;  // byte offsets in dynamic shared memory
     int wait_weights;       // 1: weights may be written by the preceding kernel -> wait first
     int debug;              // bench-only: low bits 1 = skip the mma work, 2 = skip the weight loads; 8 = timestamps
 };
@@ -99,15 +102,10 @@ __device__ __forceinline__ void mma_m16n8k32_u8s8(int (&c)[4], uint32_t a0, uint
 
 // Shared memory carve-up (dynamic):
 //   [0, 512) full mbarriers, [512, 1024) empty mbarriers, [1024, 1088) flags
-//   [1088, 1152)  per-warp amax f32 [16], [1280, 1536) limb sums s32 [16][4]
-//   [1536, ..)    ls: limb-sum slots s32, one per (granule, n-tile, column)
-//   [xf_off, ..)  xf: mma-B vectors (8 bytes per (granule, n-tile, column, t, word))
 //   [red_off,..)  red[rt][NW][NT*8 columns][16] s32
 //   [ring_off, ...)  stages x 16 x pitch bytes
 constexpr int MISC_OFF = 1024;
-constexpr int AMAX_OFF = 1088;
-constexpr int LSUM_OFF = 1280;
-constexpr int LS_OFF = 1536;
+constexpr int RED_OFF = 1152;
 
 template <int NW, int GPW, int NT>
 __global__ void __launch_bounds__(NW * 32, 1) gemv_kernel(const GemvParams p) {
@@ -117,12 +115,8 @@ __global__ void __launch_bounds__(NW * 32, 1) gemv_kernel(const GemvParams p) {
     constexpr int CH = NT == 1 ? 4 : 2;            // independent IMMA accumulator chains per n-tile
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t smem_base = smem_u32(smem);
-    float* amax_w = reinterpret_cast<float*>(smem + AMAX_OFF);     // one slot per warp
-    int* lsum_s = reinterpret_cast<int*>(smem + LSUM_OFF);          // [batch row][limb] after consolidation
-    int* ls = reinterpret_cast<int*>(smem + LS_OFF);                // per (granule, n-tile, column) partial sums
     int* red = reinterpret_cast<int*>(smem + p.red_off);
     volatile int* flag = reinterpret_cast<volatile int*>(smem + MISC_OFF);
-    const uint32_t xf = smem_base + p.xf_off;
     const uint32_t ring = smem_base + p.ring_off;
     const int S = p.stages;
     const int dbg = p.debug & 7;
@@ -206,151 +200,23 @@ __global__ void __launch_bounds__(NW * 32, 1) gemv_kernel(const GemvParams p) {
     pdl_wait();   // x (and the output / workspace) belong to the stream-ordered predecessor
     stamp(3);
 
-    // ---- x operand, built cooperatively ONCE per CTA.
-    // item = (granule gq, n-tile nt, batch row h of the tile, t, word j) -> the 8 columns
-    // k0 + 32t + 8j + {0..7} of batch row m = 2nt + h.  X = round(x * 2^e) is split into four signed
-    // base-256 digits; digit l of the 8 values is stored as the two B registers of IMMA j in mma
-    // column 4h + l: {X0,X2,X4,X6} (meets the low nibbles) and {X1,X3,X5,X7} (high nibbles).
-    const int kslab0 = g0 * GRAN_K;
+    // ---- x operand: prepared ONCE per launch by xprep_kernel (below) as an image of the mma B
+    // fragments in global memory (L2-resident, 8 bytes per (granule, n-tile, column, t, word)); every
+    // lane pulls its own registers with two coalesced 16-byte loads per (granule, n-tile).  Building
+    // the operand inside each of the 148 CTAs was the longest phase of this kernel
+    // (profiles/r01_gemv_notes.md).
     const int rg = p.rg, rgs = p.rg_shift;
-    const int hs = rgs - 2;                                  // log2(batch rows per n-tile that are stored)
-    const int items = ng * NT * 16 << hs;
-    auto decode = [&](int it, int& m, uint32_t& slot, int64_t& base) {
-        const int t_ = it & 3, j = (it >> 2) & 3, h = (it >> 4) & ((1 << hs) - 1);
-        const int rest = it >> (4 + hs);
-        const int nt = rest % NT, gq = rest / NT;
-        m = nt * 2 + h;
-        base = (int64_t)m * p.K + kslab0 + gq * GRAN_K + t_ * 32 + j * 8;
-        // lane (column c, t) of (gq, nt) reads its 4 words (32 bytes) contiguously; c = 4h + limb
-        slot = (uint32_t)((((((gq * NT + nt) << rgs) + 4 * h) * 4 + t_) * 4 + j) * 8);
-    };
-    // ONE power-of-two scale for the CTA's block of x: amax * 2^e in [2^29, 2^30) (e is exact to undo)
-    auto scale_exp = [&]() {
-        float am = 0.0f;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) am = fmaxf(am, amax_w[w]);
-        int ex = 0;
-        if (am > 0.0f && am < INFINITY) ex = max(-96, min(126, 156 - (int)(__float_as_uint(am) >> 23)));
-        return ex;
-    };
-    // Items are handled in batches of BATCH per thread so that a batch's global loads are in flight
-    // together.  When the CTA's whole share of x is one batch (M = 1 at K = 4096: one item per
-    // thread) it stays in registers across the amax barrier: x is read exactly once.
-    constexpr int BATCH = 2;
-    const int nbatch = (items + BATCH * NTHR - 1) / (BATCH * NTHR);
-    float v[BATCH][8];
-    auto load_batch = [&](int b, float& am) {
-#pragma unroll
-        for (int u = 0; u < BATCH; ++u) {
-            const int it = (b * BATCH + u) * NTHR + ctid;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[u][i] = 0.0f;
-            if (it < items) {
-                int m;
-                uint32_t slot;
-                int64_t base;
-                decode(it, m, slot, base);
-                if (m < p.M) {
-                    float a[4], b4[4];
-                    load4f(p.x, p.x_dtype, base, a);
-                    load4f(p.x, p.x_dtype, base + 4, b4);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        v[u][i] = a[i]; v[u][4 + i] = b4[i];
-                        am = fmaxf(am, fmaxf(fabsf(a[i]), fabsf(b4[i])));
-                    }
-                }
-            }
-        }
-    };
-    float am = 0.0f;
-    if (nbatch == 1) {
-        load_batch(0, am);
-    } else {
-        for (int k = ctid * 4; k < p.M * ng * GRAN_K; k += NTHR * 4) {      // coalesced sweep of x[:, slab]
-            const int m = k / (ng * GRAN_K), kk = k - m * (ng * GRAN_K);
-            float a[4];
-            load4f(p.x, p.x_dtype, (int64_t)m * p.K + kslab0 + kk, a);
-            am = fmaxf(am, fmaxf(fmaxf(fabsf(a[0]), fabsf(a[1])), fmaxf(fabsf(a[2]), fabsf(a[3]))));
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, o));
-    if (lane == 0) amax_w[warp] = am;
-    named_bar_sync(1, NTHR);
-    stamp(4);
-    const float up = __uint_as_float((uint32_t)(127 + scale_exp()) << 23);
-#pragma unroll 1
-    for (int b = 0; b < nbatch; ++b) {
-        float dummy = 0.0f;
-        if (nbatch > 1) load_batch(b, dummy);
-#pragma unroll
-        for (int u = 0; u < BATCH; ++u) {
-            const int it = (b * BATCH + u) * NTHR + ctid;
-            if (it < items) {                       // warp-uniform: items is a multiple of 64
-                int m;
-                uint32_t slot;
-                int64_t base;
-                decode(it, m, slot, base);
-                uint32_t D[8];
-                int slo = 0, shi = 0;               // sum of X as (X & 0xffff) and (X >> 16): exact in s32
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int X = __float2int_rn(v[u][i] * up);
-                    slo += X & 0xffff;
-                    shi += X >> 16;
-                    D[i] = (uint32_t)(X + 0x00808080) ^ 0x00808080u;     // byte l = signed base-256 digit l
-                }
-                // 4x4 byte transposes: digit l of the even values -> lo[l], of the odd values -> hi[l]
-                const uint32_t e0 = __byte_perm(D[0], D[2], 0x5140), e1 = __byte_perm(D[4], D[6], 0x5140);
-                const uint32_t e2 = __byte_perm(D[0], D[2], 0x7362), e3 = __byte_perm(D[4], D[6], 0x7362);
-                const uint32_t o0 = __byte_perm(D[1], D[3], 0x5140), o1 = __byte_perm(D[5], D[7], 0x5140);
-                const uint32_t o2 = __byte_perm(D[1], D[3], 0x7362), o3 = __byte_perm(D[5], D[7], 0x7362);
-                const uint32_t lo[4] = {__byte_perm(e0, e1, 0x5410), __byte_perm(e0, e1, 0x7632),
-                                        __byte_perm(e2, e3, 0x5410), __byte_perm(e2, e3, 0x7632)};
-                const uint32_t hi[4] = {__byte_perm(o0, o1, 0x5410), __byte_perm(o0, o1, 0x7632),
-                                        __byte_perm(o2, o3, 0x5410), __byte_perm(o2, o3, 0x7632)};
-#pragma unroll
-                for (int l = 0; l < 4; ++l)        // mma column 4h + l is 128 bytes further per limb
-                    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(xf + slot + 128u * l), "r"(lo[l]), "r"(hi[l]) : "memory");
-                // the 16 lanes (t, word) of an item group cover one (granule, n-tile, batch row): their sum
-                // of X goes to that group's slot -- plain stores, no atomics
-#pragma unroll
-                for (int o = 8; o > 0; o >>= 1) {
-                    slo += __shfl_xor_sync(0xffffffffu, slo, o);
-                    shi += __shfl_xor_sync(0xffffffffu, shi, o);
-                }
-                if ((lane & 15) == 0) { ls[(it >> 4) * 2] = slo; ls[(it >> 4) * 2 + 1] = shi; }
-            }
-        }
-    }
-    stamp(10);
-    if ((p.debug & 8) && threadIdx.x == NTHR - 1 && blockIdx.x < 256) g_gemv_prof[blockIdx.x * 16 + 11] = clock64();
-    named_bar_sync(1, NTHR);
-    stamp(5);
-    if (warp == 0) {                 // sum_k X per batch row (two s32 halves), read by the epilogue after its barrier
-#pragma unroll 1
-        for (int mh = 0; mh < p.M * 2; ++mh) {
-            const int m = mh >> 1, half = mh & 1;
-            const int nt = m >> 1, h = m & 1;
-            int a = 0;
-            for (int gq = lane; gq < ng; gq += 32) a += ls[((((gq * NT + nt) << hs) + h) << 1) + half];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-            if (lane == 0) lsum_s[mh] = a;
-        }
-    }
     uint32_t bf[GPW][NT][4][2];
 #pragma unroll
     for (int q = 0; q < GPW; ++q) {
-        const int gq = warp + q * NW;
+        const int gq = g0 + warp + q * NW;                      // granule index in the whole K
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
             uint4 v0 = make_uint4(0u, 0u, 0u, 0u), v1 = v0;
-            if (gq < ng && g < rg) {
-                const uint32_t a = xf + (uint32_t)(((((gq * NT + nt) << rgs) + g) * 4 + t) * 32);
-                v0 = lds128(a);
-                v1 = lds128(a + 16);
+            if (warp + q * NW < ng && g < rg) {
+                const uint8_t* a = p.ximg + (size_t)(((((gq * NT + nt) << rgs) + g) * 4 + t) * 32);
+                v0 = ldg_nc_v4(a);
+                v1 = ldg_nc_v4(a + 16);
             }
             bf[q][nt][0][0] = v0.x; bf[q][nt][0][1] = v0.y; bf[q][nt][1][0] = v0.z; bf[q][nt][1][1] = v0.w;
             bf[q][nt][2][0] = v1.x; bf[q][nt][2][1] = v1.y; bf[q][nt][3][0] = v1.z; bf[q][nt][3][1] = v1.w;
@@ -479,8 +345,6 @@ __global__ void __launch_bounds__(NW * 32, 1) gemv_kernel(const GemvParams p) {
             // four limb lanes of a quad combine through shuffles into sum_k q*X (exact s64)
             const int nt_round = i + 1 - round_first;
             const int total = nt_round * TILE_ROWS * p.M * LIMBS;
-            const int ex = scale_exp();
-            const double down = __longlong_as_double((long long)(1023 - ex) << 52);   // 2^-e
             for (int idx0 = 0; idx0 < total; idx0 += NTHR) {
                 const int idx = idx0 + ctid;
                 const int l = idx & 3, er = (idx >> 2) & (TILE_ROWS - 1);
@@ -501,7 +365,10 @@ __global__ void __launch_bounds__(NW * 32, 1) gemv_kernel(const GemvParams p) {
                 a += __shfl_xor_sync(0xffffffffu, a, 1);
                 a += __shfl_xor_sync(0xffffffffu, a, 2);
                 if (ok && l == 0) {
-                    const double tx = (double)lsum_s[em * 2] + 65536.0 * (double)lsum_s[em * 2 + 1];   // sum_k X
+                    // header of batch row em: {e, -, -, -} then per slab {sum(X & 0xffff), sum(X >> 16)}
+                    const int* hdr = p.xhdr + em * XHDR_INTS;
+                    const double down = __longlong_as_double((long long)(1023 - hdr[0]) << 52);   // 2^-e
+                    const double tx = (double)hdr[4 + 2 * slab] + 65536.0 * (double)hdr[5 + 2 * slab];   // sum_k X
                     const float v = sc * (float)(((double)a - (double)zp * tx) * down);
                     if (p.nslab == 1) store_y(p.y, p.y_dtype, (int64_t)em * p.N + row, v);
                     else p.part[((int64_t)slab * p.M + em) * p.N + row] = v;
@@ -536,8 +403,122 @@ __global__ void __launch_bounds__(NW * 32, 1) gemv_kernel(const GemvParams p) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// x operand preparation: one CTA per stored batch row.  X = round(x * 2^e) with the row's own
+// power-of-two scale (amax * 2^e in [2^29, 2^30)), cut into four signed base-256 digits; digit l of
+// the 8 values k0 + 32t + 8j + {0..7} is stored as the two B registers of IMMA j in mma column
+// 4h + l: {X0,X2,X4,X6} (meets the low nibbles) and {X1,X3,X5,X7} (high nibbles).
+// Also emits, per batch row, e and the exact sum of X over every K slab (two s32 halves).
+struct XprepParams {
+    const void* x;
+    uint8_t* img;
+    int* hdr;
+    int x_dtype, M, K, G, NT, rg_shift;
+    int nslab, gran_q, gran_rem;
+};
+
+constexpr int XP_THREADS = 512;
+
+__global__ void __launch_bounds__(XP_THREADS) xprep_kernel(const XprepParams p) {
+    __shared__ float s_amax[XP_THREADS / 32];
+    __shared__ int s_ls[2 * 1024];                       // per granule {sum lo16, sum hi16}
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int hs = p.rg_shift - 2;
+    const int nt = blockIdx.x >> hs, h = blockIdx.x & ((1 << hs) - 1);
+    const int m = nt * 2 + h;
+    pdl_launch_dependents();
+    pdl_wait();                                          // x belongs to the stream-ordered predecessor
+    const int items = p.G * 16;                          // (granule, word j, t)
+    auto slot_of = [&](int it) {
+        const int t_ = it & 3, j = (it >> 2) & 3, gq = it >> 4;
+        return (size_t)((((((gq * p.NT + nt) << p.rg_shift) + 4 * h) * 4 + t_) * 4 + j) * 8);
+    };
+    if (m >= p.M) {                                      // unused batch row of the last n-tile: zero columns
+        for (int it = threadIdx.x; it < items; it += XP_THREADS)
+#pragma unroll
+            for (int l = 0; l < 4; ++l) *reinterpret_cast<uint2*>(p.img + slot_of(it) + 128 * l) = make_uint2(0u, 0u);
+        return;
+    }
+    float am = 0.0f;
+    for (int k = threadIdx.x * 4; k < p.K; k += XP_THREADS * 4) {
+        float a[4];
+        load4f(p.x, p.x_dtype, (int64_t)m * p.K + k, a);
+        am = fmaxf(am, fmaxf(fmaxf(fabsf(a[0]), fabsf(a[1])), fmaxf(fabsf(a[2]), fabsf(a[3]))));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, o));
+    if (lane == 0) s_amax[warp] = am;
+    __syncthreads();
+    am = 0.0f;
+#pragma unroll
+    for (int w = 0; w < XP_THREADS / 32; ++w) am = fmaxf(am, s_amax[w]);
+    int ex = 0;
+    if (am > 0.0f && am < INFINITY) ex = max(-96, min(126, 156 - (int)(__float_as_uint(am) >> 23)));
+    const float up = __uint_as_float((uint32_t)(127 + ex) << 23);
+    for (int it0 = 0; it0 < items; it0 += XP_THREADS) {            // items is a multiple of 16, not of 32:
+        const int it = it0 + threadIdx.x;                          // all lanes take part in the shuffles
+        const bool active = it < items;
+        const int t_ = it & 3, j = (it >> 2) & 3, gq = it >> 4;
+        float v[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+        if (active) {
+            float a[4], b[4];
+            const int64_t base = (int64_t)m * p.K + gq * GRAN_K + t_ * 32 + j * 8;
+            load4f(p.x, p.x_dtype, base, a);
+            load4f(p.x, p.x_dtype, base + 4, b);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { v[i] = a[i]; v[4 + i] = b[i]; }
+        }
+        uint32_t D[8];
+        int slo = 0, shi = 0;                            // sum of X as (X & 0xffff) and (X >> 16): exact in s32
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int X = __float2int_rn(v[i] * up);
+            slo += X & 0xffff;
+            shi += X >> 16;
+            D[i] = (uint32_t)(X + 0x00808080) ^ 0x00808080u;       // byte l = signed base-256 digit l
+        }
+        // 4x4 byte transposes: digit l of the even values -> lo[l], of the odd values -> hi[l]
+        const uint32_t e0 = __byte_perm(D[0], D[2], 0x5140), e1 = __byte_perm(D[4], D[6], 0x5140);
+        const uint32_t e2 = __byte_perm(D[0], D[2], 0x7362), e3 = __byte_perm(D[4], D[6], 0x7362);
+        const uint32_t o0 = __byte_perm(D[1], D[3], 0x5140), o1 = __byte_perm(D[5], D[7], 0x5140);
+        const uint32_t o2 = __byte_perm(D[1], D[3], 0x7362), o3 = __byte_perm(D[5], D[7], 0x7362);
+        const uint32_t lo[4] = {__byte_perm(e0, e1, 0x5410), __byte_perm(e0, e1, 0x7632),
+                                __byte_perm(e2, e3, 0x5410), __byte_perm(e2, e3, 0x7632)};
+        const uint32_t hi[4] = {__byte_perm(o0, o1, 0x5410), __byte_perm(o0, o1, 0x7632),
+                                __byte_perm(o2, o3, 0x5410), __byte_perm(o2, o3, 0x7632)};
+        if (active) {
+            const size_t slot = slot_of(it);
+#pragma unroll
+            for (int l = 0; l < 4; ++l) *reinterpret_cast<uint2*>(p.img + slot + 128 * l) = make_uint2(lo[l], hi[l]);
+        }
+        // the 16 lanes (t, word) of a granule: their sum of X goes to the granule's slot (plain stores)
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+            slo += __shfl_xor_sync(0xffffffffu, slo, o);
+            shi += __shfl_xor_sync(0xffffffffu, shi, o);
+        }
+        if (active && (lane & 15) == 0 && gq < 1024) { s_ls[2 * gq] = slo; s_ls[2 * gq + 1] = shi; }
+    }
+    __syncthreads();
+    // header: {e, 0, 0, 0}, then per K slab the exact sum of X (warp `slab` adds its granules)
+    int* hdr = p.hdr + m * XHDR_INTS;
+    if (threadIdx.x == 0) hdr[0] = ex;
+    if (warp < p.nslab) {
+        const int g0 = warp * p.gran_q + min(warp, p.gran_rem);
+        const int ng = p.gran_q + (warp < p.gran_rem ? 1 : 0);
+        int alo = 0, ahi = 0;
+        for (int gq = lane; gq < ng; gq += 32) { alo += s_ls[2 * (g0 + gq)]; ahi += s_ls[2 * (g0 + gq) + 1]; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            alo += __shfl_xor_sync(0xffffffffu, alo, o);
+            ahi += __shfl_xor_sync(0xffffffffu, ahi, o);
+        }
+        if (lane == 0) { hdr[4 + 2 * warp] = alo; hdr[5 + 2 * warp] = ahi; }
+    }
+}
+
 struct GemvConfig {
-    int nw, gpw, nt, nslab, nrb, stages, whole_row, contig, pitch, rt, xf_off, ring_off, red_off, rg;
+    int nw, gpw, nt, nslab, nrb, stages, whole_row, contig, pitch, rt, ring_off, red_off, rg;
     size_t smem;
 };
 
@@ -575,9 +556,7 @@ bool plan(const DeviceInfo& dev, int64_t M, int64_t N, int64_t K, GemvConfig* c)
             int rt = 32768 / red_tile;
             if (rt < 1) rt = 1;
             if (rt > ntiles) rt = ntiles;
-            const int xf_bytes = ng * nt * rg * 128;              // 16 (t, word) slots of 8 bytes per column
-            const int xf_off = ((LS_OFF + ng * nt * (rg / 4) * 8 + 127) / 128) * 128;
-            const int red_off = ((xf_off + xf_bytes + 127) / 128) * 128;
+            const int red_off = RED_OFF;
             const int ring_off = ((red_off + rt * red_tile + 127) / 128) * 128;
             // stage = 16 rows x the whole slab row when at least 3 of those fit (fewest, largest bulk
             // copies: the TMA unit accepts one every ~18 clk), else 16 rows x NW granules
@@ -608,7 +587,7 @@ bool plan(const DeviceInfo& dev, int64_t M, int64_t N, int64_t K, GemvConfig* c)
                 found = true;
                 c->nw = nw; c->gpw = gpw; c->nt = nt; c->nslab = ns; c->nrb = nrb; c->stages = stages;
                 c->whole_row = whole_row; c->contig = contig;
-                c->pitch = pitch; c->rt = rt; c->xf_off = xf_off; c->ring_off = ring_off; c->red_off = red_off;
+                c->pitch = pitch; c->rt = rt; c->ring_off = ring_off; c->red_off = red_off;
                 c->rg = rg;
                 c->smem = (size_t)ring_off + (size_t)stages * stage_bytes;
             }
@@ -651,9 +630,14 @@ bool gemv_supported(int64_t M, int64_t N, int64_t K, int x_dtype) {
     return plan(d, M, N, K, &c);
 }
 
+// workspace: [tickets MAX_RB u32][x headers 8 x XHDR_INTS s32][x image, 2 alternating copies][slab partials]
+static size_t ximg_bytes(int64_t K) { return (size_t)(K / GRAN_K) * 4 * 8 * 128; }   // NT <= 4, rg <= 8
+constexpr size_t WS_HDR_OFF = (size_t)MAX_RB * 4;
+constexpr size_t WS_IMG_OFF = WS_HDR_OFF + 2 * 8 * XHDR_INTS * 4;
+
 size_t gemv_ws_bytes(int64_t M, int64_t N, int64_t K) {
     if (!gemv_supported(M, N, K, B200Q_F32)) return 0;
-    return (size_t)MAX_RB * 4 + (size_t)MAX_SLABS * M * N * 4;
+    return WS_IMG_OFF + 2 * ximg_bytes(K) + (size_t)MAX_SLABS * M * N * 4;
 }
 
 int launch_gemv(const DeviceInfo& dev, const void* x, int x_dtype, const uint8_t* packed,
@@ -672,18 +656,42 @@ int launch_gemv(const DeviceInfo& dev, const void* x, int x_dtype, const uint8_t
     const int G = (int)(K / GRAN_K);
     p.gran_q = G / c.nslab; p.gran_rem = G % c.nslab;
     p.stages = c.stages; p.whole_row = c.whole_row; p.contig = c.contig; p.pitch = c.pitch; p.rt = c.rt;
-    p.xf_off = c.xf_off; p.ring_off = c.ring_off; p.red_off = c.red_off;
+    p.ring_off = c.ring_off; p.red_off = c.red_off;
     p.rg = c.rg; p.rg_shift = c.rg == 4 ? 2 : 3;
     const bool is_static = (flags & B200Q_FLAG_STATIC_WEIGHTS) != 0;
     const bool pdl = tuning().gemv_pdl != 0;
     p.wait_weights = is_static ? 0 : 1;
     p.debug = tuning().gemv_debug > 0 ? tuning().gemv_debug : 0;
-    if (c.nslab > 1) {
-        const size_t need = (size_t)MAX_RB * 4 + (size_t)c.nslab * M * N * 4;
+    {
+        const size_t need = WS_IMG_OFF + 2 * ximg_bytes(K) + (c.nslab > 1 ? (size_t)c.nslab * M * N * 4 : 0);
         if (!ws || ws_bytes < need) return set_error(B200Q_EWORKSPACE, "gemv: workspace too small (%zu < %zu)", ws_bytes, need);
-        if (reinterpret_cast<uintptr_t>(ws) & 15) return set_error(B200Q_EALIGN, "gemv: workspace must be 16-byte aligned");
-        p.tickets = static_cast<unsigned int*>(ws);
-        p.part = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + (size_t)MAX_RB * 4);
+        if (reinterpret_cast<uintptr_t>(ws) & 127) return set_error(B200Q_EALIGN, "gemv: workspace must be 128-byte aligned");
+        uint8_t* w8 = static_cast<uint8_t*>(ws);
+        // the x image / header alternate between two copies: the preparation of launch i+1 may overlap
+        // (programmatic dependent launch) CTAs of launch i that still hold pointers into copy i
+        static thread_local unsigned flip = 0;
+        flip ^= 1u;
+        p.tickets = reinterpret_cast<unsigned int*>(w8);
+        int* hdr = reinterpret_cast<int*>(w8 + WS_HDR_OFF) + flip * 8 * XHDR_INTS;
+        uint8_t* img = w8 + WS_IMG_OFF + flip * ximg_bytes(K);
+        p.xhdr = hdr;
+        p.ximg = img;
+        p.part = reinterpret_cast<float*>(w8 + WS_IMG_OFF + 2 * ximg_bytes(K));
+        XprepParams xp{};
+        xp.x = x; xp.img = img; xp.hdr = hdr; xp.x_dtype = x_dtype; xp.M = (int)M; xp.K = (int)K; xp.G = G;
+        xp.NT = c.nt; xp.rg_shift = p.rg_shift; xp.nslab = c.nslab; xp.gran_q = p.gran_q; xp.gran_rem = p.gran_rem;
+        if (G > 1024) return set_error(B200Q_EINVAL, "gemv: K > 131072 not supported");
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)(c.nt * (c.rg / 4)));
+        cfg.blockDim = dim3(XP_THREADS);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = st;
+        cudaLaunchAttribute attrs[1];
+        attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attrs[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attrs;
+        cfg.numAttrs = pdl ? 1 : 0;
+        B200Q_CUDA(cudaLaunchKernelEx(&cfg, xprep_kernel, xp));
     }
 #define B200Q_GEMV_CASE(NW_, GPW_, NT_) \
     if (c.nw == NW_ && c.gpw == GPW_ && c.nt == NT_) return launch_inst<NW_, GPW_, NT_>(c, p, pdl, st);

@@ -8,7 +8,7 @@ from b200q_pkg import pkg
 _lib = pkg._lib; lib = _lib.load()
 lib.b200q_debug_read_prof.argtypes = [ctypes.c_void_p]
 dev = torch.device("cuda", 0)
-names = ["start", "bar-init", "issued", "pdl_wait", "pass1", "pass2", "bf-loaded", "main-done", "red-bar", "epilogue", "t0-conv", "t511-conv"]
+names = ["start", "bar-init", "issued", "pdl_wait", "-", "-", "bf-loaded", "main-done", "red-bar", "epilogue"]
 for (K, N, M) in [(4096, 11008, 1), (4096, 11008, 4), (11008, 4096, 1)]:
     layers = []
     for i in range(12):
@@ -26,7 +26,7 @@ for (K, N, M) in [(4096, 11008, 1), (4096, 11008, 4), (11008, 4096, 1)]:
     torch.cuda.synchronize()
     buf = np.zeros(256 * 16, dtype=np.int64)
     _lib.check(lib.b200q_debug_read_prof(buf.ctypes.data), "read")
-    t = buf.reshape(256, 16)[:148, :12]
+    t = buf.reshape(256, 16)[:148, :10]
     rel = t - t[:, :1]
     print(f"K={K} N={N} M={M}: cycles since CTA start (median / max over 148 CTAs)")
     for i, n in enumerate(names):

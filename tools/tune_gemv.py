@@ -78,12 +78,12 @@ def main():
         layers = make_pool(N, K, 24, dev)
         nbytes = lambda M: N * K // 2 + 8 * N + 4 * M * K + 4 * M * N
         configs = [
-            ({"force_path": 2}, 1, True), ({"force_path": 4}, 1, True),
+            ({"force_path": 2}, 1, True),
             ({"force_path": 2, "gemv_debug": 1}, 1, True), ({"force_path": 2, "gemv_debug": 2}, 1, True),
             ({"force_path": 2, "gemv_warps": 8}, 1, True), ({"force_path": 2, "gemv_slabs": 2}, 1, True),
-            ({"force_path": 2, "gemv_pdl": 0}, 1, True),
-            ({"force_path": 2}, 2, True), ({"force_path": 2}, 4, True), ({"force_path": 2}, 8, True), ({"force_path": 2}, 16, True),
-            ({"force_path": 2, "gemv_warps": 8}, 8, True), ({"force_path": 2, "gemv_warps": 8}, 16, True),
+            ({"force_path": 2, "gemv_pdl": 0}, 1, True), ({"force_path": 2}, 1, False),
+            ({"force_path": 2}, 2, True), ({"force_path": 2}, 4, True), ({"force_path": 2}, 8, True),
+            ({"force_path": 2, "gemv_warps": 8}, 4, True), ({"force_path": 2, "gemv_warps": 8}, 8, True),
         ]
         for tune, M, graph in configs:
             for k in KEYS:
