@@ -90,7 +90,7 @@ int b200q_linear_fwd(const void* x, int x_dtype, const uint8_t* packed, const fl
         return launch_gemv_tc(d, x, x_dtype, packed, scales, zps, y, y_dtype, M, N, K, ws, ws_bytes, flags, st);
     if (force != 1 && force != 3 && force != 4 && vec_ok && gemv_supported(M, N, K, x_dtype))
         return launch_gemv(d, x, x_dtype, packed, scales, zps, y, y_dtype, M, N, K, ws, ws_bytes, flags, st);
-    if (force != 1 && force != 2 && vec_ok && gemm_tc_supported(M, N, K, x_dtype, y_dtype))
+    if (force != 1 && force != 2 && force != 4 && vec_ok && gemm_tc_supported(M, N, K, x_dtype, y_dtype))
         return launch_gemm_tc(d, x, x_dtype, packed, scales, zps, y, y_dtype, M, N, K, nullptr, nullptr, 1, ws, ws_bytes, flags, st);
     if (force == 2 || force == 3 || force == 4) return set_error(B200Q_EINVAL, "linear_fwd: forced path %d does not support this shape / alignment", force);
     return launch_linear_generic(x, x_dtype, packed, scales, zps, y, y_dtype, M, N, K, nullptr, nullptr, 1, 0, st);

@@ -1,15 +1,491 @@
-// Prefill / grouped path on tcgen05 tensor cores -- placeholder until the UMMA kernel lands:
-// reports "unsupported" so the dispatcher uses the generic SIMT path.
+// Prefill / grouped (MoE) path on the 5th-generation tensor cores:
+//     Y[m, n] = sum_k X[m, k] * dequant(W)[n, k]        for M >= 9 rows (and every grouped call)
+//
+// "Swap-AB" tcgen05 GEMM: the 128 x K slab of INT4 weights is the A operand and lives in TENSOR
+// MEMORY; the activations are the B operand in shared memory (TMA, 128-byte swizzle), up to 256
+// token rows per tile, so one CTA tile is D[128 weight rows x 256 tokens] in TMEM (fp32).
+//
+//   warp 0      TMA producer: per 64-column k-block one activation tile (256 x 64 fp16, plus the
+//               low-part tile for fp32 inputs) and one packed-weight tile (128 rows x 32 bytes)
+//   warps 4-7   dequant: thread = weight row; LDS the row's 32 packed bytes, nibble -> fp16 SUBNORMAL
+//               with one LOP3 per two weights (no arithmetic), tcgen05.st into a TMEM A slot
+//   warp 1      MMA issuer: 4 (x2 for hi/lo) tcgen05.mma.kind::f16 M=128 N=256 K=16 per k-block,
+//               A from TMEM, B from shared memory; tcgen05.commit frees the stage / the A slot
+//   warps 8-11  epilogue: tcgen05.ld the accumulator, y = s_n * (D * 2^(24-e_m) - zp_n * sum_k x[m,k]),
+//               coalesced stores (a warp writes 32 consecutive n of one token row)
+//
+// The activations are prepared by xprep_gemm_kernel: per token row a power-of-two scale 2^e
+// (amax * 2^e in [2^13, 2^14)), fp16 hi part (and fp16 remainder for fp32 inputs, so that products are
+// exact to ~2^-22), columns permuted inside each group of 8 to the order the A registers come out in
+// (k0,k4,k1,k5,k2,k6,k3,k7) with the odd columns pre-scaled by 2^-4 (they meet nibbles left at bits
+// 4-7 of the fp16 mantissa = q * 2^-20 instead of q * 2^-24), plus the row sum for the zero-point term.
+//
+// Grouped mode (MoE): token rows [starts[e], ends[e]) use expert e of packed [E, N, K/2]; tiles are
+// enumerated on the device from the (device-resident) ranges, no host synchronisation.
+//
+// Reference being replaced: csrc/quantized_linear_kernel.cu:90-279 (M > 1 re-streams the weights per
+// row) and csrc/moe_int4_kernel.cu:17-90 (one CTA per expert).
+#include <cuda.h>
+#include <mutex>
 #include "internal.h"
+#include "ptx.cuh"
+#include "tc.cuh"
 
 namespace b200q {
 
-bool gemm_tc_supported(int64_t, int64_t, int64_t, int, int) { return false; }
-size_t gemm_tc_ws_bytes(int64_t, int64_t, int64_t) { return 0; }
-int launch_gemm_tc(const DeviceInfo&, const void*, int, const uint8_t*, const float*, const float*,
-                   void*, int, int64_t, int64_t, int64_t, const int32_t*, const int32_t*, int, void*, size_t,
-                   unsigned, cudaStream_t) {
-    return set_error(B200Q_EINVAL, "gemm_tc: not built");
+namespace {
+
+constexpr int BM = 128;            // weight rows per tile (UMMA M, TMEM lanes)
+constexpr int BN = 256;            // token rows per tile (UMMA N, accumulator columns)
+constexpr int BK = 64;             // k-block: one 128-byte swizzle row of fp16
+constexpr int A_SLOTS = 4;         // TMEM A ring: 4 k-blocks x 32 columns
+constexpr int A_BASE = 256;        // accumulator: columns [0, 256); A ring: [256, 384)
+constexpr int TMEM_COLS = 512;
+constexpr int GEMM_THREADS = 12 * 32;
+constexpr int X_TILE_BYTES = BN * BK * 2;      // 32 KB
+constexpr int W_TILE_BYTES = BM * (BK / 2);    // 4 KB
+constexpr int MAX_STAGES = 6;
+
+// shared memory map
+constexpr int OFF_FULL = 0;        // [MAX_STAGES]
+constexpr int OFF_EMPTY = 64;      // [MAX_STAGES]
+constexpr int OFF_AFULL = 128;     // [A_SLOTS]
+constexpr int OFF_AEMPTY = 192;    // [A_SLOTS]
+constexpr int OFF_DFULL = 256;
+constexpr int OFF_DEMPTY = 264;
+constexpr int OFF_TMEMPTR = 272;
+constexpr int OFF_TOK = 1024;      // float descale[256], rowsum[256]
+constexpr int OFF_STAGES = 4096;   // 1024-byte aligned stage buffers
+
+struct GemmParams {
+    const float* scales;
+    const float* zps;
+    void* y;
+    const float* descale;    // [R] 2^(24 - e_m)
+    const float* rowsum;     // [R] sum_k x[m, k]
+    const int32_t* starts;   // grouped: [E] device, else nullptr
+    const int32_t* ends;
+    int E;
+    int y_dtype;
+    int R, N, K;             // token rows, weight rows (per expert), columns
+    int mt_bound;            // upper bound of m-tiles (grouped: ceil(R/BN) + E)
+    int n_tiles;             // ceil(N / BM)
+    int stages;
+    int stage_bytes;
+};
+
+struct TileInfo {
+    int e, m0, mend, n0;
+};
+
+// tile index -> (expert, first token row, end of the group, first weight row); false = no such tile
+__device__ __forceinline__ bool locate(const GemmParams& p, int t, TileInfo& ti) {
+    const int nt = t / p.mt_bound, mt = t - nt * p.mt_bound;
+    if (nt >= p.n_tiles) return false;
+    ti.n0 = nt * BM;
+    if (!p.starts) {
+        ti.e = 0;
+        ti.m0 = mt * BN;
+        ti.mend = p.R;
+        return ti.m0 < p.R;
+    }
+    int rem = mt;
+    for (int e = 0; e < p.E; ++e) {
+        const int lo = max(p.starts[e], 0), hi = min(p.ends[e], p.R);
+        const int cnt = hi - lo;
+        if (cnt <= 0) continue;
+        const int tiles = (cnt + BN - 1) / BN;
+        if (rem < tiles) {
+            ti.e = e;
+            ti.m0 = lo + rem * BN;
+            ti.mend = hi;
+            return true;
+        }
+        rem -= tiles;
+    }
+    return false;
+}
+
+template <int PARTS>   // 1: fp16 activations (hi only); 2: hi + lo (fp32 activations)
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
+               const __grid_constant__ CUtensorMap map_w, const GemmParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t sb = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int S = p.stages;
+    auto full = [&](int s) { return sb + OFF_FULL + 8u * s; };
+    auto empty = [&](int s) { return sb + OFF_EMPTY + 8u * s; };
+    auto afull = [&](int a) { return sb + OFF_AFULL + 8u * a; };
+    auto aempty = [&](int a) { return sb + OFF_AEMPTY + 8u * a; };
+    const uint32_t dfull = sb + OFF_DFULL, dempty = sb + OFF_DEMPTY;
+    volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + OFF_TMEMPTR);
+    float* tok = reinterpret_cast<float*>(smem + OFF_TOK);
+    auto xh_smem = [&](int s) { return sb + OFF_STAGES + (uint32_t)s * p.stage_bytes; };
+    auto xl_smem = [&](int s) { return xh_smem(s) + X_TILE_BYTES; };
+    auto w_smem = [&](int s) { return xh_smem(s) + PARTS * X_TILE_BYTES; };
+    const int KB = p.K / BK;
+    const int total_tiles = p.n_tiles * p.mt_bound;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(full(s), 1);
+            mbar_init(empty(s), 5);          // 4 dequant warps + the MMA commit
+        }
+        for (int a = 0; a < A_SLOTS; ++a) {
+            mbar_init(afull(a), 4);
+            mbar_init(aempty(a), 1);
+        }
+        mbar_init(dfull, 1);
+        mbar_init(dempty, 4);
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(sb + OFF_TMEMPTR, TMEM_COLS);
+        tmem_relinquish();
+    }
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_xh);
+        if (PARTS == 2) tma_prefetch_desc(&map_xl);
+        tma_prefetch_desc(&map_w);
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = *tmem_ptr;
+
+    if (warp == 0) {
+        // =============================================================== TMA producer
+        if (lane == 0) {
+            int s = 0, ph = 0, it = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                TileInfo ti;
+                if (!locate(p, t, ti)) continue;
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    if (it >= S) mbar_wait(empty(s), ph ^ 1);
+                    mbar_arrive_expect_tx(full(s), (uint32_t)(PARTS * X_TILE_BYTES + W_TILE_BYTES));
+                    tma_load_2d(xh_smem(s), &map_xh, kb * BK, ti.m0, full(s));
+                    if (PARTS == 2) tma_load_2d(xl_smem(s), &map_xl, kb * BK, ti.m0, full(s));
+                    tma_load_2d(w_smem(s), &map_w, kb * (BK / 2), ti.e * p.N + ti.n0, full(s));
+                    if (++s == S) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =============================================================== MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = idesc_f16(BM, BN, 0);
+            int s = 0, ph = 0, ait = 0, li = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                TileInfo ti;
+                if (!locate(p, t, ti)) continue;
+                if (li > 0) {                                   // the epilogue has drained the accumulator
+                    mbar_wait(dempty, (li - 1) & 1);
+                    tc_fence_after_sync();
+                }
+                for (int kb = 0; kb < KB; ++kb, ++ait) {
+                    const int a = ait % A_SLOTS;
+                    mbar_wait(full(s), ph);
+                    mbar_wait(afull(a), (ait / A_SLOTS) & 1);
+                    tc_fence_after_sync();
+                    const uint32_t a_tmem = tmem + A_BASE + 32 * a;
+#pragma unroll
+                    for (int kk = 0; kk < BK / 16; ++kk) {
+                        const uint64_t bh = smem_desc(xh_smem(s) + kk * 32, 16, 1024, SWIZZLE_128B);
+                        mma_ts_f16(tmem, a_tmem + 8 * kk, bh, idesc, (kb | kk) != 0 ? 1u : 0u);
+                        if (PARTS == 2) {
+                            const uint64_t bl = smem_desc(xl_smem(s) + kk * 32, 16, 1024, SWIZZLE_128B);
+                            mma_ts_f16(tmem, a_tmem + 8 * kk, bl, idesc, 1u);
+                        }
+                    }
+                    tc_commit(empty(s));
+                    tc_commit(aempty(a));
+                    if (++s == S) { s = 0; ph ^= 1; }
+                }
+                tc_commit(dfull);
+                ++li;
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // =============================================================== dequant warps
+        const int q = warp & 3;
+        const int r = 32 * q + lane;                                // weight row of the tile = TMEM lane
+        int s = 0, ph = 0, ait = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            TileInfo ti;
+            if (!locate(p, t, ti)) continue;
+            for (int kb = 0; kb < KB; ++kb, ++ait) {
+                mbar_wait(full(s), ph);
+                const uint4 w0 = lds128(w_smem(s) + r * (BK / 2));
+                const uint4 w1 = lds128(w_smem(s) + r * (BK / 2) + 16);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty(s));               // the packed bytes are in registers
+                const int a = ait % A_SLOTS;
+                if (ait >= A_SLOTS) {
+                    mbar_wait(aempty(a), ((ait / A_SLOTS) - 1) & 1);
+                    tc_fence_after_sync();
+                }
+                const uint32_t dst = tmem + ((uint32_t)(32 * q) << 16) + A_BASE + 32 * a;
+                const uint32_t ws[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t rr[16];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        // nibble n left in the low mantissa bits of a zero-exponent fp16 is the subnormal
+                        // n * 2^-24 (bits 0-3) or n * 2^-20 (bits 4-7): exact, no arithmetic
+                        const uint32_t w = ws[4 * half + j], w2 = w >> 8;
+                        rr[4 * j + 0] = w & 0x000f000fu;
+                        rr[4 * j + 1] = w & 0x00f000f0u;
+                        rr[4 * j + 2] = w2 & 0x000f000fu;
+                        rr[4 * j + 3] = w2 & 0x00f000f0u;
+                    }
+                    tmem_st16(dst + 16 * half, rr);
+                }
+                tmem_wait_st();
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(afull(a));
+                if (++s == S) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp >= 8) {
+        // =============================================================== epilogue warps
+        const int q = warp & 3;
+        const int et = (warp - 8) * 32 + lane;                      // 0..127
+        int li = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            TileInfo ti;
+            if (!locate(p, t, ti)) continue;
+            // per-token scalars of this tile (written after the previous tile's readers are done)
+            named_bar_sync(1, 128);
+            for (int j = et; j < BN; j += 128) {
+                const int m = ti.m0 + j;
+                tok[j] = m < ti.mend ? __ldg(p.descale + m) : 0.0f;
+                tok[BN + j] = m < ti.mend ? __ldg(p.rowsum + m) : 0.0f;
+            }
+            named_bar_sync(1, 128);
+            const int n = ti.n0 + 32 * q + lane;
+            const bool n_ok = n < p.N;
+            const float sc = n_ok ? __ldg(p.scales + (int64_t)ti.e * p.N + n) : 0.0f;
+            const float zp = n_ok ? __ldg(p.zps + (int64_t)ti.e * p.N + n) : 0.0f;
+            mbar_wait(dfull, li & 1);
+            tc_fence_after_sync();
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t d[32];
+                tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + 32 * c, d);
+                tmem_wait_ld();
+                if (c == BN / 32 - 1) {                             // accumulator fully read: release it
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(dempty);
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int m = ti.m0 + 32 * c + j;
+                    if (n_ok && m < ti.mend) {
+                        const float v = sc * (__uint_as_float(d[j]) * tok[32 * c + j] - zp * tok[BN + 32 * c + j]);
+                        const int64_t o = (int64_t)m * p.N + n;
+                        if (p.y_dtype == B200Q_F32) static_cast<float*>(p.y)[o] = v;
+                        else if (p.y_dtype == B200Q_F16) static_cast<__half*>(p.y)[o] = __float2half_rn(v);
+                        else static_cast<__nv_bfloat16*>(p.y)[o] = __float2bfloat16_rn(v);
+                    }
+                }
+            }
+            ++li;
+        }
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after_sync();
+        tmem_dealloc(tmem, TMEM_COLS);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Activation preparation: one warp per token row (see the header comment).
+struct XprepGemmParams {
+    const void* x;
+    __half* xh;
+    __half* xl;       // nullptr for 16-bit inputs
+    float* descale;
+    float* rowsum;
+    int x_dtype, R, K;
+};
+
+template <typename T> __device__ __forceinline__ void ld8(const T* p, float (&v)[8]);
+template <> __device__ __forceinline__ void ld8<float>(const float* p, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <> __device__ __forceinline__ void ld8<__half>(const __half* p, float (&v)[8]) {
+    const uint4 r = *reinterpret_cast<const uint4*>(p);
+    const __half2* h = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+template <> __device__ __forceinline__ void ld8<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 r = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) xprep_gemm_kernel(const XprepGemmParams p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t m = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (m >= p.R) return;
+    const T* xr = static_cast<const T*>(p.x) + m * p.K;
+    float am = 0.0f, sum = 0.0f;
+    for (int k = lane * 8; k < p.K; k += 256) {
+        float v[8];
+        ld8<T>(xr + k, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { am = fmaxf(am, fabsf(v[i])); sum += v[i]; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, o));
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    }
+    int ex = 0;
+    if (am > 0.0f && am < INFINITY) ex = max(-100, min(100, 140 - (int)((__float_as_uint(am) >> 23) & 0xffu)));
+    const float up = __uint_as_float((uint32_t)(127 + ex) << 23), up_hi = up * 0.0625f;
+    if (lane == 0) {
+        p.descale[m] = __uint_as_float((uint32_t)(127 + 24 - ex) << 23);
+        p.rowsum[m] = sum;
+    }
+    __half* hr = p.xh + m * p.K;
+    __half* lr = p.xl ? p.xl + m * p.K : nullptr;
+    for (int k = lane * 8; k < p.K; k += 256) {
+        float v[8];
+        ld8<T>(xr + k, v);
+        // (k0,k4) (k1,k5) (k2,k6) (k3,k7): the order the A registers hold the nibbles in
+        const float s0 = v[0] * up, s4 = v[4] * up, s1 = v[1] * up_hi, s5 = v[5] * up_hi;
+        const float s2 = v[2] * up, s6 = v[6] * up, s3 = v[3] * up_hi, s7 = v[7] * up_hi;
+        __half2 h0 = __floats2half2_rn(s0, s4), h1 = __floats2half2_rn(s1, s5);
+        __half2 h2 = __floats2half2_rn(s2, s6), h3 = __floats2half2_rn(s3, s7);
+        *reinterpret_cast<uint4*>(hr + k) = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                                                       *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+        if (lr) {
+            const float2 f0 = __half22float2(h0), f1 = __half22float2(h1), f2 = __half22float2(h2), f3 = __half22float2(h3);
+            __half2 l0 = __floats2half2_rn(s0 - f0.x, s4 - f0.y), l1 = __floats2half2_rn(s1 - f1.x, s5 - f1.y);
+            __half2 l2 = __floats2half2_rn(s2 - f2.x, s6 - f2.y), l3 = __floats2half2_rn(s3 - f3.x, s7 - f3.y);
+            *reinterpret_cast<uint4*>(lr + k) = make_uint4(*reinterpret_cast<uint32_t*>(&l0), *reinterpret_cast<uint32_t*>(&l1),
+                                                           *reinterpret_cast<uint32_t*>(&l2), *reinterpret_cast<uint32_t*>(&l3));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    });
+    return fn;
+}
+
+int make_map_2d(CUtensorMap* map, CUtensorMapDataType dt, int esz, const void* base, uint64_t inner, uint64_t outer,
+                uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle sw) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return set_error(B200Q_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {inner * (uint64_t)esz};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(B200Q_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return 0;
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+bool gemm_tc_supported(int64_t M, int64_t N, int64_t K, int x_dtype, int y_dtype) {
+    (void)x_dtype; (void)y_dtype;
+    return M >= 1 && K >= 128 && K % 128 == 0 && N >= 1 && M < (1ll << 30) && N < (1ll << 30) && K <= (1 << 20);
+}
+
+// workspace: [4 KB reserved: the decode kernels keep their zeroed ticket counters there -- callers
+// share one workspace between all paths][xh R*K fp16][xl R*K fp16][descale R f32][rowsum R f32]
+constexpr size_t WS_RESERVED = 4096;
+size_t gemm_tc_ws_bytes(int64_t M, int64_t N, int64_t K) {
+    if (!gemm_tc_supported(M, N, K, B200Q_F32, B200Q_F32)) return 0;
+    return WS_RESERVED + 2 * align_up((size_t)M * K * 2, 1024) + 2 * align_up((size_t)M * 4, 1024) + 1024;
+}
+
+int launch_gemm_tc(const DeviceInfo& dev, const void* x, int x_dtype, const uint8_t* packed,
+                   const float* scales, const float* zps, void* y, int y_dtype, int64_t M,
+                   int64_t N, int64_t K, const int32_t* starts, const int32_t* ends, int E,
+                   void* ws, size_t ws_bytes, unsigned flags, cudaStream_t st) {
+    (void)flags;
+    if (!gemm_tc_supported(M, N, K, x_dtype, y_dtype)) return set_error(B200Q_EINVAL, "gemm_tc: unsupported shape");
+    const size_t need = gemm_tc_ws_bytes(M, N, K);
+    if (!ws || ws_bytes < need) return set_error(B200Q_EWORKSPACE, "gemm_tc: workspace too small (%zu < %zu)", ws_bytes, need);
+    // the tensor maps want 1024-byte aligned bases: align inside the (1 KB larger) workspace
+    uint8_t* w8 = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + WS_RESERVED + 1023) & ~(uintptr_t)1023);
+    const size_t xbytes = align_up((size_t)M * K * 2, 1024), sbytes = align_up((size_t)M * 4, 1024);
+    __half* xh = reinterpret_cast<__half*>(w8);
+    __half* xl = reinterpret_cast<__half*>(w8 + xbytes);
+    float* descale = reinterpret_cast<float*>(w8 + 2 * xbytes);
+    float* rowsum = reinterpret_cast<float*>(w8 + 2 * xbytes + sbytes);
+    const int parts = x_dtype == B200Q_F32 ? 2 : 1;
+
+    XprepGemmParams xp{x, xh, parts == 2 ? xl : nullptr, descale, rowsum, x_dtype, (int)M, (int)K};
+    const unsigned xblocks = (unsigned)((M + 7) / 8);
+    if (x_dtype == B200Q_F32) xprep_gemm_kernel<float><<<xblocks, 256, 0, st>>>(xp);
+    else if (x_dtype == B200Q_F16) xprep_gemm_kernel<__half><<<xblocks, 256, 0, st>>>(xp);
+    else xprep_gemm_kernel<__nv_bfloat16><<<xblocks, 256, 0, st>>>(xp);
+    B200Q_CUDA(cudaGetLastError());
+
+    CUtensorMap map_xh, map_xl, map_w;
+    if (int rc = make_map_2d(&map_xh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, xh, (uint64_t)K, (uint64_t)M, BK, BN, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    if (int rc = make_map_2d(&map_xl, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, parts == 2 ? xl : xh, (uint64_t)K, (uint64_t)M, BK, BN, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    const int groups = starts ? E : 1;
+    if (int rc = make_map_2d(&map_w, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, packed, (uint64_t)(K / 2), (uint64_t)groups * N, BK / 2, BM, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
+
+    GemmParams p{};
+    p.scales = scales; p.zps = zps; p.y = y; p.descale = descale; p.rowsum = rowsum;
+    p.starts = starts; p.ends = ends; p.E = groups; p.y_dtype = y_dtype;
+    p.R = (int)M; p.N = (int)N; p.K = (int)K;
+    p.mt_bound = (int)((M + BN - 1) / BN) + (starts ? E : 0);
+    p.n_tiles = (int)((N + BM - 1) / BM);
+    p.stage_bytes = parts * X_TILE_BYTES + W_TILE_BYTES;
+    int stages = (dev.max_smem_optin - OFF_STAGES) / p.stage_bytes;
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    if (stages < 2) return set_error(B200Q_EINVAL, "gemm_tc: not enough shared memory");
+    p.stages = stages;
+    const size_t smem = (size_t)OFF_STAGES + (size_t)stages * p.stage_bytes;
+    auto kfn = parts == 2 ? gemm_tc_kernel<2> : gemm_tc_kernel<1>;
+    static thread_local int attr_done[64][2] = {{0}};
+    int devi = 0;
+    B200Q_CUDA(cudaGetDevice(&devi));
+    if (devi >= 0 && devi < 64 && attr_done[devi][parts - 1] < (int)smem) {
+        B200Q_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done[devi][parts - 1] = (int)smem;
+    }
+    const long long total_tiles = (long long)p.n_tiles * p.mt_bound;
+    int grid = dev.sm_count;
+    if (total_tiles < grid) grid = (int)total_tiles;
+    if (grid < 1) grid = 1;
+    kfn<<<grid, GEMM_THREADS, smem, st>>>(map_xh, map_xl, map_w, p);
+    return check_cuda(cudaGetLastError(), "gemm_tc launch");
 }
 
 }  // namespace b200q

@@ -196,4 +196,8 @@ def test_mixtral_routed_layer_properties(pkg):
         g = moe.experts[e](xs[e]); u = moe.experts_up[e](xs[e])
         ys.append(moe.experts_down[e](torch.nn.functional.silu(g) * u))
     y2 = pkg.combine_expert_outputs(ys, r, inv, 2)
-    assert torch.allclose(y2, y, atol=2e-4, rtol=1e-3)
+    # the per-expert path (M <= 8 rows per call) runs the exact-integer decode kernel, the fused layer the
+    # tcgen05 grouped GEMM (fp16 hi/lo activations, fp32 accumulation over 4096 / 14336 terms, twice)
+    diff = (y2 - y).abs().max().item()
+    print(f"fused vs per-expert: max abs diff {diff:.3e}, |y|max {y.abs().max().item():.3f}")
+    assert diff <= 3e-4 * y.abs().max().item()
