@@ -360,7 +360,7 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
-    workload = args.workload or "gemv"
+    workload = args.workload or ("gemv" if args.gpus <= 1 and int(os.environ.get("WORLD_SIZE", "1")) <= 1 else "moe")
     if workload == "gemv":
         return run_gemv(args)
     from bench_moe import run_moe       # expert-parallel Mixtral layer
