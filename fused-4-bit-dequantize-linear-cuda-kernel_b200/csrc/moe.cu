@@ -193,9 +193,33 @@ gather_rows_kernel(const uint4* __restrict__ x, const int32_t* __restrict__ sort
 }
 
 // ------------------------------------------------------------------------------- SiLU gate
+// h[p,f] = silu(gu[p,f]) * gu[p,F+f].  HBM-bound: 16-byte loads / stores when F allows it.
+template <typename T> struct Vec16 { static constexpr int N = 16 / sizeof(T); };
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 silu_mul_kernel(const T* __restrict__ gu, int64_t R, int64_t F, T* __restrict__ h) {
+    constexpr int V = Vec16<T>::N;
+    if (F % V == 0 && (reinterpret_cast<uintptr_t>(gu) & 15) == 0 && (reinterpret_cast<uintptr_t>(h) & 15) == 0) {
+        const int64_t fv = F / V, total = R * fv;
+        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+             i += (int64_t)gridDim.x * blockDim.x) {
+            const int64_t p = i / fv, f = (i - p * fv) * V;
+            const uint4 av = *reinterpret_cast<const uint4*>(gu + p * 2 * F + f);
+            const uint4 bv = *reinterpret_cast<const uint4*>(gu + p * 2 * F + F + f);
+            uint4 ov;
+            const T* a = reinterpret_cast<const T*>(&av);
+            const T* b = reinterpret_cast<const T*>(&bv);
+            T* o = reinterpret_cast<T*>(&ov);
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                const float x = to_f32<T>(a[j]);
+                o[j] = from_f32<T>(x / (1.0f + expf(-x)) * to_f32<T>(b[j]));
+            }
+            *reinterpret_cast<uint4*>(h + p * F + f) = ov;
+        }
+        return;
+    }
     const int64_t total = R * F;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
@@ -320,7 +344,7 @@ int b200q_moe_silu_mul(const void* gu, int dtype, int64_t R, int64_t F, void* h,
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int64_t total = R * F;
     int64_t blocks = (total + 255) / 256;
-    int64_t cap = (int64_t)di.sm_count * 16;
+    int64_t cap = (int64_t)di.sm_count * 32;
     if (blocks > cap) blocks = cap;
     switch (dtype) {
         case B200Q_F32: silu_mul_kernel<float><<<static_cast<unsigned>(blocks), 256, 0, st>>>(static_cast<const float*>(gu), R, F, static_cast<float*>(h)); break;

@@ -27,7 +27,9 @@
  *     allocates device memory, never synchronises the device.  Work is enqueued on `stream`
  *     (a cudaStream_t passed as void*; NULL = legacy default stream).
  *   - outputs and workspaces are caller-owned.  A workspace must be zero-filled ONCE by the
- *     caller when it is allocated; the kernels leave it zeroed again on exit.
+ *     caller when it is allocated and is then private to ONE entry point (b200q_linear_fwd and the
+ *     two b200q_moe_grouped_fwd* may share one: their layouts reserve the same 4 KB of ticket counters);
+ *     the kernels leave the counters zeroed again on exit.  Alignment: 128 bytes.
  *   - re-entrant / thread-safe: the only global state is an immutable per-device property cache
  *     and a thread-local last-error string.
  *   - there is no CPU path.  On a machine without an sm_100 GPU the compute entry points
@@ -105,8 +107,9 @@ int b200q_dequantize_rows(const uint8_t* packed, const float* scales, const floa
 /* y[M,N] = x[M,K] @ dequant(packed[N,K/2], scales[N], zps[N])^T
  *   x_dtype / y_dtype: B200Q_F32 | B200Q_F16 | B200Q_BF16 (the reference API is f32/f32).
  *   x, y row-major and contiguous; x 16-byte aligned, packed 16-byte aligned, K even.
- *   M may be any value >= 0.  Shapes with K % 128 == 0 take the TMA-ring tensor-core paths;
- *   other even K take a generic SIMT kernel.
+ *   M may be any value >= 0.  K % 128 == 0 with 16-byte aligned pointers: M <= 8 takes the decode
+ *   kernel (TMA bulk copies, exact-integer IMMA), M >= 9 the tcgen05 GEMM; anything else a generic
+ *   SIMT kernel.
  *   ws: >= b200q_linear_ws_bytes(M,N,K) bytes (may be NULL when that is 0). */
 size_t b200q_linear_ws_bytes(int64_t M, int64_t N, int64_t K);
 int b200q_linear_fwd(const void* x, int x_dtype, const uint8_t* packed, const float* scales,
