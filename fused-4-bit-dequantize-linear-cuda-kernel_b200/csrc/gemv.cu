@@ -30,6 +30,9 @@ namespace b200q {
 // phase timestamps (SM clock) of every CTA, written when the bench-only "gemv_debug" value has
 // bit 3 (8) set; read back with b200q_debug_read_prof
 __device__ long long g_gemv_prof[256 * 16];
+// wall-clock (globaltimer, ns) of the first CTA start / last CTA end of the last 64 profiled launches
+__device__ unsigned long long g_gemv_wall[64 * 4];
+__device__ unsigned int g_gemv_launch_no;
 
 namespace {
 
@@ -65,6 +68,7 @@ struct GemvParams {
     int rg, rg_shift;       // live mma columns per n-tile (4 or 8) and log2 of it
     int red_off, ring_off;  // byte offsets in dynamic shared memory
     int wait_weights;       // 1: weights may be written by the preceding kernel -> wait first
+    unsigned int launch_no; // bench-only: slot of the wall-clock record
     int debug;              // bench-only: low bits 1 = skip the mma work, 2 = skip the weight loads; 8 = timestamps
 };
 
@@ -108,7 +112,7 @@ constexpr int MISC_OFF = 1024;
 constexpr int RED_OFF = 1152;
 
 template <int NW, int GPW, int NT>
-__global__ void __launch_bounds__(NW * 32, 1) gemv_kernel(const GemvParams p) {
+__global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) gemv_kernel(const GemvParams p) {
     constexpr int COLS = NT * 8;                   // mma columns: (batch row, limb), two batch rows per n-tile
     constexpr int NTHR = NW * 32;
     constexpr int RPW = TILE_ROWS / NW;            // stage rows issued per warp (1 or 2)
@@ -128,6 +132,8 @@ __global__ void __launch_bounds__(NW * 32, 1) gemv_kernel(const GemvParams p) {
     const bool prof = (p.debug & 8) && threadIdx.x == 0 && blockIdx.x < 256;
     auto stamp = [&](int i) { if (prof) g_gemv_prof[blockIdx.x * 16 + i] = clock64(); };
     stamp(0);
+    unsigned long long wall0 = 0;
+    if (prof) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(wall0));
     const int slab = p.nslab == 1 ? 0 : (int)(blockIdx.x % p.nslab);
     const int rb = p.nslab == 1 ? (int)blockIdx.x : (int)(blockIdx.x / p.nslab);
     const int g0 = slab * p.gran_q + min(slab, p.gran_rem);
@@ -379,6 +385,15 @@ __global__ void __launch_bounds__(NW * 32, 1) gemv_kernel(const GemvParams p) {
         }
     }
     stamp(9);
+    if (prof) {
+        unsigned long long wall1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(wall1));
+        const unsigned int ln = p.launch_no & 63u;
+        atomicMin(&g_gemv_wall[ln * 4 + 0], wall0);
+        atomicMax(&g_gemv_wall[ln * 4 + 1], wall0);
+        atomicMin(&g_gemv_wall[ln * 4 + 2], wall1);
+        atomicMax(&g_gemv_wall[ln * 4 + 3], wall1);
+    }
 
     // ---- cross-slab reduction by the last CTA of the row block (deterministic slab order)
     if (p.nslab > 1) {
@@ -539,8 +554,15 @@ bool plan(const DeviceInfo& dev, int64_t M, int64_t N, int64_t K, GemvConfig* c)
     if (tu.gemv_ctas > 0 && tu.gemv_ctas < ctas) ctas = tu.gemv_ctas;
     double best_cost = 1e30;
     bool found = false;
+    // "two layers per SM" mode (tuning key gemv_occ2, off by default): 8-warp CTAs that use at most half
+    // of the shared memory and registers, so the CTAs of the NEXT launch (programmatic dependent launch,
+    // static weights) become resident next to the running ones and prefetch their first tiles meanwhile.
+    // Measured slower (11.5 us vs 9.1 us): profiles/r01_gemv_notes.md
+    const bool occ2 = tu.gemv_occ2 != 0;
+    const int smem_budget = occ2 ? (dev.max_smem_optin - 2048) / 2 - 1024 : dev.max_smem_optin;
     for (int nw = 16; nw >= 8; nw -= 8) {
-        if (tu.gemv_warps > 0 && tu.gemv_warps != nw) continue;
+        if (occ2 && nw != 8) continue;
+        if (!occ2 && tu.gemv_warps > 0 && tu.gemv_warps != nw) continue;
         for (int ns = 1; ns <= MAX_SLABS && ns <= G; ++ns) {
             if (tu.gemv_slabs > 0 && tu.gemv_slabs != ns) continue;
             const int ng = (G + ns - 1) / ns;
@@ -553,7 +575,7 @@ bool plan(const DeviceInfo& dev, int64_t M, int64_t N, int64_t K, GemvConfig* c)
             const int rows = (int)((N + nrb - 1) / nrb);
             const int ntiles = (rows + TILE_ROWS - 1) / TILE_ROWS;
             const int red_tile = nw * nt * 8 * TILE_ROWS * 4;
-            int rt = 32768 / red_tile;
+            int rt = (occ2 ? 8192 : 32768) / red_tile;
             if (rt < 1) rt = 1;
             if (rt > ntiles) rt = ntiles;
             const int red_off = RED_OFF;
@@ -565,13 +587,13 @@ bool plan(const DeviceInfo& dev, int64_t M, int64_t N, int64_t K, GemvConfig* c)
             int pitch = contig ? ng * GRAN_B : (ng | 1) * GRAN_B;
             int stage_bytes = TILE_ROWS * pitch;
             int per_tile = 1;
-            int stages = (dev.max_smem_optin - ring_off) / stage_bytes;
+            int stages = (smem_budget - ring_off) / stage_bytes;
             if (!contig && stages < (ntiles < 3 ? ntiles : 3)) {
                 whole_row = 0;
                 pitch = ((ng < nw ? ng : nw) | 1) * GRAN_B;
                 stage_bytes = TILE_ROWS * pitch;
                 per_tile = gpw;
-                stages = (dev.max_smem_optin - ring_off) / stage_bytes;
+                stages = (smem_budget - ring_off) / stage_bytes;
             }
             if (stages > ntiles * per_tile) stages = ntiles * per_tile;
             if (stages > MAX_STAGES) stages = MAX_STAGES;
@@ -581,7 +603,7 @@ bool plan(const DeviceInfo& dev, int64_t M, int64_t N, int64_t K, GemvConfig* c)
             // warps in the last chunk, for a ring that cannot hold the whole slab, and for 8 warps
             double cost = (double)rows * ng * (1.0 + 0.03 * (ns - 1)) * (1.0 + 0.1 * ((double)gpw * nw / ng - 1.0));
             if (stages < ntiles * per_tile) cost *= 1.05;
-            if (nw == 8) cost *= 1.10;
+            if (nw == 8 && !occ2) cost *= 1.10;
             if (cost < best_cost) {
                 best_cost = cost;
                 found = true;
@@ -604,6 +626,7 @@ int launch_inst(const GemvConfig& c, const GemvParams& p, bool pdl, cudaStream_t
     B200Q_CUDA(cudaGetDevice(&dev));
     if (dev >= 0 && dev < 64 && attr_dev_smem[dev] < (int)c.smem) {
         B200Q_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
+        if (tuning().gemv_occ2) B200Q_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         attr_dev_smem[dev] = (int)c.smem;
     }
     cudaLaunchConfig_t cfg{};
@@ -663,6 +686,10 @@ int launch_gemv(const DeviceInfo& dev, const void* x, int x_dtype, const uint8_t
     p.wait_weights = is_static ? 0 : 1;
     p.debug = tuning().gemv_debug > 0 ? tuning().gemv_debug : 0;
     {
+        static thread_local unsigned launch_no = 0;
+        p.launch_no = launch_no++;
+    }
+    {
         const size_t need = WS_IMG_OFF + 2 * ximg_bytes(K) + (c.nslab > 1 ? (size_t)c.nslab * M * N * 4 : 0);
         if (!ws || ws_bytes < need) return set_error(B200Q_EWORKSPACE, "gemv: workspace too small (%zu < %zu)", ws_bytes, need);
         if (reinterpret_cast<uintptr_t>(ws) & 127) return set_error(B200Q_EALIGN, "gemv: workspace must be 128-byte aligned");
@@ -706,6 +733,16 @@ int launch_gemv(const DeviceInfo& dev, const void* x, int x_dtype, const uint8_t
 }
 
 }  // namespace b200q
+
+/* bench-only: wall-clock records (64 launches x {min start, max start, min end, max end}); reset = 1 re-arms them */
+extern "C" int b200q_debug_wall(unsigned long long* h_out, int reset) {
+    if (reset) {
+        unsigned long long init[64 * 4];
+        for (int i = 0; i < 64; ++i) { init[4 * i] = ~0ull; init[4 * i + 1] = 0; init[4 * i + 2] = ~0ull; init[4 * i + 3] = 0; }
+        return b200q::check_cuda(cudaMemcpyToSymbol(b200q::g_gemv_wall, init, sizeof(init)), "reset wall");
+    }
+    return b200q::check_cuda(cudaMemcpyFromSymbol(h_out, b200q::g_gemv_wall, sizeof(unsigned long long) * 64 * 4), "read wall");
+}
 
 /* bench-only: copy the per-CTA phase timestamps of the last profiled GEMV launch (256 x 16 int64) */
 extern "C" int b200q_debug_read_prof(long long* h_out) {

@@ -17,7 +17,7 @@ from b200q_pkg import pkg  # noqa: E402
 
 _lib = pkg._lib
 lib = _lib.load()
-KEYS = ["gemv_warps", "gemv_slabs", "gemv_stages", "gemv_pdl", "gemv_ctas", "gemv_debug", "force_path"]
+KEYS = ["gemv_warps", "gemv_slabs", "gemv_stages", "gemv_pdl", "gemv_ctas", "gemv_debug", "force_path", "gemv_occ2"]
 
 
 def make_pool(N, K, n_layers, dev):
@@ -75,15 +75,15 @@ def main():
     shapes = [(4096, 11008)] if args.quick else [(4096, 11008), (11008, 4096)]
     out = open(args.out, "w")
     for (K, N) in shapes:
-        layers = make_pool(N, K, 24, dev)
+        layers = make_pool(N, K, int(os.environ.get("POOL", "24")), dev)
         nbytes = lambda M: N * K // 2 + 8 * N + 4 * M * K + 4 * M * N
         configs = [
-            ({"force_path": 2}, 1, True),
-            ({"force_path": 2, "gemv_debug": 1}, 1, True), ({"force_path": 2, "gemv_debug": 2}, 1, True),
-            ({"force_path": 2, "gemv_warps": 8}, 1, True), ({"force_path": 2, "gemv_slabs": 2}, 1, True),
-            ({"force_path": 2, "gemv_pdl": 0}, 1, True), ({"force_path": 2}, 1, False),
-            ({"force_path": 2}, 2, True), ({"force_path": 2}, 4, True), ({"force_path": 2}, 8, True),
-            ({"force_path": 2, "gemv_warps": 8}, 4, True), ({"force_path": 2, "gemv_warps": 8}, 8, True),
+            ({"force_path": 2}, 1, True), ({"force_path": 2, "gemv_occ2": 1}, 1, True),
+            ({"force_path": 2, "gemv_occ2": 1, "gemv_stages": 2}, 1, True),
+            ({"force_path": 2, "gemv_occ2": 1, "gemv_debug": 2}, 1, True),
+            ({"force_path": 2, "gemv_occ2": 1, "gemv_pdl": 0}, 1, True),
+            ({"force_path": 2, "gemv_occ2": 1}, 2, True), ({"force_path": 2, "gemv_occ2": 1}, 4, True),
+            ({"force_path": 2, "gemv_occ2": 1}, 8, True),
         ]
         for tune, M, graph in configs:
             for k in KEYS:

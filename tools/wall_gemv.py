@@ -1,0 +1,47 @@
+"""Wall-clock (globaltimer) gaps between consecutive decode-GEMV launches inside a CUDA graph."""
+import ctypes, os, sys
+import numpy as np
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from b200q_pkg import pkg
+_lib = pkg._lib; lib = _lib.load()
+lib.b200q_debug_wall.argtypes = [ctypes.c_void_p, ctypes.c_int]
+dev = torch.device("cuda", 0)
+K, N, M = 4096, 11008, 1
+layers = []
+for i in range(24):
+    g = torch.Generator(device=dev); g.manual_seed(i)
+    layers.append((torch.randint(0, 256, (N, K // 2), generator=g, device=dev, dtype=torch.uint8),
+                   torch.rand(N, device=dev) * 0.01, torch.randint(0, 16, (N,), device=dev).float()))
+x = torch.randn(M, K, device=dev); y = torch.empty(M, N, device=dev)
+ws = torch.zeros(max(lib.b200q_linear_ws_bytes(M, N, K), 16), dtype=torch.uint8, device=dev)
+_lib.tune("gemv_debug", int(os.environ.get("DBG", "8")))
+if os.environ.get("PDL"): _lib.tune("gemv_pdl", int(os.environ["PDL"]))
+if os.environ.get("OCC2"): _lib.tune("gemv_occ2", 1)
+def launch_all(sp):
+    for (p, s, z) in layers:
+        _lib.check(lib.b200q_linear_fwd(x.data_ptr(), 0, p.data_ptr(), s.data_ptr(), z.data_ptr(), y.data_ptr(), 0,
+                                        M, N, K, ws.data_ptr(), ws.numel(), 1, sp), "fwd")
+side = torch.cuda.Stream(dev); side.wait_stream(torch.cuda.current_stream(dev))
+with torch.cuda.stream(side):
+    launch_all(side.cuda_stream)
+torch.cuda.current_stream(dev).wait_stream(side)
+g = torch.cuda.CUDAGraph()
+with torch.cuda.graph(g):
+    launch_all(torch.cuda.current_stream(dev).cuda_stream)
+for _ in range(3):
+    g.replay()
+torch.cuda.synchronize()
+_lib.check(lib.b200q_debug_wall(None, 1), "reset")
+g.replay(); torch.cuda.synchronize()
+buf = np.zeros(64 * 4, dtype=np.uint64)
+_lib.check(lib.b200q_debug_wall(buf.ctypes.data, 0), "read")
+w = buf.reshape(64, 4).astype(np.int64)
+w = w[w[:, 3] > 0]
+w = w[np.argsort(w[:, 0])]
+t0 = w[0, 0]
+print("launch: first CTA start, last CTA start, first CTA end, last CTA end (ns from the first launch); gap to next first start")
+for i in range(len(w)):
+    gap = (w[i + 1, 0] - w[i, 3]) if i + 1 < len(w) else 0
+    print(f"{i:2d}: {w[i,0]-t0:7d} {w[i,1]-t0:7d} {w[i,2]-t0:7d} {w[i,3]-t0:7d}   period {(w[i+1,0]-w[i,0]) if i+1<len(w) else 0:6d}  gap {gap:6d}")
