@@ -36,13 +36,13 @@ namespace b200q {
 namespace {
 
 constexpr int BM = 128;            // weight rows per tile (UMMA M, TMEM lanes)
-constexpr int BN = 256;            // token rows per tile (UMMA N, accumulator columns)
+// token rows per tile (UMMA N, accumulator columns) is a template parameter BN in {128, 192, 256}: with
+// BN <= 192 two accumulators fit next to the A ring (2*BN + 128 <= 512 TMEM columns) and the epilogue of
+// tile i overlaps the MMAs of tile i+1; BN = 256 has one accumulator.
 constexpr int BK = 64;             // k-block: one 128-byte swizzle row of fp16
 constexpr int A_SLOTS = 4;         // TMEM A ring: 4 k-blocks x 32 columns
-constexpr int A_BASE = 256;        // accumulator: columns [0, 256); A ring: [256, 384)
 constexpr int TMEM_COLS = 512;
 constexpr int GEMM_THREADS = 12 * 32;
-constexpr int X_TILE_BYTES = BN * BK * 2;      // 32 KB
 constexpr int W_TILE_BYTES = BM * (BK / 2);    // 4 KB
 constexpr int MAX_STAGES = 6;
 
@@ -51,9 +51,9 @@ constexpr int OFF_FULL = 0;        // [MAX_STAGES]
 constexpr int OFF_EMPTY = 64;      // [MAX_STAGES]
 constexpr int OFF_AFULL = 128;     // [A_SLOTS]
 constexpr int OFF_AEMPTY = 192;    // [A_SLOTS]
-constexpr int OFF_DFULL = 256;
-constexpr int OFF_DEMPTY = 264;
-constexpr int OFF_TMEMPTR = 272;
+constexpr int OFF_DFULL = 256;     // [2]
+constexpr int OFF_DEMPTY = 272;    // [2]
+constexpr int OFF_TMEMPTR = 288;
 constexpr int OFF_TOK = 1024;      // float descale[256], rowsum[256]
 constexpr int OFF_STAGES = 4096;   // 1024-byte aligned stage buffers
 
@@ -68,6 +68,7 @@ struct GemmParams {
     int E;
     int y_dtype;
     int R, N, K;             // token rows, weight rows (per expert), columns
+    int bn;                  // token rows per tile
     int mt_bound;            // upper bound of m-tiles (grouped: ceil(R/BN) + E)
     int n_tiles;             // ceil(N / BM)
     int stages;
@@ -85,7 +86,7 @@ __device__ __forceinline__ bool locate(const GemmParams& p, int t, TileInfo& ti)
     ti.n0 = nt * BM;
     if (!p.starts) {
         ti.e = 0;
-        ti.m0 = mt * BN;
+        ti.m0 = mt * p.bn;
         ti.mend = p.R;
         return ti.m0 < p.R;
     }
@@ -94,10 +95,10 @@ __device__ __forceinline__ bool locate(const GemmParams& p, int t, TileInfo& ti)
         const int lo = max(p.starts[e], 0), hi = min(p.ends[e], p.R);
         const int cnt = hi - lo;
         if (cnt <= 0) continue;
-        const int tiles = (cnt + BN - 1) / BN;
+        const int tiles = (cnt + p.bn - 1) / p.bn;
         if (rem < tiles) {
             ti.e = e;
-            ti.m0 = lo + rem * BN;
+            ti.m0 = lo + rem * p.bn;
             ti.mend = hi;
             return true;
         }
@@ -106,10 +107,13 @@ __device__ __forceinline__ bool locate(const GemmParams& p, int t, TileInfo& ti)
     return false;
 }
 
-template <int PARTS>   // 1: fp16 activations (hi only); 2: hi + lo (fp32 activations)
+template <int PARTS, int BN>   // PARTS 1: fp16 activations (hi only); 2: hi + lo (fp32 activations)
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
                const __grid_constant__ CUtensorMap map_w, const GemmParams p) {
+    constexpr int X_TILE_BYTES = BN * BK * 2;
+    constexpr int DBUF = 2 * BN + A_SLOTS * 32 <= TMEM_COLS ? 2 : 1;     // accumulators in TMEM
+    constexpr int A_BASE = DBUF * BN;                                    // first column of the A ring
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sb = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -118,7 +122,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
     auto empty = [&](int s) { return sb + OFF_EMPTY + 8u * s; };
     auto afull = [&](int a) { return sb + OFF_AFULL + 8u * a; };
     auto aempty = [&](int a) { return sb + OFF_AEMPTY + 8u * a; };
-    const uint32_t dfull = sb + OFF_DFULL, dempty = sb + OFF_DEMPTY;
+    auto dfull = [&](int b) { return sb + OFF_DFULL + 8u * b; };
+    auto dempty = [&](int b) { return sb + OFF_DEMPTY + 8u * b; };
     volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + OFF_TMEMPTR);
     float* tok = reinterpret_cast<float*>(smem + OFF_TOK);
     auto xh_smem = [&](int s) { return sb + OFF_STAGES + (uint32_t)s * p.stage_bytes; };
@@ -136,8 +141,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
             mbar_init(afull(a), 4);
             mbar_init(aempty(a), 1);
         }
-        mbar_init(dfull, 1);
-        mbar_init(dempty, 4);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(dfull(b), 1);
+            mbar_init(dempty(b), 4);
+        }
         fence_mbar_init();
     }
     if (warp == 1) {
@@ -179,8 +186,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 TileInfo ti;
                 if (!locate(p, t, ti)) continue;
-                if (li > 0) {                                   // the epilogue has drained the accumulator
-                    mbar_wait(dempty, (li - 1) & 1);
+                const int ab = li % DBUF;
+                const uint32_t d_tmem = tmem + ab * BN;
+                if (li >= DBUF) {                               // the epilogue has drained this accumulator
+                    mbar_wait(dempty(ab), ((li / DBUF) - 1) & 1);
                     tc_fence_after_sync();
                 }
                 for (int kb = 0; kb < KB; ++kb, ++ait) {
@@ -192,17 +201,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
 #pragma unroll
                     for (int kk = 0; kk < BK / 16; ++kk) {
                         const uint64_t bh = smem_desc(xh_smem(s) + kk * 32, 16, 1024, SWIZZLE_128B);
-                        mma_ts_f16(tmem, a_tmem + 8 * kk, bh, idesc, (kb | kk) != 0 ? 1u : 0u);
+                        mma_ts_f16(d_tmem, a_tmem + 8 * kk, bh, idesc, (kb | kk) != 0 ? 1u : 0u);
                         if (PARTS == 2) {
                             const uint64_t bl = smem_desc(xl_smem(s) + kk * 32, 16, 1024, SWIZZLE_128B);
-                            mma_ts_f16(tmem, a_tmem + 8 * kk, bl, idesc, 1u);
+                            mma_ts_f16(d_tmem, a_tmem + 8 * kk, bl, idesc, 1u);
                         }
                     }
                     tc_commit(empty(s));
                     tc_commit(aempty(a));
                     if (++s == S) { s = 0; ph ^= 1; }
                 }
-                tc_commit(dfull);
+                tc_commit(dfull(ab));
                 ++li;
             }
         }
@@ -269,17 +278,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
             const bool n_ok = n < p.N;
             const float sc = n_ok ? __ldg(p.scales + (int64_t)ti.e * p.N + n) : 0.0f;
             const float zp = n_ok ? __ldg(p.zps + (int64_t)ti.e * p.N + n) : 0.0f;
-            mbar_wait(dfull, li & 1);
+            const int ab = li % DBUF;
+            mbar_wait(dfull(ab), (li / DBUF) & 1);
             tc_fence_after_sync();
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
                 uint32_t d[32];
-                tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + 32 * c, d);
+                tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + ab * BN + 32 * c, d);
                 tmem_wait_ld();
                 if (c == BN / 32 - 1) {                             // accumulator fully read: release it
                     tc_fence_before_sync();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(dempty);
+                    if (lane == 0) mbar_arrive(dempty(ab));
                 }
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
@@ -455,8 +465,26 @@ int launch_gemm_tc(const DeviceInfo& dev, const void* x, int x_dtype, const uint
     B200Q_CUDA(cudaGetLastError());
 
     CUtensorMap map_xh, map_xl, map_w;
-    if (int rc = make_map_2d(&map_xh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, xh, (uint64_t)K, (uint64_t)M, BK, BN, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
-    if (int rc = make_map_2d(&map_xl, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, parts == 2 ? xl : xh, (uint64_t)K, (uint64_t)M, BK, BN, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    // token-tile height: fewest (waves x time per wave).  Measured per-wave time (tools/sweep_gemm_bn.py):
+    // BN = 192 (two accumulators, epilogue overlapped) takes 0.70 of a BN = 256 wave; BN = 128 is never
+    // better (64-clk MMAs run into the per-instruction floor) and is only reachable through gemm_bn.
+    const int groups_n = starts ? E : 1;
+    const int n_tiles_h = (int)((N + BM - 1) / BM);
+    int bn = 256;
+    {
+        double best = 1e30;
+        const int cand[2] = {256, 192};
+        for (int i = 0; i < 2; ++i) {
+            const long long mt = (M + cand[i] - 1) / cand[i] + (starts ? groups_n / 2 : 0);
+            const long long tiles = mt * n_tiles_h;
+            const long long waves = (tiles + dev.sm_count - 1) / dev.sm_count;
+            const double cost = (double)waves * (cand[i] == 256 ? 1.0 : 0.704);
+            if (cost < best) { best = cost; bn = cand[i]; }
+        }
+        if (tuning().gemm_bn == 128 || tuning().gemm_bn == 192 || tuning().gemm_bn == 256) bn = tuning().gemm_bn;
+    }
+    if (int rc = make_map_2d(&map_xh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, xh, (uint64_t)K, (uint64_t)M, BK, bn, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    if (int rc = make_map_2d(&map_xl, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, parts == 2 ? xl : xh, (uint64_t)K, (uint64_t)M, BK, bn, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
     const int groups = starts ? E : 1;
     if (int rc = make_map_2d(&map_w, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, packed, (uint64_t)(K / 2), (uint64_t)groups * N, BK / 2, BM, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
 
@@ -464,21 +492,26 @@ int launch_gemm_tc(const DeviceInfo& dev, const void* x, int x_dtype, const uint
     p.scales = scales; p.zps = zps; p.y = y; p.descale = descale; p.rowsum = rowsum;
     p.starts = starts; p.ends = ends; p.E = groups; p.y_dtype = y_dtype;
     p.R = (int)M; p.N = (int)N; p.K = (int)K;
-    p.mt_bound = (int)((M + BN - 1) / BN) + (starts ? E : 0);
-    p.n_tiles = (int)((N + BM - 1) / BM);
-    p.stage_bytes = parts * X_TILE_BYTES + W_TILE_BYTES;
+    p.bn = bn;
+    p.mt_bound = (int)((M + bn - 1) / bn) + (starts ? E : 0);
+    p.n_tiles = n_tiles_h;
+    p.stage_bytes = parts * bn * BK * 2 + W_TILE_BYTES;
     int stages = (dev.max_smem_optin - OFF_STAGES) / p.stage_bytes;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (stages < 2) return set_error(B200Q_EINVAL, "gemm_tc: not enough shared memory");
     p.stages = stages;
     const size_t smem = (size_t)OFF_STAGES + (size_t)stages * p.stage_bytes;
-    auto kfn = parts == 2 ? gemm_tc_kernel<2> : gemm_tc_kernel<1>;
-    static thread_local int attr_done[64][2] = {{0}};
+    typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmParams);
+    const int bi = bn == 128 ? 0 : (bn == 192 ? 1 : 2);
+    const KernelFn table[2][3] = {{gemm_tc_kernel<1, 128>, gemm_tc_kernel<1, 192>, gemm_tc_kernel<1, 256>},
+                                  {gemm_tc_kernel<2, 128>, gemm_tc_kernel<2, 192>, gemm_tc_kernel<2, 256>}};
+    KernelFn kfn = table[parts - 1][bi];
+    static thread_local int attr_done[64][2][3] = {{{0}}};
     int devi = 0;
     B200Q_CUDA(cudaGetDevice(&devi));
-    if (devi >= 0 && devi < 64 && attr_done[devi][parts - 1] < (int)smem) {
+    if (devi >= 0 && devi < 64 && attr_done[devi][parts - 1][bi] < (int)smem) {
         B200Q_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done[devi][parts - 1] = (int)smem;
+        attr_done[devi][parts - 1][bi] = (int)smem;
     }
     const long long total_tiles = (long long)p.n_tiles * p.mt_bound;
     int grid = dev.sm_count;

@@ -34,6 +34,7 @@ struct Tuning {
     int gemv_stages = -1;   // cap on ring depth
     int gemv_pdl = -1;      // 0 disables programmatic dependent launch
     int gemv_ctas = -1;     // cap on the number of CTAs (default: SM count)
+    int gemm_bn = -1;       // token-tile height of the tcgen05 GEMM (128 / 192 / 256), default: heuristic
     int gemv_occ2 = 0;      // 1: 8-warp CTAs sized so that two launches share an SM (cross-layer prefetch)
     int gemv_debug = -1;    // bench-only ablations: 1 = skip the mma work, 2 = skip the weight loads
     int force_path = -1;    // 0 auto, 1 generic SIMT, 2 gemv (mma.sync), 3 tcgen05 gemm, 4 gemv (tcgen05)
