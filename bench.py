@@ -266,26 +266,46 @@ def run_gemv(args):
     gbs_per_gpu = bytes_per_launch / per_launch_s / 1e9
     value = gbs_per_gpu * world
 
-    # ---- end to end through the public API with host buffers (QuantizedLinear.forward)
+    # ---- end to end through the public API with HOST buffers: QuantizedLinear.forward_host (one C-ABI call,
+    # b200q_linear_fwd_host, enqueues the H2D copy of x, the kernels and the D2H copy of y).  The 24 calls of a
+    # step are captured in a CUDA graph, as a decode loop would; every replay copies x from and y to pinned memory.
     mods = []
     for (p, s, z) in layers:
         m = pkg.QuantizedLinear(K_IN, N_OUT)
         m.packed_weights, m.scales, m.zero_points = p, s, z
+        m._weights_settled = True
         mods.append(m)
     xh = torch.randn(M, K_IN).pin_memory()
-    yh = torch.empty(M, N_OUT).pin_memory()
-    xd = torch.empty(M, K_IN, device=dev)
+    yhs = [torch.empty(M, N_OUT).pin_memory() for _ in mods]
+
+    def e2e_all():
+        for m, yh in zip(mods, yhs):
+            m.forward_host(xh, out=yh)
+
+    e2e_graph = None
+    if not args.no_graph:
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            e2e_all()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        e2e_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(e2e_graph):
+            e2e_all()
 
     def e2e_step():
-        for m in mods:
-            xd.copy_(xh, non_blocking=True)
-            yy = m(xd)
-            yh.copy_(yy, non_blocking=True)
+        if e2e_graph is not None:
+            e2e_graph.replay()
+        else:
+            e2e_all()
 
-    e2e_steps = max(3, min(args.steps, 50))
+    e2e_steps = max(3, min(args.steps, 100))
     for _ in range(3):
         e2e_step()
     torch.cuda.synchronize(dev)
+    ref0 = oracle.reference_quantized_linear(xh.numpy(), p0[rows], s0[rows], z0[rows], acc=np.float64)
+    e2e_err = float(np.abs(yhs[0].numpy()[:, rows] - ref0).max())
+    assert e2e_err < 1e-3, f"e2e parity check failed: max abs err {e2e_err}"
     if dist is not None:
         dist.barrier()
     e0.record()
@@ -333,7 +353,8 @@ def run_gemv(args):
                      "algorithmic_bytes_per_launch": bytes_per_launch},
         "e2e": {"value": e2e_gbs, "unit": "GB/s", "h2d_bytes_per_step": POOL * M * K_IN * 4,
                 "d2h_bytes_per_step": POOL * M * N_OUT * 4, "steps": e2e_steps,
-                "api": "QuantizedLinear.forward on pinned host activations (weights resident)"},
+                "api": "QuantizedLinear.forward_host -> b200q_linear_fwd_host (pinned host x and y, weights resident), "
+                       "24 calls per step replayed as a CUDA graph", "us_per_call": ms2 * 1e3 / (e2e_steps * POOL)},
         "gpu_launches": 2 * launches,
         "clocks": clocks.summary(),
         "parity": {"max_abs_err_vs_f64_oracle": err},
@@ -342,6 +363,24 @@ def run_gemv(args):
         line["cpu_baseline"] = {"value": cpu_gbs, "unit": "GB/s", "cores": cpu_threads, "kind": "port",
                                 "sample": f"20 x one {K_IN}->{N_OUT} layer forward, M={M}: {cpu_what} of "
                                           "dequantize_weights + F.linear", "ms_per_layer": cpu_dt * 1e3}
+    # the second clause of BASELINE.json's metric (MoE layer tokens/s) at this GPU count, as a sub-object: the
+    # 1-GPU point of the expert-parallel scaling curve that `--gpus 2/4/8` (default workload "moe") continues
+    if world == 1 and not args.no_moe:
+        try:
+            del layers, mods, graph, e2e_graph
+            torch.cuda.empty_cache()
+            import io
+            import contextlib
+            from bench_moe import run_moe
+            buf = io.StringIO()
+            margs = argparse.Namespace(steps=5, warmup=3, no_cpu=True)
+            with contextlib.redirect_stdout(buf):
+                run_moe(margs)
+            ml = json.loads(buf.getvalue().strip().splitlines()[-1])
+            line["moe"] = {k: ml[k] for k in ("metric", "value", "unit", "n_gpus", "ms_per_step", "dtype", "roofline")}
+            line["moe"]["workload"] = ml["config"]["workload"]
+        except Exception as e:      # the headline line must not depend on the extra measurement
+            line["moe"] = {"error": repr(e)[:200]}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
@@ -357,6 +396,7 @@ def main():
     ap.add_argument("--m", type=int, default=1, help="batch rows for the gemv workload (1..16)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-moe", action="store_true", help="skip the MoE-layer sub-measurement of the N=1 gemv line")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

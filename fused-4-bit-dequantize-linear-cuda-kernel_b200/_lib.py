@@ -36,6 +36,7 @@ SIGNATURES = {
     "b200q_dequantize_rows": (_i32, [_vp, _vp, _vp, _i64, _i64, _vp, _vp]),
     "b200q_linear_ws_bytes": (_sz, [_i64, _i64, _i64]),
     "b200q_linear_fwd": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _i32, _i64, _i64, _i64, _vp, _sz, _u32, _vp]),
+    "b200q_linear_fwd_host": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i64, _i64, _vp, _sz, _u32, _vp]),
     "b200q_tune_set": (_i32, [_c.c_char_p, _i32]),
     "b200q_moe_topk": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _vp]),
     "b200q_moe_permute_ws_bytes": (_sz, [_i64, _i32, _i32]),
@@ -130,6 +131,25 @@ def linear_fwd(x: torch.Tensor, packed: torch.Tensor, scales: torch.Tensor, zps:
                                    ws.data_ptr() if ws is not None else None, ws.numel() if ws is not None else 0,
                                    flags, stream_ptr(x.device)), "b200q_linear_fwd")
     return y
+
+
+def linear_fwd_host(x_host: torch.Tensor, x_dev: torch.Tensor, packed, scales, zps, y_dev: torch.Tensor,
+                    y_host: torch.Tensor, flags: int = FLAG_NONE) -> torch.Tensor:
+    """Host (pinned) activations in, host result out: H2D copy, fused kernel, D2H copy, all enqueued by one C
+    call on the current stream of the weights' device (x_dev / y_dev are the caller's staging buffers)."""
+    lib = load()
+    M, K = x_host.shape
+    N = packed.shape[0]
+    dev = packed.device
+    with torch.cuda.device(dev):
+        ws_bytes = lib.b200q_linear_ws_bytes(M, N, K)
+        ws = workspace(dev, ws_bytes, "linear") if ws_bytes else None
+        check(lib.b200q_linear_fwd_host(x_host.data_ptr(), dtype_code(x_host), x_dev.data_ptr(), packed.data_ptr(),
+                                        scales.data_ptr(), zps.data_ptr(), y_dev.data_ptr(), y_host.data_ptr(),
+                                        dtype_code(y_host), M, N, K, ws.data_ptr() if ws is not None else None,
+                                        ws.numel() if ws is not None else 0, flags, stream_ptr(dev)),
+              "b200q_linear_fwd_host")
+    return y_host
 
 
 def quantize_rows(w: torch.Tensor):

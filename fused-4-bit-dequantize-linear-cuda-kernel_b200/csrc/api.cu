@@ -96,6 +96,20 @@ int b200q_linear_fwd(const void* x, int x_dtype, const uint8_t* packed, const fl
     return launch_linear_generic(x, x_dtype, packed, scales, zps, y, y_dtype, M, N, K, nullptr, nullptr, 1, 0, st);
 }
 
+int b200q_linear_fwd_host(const void* h_x, int x_dtype, void* d_x, const uint8_t* packed, const float* scales,
+                          const float* zps, void* d_y, void* h_y, int y_dtype, int64_t M, int64_t N, int64_t K,
+                          void* ws, size_t ws_bytes, unsigned flags, void* stream) {
+    if (M < 0 || N < 0 || K < 0) return set_error(B200Q_EINVAL, "linear_fwd_host: negative size");
+    if (!elem_size(x_dtype) || !elem_size(y_dtype)) return set_error(B200Q_EINVAL, "linear_fwd_host: unsupported dtype");
+    if (M == 0 || N == 0) return 0;
+    if (!h_x || !d_x || !d_y || !h_y) return set_error(B200Q_EINVAL, "linear_fwd_host: null pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    B200Q_CUDA(cudaMemcpyAsync(d_x, h_x, (size_t)M * K * elem_size(x_dtype), cudaMemcpyHostToDevice, st));
+    if (int rc = b200q_linear_fwd(d_x, x_dtype, packed, scales, zps, d_y, y_dtype, M, N, K, ws, ws_bytes, flags, stream)) return rc;
+    B200Q_CUDA(cudaMemcpyAsync(h_y, d_y, (size_t)M * N * elem_size(y_dtype), cudaMemcpyDeviceToHost, st));
+    return 0;
+}
+
 size_t b200q_moe_grouped_ws_bytes(int64_t R, int E, int64_t N, int64_t K) {
     (void)E;
     return gemm_tc_ws_bytes(R, N, K);

@@ -40,7 +40,10 @@ class QuantizedLinear(nn.Module):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if not x.is_cuda:
-            raise RuntimeError("QuantizedLinear (b200) runs on CUDA only; move the module and the input to a B200")
+            if self.packed_weights.is_cuda and x.is_pinned():
+                return self.forward_host(x)        # host-resident caller: copies + kernel enqueued by one C call
+            raise RuntimeError("QuantizedLinear (b200) runs on CUDA only; move the module and the input to a B200 "
+                               "(or pass a pinned host tensor to a module that lives on the GPU)")
         if self.packed_weights.device != x.device:
             raise RuntimeError(f"weights are on {self.packed_weights.device}, input on {x.device}")
         return self._forward_cuda(x)
@@ -56,6 +59,24 @@ class QuantizedLinear(nn.Module):
         y = _lib.linear_fwd(x2, self.packed_weights, self.scales, self.zero_points, flags=flags)
         self._weights_settled = True
         return y.reshape(*lead, self.out_features)
+
+    def forward_host(self, x_host: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
+        """x in pinned host memory -> result in pinned host memory (asynchronous on the current stream of the
+        module's device: synchronise the stream before reading `out`).  The arithmetic runs on the GPU."""
+        x2 = x_host.reshape(-1, self.in_features)
+        M = x2.shape[0]
+        dev = self.packed_weights.device
+        st = getattr(self, "_stage", None)
+        if st is None or st[0].shape[0] != M or st[0].dtype != x2.dtype:
+            st = (torch.empty((M, self.in_features), dtype=x2.dtype, device=dev),
+                  torch.empty((M, self.out_features), dtype=x2.dtype, device=dev))
+            self._stage = st
+        if out is None:
+            out = torch.empty((M, self.out_features), dtype=x2.dtype).pin_memory()
+        flags = _lib.FLAG_STATIC_WEIGHTS if self._weights_settled else _lib.FLAG_NONE
+        _lib.linear_fwd_host(x2, st[0], self.packed_weights, self.scales, self.zero_points, st[1], out, flags=flags)
+        self._weights_settled = True
+        return out.reshape(*x_host.shape[:-1], self.out_features)
 
     def _load_from_state_dict(self, *args, **kwargs):
         self._weights_settled = False

@@ -116,8 +116,17 @@ int b200q_linear_fwd(const void* x, int x_dtype, const uint8_t* packed, const fl
                      const float* zps, void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
                      void* ws, size_t ws_bytes, unsigned flags, void* stream);
 
+/* Same with HOST activations: enqueues H2D copy of x (h_x -> the caller's device staging buffer d_x), the
+ * fused dequantize-linear, and the D2H copy of the result (d_y -> h_y) on `stream`; h_x / h_y should be
+ * pinned.  This is the call a host-resident caller of the reference's QuantizedLinear.forward maps to
+ * (python/module.py:100-118 with x on the CPU and the module on the GPU).  Capturable in a CUDA graph. */
+int b200q_linear_fwd_host(const void* h_x, int x_dtype, void* d_x, const uint8_t* packed, const float* scales,
+                          const float* zps, void* d_y, void* h_y, int y_dtype, int64_t M, int64_t N, int64_t K,
+                          void* ws, size_t ws_bytes, unsigned flags, void* stream);
+
 /* Bench / tuning hook: override a launch heuristic process-wide (key = "gemv_warps" | "gemv_slabs"
- * | "gemv_stages" | "gemv_pdl" | "gemv_ctas" | "force_path"; value < 0 restores the default).  Not needed by callers. */
+ * | "gemv_stages" | "gemv_pdl" | "gemv_ctas" | "gemv_occ2" | "gemv_debug" | "gemm_bn" | "force_path"; value < 0
+ * restores the default).  Not needed by callers. */
 int b200q_tune_set(const char* key, int value);
 
 /* ---- MoE ---------------------------------------------------------------------------------- */

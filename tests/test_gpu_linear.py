@@ -208,3 +208,20 @@ def test_extension_error_behaviour(pkg):
     with pytest.raises(RuntimeError, match="packed_weights must be a CUDA tensor"):
         ext.forward(x, p.cpu(), s, z)
     assert ext.forward(torch.zeros(0, 32, device="cuda"), p, s, z).shape == (0, 8)
+
+
+def test_forward_host_pinned(oracle, pkg):
+    """Host-resident caller: pinned x in, pinned y out through b200q_linear_fwd_host (one C-ABI call)."""
+    torch.manual_seed(3)
+    lin = torch.nn.Linear(1024, 768, bias=False)
+    ql = pkg.QuantizedLinear.from_linear(lin.cuda())
+    p, s, z = oracle.quantize_weights(lin.weight.detach().cpu().numpy())
+    for M in (1, 5, 40):
+        x = torch.randn(M, 1024).pin_memory()
+        y = ql(x)                                     # CPU pinned tensor -> forward_host
+        assert not y.is_cuda and y.shape == (M, 768)
+        torch.cuda.synchronize()
+        ref = oracle.reference_quantized_linear(x.numpy(), p, s, z, acc=np.float64)
+        assert np.abs(ref - y.numpy()).max() < 1e-3
+    with pytest.raises(RuntimeError):
+        ql(torch.randn(2, 1024))                      # pageable host memory: no silent slow path
