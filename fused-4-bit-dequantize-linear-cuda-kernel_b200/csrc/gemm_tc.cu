@@ -7,11 +7,11 @@
 //
 //   warp 0      TMA producer: per 64-column k-block one activation tile (256 x 64 fp16, plus the
 //               low-part tile for fp32 inputs) and one packed-weight tile (128 rows x 32 bytes)
-//   warps 4-7   dequant: thread = weight row; LDS the row's 32 packed bytes, nibble -> fp16 SUBNORMAL
+//   warps 4-11  dequant (two groups on alternate k-blocks): thread = weight row; LDS the row's 32 packed bytes, nibble -> fp16 SUBNORMAL
 //               with one LOP3 per two weights (no arithmetic), tcgen05.st into a TMEM A slot
 //   warp 1      MMA issuer: 4 (x2 for hi/lo) tcgen05.mma.kind::f16 M=128 N=256 K=16 per k-block,
 //               A from TMEM, B from shared memory; tcgen05.commit frees the stage / the A slot
-//   warps 8-11  epilogue: tcgen05.ld the accumulator, y = s_n * (D * 2^(24-e_m) - zp_n * sum_k x[m,k]),
+//   warps 12-15 epilogue: tcgen05.ld the accumulator, y = s_n * (D * 2^(24-e_m) - zp_n * sum_k x[m,k]),
 //               coalesced stores (a warp writes 32 consecutive n of one token row)
 //
 // The activations are prepared by xprep_gemm_kernel: per token row a power-of-two scale 2^e
@@ -42,7 +42,7 @@ constexpr int BM = 128;            // weight rows per tile (UMMA M, TMEM lanes)
 constexpr int BK = 64;             // k-block: one 128-byte swizzle row of fp16
 constexpr int A_SLOTS = 4;         // TMEM A ring: 4 k-blocks x 32 columns
 constexpr int TMEM_COLS = 512;
-constexpr int GEMM_THREADS = 12 * 32;
+constexpr int GEMM_THREADS = 16 * 32;
 constexpr int W_TILE_BYTES = BM * (BK / 2);    // 4 KB
 constexpr int MAX_STAGES = 6;
 
@@ -215,15 +215,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
                 ++li;
             }
         }
-    } else if (warp >= 4 && warp < 8) {
+    } else if (warp >= 4 && warp < 12) {
         // =============================================================== dequant warps
-        const int q = warp & 3;
+        // two groups of four warps (one warp per TMEM lane quarter) take alternate k-blocks: one group
+        // alone (LDS -> LOP3 -> tcgen05.st -> wait::st -> arrive, ~300 clk per k-block) is barely faster
+        // than the 384..512 clk the tensor core needs for the same k-block
+        const int q = warp & 3, grp = (warp - 4) >> 2;
         const int r = 32 * q + lane;                                // weight row of the tile = TMEM lane
         int s = 0, ph = 0, ait = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             TileInfo ti;
             if (!locate(p, t, ti)) continue;
             for (int kb = 0; kb < KB; ++kb, ++ait) {
+                if ((ait & 1) != grp) {                             // the other group's k-block
+                    if (++s == S) { s = 0; ph ^= 1; }
+                    continue;
+                }
                 mbar_wait(full(s), ph);
                 const uint4 w0 = lds128(w_smem(s) + r * (BK / 2));
                 const uint4 w1 = lds128(w_smem(s) + r * (BK / 2) + 16);
@@ -258,10 +265,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
                 if (++s == S) { s = 0; ph ^= 1; }
             }
         }
-    } else if (warp >= 8) {
+    } else if (warp >= 12) {
         // =============================================================== epilogue warps
         const int q = warp & 3;
-        const int et = (warp - 8) * 32 + lane;                      // 0..127
+        const int et = (warp - 12) * 32 + lane;                     // 0..127
         int li = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             TileInfo ti;
