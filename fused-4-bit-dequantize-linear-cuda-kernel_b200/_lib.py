@@ -36,6 +36,7 @@ SIGNATURES = {
     "b200q_dequantize_rows": (_i32, [_vp, _vp, _vp, _i64, _i64, _vp, _vp]),
     "b200q_linear_ws_bytes": (_sz, [_i64, _i64, _i64]),
     "b200q_linear_fwd": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _i32, _i64, _i64, _i64, _vp, _sz, _u32, _vp]),
+    "b200q_linear_fwd_next": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _i32, _i64, _i64, _i64, _vp, _sz, _u32, _vp, _vp, _sz]),
     "b200q_linear_fwd_host": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i64, _i64, _vp, _sz, _u32, _vp]),
     "b200q_tune_set": (_i32, [_c.c_char_p, _i32]),
     "b200q_moe_topk": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _vp]),
@@ -116,8 +117,10 @@ def tune(key: str, value: int) -> None:
 
 # ------------------------------------------------------------------------------------ wrappers
 def linear_fwd(x: torch.Tensor, packed: torch.Tensor, scales: torch.Tensor, zps: torch.Tensor,
-               out_dtype=None, flags: int = FLAG_NONE, out: torch.Tensor | None = None) -> torch.Tensor:
-    """y[M,N] = x[M,K] @ dequant(packed, scales, zps)^T on the current stream of x's device."""
+               out_dtype=None, flags: int = FLAG_NONE, out: torch.Tensor | None = None,
+               next_packed: torch.Tensor | None = None) -> torch.Tensor:
+    """y[M,N] = x[M,K] @ dequant(packed, scales, zps)^T on the current stream of x's device.
+    next_packed: packed weights of the fused linear that follows on this stream (L2 prefetch hint)."""
     lib = load()
     M, K = x.shape
     N = packed.shape[0]
@@ -126,10 +129,12 @@ def linear_fwd(x: torch.Tensor, packed: torch.Tensor, scales: torch.Tensor, zps:
         y = out if out is not None else torch.empty((M, N), dtype=out_dtype, device=x.device)
         ws_bytes = lib.b200q_linear_ws_bytes(M, N, K)
         ws = workspace(x.device, ws_bytes, "linear") if ws_bytes else None
-        check(lib.b200q_linear_fwd(x.data_ptr(), dtype_code(x), packed.data_ptr(), scales.data_ptr(),
-                                   zps.data_ptr(), y.data_ptr(), dtype_code(y), M, N, K,
-                                   ws.data_ptr() if ws is not None else None, ws.numel() if ws is not None else 0,
-                                   flags, stream_ptr(x.device)), "b200q_linear_fwd")
+        check(lib.b200q_linear_fwd_next(x.data_ptr(), dtype_code(x), packed.data_ptr(), scales.data_ptr(),
+                                        zps.data_ptr(), y.data_ptr(), dtype_code(y), M, N, K,
+                                        ws.data_ptr() if ws is not None else None, ws.numel() if ws is not None else 0,
+                                        flags, stream_ptr(x.device),
+                                        next_packed.data_ptr() if next_packed is not None else None,
+                                        next_packed.numel() if next_packed is not None else 0), "b200q_linear_fwd")
     return y
 
 

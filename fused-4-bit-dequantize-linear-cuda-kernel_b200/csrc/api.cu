@@ -74,6 +74,14 @@ size_t b200q_linear_ws_bytes(int64_t M, int64_t N, int64_t K) {
 int b200q_linear_fwd(const void* x, int x_dtype, const uint8_t* packed, const float* scales,
                      const float* zps, void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
                      void* ws, size_t ws_bytes, unsigned flags, void* stream) {
+    return b200q_linear_fwd_next(x, x_dtype, packed, scales, zps, y, y_dtype, M, N, K, ws, ws_bytes, flags, stream,
+                                 nullptr, 0);
+}
+
+int b200q_linear_fwd_next(const void* x, int x_dtype, const uint8_t* packed, const float* scales,
+                          const float* zps, void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
+                          void* ws, size_t ws_bytes, unsigned flags, void* stream,
+                          const uint8_t* next_packed, size_t next_bytes) {
     if (M < 0 || N < 0 || K < 0 || (K & 1)) return set_error(B200Q_EINVAL, "linear_fwd: need M,N >= 0 and even K >= 0 (M=%lld N=%lld K=%lld)", (long long)M, (long long)N, (long long)K);
     if (!elem_size(x_dtype) || !elem_size(y_dtype)) return set_error(B200Q_EINVAL, "linear_fwd: unsupported dtype (x=%d y=%d)", x_dtype, y_dtype);
     if (M == 0 || N == 0) return 0;
@@ -88,11 +96,14 @@ int b200q_linear_fwd(const void* x, int x_dtype, const uint8_t* packed, const fl
     // slower for M <= 8 (A-from-TMEM feed rate, profiles/r01_gemv_notes.md) and only runs when forced
     if (force == 4 && vec_ok && gemv_tc_supported(M, N, K))
         return launch_gemv_tc(d, x, x_dtype, packed, scales, zps, y, y_dtype, M, N, K, ws, ws_bytes, flags, st);
-    if (force != 1 && force != 3 && force != 4 && vec_ok && gemv_supported(M, N, K, x_dtype))
-        return launch_gemv(d, x, x_dtype, packed, scales, zps, y, y_dtype, M, N, K, ws, ws_bytes, flags, st);
+    if ((force <= 0 || force == 5) && (tuning().gemv_res != 0 || force == 5) && vec_ok && gemv_res_supported(M, N, K))
+        return launch_gemv_res(d, x, x_dtype, packed, scales, zps, y, y_dtype, M, N, K, flags, st, next_packed, next_bytes);
+    if (force != 1 && force != 3 && force != 4 && force != 5 && vec_ok && gemv_supported(M, N, K, x_dtype))
+        return launch_gemv(d, x, x_dtype, packed, scales, zps, y, y_dtype, M, N, K, ws, ws_bytes, flags, st,
+                           next_packed, next_bytes);
     if (force != 1 && force != 2 && force != 4 && vec_ok && gemm_tc_supported(M, N, K, x_dtype, y_dtype))
         return launch_gemm_tc(d, x, x_dtype, packed, scales, zps, y, y_dtype, M, N, K, nullptr, nullptr, 1, ws, ws_bytes, flags, st);
-    if (force == 2 || force == 3 || force == 4) return set_error(B200Q_EINVAL, "linear_fwd: forced path %d does not support this shape / alignment", force);
+    if (force == 2 || force == 3 || force == 4 || force == 5) return set_error(B200Q_EINVAL, "linear_fwd: forced path %d does not support this shape / alignment", force);
     return launch_linear_generic(x, x_dtype, packed, scales, zps, y, y_dtype, M, N, K, nullptr, nullptr, 1, 0, st);
 }
 

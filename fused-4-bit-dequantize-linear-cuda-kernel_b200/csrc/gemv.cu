@@ -67,7 +67,14 @@ struct GemvParams {
     int rt;                 // tiles per cross-warp reduction round
     int rg, rg_shift;       // live mma columns per n-tile (4 or 8) and log2 of it
     int red_off, ring_off;  // byte offsets in dynamic shared memory
+    int after_x;            // 1: the held-back tiles go out after the amax barrier instead of right after the wait
+    int early_tiles;        // contiguous mode: tiles requested before griddepcontrol.wait (the rest after the x loads)
+    int fused_x;            // 1: every CTA builds its own x operand (no xprep_kernel in the dependency chain)
     int wait_weights;       // 1: weights may be written by the preceding kernel -> wait first
+    const uint8_t* next_packed;        // optional: weights of the NEXT fused linear on this stream ...
+    unsigned long long next_bytes;     // ... this launch pulls them into L2 behind its own stream (0 = none)
+    unsigned int next_chunk;           // next_bytes / grid size
+    int pf_mode;            // how next_packed is prefetched (tuning key gemv_pf)
     unsigned int launch_no; // bench-only: slot of the wall-clock record
     int debug;              // bench-only: low bits 1 = skip the mma work, 2 = skip the weight loads; 8 = timestamps
 };
@@ -123,14 +130,21 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) gemv_kernel(const Ge
     volatile int* flag = reinterpret_cast<volatile int*>(smem + MISC_OFF);
     const uint32_t ring = smem_base + p.ring_off;
     const int S = p.stages;
-    const int dbg = p.debug & 7;
+    const int dbg = p.debug & 3;
     auto full_bar = [&](int s) { return smem_base + 8u * s; };
     auto empty_bar = [&](int s) { return smem_base + 512u + 8u * s; };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ctid = threadIdx.x;
     const bool prof = (p.debug & 8) && threadIdx.x == 0 && blockIdx.x < 256;
-    auto stamp = [&](int i) { if (prof) g_gemv_prof[blockIdx.x * 16 + i] = clock64(); };
+    auto stamp = [&](int i) {
+        if (prof) {
+            long long tnow;
+            if (p.debug & 16) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tnow));   // ns, comparable across SMs
+            else tnow = clock64();
+            g_gemv_prof[blockIdx.x * 16 + i] = tnow;
+        }
+    };
     stamp(0);
     unsigned long long wall0 = 0;
     if (prof) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(wall0));
@@ -189,30 +203,170 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) gemv_kernel(const Ge
         mbar_arrive_expect_tx(full_bar(slot), bytes);
         bulk_g2s_hint(ring + slot * stage_bytes, p.packed + (int64_t)row * row_bytes, bytes, full_bar(slot), pol);
     };
+    // cross-layer software pipelining: this CTA's share of the NEXT layer's packed weights goes to L2 behind
+    // its own tiles, so HBM keeps streaming through this launch's epilogue and the next launch's prologue
+    // and the next launch's bulk copies hit L2
+    auto prefetch_next_bulk = [&]() {
+        const unsigned long long per = (((unsigned long long)p.next_chunk) + 127ull) & ~127ull;
+        const unsigned long long beg = min(per * blockIdx.x, p.next_bytes), end = min(beg + per, p.next_bytes);
+        for (unsigned long long off = beg; off < end; off += 32768ull) {
+            const unsigned int n = (unsigned int)min(32768ull, end - off) & ~15u;
+            if (n) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.next_packed + off), "r"(n) : "memory");
+        }
+    };
+    auto prefetch_next_lines = [&]() {
+        const unsigned long long per = (((unsigned long long)p.next_chunk) + 127ull) & ~127ull;
+        const unsigned long long beg = min(per * blockIdx.x, p.next_bytes), end = min(beg + per, p.next_bytes);
+        for (unsigned long long off = beg + (unsigned long long)threadIdx.x * 128ull; off < end; off += (unsigned long long)NTHR * 128ull)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.next_packed + off) : "memory");
+    };
     if (p.wait_weights) pdl_wait();
     if (lane == 0 && dbg != 2) {
         if (p.contig) {
-            if (warp == 0)
-                for (int ti = 0; ti < ntiles && ti < S; ++ti) issue_tile(ti, ti);
+            if (warp == 0) {
+                for (int ti = 0; ti < ntiles && ti < S && ti < p.early_tiles; ++ti) issue_tile(ti, ti);
+                if (p.next_bytes && p.pf_mode == 1 && p.early_tiles >= min(ntiles, S)) prefetch_next_bulk();
+            }
         } else {
             int st = 0;
             for (int ti = 0; ti < ntiles && st < S; ++ti)
                 for (int q = 0; q < nq && st < S; ++q, ++st) issue_stage(ti, q, st);
         }
     }
+    if (p.next_bytes && dbg != 2) {
+        if (p.pf_mode == 2) prefetch_next_lines();
+        if (p.pf_mode == 3 && warp == NW - 1 && lane == 0) prefetch_next_bulk();
+    }
     stamp(2);
 
     const int g = lane >> 2, t = lane & 3;
     pdl_wait();   // x (and the output / workspace) belong to the stream-ordered predecessor
     stamp(3);
+    // tiles held back so that the x loads below (issued by the other warps at the same moment) do not queue
+    // behind the whole weight stream in the L2 slices (tuning key gemv_early)
+    auto issue_late = [&]() {
+        for (int ti = max(p.early_tiles, 0); ti < ntiles && ti < S; ++ti) issue_tile(ti, ti);
+        if (p.next_bytes && p.pf_mode == 1) prefetch_next_bulk();
+    };
+    const bool late = p.contig && warp == 0 && lane == 0 && dbg != 2 && p.early_tiles < min(ntiles, S);
+    if (late && !p.after_x) issue_late();
 
-    // ---- x operand: prepared ONCE per launch by xprep_kernel (below) as an image of the mma B
-    // fragments in global memory (L2-resident, 8 bytes per (granule, n-tile, column, t, word)); every
-    // lane pulls its own registers with two coalesced 16-byte loads per (granule, n-tile).  Building
-    // the operand inside each of the 148 CTAs was the longest phase of this kernel
-    // (profiles/r01_gemv_notes.md).
+    // ---- x operand (mma B fragments, registers).  Two ways:
+    //  * fused (default): every CTA derives it straight from x.  One pass for the per-row amax (block
+    //    reduction), then each lane converts exactly the values its own fragments hold and keeps only its
+    //    limb; no shared-memory image, no second kernel.  The dependency chain of consecutive layers is
+    //    then main -> main, which programmatic dependent launch overlaps CTA by CTA; with a preparation
+    //    kernel in between the next launch's CTAs did not start before the LAST CTA of this one had ended
+    //    (profiles/r01_gemv_notes.md, wall-clock table).
+    //  * image: prepared once per launch by xprep_kernel (below) in global memory; every lane pulls its
+    //    registers with two coalesced 16-byte loads per (granule, n-tile).
     const int rg = p.rg, rgs = p.rg_shift;
     uint32_t bf[GPW][NT][4][2];
+    __shared__ float s_amax[8 * NW];
+    __shared__ int s_tx[NW * 8 * 2];
+    __shared__ int s_ex[8];
+    __shared__ __align__(16) uint2 s_stage[NW * 64];
+    if (p.fused_x) {
+        // pass 1: amax of every batch row
+        // (in contiguous mode warp 0 is still pushing the tile copies into the memory pipe: its x loads would
+        // queue behind 150 KB of weight requests, so the other warps cover x and theirs go out first)
+        const int skip = (p.contig && NW > 1) ? 32 : 0;
+        float am[2 * NT];
+#pragma unroll
+        for (int m = 0; m < 2 * NT; ++m) am[m] = 0.0f;
+#pragma unroll
+        for (int m = 0; m < 2 * NT; ++m) {
+            if (m < p.M && ctid >= skip) {
+#pragma unroll 2
+                for (int k = (ctid - skip) * 4; k < p.K; k += (NTHR - skip) * 4) {
+                    float a[4];
+                    load4f(p.x, p.x_dtype, (int64_t)m * p.K + k, a);
+                    am[m] = fmaxf(am[m], fmaxf(fmaxf(fabsf(a[0]), fabsf(a[1])), fmaxf(fabsf(a[2]), fabsf(a[3]))));
+                }
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < 2 * NT; ++m) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) am[m] = fmaxf(am[m], __shfl_xor_sync(0xffffffffu, am[m], o));
+            if (lane == 0) s_amax[m * NW + warp] = am[m];
+        }
+        __syncthreads();
+        if (late && p.after_x) issue_late();      // x is on chip: now the weight requests may flood the L2 slices
+        stamp(4);
+        // pass 2, warp-local: the 16 (t, word) items of one granule of one batch row are converted once, by
+        // lanes 0..15 (8 values each: F2I runs at 16 / clk / SM, so no lane converts a value twice), cut into
+        // limbs, and handed to the lanes that hold them as mma columns through a 512-byte staging slot
+        const int l = g & 3, h = g >> 2;
+        uint2* stg = s_stage + warp * 64;                         // [limb][t][word] -> {b0, b1}
+#pragma unroll
+        for (int q = 0; q < GPW; ++q)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { bf[q][nt][j][0] = 0u; bf[q][nt][j][1] = 0u; }
+#pragma unroll
+        for (int em = 0; em < 2 * NT; ++em) {
+            if (em < p.M) {
+                const int nt = em >> 1, hh = em & 1;
+                float amx = 0.0f;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) amx = fmaxf(amx, s_amax[em * NW + w]);
+                int ex = 0;
+                if (amx > 0.0f && amx < INFINITY) ex = max(-96, min(126, 156 - (int)(__float_as_uint(amx) >> 23)));
+                const float up = __uint_as_float((uint32_t)(127 + ex) << 23);
+                int slo = 0, shi = 0;                              // sum of X as (X & 0xffff), (X >> 16): exact in s32
+#pragma unroll
+                for (int q = 0; q < GPW; ++q) {
+                    if (warp + q * NW < ng) {                      // warp-uniform
+                        if (lane < 16) {
+                            const int t_ = lane >> 2, j_ = lane & 3;
+                            float a[4], b[4];
+                            const int64_t base = (int64_t)em * p.K + (int64_t)(g0 + warp + q * NW) * GRAN_K + t_ * 32 + j_ * 8;
+                            load4f(p.x, p.x_dtype, base, a);
+                            load4f(p.x, p.x_dtype, base + 4, b);
+                            uint32_t D[8];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int X0 = __float2int_rn(a[i] * up), X1 = __float2int_rn(b[i] * up);
+                                slo += (X0 & 0xffff) + (X1 & 0xffff);
+                                shi += (X0 >> 16) + (X1 >> 16);
+                                D[i] = (uint32_t)(X0 + 0x00808080) ^ 0x00808080u;      // byte l = signed base-256 digit l
+                                D[4 + i] = (uint32_t)(X1 + 0x00808080) ^ 0x00808080u;
+                            }
+                            // 4x4 byte transposes: digit l of the even values -> b0 (meets the low nibbles), odd -> b1
+                            const uint32_t e0 = __byte_perm(D[0], D[2], 0x5140), e1 = __byte_perm(D[4], D[6], 0x5140);
+                            const uint32_t e2 = __byte_perm(D[0], D[2], 0x7362), e3 = __byte_perm(D[4], D[6], 0x7362);
+                            const uint32_t o0 = __byte_perm(D[1], D[3], 0x5140), o1 = __byte_perm(D[5], D[7], 0x5140);
+                            const uint32_t o2 = __byte_perm(D[1], D[3], 0x7362), o3 = __byte_perm(D[5], D[7], 0x7362);
+                            stg[0 * 16 + lane] = make_uint2(__byte_perm(e0, e1, 0x5410), __byte_perm(o0, o1, 0x5410));
+                            stg[1 * 16 + lane] = make_uint2(__byte_perm(e0, e1, 0x7632), __byte_perm(o0, o1, 0x7632));
+                            stg[2 * 16 + lane] = make_uint2(__byte_perm(e2, e3, 0x5410), __byte_perm(o2, o3, 0x5410));
+                            stg[3 * 16 + lane] = make_uint2(__byte_perm(e2, e3, 0x7632), __byte_perm(o2, o3, 0x7632));
+                        }
+                        __syncwarp();
+                        if (h == hh && g < rg) {
+                            const uint4 v0 = *reinterpret_cast<const uint4*>(stg + (l * 4 + t) * 4);
+                            const uint4 v1 = *reinterpret_cast<const uint4*>(stg + (l * 4 + t) * 4 + 2);
+                            bf[q][nt][0][0] = v0.x; bf[q][nt][0][1] = v0.y; bf[q][nt][1][0] = v0.z; bf[q][nt][1][1] = v0.w;
+                            bf[q][nt][2][0] = v1.x; bf[q][nt][2][1] = v1.y; bf[q][nt][3][0] = v1.z; bf[q][nt][3][1] = v1.w;
+                        }
+                        __syncwarp();
+                    }
+                }
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) {
+                    slo += __shfl_xor_sync(0xffffffffu, slo, o);
+                    shi += __shfl_xor_sync(0xffffffffu, shi, o);
+                }
+                if (lane == 0) {
+                    s_tx[(warp * 8 + em) * 2] = slo;
+                    s_tx[(warp * 8 + em) * 2 + 1] = shi;
+                    if (warp == 0) s_ex[em] = ex;
+                }
+            }
+        }
+    } else {
 #pragma unroll
     for (int q = 0; q < GPW; ++q) {
         const int gq = g0 + warp + q * NW;                      // granule index in the whole K
@@ -228,6 +382,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) gemv_kernel(const Ge
             bf[q][nt][2][0] = v1.x; bf[q][nt][2][1] = v1.y; bf[q][nt][3][0] = v1.z; bf[q][nt][3][1] = v1.w;
         }
     }
+    }
     stamp(6);
 
     // ---- main loop: tiles of 16 rows; per tile nq stages (one granule of this warp in each)
@@ -239,6 +394,14 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) gemv_kernel(const Ge
         rtq = adv - rti * nq;
     }
     int round_first = 0;           // first tile of the current reduction round
+    // scale / zero point of the first output this thread will finish (first pass of the first round's
+    // epilogue), fetched now so that their latency is hidden behind the main loop
+    float pre_sc = 0.0f, pre_zp = 0.0f;
+    {
+        const int er = (ctid >> 2) & (TILE_ROWS - 1), j = (ctid >> 6) / p.M;
+        const int row = r0 + j * TILE_ROWS + er;
+        if ((ctid & 3) == 0 && j < min(p.rt, ntiles) && row < r1) { pre_sc = __ldg(p.scales + row); pre_zp = __ldg(p.zps + row); }
+    }
     for (int i = 0; i < ntiles; ++i) {
         int acc[NT][CH][4];
 #pragma unroll
@@ -271,8 +434,10 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) gemv_kernel(const Ge
                     const uint32_t a0 = wl[j] & 0x0f0f0f0fu, a2 = (wl[j] >> 4) & 0x0f0f0f0fu;   // row g
                     const uint32_t a1 = wh[j] & 0x0f0f0f0fu, a3 = (wh[j] >> 4) & 0x0f0f0f0fu;   // row g + 8
 #pragma unroll
-                    for (int nt = 0; nt < NT; ++nt)
+                    for (int nt = 0; nt < NT; ++nt) {
+                        if (p.debug & 4) { acc[nt][(q * 4 + j) % CH][0] += (int)(a0 ^ a1 ^ a2 ^ a3 ^ bf[q][nt][j][0] ^ bf[q][nt][j][1]); continue; }
                         mma_m16n8k32_u8s8(acc[nt][(q * 4 + j) % CH], a0, a1, a2, a3, bf[q][nt][j][0], bf[q][nt][j][1]);
+                    }
                 }
             }
             __syncwarp();
@@ -327,6 +492,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) gemv_kernel(const Ge
                 }
             }
         }
+        if (i < 5) stamp(10 + i);
         // this warp's partial of tile i -> red[i - round_first][warp][col][row]   (no barrier here)
         int* rbuf = red + ((i - round_first) * NW + warp) * (COLS * TILE_ROWS);
 #pragma unroll
@@ -359,7 +525,8 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) gemv_kernel(const Ge
                 const int row = r0 + (round_first + j) * TILE_ROWS + er;
                 const bool ok = idx < total && row < r1;
                 float sc = 0.0f, zp = 0.0f;
-                if (ok && l == 0) { sc = __ldg(p.scales + row); zp = __ldg(p.zps + row); }
+                if (round_first == 0 && idx0 == 0) { sc = pre_sc; zp = pre_zp; }
+                else if (ok && l == 0) { sc = __ldg(p.scales + row); zp = __ldg(p.zps + row); }
                 long long a = 0;
                 if (ok) {
                     const int* rr = red + (j * NW) * (COLS * TILE_ROWS) + (em * LIMBS + l) * TILE_ROWS + er;
@@ -372,9 +539,18 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) gemv_kernel(const Ge
                 a += __shfl_xor_sync(0xffffffffu, a, 2);
                 if (ok && l == 0) {
                     // header of batch row em: {e, -, -, -} then per slab {sum(X & 0xffff), sum(X >> 16)}
-                    const int* hdr = p.xhdr + em * XHDR_INTS;
-                    const double down = __longlong_as_double((long long)(1023 - hdr[0]) << 52);   // 2^-e
-                    const double tx = (double)hdr[4 + 2 * slab] + 65536.0 * (double)hdr[5 + 2 * slab];   // sum_k X
+                    int ex, tlo, thi;
+                    if (p.fused_x) {
+                        ex = s_ex[em];
+                        tlo = 0; thi = 0;
+#pragma unroll
+                        for (int w = 0; w < NW; ++w) { tlo += s_tx[(w * 8 + em) * 2]; thi += s_tx[(w * 8 + em) * 2 + 1]; }
+                    } else {
+                        const int* hdr = p.xhdr + em * XHDR_INTS;
+                        ex = hdr[0]; tlo = hdr[4 + 2 * slab]; thi = hdr[5 + 2 * slab];
+                    }
+                    const double down = __longlong_as_double((long long)(1023 - ex) << 52);   // 2^-e
+                    const double tx = (double)tlo + 65536.0 * (double)thi;   // sum_k X over this slab
                     const float v = sc * (float)(((double)a - (double)zp * tx) * down);
                     if (p.nslab == 1) store_y(p.y, p.y_dtype, (int64_t)em * p.N + row, v);
                     else p.part[((int64_t)slab * p.M + em) * p.N + row] = v;
@@ -559,7 +735,8 @@ bool plan(const DeviceInfo& dev, int64_t M, int64_t N, int64_t K, GemvConfig* c)
     // static weights) become resident next to the running ones and prefetch their first tiles meanwhile.
     // Measured slower (11.5 us vs 9.1 us): profiles/r01_gemv_notes.md
     const bool occ2 = tu.gemv_occ2 != 0;
-    const int smem_budget = occ2 ? (dev.max_smem_optin - 2048) / 2 - 1024 : dev.max_smem_optin;
+    constexpr int STATIC_SMEM = 12 * 1024;   // s_amax, s_tx, s_ex, s_stage of gemv_kernel (10.6 KB at 16 warps)
+    const int smem_budget = occ2 ? (dev.max_smem_optin - 2048) / 2 - 1024 - STATIC_SMEM : dev.max_smem_optin - STATIC_SMEM;
     for (int nw = 16; nw >= 8; nw -= 8) {
         if (occ2 && nw != 8) continue;
         if (!occ2 && tu.gemv_warps > 0 && tu.gemv_warps != nw) continue;
@@ -578,6 +755,10 @@ bool plan(const DeviceInfo& dev, int64_t M, int64_t N, int64_t K, GemvConfig* c)
             int rt = (occ2 ? 8192 : 32768) / red_tile;
             if (rt < 1) rt = 1;
             if (rt > ntiles) rt = ntiles;
+            // one round (one barrier + one epilogue per CTA) whenever the partials of all tiles and the whole
+            // slab still fit next to each other
+            if (!occ2 && rt < ntiles && ns == 1 &&
+                RED_OFF + ntiles * red_tile + 128 + ntiles * TILE_ROWS * ng * GRAN_B <= smem_budget) rt = ntiles;
             const int red_off = RED_OFF;
             const int ring_off = ((red_off + rt * red_tile + 127) / 128) * 128;
             // stage = 16 rows x the whole slab row when at least 3 of those fit (fewest, largest bulk
@@ -665,7 +846,8 @@ size_t gemv_ws_bytes(int64_t M, int64_t N, int64_t K) {
 
 int launch_gemv(const DeviceInfo& dev, const void* x, int x_dtype, const uint8_t* packed,
                 const float* scales, const float* zps, void* y, int y_dtype, int64_t M, int64_t N,
-                int64_t K, void* ws, size_t ws_bytes, unsigned flags, cudaStream_t st) {
+                int64_t K, void* ws, size_t ws_bytes, unsigned flags, cudaStream_t st,
+                const uint8_t* next_packed, size_t next_bytes) {
     GemvConfig c;
     if (!plan(dev, M, N, K, &c)) return set_error(B200Q_EINVAL, "gemv: unsupported shape M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
     if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(packed) & 15))
@@ -685,6 +867,14 @@ int launch_gemv(const DeviceInfo& dev, const void* x, int x_dtype, const uint8_t
     const bool pdl = tuning().gemv_pdl != 0;
     p.wait_weights = is_static ? 0 : 1;
     p.debug = tuning().gemv_debug > 0 ? tuning().gemv_debug : 0;
+    p.pf_mode = tuning().gemv_pf;
+    p.fused_x = tuning().gemv_xprep == 0;
+    p.early_tiles = (tuning().gemv_early >= 0 && p.fused_x) ? tuning().gemv_early : 1 << 20;
+    p.after_x = 0;
+    if (tuning().gemv_early == -2 && p.fused_x) { p.early_tiles = 0; p.after_x = 1; }
+    p.next_packed = next_packed;
+    p.next_bytes = next_packed && (reinterpret_cast<uintptr_t>(next_packed) & 15) == 0 ? next_bytes : 0;
+    p.next_chunk = (unsigned int)(p.next_bytes / (unsigned long long)(c.nslab * c.nrb));
     {
         static thread_local unsigned launch_no = 0;
         p.launch_no = launch_no++;
@@ -718,7 +908,7 @@ int launch_gemv(const DeviceInfo& dev, const void* x, int x_dtype, const uint8_t
         attrs[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attrs;
         cfg.numAttrs = pdl ? 1 : 0;
-        B200Q_CUDA(cudaLaunchKernelEx(&cfg, xprep_kernel, xp));
+        if (!p.fused_x) B200Q_CUDA(cudaLaunchKernelEx(&cfg, xprep_kernel, xp));
     }
 #define B200Q_GEMV_CASE(NW_, GPW_, NT_) \
     if (c.nw == NW_ && c.gpw == GPW_ && c.nt == NT_) return launch_inst<NW_, GPW_, NT_>(c, p, pdl, st);

@@ -35,9 +35,13 @@ struct Tuning {
     int gemv_pdl = -1;      // 0 disables programmatic dependent launch
     int gemv_ctas = -1;     // cap on the number of CTAs (default: SM count)
     int gemm_bn = -1;       // token-tile height of the tcgen05 GEMM (128 / 192 / 256), default: heuristic
+    int gemv_res = 1;       // 0: never use the resident-slab decode kernel
+    int gemv_early = -1;    // tiles requested before the x loads (-1: all)
+    int gemv_xprep = 0;     // 0: x operand built inside every CTA (default); 1: by a separate preparation kernel
+    int gemv_pf = 1;        // next-layer L2 prefetch: 0 off, 1 bulk by the producer lane, 2 per-thread lines, 3 bulk by the last warp
     int gemv_occ2 = 0;      // 1: 8-warp CTAs sized so that two launches share an SM (cross-layer prefetch)
     int gemv_debug = -1;    // bench-only ablations: 1 = skip the mma work, 2 = skip the weight loads
-    int force_path = -1;    // 0 auto, 1 generic SIMT, 2 gemv (mma.sync), 3 tcgen05 gemm, 4 gemv (tcgen05)
+    int force_path = -1;    // 0 auto, 1 generic SIMT, 2 gemv (mma.sync), 3 tcgen05 gemm, 4 gemv (tcgen05), 5 gemv (resident slab)
 };
 const Tuning& tuning();
 
@@ -63,7 +67,15 @@ bool gemv_supported(int64_t M, int64_t N, int64_t K, int x_dtype);
 size_t gemv_ws_bytes(int64_t M, int64_t N, int64_t K);
 int launch_gemv(const DeviceInfo& dev, const void* x, int x_dtype, const uint8_t* packed,
                 const float* scales, const float* zps, void* y, int y_dtype, int64_t M, int64_t N,
-                int64_t K, void* ws, size_t ws_bytes, unsigned flags, cudaStream_t st);
+                int64_t K, void* ws, size_t ws_bytes, unsigned flags, cudaStream_t st,
+                const uint8_t* next_packed = nullptr, size_t next_bytes = 0);
+
+// decode GEMV, resident-slab variant (gemv_res.cu): M <= 8, K % 128 == 0, K <= 6144 and the CTA's rows fit in
+// shared memory; no workspace
+bool gemv_res_supported(int64_t M, int64_t N, int64_t K);
+int launch_gemv_res(const DeviceInfo& dev, const void* x, int x_dtype, const uint8_t* packed, const float* scales,
+                    const float* zps, void* y, int y_dtype, int64_t M, int64_t N, int64_t K, unsigned flags,
+                    cudaStream_t st, const uint8_t* next_packed, size_t next_bytes);
 
 // decode GEMV on tcgen05 (weights -> TMEM A operand), M <= 8, K % 128 == 0
 bool gemv_tc_supported(int64_t M, int64_t N, int64_t K);

@@ -27,6 +27,14 @@ class QuantizedLinear(nn.Module):
         # Weights written by a kernel that may still be running (from_linear) must not be
         # prefetched ahead of it; the first forward therefore runs without the static-weights flag.
         self._weights_settled = False
+        object.__setattr__(self, "_next", None)   # not a sub-module: only a prefetch hint, see set_next
+
+    def set_next(self, next_layer: "QuantizedLinear | None") -> "QuantizedLinear":
+        """Tell this layer which fused linear follows it in the decode loop: its decode kernel then pulls
+        that layer's packed weights into L2 behind its own weight stream, so HBM keeps streaming between
+        the two launches.  A hint only (L2 is coherent): results are unchanged whatever runs next."""
+        object.__setattr__(self, "_next", next_layer)
+        return self
 
     @classmethod
     def from_linear(cls, linear: nn.Linear) -> "QuantizedLinear":
@@ -56,7 +64,8 @@ class QuantizedLinear(nn.Module):
         if not x2.is_contiguous():
             x2 = x2.contiguous()
         flags = _lib.FLAG_STATIC_WEIGHTS if self._weights_settled else _lib.FLAG_NONE
-        y = _lib.linear_fwd(x2, self.packed_weights, self.scales, self.zero_points, flags=flags)
+        nxt = self._next.packed_weights if self._next is not None else None
+        y = _lib.linear_fwd(x2, self.packed_weights, self.scales, self.zero_points, flags=flags, next_packed=nxt)
         self._weights_settled = True
         return y.reshape(*lead, self.out_features)
 

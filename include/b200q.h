@@ -116,6 +116,16 @@ int b200q_linear_fwd(const void* x, int x_dtype, const uint8_t* packed, const fl
                      const float* zps, void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
                      void* ws, size_t ws_bytes, unsigned flags, void* stream);
 
+/* Same, plus a hint for decoders that know which fused linear follows on this stream: the packed
+ * weights of the NEXT call (`next_packed`, `next_bytes`, 16-byte aligned; NULL / 0 = none).  The decode
+ * kernel pulls them into L2 behind its own weight stream (cp.async.bulk.prefetch.L2), so HBM keeps
+ * streaming through its epilogue and the next call's prologue.  Purely a performance hint: results are
+ * identical, and the next call may be anything. */
+int b200q_linear_fwd_next(const void* x, int x_dtype, const uint8_t* packed, const float* scales,
+                          const float* zps, void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
+                          void* ws, size_t ws_bytes, unsigned flags, void* stream,
+                          const uint8_t* next_packed, size_t next_bytes);
+
 /* Same with HOST activations: enqueues H2D copy of x (h_x -> the caller's device staging buffer d_x), the
  * fused dequantize-linear, and the D2H copy of the result (d_y -> h_y) on `stream`; h_x / h_y should be
  * pinned.  This is the call a host-resident caller of the reference's QuantizedLinear.forward maps to

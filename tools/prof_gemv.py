@@ -8,7 +8,7 @@ from b200q_pkg import pkg
 _lib = pkg._lib; lib = _lib.load()
 lib.b200q_debug_read_prof.argtypes = [ctypes.c_void_p]
 dev = torch.device("cuda", 0)
-names = ["start", "bar-init", "issued", "pdl_wait", "-", "-", "bf-loaded", "main-done", "red-bar", "epilogue"]
+names = ["start", "bar-init", "issued", "pdl_wait", "amax", "-", "bf-loaded", "main-done", "red-bar", "epilogue"]
 for (K, N, M) in [(4096, 11008, 1), (4096, 11008, 4), (11008, 4096, 1)]:
     layers = []
     for i in range(12):
@@ -17,7 +17,8 @@ for (K, N, M) in [(4096, 11008, 1), (4096, 11008, 4), (11008, 4096, 1)]:
                        torch.rand(N, device=dev) * 0.01, torch.randint(0, 16, (N,), device=dev).float()))
     x = torch.randn(M, K, device=dev); y = torch.empty(M, N, device=dev)
     ws = torch.zeros(max(lib.b200q_linear_ws_bytes(M, N, K), 16), dtype=torch.uint8, device=dev)
-    _lib.tune("force_path", 2); _lib.tune("gemv_debug", 8)
+    _lib.tune("force_path", 2); _lib.tune("gemv_debug", 8); _lib.tune("gemv_pf", 0)
+    _lib.tune("gemv_xprep", int(os.environ.get("XPREP", "0")))
     sp = torch.cuda.current_stream().cuda_stream
     for rep in range(3):
         for (p, s, z) in layers:

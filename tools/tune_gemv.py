@@ -17,7 +17,7 @@ from b200q_pkg import pkg  # noqa: E402
 
 _lib = pkg._lib
 lib = _lib.load()
-KEYS = ["gemv_warps", "gemv_slabs", "gemv_stages", "gemv_pdl", "gemv_ctas", "gemv_debug", "force_path", "gemv_occ2"]
+KEYS = ["gemv_warps", "gemv_slabs", "gemv_stages", "gemv_pdl", "gemv_ctas", "gemv_debug", "force_path", "gemv_occ2", "gemv_pf", "gemv_xprep", "gemv_early", "gemv_res"]
 
 
 def make_pool(N, K, n_layers, dev):
@@ -37,10 +37,15 @@ def measure(layers, M, N, K, dev, steps=100, graph=True, flags=_lib.FLAG_STATIC_
     y = torch.empty(M, N, device=dev)
     ws = torch.zeros(max(lib.b200q_linear_ws_bytes(M, N, K), 16), dtype=torch.uint8, device=dev)
 
+    use_next = os.environ.get("NEXT", "1") == "1"
+
     def launch_all(sp):
-        for (p, s, z) in layers:
-            _lib.check(lib.b200q_linear_fwd(x.data_ptr(), 0, p.data_ptr(), s.data_ptr(), z.data_ptr(), y.data_ptr(), 0,
-                                            M, N, K, ws.data_ptr(), ws.numel(), flags, sp), "linear_fwd")
+        for i in range(max(24, len(layers))):               # always 24+ launches per graph replay
+            p, s, z = layers[i % len(layers)]
+            nxt = layers[(i + (0 if os.environ.get("NEXT_SELF") else 1)) % len(layers)][0]
+            _lib.check(lib.b200q_linear_fwd_next(x.data_ptr(), 0, p.data_ptr(), s.data_ptr(), z.data_ptr(), y.data_ptr(), 0,
+                                                 M, N, K, ws.data_ptr(), ws.numel(), flags, sp,
+                                                 nxt.data_ptr() if use_next else None, nxt.numel() if use_next else 0), "linear_fwd")
 
     g = None
     if graph:
@@ -62,7 +67,7 @@ def measure(layers, M, N, K, dev, steps=100, graph=True, flags=_lib.FLAG_STATIC_
         run()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) * 1e3 / (steps * len(layers))
+    return e0.elapsed_time(e1) * 1e3 / (steps * max(24, len(layers)))
 
 
 def main():
@@ -78,12 +83,11 @@ def main():
         layers = make_pool(N, K, int(os.environ.get("POOL", "24")), dev)
         nbytes = lambda M: N * K // 2 + 8 * N + 4 * M * K + 4 * M * N
         configs = [
-            ({"force_path": 2}, 1, True), ({"force_path": 2, "gemv_occ2": 1}, 1, True),
-            ({"force_path": 2, "gemv_occ2": 1, "gemv_stages": 2}, 1, True),
-            ({"force_path": 2, "gemv_occ2": 1, "gemv_debug": 2}, 1, True),
-            ({"force_path": 2, "gemv_occ2": 1, "gemv_pdl": 0}, 1, True),
-            ({"force_path": 2, "gemv_occ2": 1}, 2, True), ({"force_path": 2, "gemv_occ2": 1}, 4, True),
-            ({"force_path": 2, "gemv_occ2": 1}, 8, True),
+            ({"force_path": 2, "gemv_xprep": 1}, 1, True), ({"force_path": 2}, 1, True),
+            ({"gemv_pf": 0}, 1, True), ({"gemv_pf": 1}, 1, True), ({"gemv_pf": 0, "gemv_early": 0}, 1, True),
+            ({"gemv_pf": 0, "gemv_debug": 2}, 1, True),
+            ({"gemv_pf": 0}, 2, True), ({"gemv_pf": 0}, 4, True), ({"gemv_pf": 0}, 8, True),
+            ({"force_path": 2, "gemv_xprep": 1}, 8, True), ({"force_path": 2}, 8, True),
         ]
         for tune, M, graph in configs:
             for k in KEYS:
