@@ -207,11 +207,16 @@ def run_gemv(args):
     ws_bytes = lib.b200q_linear_ws_bytes(M, N_OUT, K_IN)
     ws = torch.zeros(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
 
+    # a decode loop knows which fused linear follows: each call names the next layer's packed weights so the
+    # kernel can pull them into L2 behind its own weight stream (b200q_linear_fwd_next; --no-hint turns it off)
     def launch_all(stream_ptr):
-        for (p, s, z) in layers:
-            _lib.check(lib.b200q_linear_fwd(x.data_ptr(), _lib.F32, p.data_ptr(), s.data_ptr(), z.data_ptr(),
-                                            y.data_ptr(), _lib.F32, M, N_OUT, K_IN, ws.data_ptr(), ws.numel(),
-                                            _lib.FLAG_STATIC_WEIGHTS, stream_ptr), "b200q_linear_fwd")
+        for i, (p, s, z) in enumerate(layers):
+            nxt = None if args.no_hint else layers[(i + 1) % len(layers)][0]
+            _lib.check(lib.b200q_linear_fwd_next(x.data_ptr(), _lib.F32, p.data_ptr(), s.data_ptr(), z.data_ptr(),
+                                                 y.data_ptr(), _lib.F32, M, N_OUT, K_IN, ws.data_ptr(), ws.numel(),
+                                                 _lib.FLAG_STATIC_WEIGHTS, stream_ptr,
+                                                 nxt.data_ptr() if nxt is not None else None,
+                                                 nxt.numel() if nxt is not None else 0), "b200q_linear_fwd_next")
 
     # correctness spot check before timing (oracle used as the checker only)
     oracle = oracle_module()
@@ -260,7 +265,7 @@ def run_gemv(args):
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    launches = args.steps * POOL            # fused dequantize-linear calls; each is 2 kernels (xprep + gemv)
+    launches = args.steps * POOL            # fused dequantize-linear calls; each is ONE kernel (gemv_res_kernel)
     per_launch_s = ms * 1e-3 / launches
     bytes_per_launch = gemv_bytes(M, N_OUT, K_IN)
     gbs_per_gpu = bytes_per_launch / per_launch_s / 1e9
@@ -341,7 +346,7 @@ def run_gemv(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {
             "workload": f"Llama-7B MLP INT4 decode GEMV M={M} ({K_IN}->{N_OUT}), configs[1]", "M": M, "K": K_IN,
-            "N": N_OUT, "launches_per_step": POOL,
+            "N": N_OUT, "launches_per_step": POOL, "next_layer_l2_hint": not args.no_hint,
             "l2": f"inputs larger than L2: weight pool of {POOL} layers = {POOL * N_OUT * K_IN // 2 / 1e6:.0f} MB "
                   "cycled round-robin (L2 is 126 MB)",
             "cuda_graph": graph is not None, "pdl": True,
@@ -355,7 +360,7 @@ def run_gemv(args):
                 "d2h_bytes_per_step": POOL * M * N_OUT * 4, "steps": e2e_steps,
                 "api": "QuantizedLinear.forward_host -> b200q_linear_fwd_host (pinned host x and y, weights resident), "
                        "24 calls per step replayed as a CUDA graph", "us_per_call": ms2 * 1e3 / (e2e_steps * POOL)},
-        "gpu_launches": 2 * launches,
+        "gpu_launches": launches,
         "clocks": clocks.summary(),
         "parity": {"max_abs_err_vs_f64_oracle": err},
     }
@@ -395,6 +400,7 @@ def main():
     ap.add_argument("--workload", default=None, choices=["gemv", "moe"])
     ap.add_argument("--m", type=int, default=1, help="batch rows for the gemv workload (1..16)")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-hint", action="store_true", help="gemv workload: do not name the next layer's weights (no L2 prefetch)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-moe", action="store_true", help="skip the MoE-layer sub-measurement of the N=1 gemv line")
     args = ap.parse_args()

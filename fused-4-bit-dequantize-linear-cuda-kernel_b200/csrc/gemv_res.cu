@@ -1,9 +1,9 @@
 // Decode path, "resident slab" variant: y[M,N] = x[M,K] @ dequant(W)^T for M <= 8 when a CTA's whole
 // share of W (its rows x K/2 packed bytes) fits in shared memory next to the x operand.
 //
-// Same arithmetic as gemv.cu (exact integers: u8 nibbles x signed base-256 limbs of round(x * 2^e) on
-// IMMA m16n8k32, s32 accumulation, fp64 epilogue) and therefore bit-identical results; what differs is
-// the amount of code every warp executes.  gemv.cu spends ~1.1 k - 1.8 k instructions per warp per launch,
+// Same kind of arithmetic as gemv.cu (exact integers: u8 weight bytes x signed base-256 limbs of a fixed-point
+// x on IMMA m16n8k32, s32 accumulation, fp64 epilogue: results do not depend on the summation order); what
+// differs is the amount of code every warp executes and that the nibbles are never widened (main loop).  gemv.cu spends ~1.1 k - 1.8 k instructions per warp per launch,
 // most of them outside the 5-tile main loop (profiles/r01_gemv_notes.md): with 16 warps on 4 schedulers
 // that is 2 - 4 us of pure issue time.  This kernel
 //   * has no ring: tile i is ONE bulk copy into its own slot with its own single-use mbarrier;
@@ -36,6 +36,11 @@ constexpr int TILE_ROWS = 16;
 constexpr int GRAN_K = 128;
 constexpr int GRAN_B = 64;
 constexpr int MAX_TILES = 32;
+constexpr int ACC_CS = 20;           // ints between the columns of an acc plane: 16 rows + 4 (RED.ADD of a warp hits 32 banks)
+constexpr int ACC_PLANE = 8 * ACC_CS;
+// acc is replicated R = 8 / NT times (warp w adds into replica w % R): shared-memory atomics to ONE address from
+// 16 warps serialise at ~60 clk each, which used to show up as 0.5 us between the last tile and the epilogue
+constexpr int ACC_REPS_X_NT = 8;
 
 struct ResParams {
     const void* x;
@@ -50,10 +55,13 @@ struct ResParams {
     int M, N, K;
     int rows_q, rows_rem;            // CTA b owns rows_q (+1 if b < rows_rem) rows
     int G;                           // K / 128
+    int pitch;                       // bytes between the rows of a tile in shared memory
     int acc_off, img_off, tile_off;  // byte offsets in dynamic shared memory
     int wait_weights;                // 1: weights may be written by the preceding kernel
     int early_tiles;                 // tiles requested before griddepcontrol.wait
     int pf_mode;
+    int slots;                       // 1 (M <= 2): per-warp partial slots (plain stores) instead of shared-memory atomics
+    int slots_alias;                 // the slots reach into the x image: barrier before the first store
     unsigned int launch_no;
     int debug;
 };
@@ -105,10 +113,10 @@ __device__ __forceinline__ void red_add_s32(uint32_t addr, int v) {
 //   [0, 256)        mbarriers, one per tile
 //   [256, 1280)     s_amax[8][16] f32   (then s_up[8] f32 at +512, s_ex[8] s32 at +544, s_txs[8][2] s32 at +576)
 //   [1280, 2304)    s_tx[16 warps][8 rows][2] s32
-//   [acc_off, ..)   acc[tile][NT*8 columns][16 rows] s32   (zeroed, RED.ADD target)
+//   [acc_off, ..)   acc[8/NT replicas][tile][NT*8 columns][ACC_CS] s32   (zeroed, RED.ADD target; 16 rows + 4 pad per column)
 //   [img_off, ..)   x image of ONE n-tile (two batch rows): [h][granule][limb][t][word] x {b0, b1}
 //   [tile_off, ..)  tiles: ntiles x 16 rows x K/2 bytes
-constexpr int OFF_AMAX = 256, OFF_UP = 768, OFF_EX = 800, OFF_TXS = 832, OFF_TX = 1280, OFF_END = 2304;
+constexpr int OFF_AMAX = 256, OFF_EX = 800, OFF_TXS = 832, OFF_TX = 1280, OFF_END = 2304;
 
 template <int GPW, int NT>
 __global__ void __launch_bounds__(NTHR, 1) gemv_res_kernel(const ResParams p) {
@@ -133,9 +141,9 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_res_kernel(const ResParams p) {
     const int nrows = p.rows_q + (b < p.rows_rem ? 1 : 0);
     const int ntiles = (nrows + TILE_ROWS - 1) / TILE_ROWS;
     const int row_bytes = p.K >> 1;
-    const uint32_t tile_bytes = (uint32_t)(TILE_ROWS * row_bytes);
+    const int pitch = p.pitch;                                    // = 64 mod 128: 8 rows x 64 B touch every bank once
+    const uint32_t tile_bytes = (uint32_t)(TILE_ROWS * pitch);
     float* s_amax = reinterpret_cast<float*>(smem + OFF_AMAX);
-    float* s_up = reinterpret_cast<float*>(smem + OFF_UP);
     int* s_ex = reinterpret_cast<int*>(smem + OFF_EX);
     int* s_txs = reinterpret_cast<int*>(smem + OFF_TXS);
     int* s_tx = reinterpret_cast<int*>(smem + OFF_TX);
@@ -146,18 +154,25 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_res_kernel(const ResParams p) {
         for (int i = 0; i < ntiles; ++i) mbar_init(sbase + 8u * i, 1);
         fence_mbar_init();
     }
-    for (int i = tid; i < ntiles * NT * 128; i += NTHR) acc[i] = 0;
+    constexpr int R = ACC_REPS_X_NT / NT;
+    const int rep_ints = ntiles * NT * ACC_PLANE;
+    if (!p.slots)
+        for (int i = tid; i < R * rep_ints; i += NTHR) acc[i] = 0;
     __syncthreads();
     pdl_launch_dependents();
     stamp(1);
 
     const bool skip_loads = (p.debug & 2) != 0;
-    auto issue_tile = [&](int i) {
+    // tile i = 16 row copies (warp w issues row w) into a slot whose rows are `pitch` bytes apart; thread 0
+    // arms the tile's barrier with the byte count (complete_tx may run ahead of expect_tx: the phase cannot
+    // complete before thread 0's arrival)
+    const uint64_t pol = policy_evict_first();
+    auto issue_tile = [&](int i) {                                // lane 0 of every warp
         const int rows = min(TILE_ROWS, nrows - i * TILE_ROWS);
-        const uint32_t bytes = (uint32_t)(rows * row_bytes);
-        mbar_arrive_expect_tx(sbase + 8u * i, bytes);
-        bulk_g2s_hint(sbase + p.tile_off + i * tile_bytes, p.packed + (int64_t)(r0 + i * TILE_ROWS) * row_bytes, bytes,
-                      sbase + 8u * i, policy_evict_first());
+        if (warp == 0) mbar_arrive_expect_tx(sbase + 8u * i, (uint32_t)(rows * row_bytes));
+        if (warp < rows)
+            bulk_g2s_hint(sbase + p.tile_off + i * tile_bytes + warp * pitch,
+                          p.packed + (int64_t)(r0 + i * TILE_ROWS + warp) * row_bytes, (uint32_t)row_bytes, sbase + 8u * i, pol);
     };
     auto prefetch_next = [&]() {
         if (!p.next_bytes || p.pf_mode != 1) return;
@@ -169,22 +184,54 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_res_kernel(const ResParams p) {
         }
     };
     if (p.wait_weights) pdl_wait();
-    const int early = min(p.early_tiles, ntiles);
-    if (tid == 0 && !skip_loads) {
+    // staged requests (tuning key gemv_early = a + 10 * b): a tiles before griddepcontrol.wait, b more once the
+    // x loads are in flight, the rest when the x operand is built -- bounds what queues ahead of the x loads
+    const int early = min(p.early_tiles % 10, ntiles);
+    const int mid = min(early + p.early_tiles / 10, ntiles);
+    if (lane == 0 && !skip_loads) {
         for (int i = 0; i < early; ++i) issue_tile(i);
-        if (early == ntiles) prefetch_next();
+        if (early == ntiles && warp == NW - 1) prefetch_next();
     }
     stamp(2);
     pdl_wait();          // x (and y) belong to the stream-ordered predecessor
     stamp(3);
-    if (tid == 0 && !skip_loads && early < ntiles) {
-        for (int i = early; i < ntiles; ++i) issue_tile(i);
-        prefetch_next();
-    }
+    // tiles held back (tuning key gemv_early) are requested only after this warp's x loads are in flight, so
+    // that those do not queue behind the weight stream
+    auto issue_range = [&](int from, int to) {
+        if (lane == 0 && !skip_loads && from < to) {
+            for (int i = from; i < to; ++i) issue_tile(i);
+            if (to == ntiles && warp == NW - 1) prefetch_next();
+        }
+    };
+    auto issue_late = [&]() { issue_range(early, mid); };
 
-    // ---- pass 1: amax of every batch row (coalesced float4 / 8-byte loads, all threads)
-    {
-        const int K8 = p.K >> 3;
+    // ---- pass 1: amax of every batch row (coalesced 32-byte loads, all threads).  With one n-tile and at most
+    // two items (8 activations each) per thread, the values stay in registers for pass 2.
+    const int K8 = p.K >> 3;
+    const bool keep = NT == 1 && p.M * K8 <= 2 * NTHR;
+    float xv[2][8];
+    if (keep) {
+        float am0 = 0.0f, am1 = 0.0f;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) xv[s][e] = 0.0f;
+            if (tid + s * NTHR < p.M * K8) load8f(p.x, p.x_dtype, (int64_t)(tid + s * NTHR) * 8, xv[s]);
+        }
+        issue_late();
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            float a = 0.0f;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) a = fmaxf(a, fabsf(xv[s][e]));
+            if (tid + s * NTHR >= K8) am1 = fmaxf(am1, a); else am0 = fmaxf(am0, a);
+        }
+        // non-negative floats order like their bit patterns: one REDUX per row instead of five shuffles
+        const unsigned int u0 = __reduce_max_sync(0xffffffffu, __float_as_uint(am0));
+        const unsigned int u1 = __reduce_max_sync(0xffffffffu, __float_as_uint(am1));
+        if (lane == 0) { s_amax[warp] = __uint_as_float(u0); s_amax[NW + warp] = __uint_as_float(u1); }
+    } else {
+        issue_late();
         for (int m = 0; m < p.M; ++m) {
             float am = 0.0f;
             for (int i = tid; i < K8; i += NTHR) {
@@ -199,18 +246,14 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_res_kernel(const ResParams p) {
         }
     }
     __syncthreads();
-    if (warp < p.M) {            // warp m: exponent of batch row m
-        float am = lane < NW ? s_amax[warp * NW + lane] : 0.0f;
-#pragma unroll
-        for (int o = 8; o > 0; o >>= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, o));
+    // every warp derives the rows' exponents itself (one LDS + one REDUX per row): no second barrier
+    auto row_exp = [&](int m) {
+        const unsigned int u = __reduce_max_sync(0xffffffffu, lane < NW ? __float_as_uint(s_amax[m * NW + lane]) : 0u);
+        const float am = __uint_as_float(u);
         int ex = 0;
-        if (am > 0.0f && am < INFINITY) ex = max(-96, min(126, 156 - (int)(__float_as_uint(am) >> 23)));
-        if (lane == 0) {
-            s_ex[warp] = ex;
-            s_up[warp] = __uint_as_float((uint32_t)(127 + ex) << 23);
-        }
-    }
-    __syncthreads();
+        if (am > 0.0f && am < INFINITY) ex = max(-96, min(126, 155 - (int)(u >> 23)));
+        return ex;
+    };
     stamp(4);
 
     // ---- pass 2: x image of one n-tile at a time, then every lane pulls its B fragments
@@ -223,25 +266,30 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_res_kernel(const ResParams p) {
         const int live_rows = min(2, p.M - 2 * nt);          // batch rows of this n-tile that exist (may be <= 0)
         if (nt > 0) __syncthreads();                          // the image is reused
         int slo0 = 0, shi0 = 0, slo1 = 0, shi1 = 0;           // sum of X as (X & 0xffff), (X >> 16): exact in s32
+        const int ex0 = live_rows > 0 ? row_exp(2 * nt) : 0, ex1 = live_rows > 1 ? row_exp(2 * nt + 1) : 0;
+        const float up0 = __uint_as_float((uint32_t)(127 + ex0) << 23), up1 = __uint_as_float((uint32_t)(127 + ex1) << 23);
+        if (tid == 0) { s_ex[2 * nt] = ex0; s_ex[2 * nt + 1] = ex1; }
         const int items = live_rows * G * 16;                 // 8 values each
-        for (int it = tid; it < items; it += NTHR) {
+        auto convert = [&](int it, const float (&v)[8]) {
             const int hh = it >= G * 16 ? 1 : 0;
             const int r = it - hh * G * 16;                   // = k / 8: (granule, t, word)
-            const int em = 2 * nt + hh;
-            float v[8];
-            load8f(p.x, p.x_dtype, (int64_t)em * p.K + r * 8, v);
-            const float up = s_up[em];
+            const float up = hh ? up1 : up0, up16 = up * 0.0625f;
             uint32_t D[8];
             int a_lo = 0, a_hi = 0;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int X = __float2int_rn(v[i] * up);
-                a_lo += X & 0xffff;
-                a_hi += X >> 16;
-                D[i] = (uint32_t)(X + 0x00808080) ^ 0x00808080u;       // byte l = signed base-256 digit l
+            for (int i = 0; i < 4; ++i) {
+                // even column: Xe = round(x 2^e); odd column: Xo = round(x 2^(e-4)), carried as Z = Xo - Xe (see
+                // the main loop: the raw packed byte q_lo + 16 q_hi meets Xe, the masked byte 16 q_hi meets Z)
+                const int Xe = __float2int_rn(v[2 * i] * up);
+                const int Xo = __float2int_rn(v[2 * i + 1] * up16);
+                const int Z = Xo - Xe, Xo16 = Xo << 4;
+                a_lo += (Xe & 0xffff) + (Xo16 & 0xffff);
+                a_hi += (Xe >> 16) + (Xo16 >> 16);
+                D[2 * i] = (uint32_t)(Xe + 0x00808080) ^ 0x00808080u;      // byte l = signed base-256 digit l
+                D[2 * i + 1] = (uint32_t)(Z + 0x00808080) ^ 0x00808080u;
             }
             if (hh) { slo1 += a_lo; shi1 += a_hi; } else { slo0 += a_lo; shi0 += a_hi; }
-            // 4x4 byte transposes: digit l of the even values -> b0 (meets the low nibbles), odd -> b1
+            // 4x4 byte transposes: digit l of the four Xe -> b0 (meets the raw bytes), of the four Z -> b1 (high nibbles x 16)
             const uint32_t e0 = __byte_perm(D[0], D[2], 0x5140), e1 = __byte_perm(D[4], D[6], 0x5140);
             const uint32_t e2 = __byte_perm(D[0], D[2], 0x7362), e3 = __byte_perm(D[4], D[6], 0x7362);
             const uint32_t o0 = __byte_perm(D[1], D[3], 0x5140), o1 = __byte_perm(D[5], D[7], 0x5140);
@@ -251,15 +299,24 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_res_kernel(const ResParams p) {
             dst[1 * 16] = make_uint2(__byte_perm(e0, e1, 0x7632), __byte_perm(o0, o1, 0x7632));
             dst[2 * 16] = make_uint2(__byte_perm(e2, e3, 0x5410), __byte_perm(o2, o3, 0x5410));
             dst[3 * 16] = make_uint2(__byte_perm(e2, e3, 0x7632), __byte_perm(o2, o3, 0x7632));
+        };
+        if (keep) {
+#pragma unroll
+            for (int s = 0; s < 2; ++s)
+                if (tid + s * NTHR < items) convert(tid + s * NTHR, xv[s]);
+        } else {
+            for (int it = tid; it < items; it += NTHR) {
+                const int hh = it >= G * 16 ? 1 : 0;
+                float v[8];
+                load8f(p.x, p.x_dtype, (int64_t)(2 * nt + hh) * p.K + (it - hh * G * 16) * 8, v);
+                convert(it, v);
+            }
         }
         if (live_rows > 0) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                slo0 += __shfl_xor_sync(0xffffffffu, slo0, o);
-                shi0 += __shfl_xor_sync(0xffffffffu, shi0, o);
-                slo1 += __shfl_xor_sync(0xffffffffu, slo1, o);
-                shi1 += __shfl_xor_sync(0xffffffffu, shi1, o);
-            }
+            slo0 = __reduce_add_sync(0xffffffffu, slo0);
+            shi0 = __reduce_add_sync(0xffffffffu, shi0);
+            slo1 = __reduce_add_sync(0xffffffffu, slo1);
+            shi1 = __reduce_add_sync(0xffffffffu, shi1);
             if (lane == 0) {
                 *reinterpret_cast<int4*>(s_tx + (warp * 8 + 2 * nt) * 2) = make_int4(slo0, shi0, slo1, shi1);
             }
@@ -278,28 +335,34 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_res_kernel(const ResParams p) {
             bf[q][nt][0][0] = v0.x; bf[q][nt][0][1] = v0.y; bf[q][nt][1][0] = v0.z; bf[q][nt][1][1] = v0.w;
             bf[q][nt][2][0] = v1.x; bf[q][nt][2][1] = v1.y; bf[q][nt][3][0] = v1.z; bf[q][nt][3][1] = v1.w;
         }
-        if (tid < 2 && tid < live_rows) {                     // exact sum of X of one batch row over all warps
-            int alo = 0, ahi = 0;
-#pragma unroll
-            for (int w = 0; w < NW; ++w) { alo += s_tx[(w * 8 + 2 * nt + tid) * 2]; ahi += s_tx[(w * 8 + 2 * nt + tid) * 2 + 1]; }
-            s_txs[(2 * nt + tid) * 2] = alo;
-            s_txs[(2 * nt + tid) * 2 + 1] = ahi;
+        if (warp >= NW - 2 && NW - 1 - warp < live_rows) {    // warps 15, 14: exact sum of X of one batch row over all warps
+            const int em = 2 * nt + (NW - 1 - warp);
+            int alo = lane < NW ? s_tx[(lane * 8 + em) * 2] : 0, ahi = lane < NW ? s_tx[(lane * 8 + em) * 2 + 1] : 0;
+            alo = __reduce_add_sync(0xffffffffu, alo);
+            ahi = __reduce_add_sync(0xffffffffu, ahi);
+            if (lane == 0) { s_txs[em * 2] = alo; s_txs[em * 2 + 1] = ahi; }
         }
     }
+    issue_range(mid, ntiles);
     stamp(6);
 
     // scale / zero point of the first output of this thread, fetched now (latency hidden by the main loop)
     const int outs = ntiles * TILE_ROWS * p.M;
     float pre_sc = 0.0f, pre_zp = 0.0f;
-    if (tid < outs) {
+    if (NT == 1 && p.slots) {
+        const int rest = tid >> 6, row = r0 + (p.M == 1 ? rest : (rest >> 1)) * TILE_ROWS + ((tid >> 2) & 15);
+        if ((tid & 3) == 0 && tid < outs * 4 && row < r0 + nrows) { pre_sc = __ldg(p.scales + row); pre_zp = __ldg(p.zps + row); }
+    } else if (tid < outs) {
         const int row = r0 + (tid >> 4) / p.M * TILE_ROWS + (tid & 15);
         if (row < r0 + nrows) { pre_sc = __ldg(p.scales + row); pre_zp = __ldg(p.zps + row); }
     }
 
     // ---- main loop: one 16-row tile per iteration, this warp's granules warp, warp + 16, ...
-    const uint32_t lane_off = (uint32_t)(g * row_bytes + warp * GRAN_B + t * 16);
-    const uint32_t acc_lane = sbase + p.acc_off + (uint32_t)((2 * t * TILE_ROWS + g) * 4);
+    const uint32_t lane_off = (uint32_t)(g * pitch + warp * GRAN_B + t * 16);
+    const uint32_t acc_lane = sbase + p.acc_off + (uint32_t)(((warp % R) * rep_ints + 2 * t * ACC_CS + g) * 4);
     const bool cols_live = p.M > 1 || t < 2;                   // M == 1: mma columns 4..7 are empty
+    const int slot_ints = (p.M == 1 ? 4 : 8) * ACC_CS;         // slots mode: ints per (tile, warp)
+    if (p.slots_alias) __syncthreads();                        // every lane has read its fragments from the image
     for (int i = 0; i < ntiles; ++i) {
         int c[NT][2][4];
 #pragma unroll
@@ -317,7 +380,7 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_res_kernel(const ResParams p) {
             hi[q] = lo[q];
             if (warp + q * NW < G) {
                 lo[q] = lds128(tb + q * NW * GRAN_B);
-                hi[q] = lds128(tb + q * NW * GRAN_B + 8 * row_bytes);
+                hi[q] = lds128(tb + q * NW * GRAN_B + 8 * pitch);
             }
         }
 #pragma unroll
@@ -326,22 +389,35 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_res_kernel(const ResParams p) {
             const uint32_t wh[4] = {hi[q].x, hi[q].y, hi[q].z, hi[q].w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const uint32_t a0 = wl[j] & 0x0f0f0f0fu, a2 = (wl[j] >> 4) & 0x0f0f0f0fu;   // row g
-                const uint32_t a1 = wh[j] & 0x0f0f0f0fu, a3 = (wh[j] >> 4) & 0x0f0f0f0fu;   // row g + 8
+                // no nibble extraction: sum_k (q_lo + 16 q_hi) Xe + (16 q_hi) (Xo - Xe) = sum_k q_lo Xe + q_hi 16 Xo.
+                // LOP3 / SHF run at half rate on the INT pipe; the 48 of them per tile that a plain
+                // nibble -> byte widening costs were what bounded this loop (profiles/r01_gemv_notes.md)
+                const uint32_t a0 = wl[j], a2 = wl[j] & 0xf0f0f0f0u;   // row g
+                const uint32_t a1 = wh[j], a3 = wh[j] & 0xf0f0f0f0u;   // row g + 8
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) imma(c[nt][j & 1], a0, a1, a2, a3, bf[q][nt][j][0], bf[q][nt][j][1]);
             }
         }
         if (i < 5) stamp(10 + i);
         // the 16 warps add their partials of tile i into acc[i][column][row] (exact, order independent)
-        if (cols_live) {
+        if (NT == 1 && p.slots) {
+            // own slot of (tile, warp): plain stores.  (A shared-memory atomic costs the LSU ~10 clk per warp
+            // instruction; 320 of them per launch drained for 0.5 us after the last tile.)
+            if (cols_live) {
+                int* sl = acc + (i * NW + warp) * slot_ints + 2 * t * ACC_CS + g;
+                sl[0] = c[0][0][0] + c[0][1][0];
+                sl[ACC_CS] = c[0][0][1] + c[0][1][1];
+                sl[8] = c[0][0][2] + c[0][1][2];
+                sl[ACC_CS + 8] = c[0][0][3] + c[0][1][3];
+            }
+        } else if (cols_live) {
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) {
-                const uint32_t a = acc_lane + (uint32_t)(((i * NT + nt) * 8) * TILE_ROWS * 4);
+                const uint32_t a = acc_lane + (uint32_t)((i * NT + nt) * ACC_PLANE * 4);
                 red_add_s32(a, c[nt][0][0] + c[nt][1][0]);                            // (row g,     col 2t)
-                red_add_s32(a + TILE_ROWS * 4, c[nt][0][1] + c[nt][1][1]);            // (row g,     col 2t + 1)
+                red_add_s32(a + ACC_CS * 4, c[nt][0][1] + c[nt][1][1]);               // (row g,     col 2t + 1)
                 red_add_s32(a + 32, c[nt][0][2] + c[nt][1][2]);                       // (row g + 8, col 2t)
-                red_add_s32(a + TILE_ROWS * 4 + 32, c[nt][0][3] + c[nt][1][3]);       // (row g + 8, col 2t + 1)
+                red_add_s32(a + ACC_CS * 4 + 32, c[nt][0][3] + c[nt][1][3]);          // (row g + 8, col 2t + 1)
             }
         }
     }
@@ -349,6 +425,49 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_res_kernel(const ResParams p) {
     __syncthreads();
     stamp(8);
 
+    auto finish = [&](long long a, int em, int row, float sc, float zp) {
+        const int ex = s_ex[em];
+        const long long txl = (long long)s_txs[em * 2] + ((long long)s_txs[em * 2 + 1] << 16);     // sum_k X (exact)
+        const int zi = __float2int_rn(zp);
+        float v;
+        if ((float)zi == zp && zi >= -32768 && zi <= 32767 && ex >= -126) {
+            // quantiser-made zero points are integers: a - zp * sum X exactly in s64, ONE rounding to fp32 (the
+            // same value the fp64 expression below rounds to), then the exact power of two and the scale
+            v = sc * (__ll2float_rn(a - (long long)zi * txl) * __uint_as_float((uint32_t)(127 - ex) << 23));
+        } else {
+            const double down = __longlong_as_double((long long)(1023 - ex) << 52);                // 2^-e
+            v = sc * (float)(((double)a - (double)zp * (double)txl) * down);
+        }
+        store_out(p.y, p.y_dtype, (int64_t)em * p.N + row, v);
+    };
+    if (NT == 1 && p.slots) {
+        // four threads per output (one per limb) add the 16 warp slots; the quad combines through shuffles
+        const int total = outs * 4;
+        for (int idx0 = 0; idx0 < total; idx0 += NTHR) {
+            const int idx = idx0 + tid;
+            const int lq = idx & 3, er = (idx >> 2) & 15, rest = idx >> 6;
+            const int em = p.M == 1 ? 0 : (rest & 1), ti = p.M == 1 ? rest : (rest >> 1);
+            const int row = r0 + ti * TILE_ROWS + er;
+            const bool ok = idx < total && row < r0 + nrows;
+            long long a = 0;
+            if (ok) {
+                const int* sl = acc + (ti * NW) * slot_ints + (em * 4 + lq) * ACC_CS + er;
+                int a32 = 0;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) a32 += sl[w * slot_ints];
+                a = (long long)a32 << (8 * lq);
+            }
+            a += __shfl_xor_sync(0xffffffffu, a, 1);
+            a += __shfl_xor_sync(0xffffffffu, a, 2);
+            if (a != 0x123456789abcll) stamp(15);
+            if (ok && lq == 0) {
+                float sc, zp;
+                if (idx0 == 0) { sc = pre_sc; zp = pre_zp; }
+                else { sc = __ldg(p.scales + row); zp = __ldg(p.zps + row); }
+                finish(a, em, row, sc, zp);
+            }
+        }
+    } else
     // ---- epilogue: one thread per output (tile, batch row, row): limbs -> sum_k q*X (exact s64),
     // y = s * 2^-e * (sum_k q*X - zp * sum_k X)
     for (int o = tid; o < outs; o += NTHR) {
@@ -359,13 +478,14 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_res_kernel(const ResParams p) {
         float sc, zp;
         if (o == tid) { sc = pre_sc; zp = pre_zp; }
         else { sc = __ldg(p.scales + row); zp = __ldg(p.zps + row); }
-        const int* a4 = acc + (ti * NT * 8 + em * 4) * TILE_ROWS + er;
-        const long long a = (long long)a4[0] + ((long long)a4[TILE_ROWS] << 8) + ((long long)a4[2 * TILE_ROWS] << 16) +
-                            ((long long)a4[3 * TILE_ROWS] << 24);
-        const double down = __longlong_as_double((long long)(1023 - s_ex[em]) << 52);            // 2^-e
-        const double tx = (double)s_txs[em * 2] + 65536.0 * (double)s_txs[em * 2 + 1];           // sum_k X
-        const float v = sc * (float)(((double)a - (double)zp * tx) * down);
-        store_out(p.y, p.y_dtype, (int64_t)em * p.N + row, v);
+        const int* a4 = acc + (ti * NT * 8 + em * 4) * ACC_CS + er;
+        int l0 = 0, l1 = 0, l2 = 0, l3 = 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            l0 += a4[r * rep_ints]; l1 += a4[r * rep_ints + ACC_CS]; l2 += a4[r * rep_ints + 2 * ACC_CS]; l3 += a4[r * rep_ints + 3 * ACC_CS];
+        }
+        const long long a = (long long)l0 + ((long long)l1 << 8) + ((long long)l2 << 16) + ((long long)l3 << 24);
+        finish(a, em, row, sc, zp);
     }
     stamp(9);
     if (prof) {
@@ -381,7 +501,7 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_res_kernel(const ResParams p) {
 
 struct ResPlan {
     int grid, gpw, nt, ntiles;
-    int acc_off, img_off, tile_off;
+    int acc_off, img_off, tile_off, pitch, slots, slots_alias;
     size_t smem;
 };
 
@@ -400,9 +520,14 @@ bool plan_res(int sm_count, int max_smem, int64_t M, int64_t N, int64_t K, ResPl
     c->grid = grid; c->gpw = (G + NW - 1) / NW; c->nt = nt; c->ntiles = ntiles;
     if (c->gpw * nt > 8) return false;                              // B fragments must stay in registers
     c->acc_off = OFF_END;
-    c->img_off = (c->acc_off + ntiles * nt * 512 + 127) / 128 * 128;
+    c->img_off = (c->acc_off + ACC_REPS_X_NT * ntiles * ACC_PLANE * 4 + 127) / 128 * 128;
     c->tile_off = (c->img_off + 2 * G * 512 + 127) / 128 * 128;    // image: 2 rows x G granules x 4 limbs x 16 x 8 B
-    c->smem = (size_t)c->tile_off + (size_t)ntiles * TILE_ROWS * (K / 2);
+    // M <= 2: per-warp partial slots live in the acc region and, for M == 2, on into the x image (dead by then)
+    const int slot_bytes = NW * ntiles * (M == 1 ? 4 : 8) * ACC_CS * 4;
+    c->slots = nt == 1 && slot_bytes <= c->tile_off - c->acc_off;
+    c->slots_alias = c->slots && slot_bytes > c->img_off - c->acc_off;
+    c->pitch = (int)(K / 2) + ((K / 2) % 128 == 0 ? 64 : 0);
+    c->smem = (size_t)c->tile_off + (size_t)ntiles * TILE_ROWS * c->pitch;
     return c->smem <= (size_t)max_smem;
 }
 
@@ -450,9 +575,10 @@ int launch_gemv_res(const DeviceInfo& dev, const void* x, int x_dtype, const uin
     p.M = (int)M; p.N = (int)N; p.K = (int)K;
     p.rows_q = (int)(N / c.grid); p.rows_rem = (int)(N % c.grid);
     p.G = (int)(K / GRAN_K);
-    p.acc_off = c.acc_off; p.img_off = c.img_off; p.tile_off = c.tile_off;
+    p.acc_off = c.acc_off; p.img_off = c.img_off; p.tile_off = c.tile_off; p.pitch = c.pitch;
+    p.slots = c.slots; p.slots_alias = c.slots_alias;
     p.wait_weights = (flags & B200Q_FLAG_STATIC_WEIGHTS) ? 0 : 1;
-    p.early_tiles = tuning().gemv_early >= 0 ? tuning().gemv_early : MAX_TILES;
+    p.early_tiles = tuning().gemv_early >= 0 ? tuning().gemv_early : 91;     // default: one tile up front, the rest behind the x loads (tools/tune_gemv.py sweep)
     p.pf_mode = tuning().gemv_pf;
     p.next_packed = next_packed;
     p.next_bytes = next_packed && (reinterpret_cast<uintptr_t>(next_packed) & 15) == 0 ? next_bytes : 0;

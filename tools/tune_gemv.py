@@ -82,13 +82,8 @@ def main():
     for (K, N) in shapes:
         layers = make_pool(N, K, int(os.environ.get("POOL", "24")), dev)
         nbytes = lambda M: N * K // 2 + 8 * N + 4 * M * K + 4 * M * N
-        configs = [
-            ({"force_path": 2, "gemv_xprep": 1}, 1, True), ({"force_path": 2}, 1, True),
-            ({"gemv_pf": 0}, 1, True), ({"gemv_pf": 1}, 1, True), ({"gemv_pf": 0, "gemv_early": 0}, 1, True),
-            ({"gemv_pf": 0, "gemv_debug": 2}, 1, True),
-            ({"gemv_pf": 0}, 2, True), ({"gemv_pf": 0}, 4, True), ({"gemv_pf": 0}, 8, True),
-            ({"force_path": 2, "gemv_xprep": 1}, 8, True), ({"force_path": 2}, 8, True),
-        ]
+        configs = [({"gemv_pf": pf, "gemv_early": e}, 1, True) for pf in (1, 0)
+                   for e in (1, 2, 3, 10, 20, 30, 90, 11, 12, 21, 22, 31, 91, 92, 93)]
         for tune, M, graph in configs:
             for k in KEYS:
                 _lib.tune(k, -1)
