@@ -55,7 +55,6 @@ struct ResParams {
     int M, N, K;
     int rows_q, rows_rem;            // CTA b owns rows_q (+1 if b < rows_rem) rows
     int G;                           // K / 128
-    int pitch;                       // bytes between the rows of a tile in shared memory
     int acc_off, img_off, tile_off;  // byte offsets in dynamic shared memory
     int wait_weights;                // 1: weights may be written by the preceding kernel
     int early_tiles;                 // tiles requested before griddepcontrol.wait
@@ -141,8 +140,12 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_res_kernel(const ResParams p) {
     const int nrows = p.rows_q + (b < p.rows_rem ? 1 : 0);
     const int ntiles = (nrows + TILE_ROWS - 1) / TILE_ROWS;
     const int row_bytes = p.K >> 1;
-    const int pitch = p.pitch;                                    // = 64 mod 128: 8 rows x 64 B touch every bank once
-    const uint32_t tile_bytes = (uint32_t)(TILE_ROWS * pitch);
+    // A tile is TWO bulk copies: rows 0..7 at offset 0 and rows 8..15 at offset 8 * row_bytes + 64.  An LDS.128 of
+    // a warp fetches four rows of each half (mma row g <-> tile row perm(g), below): with row_bytes a multiple of
+    // 128 the two halves then sit in complementary 64-byte windows and the 8 rows x 64 B touch every bank exactly
+    // four times (no conflicts) -- without one copy per padded row.
+    const uint32_t tile_bytes = (uint32_t)(TILE_ROWS * row_bytes + 128);
+    const uint32_t half_off = (uint32_t)(8 * row_bytes + 64);
     float* s_amax = reinterpret_cast<float*>(smem + OFF_AMAX);
     int* s_ex = reinterpret_cast<int*>(smem + OFF_EX);
     int* s_txs = reinterpret_cast<int*>(smem + OFF_TXS);
@@ -162,17 +165,23 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_res_kernel(const ResParams p) {
     pdl_launch_dependents();
     stamp(1);
 
+    // mma row (0..15) -> row of the tile, see the tile layout above
+    auto tile_row = [](int er) { return ((er & 1) << 3) + ((er & 8) >> 1) + ((er & 7) >> 1); };
     const bool skip_loads = (p.debug & 2) != 0;
-    // tile i = 16 row copies (warp w issues row w) into a slot whose rows are `pitch` bytes apart; thread 0
-    // arms the tile's barrier with the byte count (complete_tx may run ahead of expect_tx: the phase cannot
-    // complete before thread 0's arrival)
+    // the two copies of tile i are issued by lane 0 of warps 2i and 2i + 1 (mod 16); the first also arms the tile's
+    // barrier with the byte count of both (complete_tx may run ahead of expect_tx: the phase cannot complete before
+    // that arrival)
     const uint64_t pol = policy_evict_first();
-    auto issue_tile = [&](int i) {                                // lane 0 of every warp
+    auto issue_tile = [&](int i) {                                // lane 0 of every warp calls this
         const int rows = min(TILE_ROWS, nrows - i * TILE_ROWS);
-        if (warp == 0) mbar_arrive_expect_tx(sbase + 8u * i, (uint32_t)(rows * row_bytes));
-        if (warp < rows)
-            bulk_g2s_hint(sbase + p.tile_off + i * tile_bytes + warp * pitch,
-                          p.packed + (int64_t)(r0 + i * TILE_ROWS + warp) * row_bytes, (uint32_t)row_bytes, sbase + 8u * i, pol);
+        const uint32_t bar = sbase + 8u * i, dst = sbase + p.tile_off + i * tile_bytes;
+        const uint8_t* src = p.packed + (int64_t)(r0 + i * TILE_ROWS) * row_bytes;
+        if (warp == ((2 * i) & (NW - 1))) {
+            mbar_arrive_expect_tx(bar, (uint32_t)(rows * row_bytes));
+            bulk_g2s_hint(dst, src, (uint32_t)(min(rows, 8) * row_bytes), bar, pol);
+        } else if (warp == ((2 * i + 1) & (NW - 1)) && rows > 8) {
+            bulk_g2s_hint(dst + half_off, src + 8 * row_bytes, (uint32_t)((rows - 8) * row_bytes), bar, pol);
+        }
     };
     auto prefetch_next = [&]() {
         if (!p.next_bytes || p.pf_mode != 1) return;
@@ -212,24 +221,31 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_res_kernel(const ResParams p) {
     float xv[2][8];
     if (keep) {
         float am0 = 0.0f, am1 = 0.0f;
+        const bool two = p.M * K8 > NTHR;                      // uniform: a second item per thread exists
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) xv[s][e] = 0.0f;
-            if (tid + s * NTHR < p.M * K8) load8f(p.x, p.x_dtype, (int64_t)(tid + s * NTHR) * 8, xv[s]);
-        }
+        for (int e = 0; e < 8; ++e) { xv[0][e] = 0.0f; xv[1][e] = 0.0f; }
+        if (tid < p.M * K8) load8f(p.x, p.x_dtype, (int64_t)tid * 8, xv[0]);
+        if (two && tid + NTHR < p.M * K8) load8f(p.x, p.x_dtype, (int64_t)(tid + NTHR) * 8, xv[1]);
         issue_late();
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
+        {
             float a = 0.0f;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) a = fmaxf(a, fabsf(xv[s][e]));
-            if (tid + s * NTHR >= K8) am1 = fmaxf(am1, a); else am0 = fmaxf(am0, a);
+            for (int e = 0; e < 8; ++e) a = fmaxf(a, fabsf(xv[0][e]));
+            if (tid >= K8) am1 = a; else am0 = a;
+        }
+        if (two) {
+            float a = 0.0f;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) a = fmaxf(a, fabsf(xv[1][e]));
+            if (tid + NTHR >= K8) am1 = fmaxf(am1, a); else am0 = fmaxf(am0, a);
         }
         // non-negative floats order like their bit patterns: one REDUX per row instead of five shuffles
         const unsigned int u0 = __reduce_max_sync(0xffffffffu, __float_as_uint(am0));
-        const unsigned int u1 = __reduce_max_sync(0xffffffffu, __float_as_uint(am1));
-        if (lane == 0) { s_amax[warp] = __uint_as_float(u0); s_amax[NW + warp] = __uint_as_float(u1); }
+        if (lane == 0) s_amax[warp] = __uint_as_float(u0);
+        if (p.M > 1) {
+            const unsigned int u1 = __reduce_max_sync(0xffffffffu, __float_as_uint(am1));
+            if (lane == 0) s_amax[NW + warp] = __uint_as_float(u1);
+        }
     } else {
         issue_late();
         for (int m = 0; m < p.M; ++m) {
@@ -301,9 +317,8 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_res_kernel(const ResParams p) {
             dst[3 * 16] = make_uint2(__byte_perm(e2, e3, 0x7632), __byte_perm(o2, o3, 0x7632));
         };
         if (keep) {
-#pragma unroll
-            for (int s = 0; s < 2; ++s)
-                if (tid + s * NTHR < items) convert(tid + s * NTHR, xv[s]);
+            if (tid < items) convert(tid, xv[0]);
+            if (tid + NTHR < items) convert(tid + NTHR, xv[1]);
         } else {
             for (int it = tid; it < items; it += NTHR) {
                 const int hh = it >= G * 16 ? 1 : 0;
@@ -350,15 +365,17 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_res_kernel(const ResParams p) {
     const int outs = ntiles * TILE_ROWS * p.M;
     float pre_sc = 0.0f, pre_zp = 0.0f;
     if (NT == 1 && p.slots) {
-        const int rest = tid >> 6, row = r0 + (p.M == 1 ? rest : (rest >> 1)) * TILE_ROWS + ((tid >> 2) & 15);
+        const int rest = tid >> 6, row = r0 + (p.M == 1 ? rest : (rest >> 1)) * TILE_ROWS + tile_row((tid >> 2) & 15);
         if ((tid & 3) == 0 && tid < outs * 4 && row < r0 + nrows) { pre_sc = __ldg(p.scales + row); pre_zp = __ldg(p.zps + row); }
     } else if (tid < outs) {
-        const int row = r0 + (tid >> 4) / p.M * TILE_ROWS + (tid & 15);
+        const int row = r0 + (tid >> 4) / p.M * TILE_ROWS + tile_row(tid & 15);
         if (row < r0 + nrows) { pre_sc = __ldg(p.scales + row); pre_zp = __ldg(p.zps + row); }
     }
 
     // ---- main loop: one 16-row tile per iteration, this warp's granules warp, warp + 16, ...
-    const uint32_t lane_off = (uint32_t)(g * pitch + warp * GRAN_B + t * 16);
+    // mma rows g (a0 / a2) and g + 8 (a1 / a3) of this lane <-> tile rows perm(g) and perm(g) + 4:
+    // even g -> first half, row g / 2; odd g -> second half, row 8 + g / 2
+    const uint32_t lane_off = (uint32_t)((g & 1) * half_off + (g >> 1) * row_bytes + warp * GRAN_B + t * 16);
     const uint32_t acc_lane = sbase + p.acc_off + (uint32_t)(((warp % R) * rep_ints + 2 * t * ACC_CS + g) * 4);
     const bool cols_live = p.M > 1 || t < 2;                   // M == 1: mma columns 4..7 are empty
     const int slot_ints = (p.M == 1 ? 4 : 8) * ACC_CS;         // slots mode: ints per (tile, warp)
@@ -380,7 +397,7 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_res_kernel(const ResParams p) {
             hi[q] = lo[q];
             if (warp + q * NW < G) {
                 lo[q] = lds128(tb + q * NW * GRAN_B);
-                hi[q] = lds128(tb + q * NW * GRAN_B + 8 * pitch);
+                hi[q] = lds128(tb + q * NW * GRAN_B + 4 * row_bytes);
             }
         }
 #pragma unroll
@@ -447,19 +464,17 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_res_kernel(const ResParams p) {
             const int idx = idx0 + tid;
             const int lq = idx & 3, er = (idx >> 2) & 15, rest = idx >> 6;
             const int em = p.M == 1 ? 0 : (rest & 1), ti = p.M == 1 ? rest : (rest >> 1);
-            const int row = r0 + ti * TILE_ROWS + er;
+            const int row = r0 + ti * TILE_ROWS + tile_row(er);
             const bool ok = idx < total && row < r0 + nrows;
-            long long a = 0;
+            int a32 = 0;
             if (ok) {
                 const int* sl = acc + (ti * NW) * slot_ints + (em * 4 + lq) * ACC_CS + er;
-                int a32 = 0;
 #pragma unroll
                 for (int w = 0; w < NW; ++w) a32 += sl[w * slot_ints];
-                a = (long long)a32 << (8 * lq);
             }
-            a += __shfl_xor_sync(0xffffffffu, a, 1);
-            a += __shfl_xor_sync(0xffffffffu, a, 2);
-            if (a != 0x123456789abcll) stamp(15);
+            const int l1 = __shfl_down_sync(0xffffffffu, a32, 1), l2 = __shfl_down_sync(0xffffffffu, a32, 2),
+                      l3 = __shfl_down_sync(0xffffffffu, a32, 3);
+            const long long a = (long long)a32 + ((long long)l1 << 8) + ((long long)l2 << 16) + ((long long)l3 << 24);
             if (ok && lq == 0) {
                 float sc, zp;
                 if (idx0 == 0) { sc = pre_sc; zp = pre_zp; }
@@ -473,7 +488,7 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_res_kernel(const ResParams p) {
     for (int o = tid; o < outs; o += NTHR) {
         const int er = o & 15, rest = o >> 4;
         const int em = rest % p.M, ti = rest / p.M;
-        const int row = r0 + ti * TILE_ROWS + er;
+        const int row = r0 + ti * TILE_ROWS + tile_row(er);
         if (row >= r0 + nrows) continue;
         float sc, zp;
         if (o == tid) { sc = pre_sc; zp = pre_zp; }
@@ -501,7 +516,7 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_res_kernel(const ResParams p) {
 
 struct ResPlan {
     int grid, gpw, nt, ntiles;
-    int acc_off, img_off, tile_off, pitch, slots, slots_alias;
+    int acc_off, img_off, tile_off, slots, slots_alias;
     size_t smem;
 };
 
@@ -526,8 +541,7 @@ bool plan_res(int sm_count, int max_smem, int64_t M, int64_t N, int64_t K, ResPl
     const int slot_bytes = NW * ntiles * (M == 1 ? 4 : 8) * ACC_CS * 4;
     c->slots = nt == 1 && slot_bytes <= c->tile_off - c->acc_off;
     c->slots_alias = c->slots && slot_bytes > c->img_off - c->acc_off;
-    c->pitch = (int)(K / 2) + ((K / 2) % 128 == 0 ? 64 : 0);
-    c->smem = (size_t)c->tile_off + (size_t)ntiles * TILE_ROWS * c->pitch;
+    c->smem = (size_t)c->tile_off + (size_t)ntiles * (TILE_ROWS * (K / 2) + 128);
     return c->smem <= (size_t)max_smem;
 }
 
@@ -575,10 +589,10 @@ int launch_gemv_res(const DeviceInfo& dev, const void* x, int x_dtype, const uin
     p.M = (int)M; p.N = (int)N; p.K = (int)K;
     p.rows_q = (int)(N / c.grid); p.rows_rem = (int)(N % c.grid);
     p.G = (int)(K / GRAN_K);
-    p.acc_off = c.acc_off; p.img_off = c.img_off; p.tile_off = c.tile_off; p.pitch = c.pitch;
+    p.acc_off = c.acc_off; p.img_off = c.img_off; p.tile_off = c.tile_off;
     p.slots = c.slots; p.slots_alias = c.slots_alias;
     p.wait_weights = (flags & B200Q_FLAG_STATIC_WEIGHTS) ? 0 : 1;
-    p.early_tiles = tuning().gemv_early >= 0 ? tuning().gemv_early : 91;     // default: one tile up front, the rest behind the x loads (tools/tune_gemv.py sweep)
+    p.early_tiles = tuning().gemv_early >= 0 ? tuning().gemv_early : 92;     // default: two tiles up front, the rest behind the x loads (tools/tune_gemv.py sweep)
     p.pf_mode = tuning().gemv_pf;
     p.next_packed = next_packed;
     p.next_bytes = next_packed && (reinterpret_cast<uintptr_t>(next_packed) & 15) == 0 ? next_bytes : 0;

@@ -82,8 +82,8 @@ def main():
     for (K, N) in shapes:
         layers = make_pool(N, K, int(os.environ.get("POOL", "24")), dev)
         nbytes = lambda M: N * K // 2 + 8 * N + 4 * M * K + 4 * M * N
-        configs = [({"gemv_pf": pf, "gemv_early": e}, 1, True) for pf in (1, 0)
-                   for e in (1, 2, 3, 10, 20, 30, 90, 11, 12, 21, 22, 31, 91, 92, 93)]
+        configs = [({"gemv_pf": pf, "gemv_early": e}, 1, True) for pf in (1,)
+                   for e in (91, 92, 93, 94, 95, 2, 3, 30, 31, 21, 12, 22, 41, 32, 91)]
         for tune, M, graph in configs:
             for k in KEYS:
                 _lib.tune(k, -1)

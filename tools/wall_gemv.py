@@ -60,9 +60,9 @@ for i in range(len(w)):
 if int(os.environ.get("DBG", "8")) & 16:
     pb = np.zeros(256 * 16, dtype=np.int64)
     _lib.check(dbg_prof(pb.ctypes.data), "read prof")
-    t = pb.reshape(256, 16)[:148, :16]
+    t = pb.reshape(256, 16)[:148, :15]
     ref = w[-2, 3] if len(w) > 1 else t[:, 0].min()          # last CTA end of the previous launch
-    names = ["start", "bar-init", "issued", "pdl_wait", "amax", "-", "bf-loaded", "main-done", "red-bar", "epilogue", "tile0", "tile1", "tile2", "tile3", "tile4", "sum-done"]
+    names = ["start", "bar-init", "issued", "pdl_wait", "amax", "-", "bf-loaded", "main-done", "red-bar", "epilogue", "tile0", "tile1", "tile2", "tile3", "tile4"]
     print("last launch, ns relative to the LAST CTA end of the previous launch (min / median / max over CTAs)")
     for i, n in enumerate(names):
         if n == "-": continue
