@@ -101,7 +101,7 @@ int b200q_linear_fwd_next(const void* x, int x_dtype, const uint8_t* packed, con
     if (force != 1 && force != 3 && force != 4 && force != 5 && vec_ok && gemv_supported(M, N, K, x_dtype))
         return launch_gemv(d, x, x_dtype, packed, scales, zps, y, y_dtype, M, N, K, ws, ws_bytes, flags, st,
                            next_packed, next_bytes);
-    if (force != 1 && force != 2 && force != 4 && vec_ok && gemm_tc_supported(M, N, K, x_dtype, y_dtype))
+    if (force != 1 && force != 2 && force != 4 && force != 5 && vec_ok && gemm_tc_supported(M, N, K, x_dtype, y_dtype))
         return launch_gemm_tc(d, x, x_dtype, packed, scales, zps, y, y_dtype, M, N, K, nullptr, nullptr, 1, ws, ws_bytes, flags, st);
     if (force == 2 || force == 3 || force == 4 || force == 5) return set_error(B200Q_EINVAL, "linear_fwd: forced path %d does not support this shape / alignment", force);
     return launch_linear_generic(x, x_dtype, packed, scales, zps, y, y_dtype, M, N, K, nullptr, nullptr, 1, 0, st);

@@ -225,3 +225,79 @@ def test_forward_host_pinned(oracle, pkg):
         assert np.abs(ref - y.numpy()).max() < 1e-3
     with pytest.raises(RuntimeError):
         ql(torch.randn(2, 1024))                      # pageable host memory: no silent slow path
+
+
+# ---- decode kernels: resident-slab (gemv_res.cu, force_path 5) and ring (gemv.cu, force_path 2) ----------
+@pytest.mark.parametrize("M", [1, 2, 3, 5, 8])
+@pytest.mark.parametrize("N,K", [(1, 128), (7, 128), (9, 256), (16, 384), (200, 1024), (2371, 2048), (11008, 4096),
+                                 (3000, 6144)])
+def test_resident_slab_kernel_edge_shapes(oracle, pkg, M, N, K):
+    """Ragged row counts (last tile with <= 8 and > 8 rows, fewer tiles than SMs), every batch size of the decode
+    path, one to three granules per warp; both decode kernels against the float64 oracle and against each other."""
+    rng = np.random.default_rng(1000 * M + N + K)
+    packed = rng.integers(0, 256, size=(N, K // 2), dtype=np.uint8)
+    scales = (rng.random(N, dtype=np.float32) * 0.01 + 0.001).astype(np.float32)
+    zps = rng.integers(0, 16, size=N).astype(np.float32)
+    x = (rng.standard_normal((M, K)) * rng.choice([1e-3, 1.0, 300.0], size=(M, 1))).astype(np.float32)
+    P, S, Z, X = cuda(packed), cuda(scales), cuda(zps), cuda(x)
+    rows = np.arange(N) if N <= 512 else rng.choice(N, size=512, replace=False)
+    ref = oracle.reference_quantized_linear(x, packed[rows], scales[rows], zps[rows], acc=np.float64)
+    outs = {}
+    for path in (5, 2):
+        pkg._lib.tune("force_path", path)
+        try:
+            outs[path] = pkg._lib.linear_fwd(X, P, S, Z).cpu().numpy()
+        except RuntimeError:
+            # the resident-slab kernel keeps the B fragments of a warp in registers: (K / 2048) * ceil(M / 2) <= 8
+            assert path == 5 and -(-K // 2048) * (1 if M <= 2 else 2 if M <= 4 else 4) > 8
+            continue
+        finally:
+            pkg._lib.tune("force_path", -1)
+        for m in range(M):          # rows have very different magnitudes: the bar is per batch row
+            err = np.abs(ref[m] - outs[path][m, rows]).max()
+            assert err <= 1e-6 * np.abs(ref[m]).max() + 1e-30, f"path {path} row {m}: {err} vs |y|max {np.abs(ref[m]).max()}"
+    if 5 in outs:
+        # the two kernels quantise the odd columns of x on different grids: equal to ~1e-7, not bit-equal
+        for m in range(M):
+            assert np.abs(outs[5][m] - outs[2][m]).max() <= 1e-6 * np.abs(outs[2][m]).max() + 1e-30
+        # default dispatch picks the resident-slab kernel for these shapes: bit-identical with the forced run
+        assert np.array_equal(pkg._lib.linear_fwd(X, P, S, Z).cpu().numpy(), outs[5])
+
+
+def test_next_layer_hint_does_not_change_results(oracle, pkg):
+    """b200q_linear_fwd_next / QuantizedLinear.set_next: an L2 prefetch hint only."""
+    rng = np.random.default_rng(5)
+    N, K = 11008, 4096
+    layers = []
+    for i in range(3):
+        m = pkg.QuantizedLinear(K, N).cuda()
+        m.packed_weights = cuda(rng.integers(0, 256, size=(N, K // 2), dtype=np.uint8))
+        m.scales = cuda((rng.random(N, dtype=np.float32) * 0.01 + 0.001).astype(np.float32))
+        m.zero_points = cuda(rng.integers(0, 16, size=N).astype(np.float32))
+        layers.append(m)
+    x = cuda(rng.standard_normal((1, K), dtype=np.float32))
+    plain = [m(x).cpu().numpy() for m in layers]
+    plain = [m(x).cpu().numpy() for m in layers]            # second pass: static-weights fast path
+    for i, m in enumerate(layers):
+        m.set_next(layers[(i + 1) % 3])
+    hinted = [m(x).cpu().numpy() for m in layers]
+    for a, b in zip(plain, hinted):
+        assert np.array_equal(a, b)
+    # a hint that points at something unrelated (or misaligned) is harmless too
+    y = pkg._lib.linear_fwd(x, layers[0].packed_weights, layers[0].scales, layers[0].zero_points,
+                            next_packed=layers[1].packed_weights.view(-1)[1:4097])
+    assert np.array_equal(y.cpu().numpy(), plain[0])
+
+
+def test_decode_non_integer_zero_points(oracle, pkg):
+    """Zero points given by the caller (b200q_quantize_rows_given) need not be integers: the epilogue then takes its
+    fp64 branch."""
+    rng = np.random.default_rng(11)
+    N, K, M = 300, 1024, 2
+    packed = rng.integers(0, 256, size=(N, K // 2), dtype=np.uint8)
+    scales = (rng.random(N, dtype=np.float32) * 0.01 + 0.001).astype(np.float32)
+    zps = (rng.random(N, dtype=np.float32) * 15).astype(np.float32)
+    x = rng.standard_normal((M, K), dtype=np.float32)
+    ref = oracle.reference_quantized_linear(x, packed, scales, zps, acc=np.float64)
+    out = pkg._lib.linear_fwd(cuda(x), cuda(packed), cuda(scales), cuda(zps)).cpu().numpy()
+    assert np.abs(ref - out).max() <= 2e-5 * np.abs(ref).max()
