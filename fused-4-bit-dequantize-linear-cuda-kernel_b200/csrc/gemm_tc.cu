@@ -73,6 +73,13 @@ struct GemmParams {
     int n_tiles;             // ceil(N / BM)
     int stages;
     int stage_bytes;
+    // stream-K (plain linear with a badly quantised last wave): CTA c owns k-blocks [c*skq + min(c, skr), ...) of the
+    // linearised (tile, k-block) space; a tile cut between CTAs is finished by the CTA that holds its last k-block,
+    // the others publish their fp32 partial accumulator (workspace slot = CTA index) and raise a flag
+    int sk;                  // 0: whole tiles, round-robin
+    int skq, skr;
+    float* part;             // [grid][BN][BM] fp32
+    unsigned int* flags;     // [grid], zero between launches
 };
 
 struct TileInfo {
@@ -105,6 +112,53 @@ __device__ __forceinline__ bool locate(const GemmParams& p, int t, TileInfo& ti)
         rem -= tiles;
     }
     return false;
+}
+
+// One unit of work of a CTA: k-blocks [kb0, kb1) of tile ti.  publish: the tile's last k-block belongs to another
+// CTA, hand the partial accumulator over; nadd > 0: add the partials of CTAs [c0, c0 + nadd) before the epilogue.
+struct Item {
+    TileInfo ti;
+    int kb0, kb1, publish, nadd, c0;
+};
+
+__device__ __forceinline__ int sk_begin(const GemmParams& p, int c) { return c * p.skq + min(c, p.skr); }
+__device__ __forceinline__ int sk_owner(const GemmParams& p, int pos) {
+    const int big = p.skr * (p.skq + 1);
+    return pos < big ? pos / (p.skq + 1) : p.skr + (pos - big) / p.skq;
+}
+
+// calls body(item) for every work item of this CTA, in the same order in every warp role
+template <typename F>
+__device__ __forceinline__ void for_each_item(const GemmParams& p, int KB, int total_tiles, F&& body) {
+    Item it;
+    if (!p.sk) {
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            if (!locate(p, t, it.ti)) continue;
+            it.kb0 = 0; it.kb1 = KB; it.publish = 0; it.nadd = 0; it.c0 = 0;
+            body(it);
+        }
+        return;
+    }
+    const int beg = sk_begin(p, blockIdx.x), end = sk_begin(p, blockIdx.x + 1);
+    // publish first (the head of the LAST tile of the range), then everything else in order: a CTA never waits for
+    // a partial before it has handed out its own, so the flags cannot deadlock
+    const int last_t = (end - 1) / KB;
+    const bool last_cut = end > beg && end < (last_t + 1) * KB;
+    if (last_cut) {
+        locate(p, last_t, it.ti);
+        it.kb0 = max(beg, last_t * KB) - last_t * KB; it.kb1 = end - last_t * KB; it.publish = 1; it.nadd = 0; it.c0 = 0;
+        body(it);
+    }
+    const int stop = last_cut ? max(beg, last_t * KB) : end;
+    for (int pos = beg; pos < stop;) {
+        const int t = pos / KB;
+        locate(p, t, it.ti);
+        it.kb0 = pos - t * KB; it.kb1 = KB; it.publish = 0;
+        it.c0 = it.kb0 ? sk_owner(p, t * KB) : 0;
+        it.nadd = it.kb0 ? (int)blockIdx.x - it.c0 : 0;
+        body(it);
+        pos = (t + 1) * KB;
+    }
 }
 
 template <int PARTS, int BN>   // PARTS 1: fp16 activations (hi only); 2: hi + lo (fp32 activations)
@@ -160,15 +214,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = *tmem_ptr;
+    pdl_wait();       // barriers, TMEM and descriptors are set up: now wait for the activation preparation kernel
 
     if (warp == 0) {
         // =============================================================== TMA producer
         if (lane == 0) {
             int s = 0, ph = 0, it = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                TileInfo ti;
-                if (!locate(p, t, ti)) continue;
-                for (int kb = 0; kb < KB; ++kb, ++it) {
+            for_each_item(p, KB, total_tiles, [&](const Item& w) {
+                const TileInfo& ti = w.ti;
+                for (int kb = w.kb0; kb < w.kb1; ++kb, ++it) {
                     if (it >= S) mbar_wait(empty(s), ph ^ 1);
                     mbar_arrive_expect_tx(full(s), (uint32_t)(PARTS * X_TILE_BYTES + W_TILE_BYTES));
                     tma_load_2d(xh_smem(s), &map_xh, kb * BK, ti.m0, full(s));
@@ -176,23 +230,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
                     tma_load_2d(w_smem(s), &map_w, kb * (BK / 2), ti.e * p.N + ti.n0, full(s));
                     if (++s == S) { s = 0; ph ^= 1; }
                 }
-            }
+            });
         }
     } else if (warp == 1) {
         // =============================================================== MMA issuer
         if (lane == 0) {
             const uint32_t idesc = idesc_f16(BM, BN, 0);
             int s = 0, ph = 0, ait = 0, li = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                TileInfo ti;
-                if (!locate(p, t, ti)) continue;
+            for_each_item(p, KB, total_tiles, [&](const Item& w) {
                 const int ab = li % DBUF;
                 const uint32_t d_tmem = tmem + ab * BN;
                 if (li >= DBUF) {                               // the epilogue has drained this accumulator
                     mbar_wait(dempty(ab), ((li / DBUF) - 1) & 1);
                     tc_fence_after_sync();
                 }
-                for (int kb = 0; kb < KB; ++kb, ++ait) {
+                for (int kb = w.kb0; kb < w.kb1; ++kb, ++ait) {
                     const int a = ait % A_SLOTS;
                     mbar_wait(full(s), ph);
                     mbar_wait(afull(a), (ait / A_SLOTS) & 1);
@@ -201,7 +253,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
 #pragma unroll
                     for (int kk = 0; kk < BK / 16; ++kk) {
                         const uint64_t bh = smem_desc(xh_smem(s) + kk * 32, 16, 1024, SWIZZLE_128B);
-                        mma_ts_f16(d_tmem, a_tmem + 8 * kk, bh, idesc, (kb | kk) != 0 ? 1u : 0u);
+                        mma_ts_f16(d_tmem, a_tmem + 8 * kk, bh, idesc, (kb > w.kb0 || kk) ? 1u : 0u);
                         if (PARTS == 2) {
                             const uint64_t bl = smem_desc(xl_smem(s) + kk * 32, 16, 1024, SWIZZLE_128B);
                             mma_ts_f16(d_tmem, a_tmem + 8 * kk, bl, idesc, 1u);
@@ -213,7 +265,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
                 }
                 tc_commit(dfull(ab));
                 ++li;
-            }
+            });
         }
     } else if (warp >= 4 && warp < 12) {
         // =============================================================== dequant warps
@@ -223,10 +275,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
         const int q = warp & 3, grp = (warp - 4) >> 2;
         const int r = 32 * q + lane;                                // weight row of the tile = TMEM lane
         int s = 0, ph = 0, ait = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-            TileInfo ti;
-            if (!locate(p, t, ti)) continue;
-            for (int kb = 0; kb < KB; ++kb, ++ait) {
+        for_each_item(p, KB, total_tiles, [&](const Item& w) {
+            for (int kb = w.kb0; kb < w.kb1; ++kb, ++ait) {
                 if ((ait & 1) != grp) {                             // the other group's k-block
                     if (++s == S) { s = 0; ph ^= 1; }
                     continue;
@@ -264,15 +314,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
                 if (lane == 0) mbar_arrive(afull(a));
                 if (++s == S) { s = 0; ph ^= 1; }
             }
-        }
+        });
     } else if (warp >= 12) {
         // =============================================================== epilogue warps
         const int q = warp & 3;
         const int et = (warp - 12) * 32 + lane;                     // 0..127
         int li = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-            TileInfo ti;
-            if (!locate(p, t, ti)) continue;
+        for_each_item(p, KB, total_tiles, [&](const Item& w) {
+            const TileInfo& ti = w.ti;
+            const int ab = li % DBUF;
+            if (w.publish) {
+                // ---- stream-K: hand the raw partial accumulator to the CTA that finishes this tile
+                float* dst = p.part + (size_t)blockIdx.x * (BM * BN) + 32 * q + lane;
+                mbar_wait(dfull(ab), (li / DBUF) & 1);
+                tc_fence_after_sync();
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t d[32];
+                    tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + ab * BN + 32 * c, d);
+                    tmem_wait_ld();
+                    if (c == BN / 32 - 1) {
+                        tc_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(dempty(ab));
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) __stcg(dst + (32 * c + j) * BM, __uint_as_float(d[j]));
+                }
+                __threadfence();
+                named_bar_sync(1, 128);
+                if (et == 0) {
+                    __threadfence();
+                    atomicExch(p.flags + blockIdx.x, 1u);
+                }
+                ++li;
+                return;
+            }
             // per-token scalars of this tile (written after the previous tile's readers are done)
             named_bar_sync(1, 128);
             for (int j = et; j < BN; j += 128) {
@@ -280,12 +357,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
                 tok[j] = m < ti.mend ? __ldg(p.descale + m) : 0.0f;
                 tok[BN + j] = m < ti.mend ? __ldg(p.rowsum + m) : 0.0f;
             }
+            if (w.nadd > 0 && et < w.nadd) {
+                // ---- stream-K: wait (bounded) for the partials of the CTAs that hold the head of this tile
+                volatile unsigned int* f = p.flags + w.c0 + et;
+                for (unsigned spin = 0; *f == 0u && spin < (1u << 24); ++spin) __nanosleep(64);
+                __threadfence();
+            }
             named_bar_sync(1, 128);
             const int n = ti.n0 + 32 * q + lane;
             const bool n_ok = n < p.N;
             const float sc = n_ok ? __ldg(p.scales + (int64_t)ti.e * p.N + n) : 0.0f;
             const float zp = n_ok ? __ldg(p.zps + (int64_t)ti.e * p.N + n) : 0.0f;
-            const int ab = li % DBUF;
             mbar_wait(dfull(ab), (li / DBUF) & 1);
             tc_fence_after_sync();
 #pragma unroll 1
@@ -297,6 +379,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
                     tc_fence_before_sync();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(dempty(ab));
+                }
+                for (int a = 0; a < w.nadd; ++a) {                  // fixed order: deterministic
+                    const float* src = p.part + (size_t)(w.c0 + a) * (BM * BN) + 32 * q + lane;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) d[j] = __float_as_uint(__uint_as_float(d[j]) + __ldcg(src + (32 * c + j) * BM));
                 }
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
@@ -310,8 +397,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
                     }
                 }
             }
+            if (w.nadd > 0) {                                       // leave the flags zeroed for the next launch
+                named_bar_sync(1, 128);
+                if (et < w.nadd) p.flags[w.c0 + et] = 0u;
+            }
             ++li;
-        }
+        });
     }
 
     tc_fence_before_sync();
@@ -398,6 +489,82 @@ __global__ void __launch_bounds__(256) xprep_gemm_kernel(const XprepGemmParams p
     }
 }
 
+// Same preparation, 128 threads per token row (two rows per block), K <= NCH * 1024: every thread issues all its
+// loads up front and keeps the values in registers, so a row costs ONE trip to memory plus a block reduction
+// (the warp-per-row kernel above walks the row twice with one load in flight: 8 us for 256 rows).
+template <typename T, int NCH>
+__global__ void __launch_bounds__(256) xprep_gemm_rows_kernel(const XprepGemmParams p) {
+    __shared__ float s_am[2][4], s_sum[2][4];
+    pdl_launch_dependents();                        // the GEMM's CTAs may set themselves up meanwhile
+    const int rt = threadIdx.x & 127, rw = threadIdx.x >> 7, lane = threadIdx.x & 31, w4 = (threadIdx.x >> 5) & 3;
+    const int64_t m = (int64_t)blockIdx.x * 2 + rw;
+    const bool row_ok = m < p.R;
+    const T* xr = static_cast<const T*>(p.x) + (row_ok ? m : 0) * p.K;
+    float v[NCH][8];
+    float am = 0.0f, sum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+        const int k = i * 1024 + rt * 8;
+        if (row_ok && k < p.K) ld8<T>(xr + k, v[i]);
+        else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[i][j] = 0.0f;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NCH; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { am = fmaxf(am, fabsf(v[i][j])); sum += v[i][j]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, o));
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    }
+    if (lane == 0) { s_am[rw][w4] = am; s_sum[rw][w4] = sum; }
+    __syncthreads();
+    am = fmaxf(fmaxf(s_am[rw][0], s_am[rw][1]), fmaxf(s_am[rw][2], s_am[rw][3]));
+    sum = (s_sum[rw][0] + s_sum[rw][1]) + (s_sum[rw][2] + s_sum[rw][3]);
+    if (!row_ok) return;
+    int ex = 0;
+    if (am > 0.0f && am < INFINITY) ex = max(-100, min(100, 140 - (int)((__float_as_uint(am) >> 23) & 0xffu)));
+    const float up = __uint_as_float((uint32_t)(127 + ex) << 23), up_hi = up * 0.0625f;
+    if (rt == 0) {
+        p.descale[m] = __uint_as_float((uint32_t)(127 + 24 - ex) << 23);
+        p.rowsum[m] = sum;
+    }
+    __half* hr = p.xh + m * p.K;
+    __half* lr = p.xl ? p.xl + m * p.K : nullptr;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+        const int k = i * 1024 + rt * 8;
+        if (k >= p.K) continue;
+        // (k0,k4) (k1,k5) (k2,k6) (k3,k7): the order the A registers hold the nibbles in
+        const float s0 = v[i][0] * up, s4 = v[i][4] * up, s1 = v[i][1] * up_hi, s5 = v[i][5] * up_hi;
+        const float s2 = v[i][2] * up, s6 = v[i][6] * up, s3 = v[i][3] * up_hi, s7 = v[i][7] * up_hi;
+        __half2 h0 = __floats2half2_rn(s0, s4), h1 = __floats2half2_rn(s1, s5);
+        __half2 h2 = __floats2half2_rn(s2, s6), h3 = __floats2half2_rn(s3, s7);
+        *reinterpret_cast<uint4*>(hr + k) = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                                                       *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+        if (lr) {
+            const float2 f0 = __half22float2(h0), f1 = __half22float2(h1), f2 = __half22float2(h2), f3 = __half22float2(h3);
+            __half2 l0 = __floats2half2_rn(s0 - f0.x, s4 - f0.y), l1 = __floats2half2_rn(s1 - f1.x, s5 - f1.y);
+            __half2 l2 = __floats2half2_rn(s2 - f2.x, s6 - f2.y), l3 = __floats2half2_rn(s3 - f3.x, s7 - f3.y);
+            *reinterpret_cast<uint4*>(lr + k) = make_uint4(*reinterpret_cast<uint32_t*>(&l0), *reinterpret_cast<uint32_t*>(&l1),
+                                                           *reinterpret_cast<uint32_t*>(&l2), *reinterpret_cast<uint32_t*>(&l3));
+        }
+    }
+}
+
+template <typename T>
+int launch_xprep(const XprepGemmParams& xp, int64_t M, int64_t K, cudaStream_t st) {
+    const unsigned blocks2 = (unsigned)((M + 1) / 2);
+    if (K <= 4096) xprep_gemm_rows_kernel<T, 4><<<blocks2, 256, 0, st>>>(xp);
+    else if (K <= 8192) xprep_gemm_rows_kernel<T, 8><<<blocks2, 256, 0, st>>>(xp);
+    else if (K <= 16384) xprep_gemm_rows_kernel<T, 16><<<blocks2, 256, 0, st>>>(xp);
+    else xprep_gemm_kernel<T><<<(unsigned)((M + 7) / 8), 256, 0, st>>>(xp);
+    return check_cuda(cudaGetLastError(), "xprep launch");
+}
+
 // ---------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -442,9 +609,12 @@ bool gemm_tc_supported(int64_t M, int64_t N, int64_t K, int x_dtype, int y_dtype
 // workspace: [4 KB reserved: the decode kernels keep their zeroed ticket counters there -- callers
 // share one workspace between all paths][xh R*K fp16][xl R*K fp16][descale R f32][rowsum R f32]
 constexpr size_t WS_RESERVED = 4096;
+// stream-K partial accumulators: one [256][128] fp32 slot per CTA (the flags live in the reserved 4 KB)
+constexpr int SK_MAX_CTAS = 160;
+constexpr size_t SK_PART_BYTES = (size_t)SK_MAX_CTAS * 256 * BM * 4;
 size_t gemm_tc_ws_bytes(int64_t M, int64_t N, int64_t K) {
     if (!gemm_tc_supported(M, N, K, B200Q_F32, B200Q_F32)) return 0;
-    return WS_RESERVED + 2 * align_up((size_t)M * K * 2, 1024) + 2 * align_up((size_t)M * 4, 1024) + 1024;
+    return WS_RESERVED + 2 * align_up((size_t)M * K * 2, 1024) + 2 * align_up((size_t)M * 4, 1024) + 1024 + SK_PART_BYTES;
 }
 
 int launch_gemm_tc(const DeviceInfo& dev, const void* x, int x_dtype, const uint8_t* packed,
@@ -465,11 +635,9 @@ int launch_gemm_tc(const DeviceInfo& dev, const void* x, int x_dtype, const uint
     const int parts = x_dtype == B200Q_F32 ? 2 : 1;
 
     XprepGemmParams xp{x, xh, parts == 2 ? xl : nullptr, descale, rowsum, x_dtype, (int)M, (int)K};
-    const unsigned xblocks = (unsigned)((M + 7) / 8);
-    if (x_dtype == B200Q_F32) xprep_gemm_kernel<float><<<xblocks, 256, 0, st>>>(xp);
-    else if (x_dtype == B200Q_F16) xprep_gemm_kernel<__half><<<xblocks, 256, 0, st>>>(xp);
-    else xprep_gemm_kernel<__nv_bfloat16><<<xblocks, 256, 0, st>>>(xp);
-    B200Q_CUDA(cudaGetLastError());
+    if (x_dtype == B200Q_F32) { if (int rc = launch_xprep<float>(xp, M, K, st)) return rc; }
+    else if (x_dtype == B200Q_F16) { if (int rc = launch_xprep<__half>(xp, M, K, st)) return rc; }
+    else { if (int rc = launch_xprep<__nv_bfloat16>(xp, M, K, st)) return rc; }
 
     CUtensorMap map_xh, map_xl, map_w;
     // token-tile height: fewest (waves x time per wave).  Measured per-wave time (tools/sweep_gemm_bn.py):
@@ -490,6 +658,22 @@ int launch_gemm_tc(const DeviceInfo& dev, const void* x, int x_dtype, const uint
         }
         if (tuning().gemm_bn == 128 || tuning().gemm_bn == 192 || tuning().gemm_bn == 256) bn = tuning().gemm_bn;
     }
+    // stream-K instead of whole tiles when the only wave is less than half full (plain linear): 256-token tiles,
+    // the k-blocks of all tiles dealt out evenly over the SMs.  Measured (tools/run_gemm_sk.py, bench_gemm.py):
+    // 11008 -> 4096 (32 weight-row tiles) M = 256 +28 %, M = 512 +17 %; with fuller waves the two extra
+    // un-overlapped accumulator drains per CTA cost more than the balance gains (4096 -> 11008 M = 512: -37 %).
+    int sk = 0, skq = 0, skr = 0, sk_grid = 0;
+    if (!starts && tuning().gemm_sk != 0) {
+        const long long tiles256 = ((M + 255) / 256) * n_tiles_h;
+        const long long waves = (tiles256 + dev.sm_count - 1) / dev.sm_count;
+        const double fill = (double)tiles256 / (double)(waves * dev.sm_count);
+        const long long total_kb = tiles256 * (K / BK);
+        const int g = dev.sm_count < SK_MAX_CTAS ? dev.sm_count : SK_MAX_CTAS;
+        if ((tuning().gemm_sk > 0 || (fill < 0.5 && waves == 1)) && total_kb / g >= 8 && tiles256 <= 100000) {
+            sk = 1; bn = 256; sk_grid = g;
+            skq = (int)(total_kb / g); skr = (int)(total_kb % g);
+        }
+    }
     if (int rc = make_map_2d(&map_xh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, xh, (uint64_t)K, (uint64_t)M, BK, bn, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
     if (int rc = make_map_2d(&map_xl, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, parts == 2 ? xl : xh, (uint64_t)K, (uint64_t)M, BK, bn, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
     const int groups = starts ? E : 1;
@@ -507,6 +691,9 @@ int launch_gemm_tc(const DeviceInfo& dev, const void* x, int x_dtype, const uint
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (stages < 2) return set_error(B200Q_EINVAL, "gemm_tc: not enough shared memory");
     p.stages = stages;
+    p.sk = sk; p.skq = skq; p.skr = skr;
+    p.part = reinterpret_cast<float*>(w8 + 2 * xbytes + 2 * sbytes);
+    p.flags = reinterpret_cast<unsigned int*>(ws);
     const size_t smem = (size_t)OFF_STAGES + (size_t)stages * p.stage_bytes;
     typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmParams);
     const int bi = bn == 128 ? 0 : (bn == 192 ? 1 : 2);
@@ -524,8 +711,18 @@ int launch_gemm_tc(const DeviceInfo& dev, const void* x, int x_dtype, const uint
     int grid = dev.sm_count;
     if (total_tiles < grid) grid = (int)total_tiles;
     if (grid < 1) grid = 1;
-    kfn<<<grid, GEMM_THREADS, smem, st>>>(map_xh, map_xl, map_w, p);
-    return check_cuda(cudaGetLastError(), "gemm_tc launch");
+    if (sk) grid = sk_grid;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attrs[1];
+    attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attrs;
+    cfg.numAttrs = 1;
+    return check_cuda(cudaLaunchKernelEx(&cfg, kfn, map_xh, map_xl, map_w, p), "gemm_tc launch");
 }
 
 }  // namespace b200q

@@ -10,6 +10,7 @@ p = torch.randint(0, 256, (N, K // 2), device=dev, dtype=torch.uint8)
 s = torch.rand(N, device=dev) * 0.01 + 0.001
 z = torch.randint(0, 16, (N,), device=dev).float()
 x = torch.randn(M, K, device=dev).to(torch.bfloat16)
+if os.environ.get("SK"): pkg._lib.tune("gemm_sk", int(os.environ["SK"]))
 for _ in range(4):
     y = pkg._lib.linear_fwd(x, p, s, z)
 torch.cuda.synchronize()
