@@ -313,9 +313,10 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) gemv_kernel(const Ge
 #pragma unroll
                 for (int w = 0; w < NW; ++w) amx = fmaxf(amx, s_amax[em * NW + w]);
                 int ex = 0;
-                if (amx > 0.0f && amx < INFINITY) ex = max(-96, min(126, 156 - (int)(__float_as_uint(amx) >> 23)));
+                if (amx > 0.0f && amx < INFINITY) ex = max(-96, min(126, 155 - (int)(__float_as_uint(amx) >> 23)));
                 const float up = __uint_as_float((uint32_t)(127 + ex) << 23);
                 int slo = 0, shi = 0;                              // sum of X as (X & 0xffff), (X >> 16): exact in s32
+                const float up16 = up * 0.0625f;
 #pragma unroll
                 for (int q = 0; q < GPW; ++q) {
                     if (warp + q * NW < ng) {                      // warp-uniform
@@ -327,14 +328,19 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) gemv_kernel(const Ge
                             load4f(p.x, p.x_dtype, base + 4, b);
                             uint32_t D[8];
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const int X0 = __float2int_rn(a[i] * up), X1 = __float2int_rn(b[i] * up);
-                                slo += (X0 & 0xffff) + (X1 & 0xffff);
-                                shi += (X0 >> 16) + (X1 >> 16);
-                                D[i] = (uint32_t)(X0 + 0x00808080) ^ 0x00808080u;      // byte l = signed base-256 digit l
-                                D[4 + i] = (uint32_t)(X1 + 0x00808080) ^ 0x00808080u;
+                            for (int i = 0; i < 2; ++i) {
+                                // even column: Xe = round(x 2^e); odd column: Xo = round(x 2^(e-4)), carried as
+                                // Z = Xo - Xe: the raw packed byte q_lo + 16 q_hi meets Xe, the masked byte 16 q_hi meets Z
+                                const int Xe0 = __float2int_rn(a[2 * i] * up), Xo0 = __float2int_rn(a[2 * i + 1] * up16);
+                                const int Xe1 = __float2int_rn(b[2 * i] * up), Xo1 = __float2int_rn(b[2 * i + 1] * up16);
+                                slo += (Xe0 & 0xffff) + ((Xo0 << 4) & 0xffff) + (Xe1 & 0xffff) + ((Xo1 << 4) & 0xffff);
+                                shi += (Xe0 >> 16) + ((Xo0 << 4) >> 16) + (Xe1 >> 16) + ((Xo1 << 4) >> 16);
+                                D[2 * i] = (uint32_t)(Xe0 + 0x00808080) ^ 0x00808080u;      // byte l = signed base-256 digit l
+                                D[2 * i + 1] = (uint32_t)(Xo0 - Xe0 + 0x00808080) ^ 0x00808080u;
+                                D[4 + 2 * i] = (uint32_t)(Xe1 + 0x00808080) ^ 0x00808080u;
+                                D[5 + 2 * i] = (uint32_t)(Xo1 - Xe1 + 0x00808080) ^ 0x00808080u;
                             }
-                            // 4x4 byte transposes: digit l of the even values -> b0 (meets the low nibbles), odd -> b1
+                            // 4x4 byte transposes: digit l of the four Xe -> b0 (meets the raw bytes), of the four Z -> b1
                             const uint32_t e0 = __byte_perm(D[0], D[2], 0x5140), e1 = __byte_perm(D[4], D[6], 0x5140);
                             const uint32_t e2 = __byte_perm(D[0], D[2], 0x7362), e3 = __byte_perm(D[4], D[6], 0x7362);
                             const uint32_t o0 = __byte_perm(D[1], D[3], 0x5140), o1 = __byte_perm(D[5], D[7], 0x5140);
@@ -431,13 +437,12 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) gemv_kernel(const Ge
                 const uint32_t wh[4] = {hi[q].x, hi[q].y, hi[q].z, hi[q].w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const uint32_t a0 = wl[j] & 0x0f0f0f0fu, a2 = (wl[j] >> 4) & 0x0f0f0f0fu;   // row g
-                    const uint32_t a1 = wh[j] & 0x0f0f0f0fu, a3 = (wh[j] >> 4) & 0x0f0f0f0fu;   // row g + 8
+                    // no nibble widening (see gemv_res.cu): (q_lo + 16 q_hi) Xe + 16 q_hi (Xo - Xe) = q_lo Xe + q_hi 16 Xo
+                    const uint32_t a0 = wl[j], a2 = wl[j] & 0xf0f0f0f0u;   // row g
+                    const uint32_t a1 = wh[j], a3 = wh[j] & 0xf0f0f0f0u;   // row g + 8
 #pragma unroll
-                    for (int nt = 0; nt < NT; ++nt) {
-                        if (p.debug & 4) { acc[nt][(q * 4 + j) % CH][0] += (int)(a0 ^ a1 ^ a2 ^ a3 ^ bf[q][nt][j][0] ^ bf[q][nt][j][1]); continue; }
+                    for (int nt = 0; nt < NT; ++nt)
                         mma_m16n8k32_u8s8(acc[nt][(q * 4 + j) % CH], a0, a1, a2, a3, bf[q][nt][j][0], bf[q][nt][j][1]);
-                    }
                 }
             }
             __syncwarp();
@@ -468,8 +473,8 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) gemv_kernel(const Ge
                         const uint32_t wh[4] = {hi.x, hi.y, hi.z, hi.w};
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const uint32_t a0 = wl[j] & 0x0f0f0f0fu, a2 = (wl[j] >> 4) & 0x0f0f0f0fu;
-                            const uint32_t a1 = wh[j] & 0x0f0f0f0fu, a3 = (wh[j] >> 4) & 0x0f0f0f0fu;
+                            const uint32_t a0 = wl[j], a2 = wl[j] & 0xf0f0f0f0u;
+                            const uint32_t a1 = wh[j], a3 = wh[j] & 0xf0f0f0f0u;
 #pragma unroll
                             for (int nt = 0; nt < NT; ++nt)
                                 mma_m16n8k32_u8s8(acc[nt][j % CH], a0, a1, a2, a3, bf[q][nt][j][0], bf[q][nt][j][1]);
@@ -644,7 +649,7 @@ __global__ void __launch_bounds__(XP_THREADS) xprep_kernel(const XprepParams p) 
 #pragma unroll
     for (int w = 0; w < XP_THREADS / 32; ++w) am = fmaxf(am, s_amax[w]);
     int ex = 0;
-    if (am > 0.0f && am < INFINITY) ex = max(-96, min(126, 156 - (int)(__float_as_uint(am) >> 23)));
+    if (am > 0.0f && am < INFINITY) ex = max(-96, min(126, 155 - (int)(__float_as_uint(am) >> 23)));
     const float up = __uint_as_float((uint32_t)(127 + ex) << 23);
     for (int it0 = 0; it0 < items; it0 += XP_THREADS) {            // items is a multiple of 16, not of 32:
         const int it = it0 + threadIdx.x;                          // all lanes take part in the shuffles
@@ -662,11 +667,12 @@ __global__ void __launch_bounds__(XP_THREADS) xprep_kernel(const XprepParams p) 
         uint32_t D[8];
         int slo = 0, shi = 0;                            // sum of X as (X & 0xffff) and (X >> 16): exact in s32
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int X = __float2int_rn(v[i] * up);
-            slo += X & 0xffff;
-            shi += X >> 16;
-            D[i] = (uint32_t)(X + 0x00808080) ^ 0x00808080u;       // byte l = signed base-256 digit l
+        for (int i = 0; i < 4; ++i) {
+            const int Xe = __float2int_rn(v[2 * i] * up), Xo = __float2int_rn(v[2 * i + 1] * (up * 0.0625f));
+            slo += (Xe & 0xffff) + ((Xo << 4) & 0xffff);
+            shi += (Xe >> 16) + ((Xo << 4) >> 16);
+            D[2 * i] = (uint32_t)(Xe + 0x00808080) ^ 0x00808080u;       // byte l = signed base-256 digit l
+            D[2 * i + 1] = (uint32_t)(Xo - Xe + 0x00808080) ^ 0x00808080u;
         }
         // 4x4 byte transposes: digit l of the even values -> lo[l], of the odd values -> hi[l]
         const uint32_t e0 = __byte_perm(D[0], D[2], 0x5140), e1 = __byte_perm(D[4], D[6], 0x5140);

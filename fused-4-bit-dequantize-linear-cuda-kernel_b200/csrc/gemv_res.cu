@@ -54,7 +54,10 @@ struct ResParams {
     int x_dtype, y_dtype;
     int M, N, K;
     int rows_q, rows_rem;            // CTA b owns rows_q (+1 if b < rows_rem) rows
-    int G;                           // K / 128
+    int nslab;                       // CTAs of one cluster that split K (1: no cluster)
+    int gran_q, gran_rem;            // K / 128 granules dealt out over the slabs: slab s has gran_q (+1 if s < gran_rem)
+    int pitch;                       // nslab > 1: bytes between the rows of a tile in shared memory (= 64 mod 128)
+    int xbuf_off, outs_cap;          // nslab > 1: exchange buffer [nslab][outs_cap] s64 + [nslab][8][2] s32 in the leader
     int acc_off, img_off, tile_off;  // byte offsets in dynamic shared memory
     int wait_weights;                // 1: weights may be written by the preceding kernel
     int early_tiles;                 // tiles requested before griddepcontrol.wait
@@ -104,6 +107,10 @@ __device__ __forceinline__ void imma(int (&c)[4], uint32_t a0, uint32_t a1, uint
         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
+__device__ __forceinline__ void st_cluster_b64(uint32_t cluster_addr, long long v) {
+    asm volatile("st.shared::cluster.b64 [%0], %1;" ::"r"(cluster_addr), "l"(v) : "memory");
+}
+
 __device__ __forceinline__ void red_add_s32(uint32_t addr, int v) {
     asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
@@ -117,7 +124,7 @@ __device__ __forceinline__ void red_add_s32(uint32_t addr, int v) {
 //   [tile_off, ..)  tiles: ntiles x 16 rows x K/2 bytes
 constexpr int OFF_AMAX = 256, OFF_EX = 800, OFF_TXS = 832, OFF_TX = 1280, OFF_END = 2304;
 
-template <int GPW, int NT>
+template <int GPW, int NT, bool SPLIT>   // SPLIT: K cut over the CTAs of a cluster (compile-time, so that the common case pays nothing)
 __global__ void __launch_bounds__(NTHR, 1) gemv_res_kernel(const ResParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
@@ -135,7 +142,13 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_res_kernel(const ResParams p) {
     unsigned long long wall0 = 0;
     if (prof) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(wall0));
 
-    const int b = blockIdx.x;
+    // K split: the nslab CTAs of a cluster own consecutive granule ranges of the same rows; their exact integer
+    // partials meet in the leader's shared memory (DSMEM), so the result is still rounded once
+    const int nslab = SPLIT ? p.nslab : 1;
+    const int slab = SPLIT ? (int)(blockIdx.x % nslab) : 0;
+    const int b = SPLIT ? (int)(blockIdx.x / nslab) : (int)blockIdx.x;
+    const int g0 = slab * p.gran_q + min(slab, p.gran_rem);
+    const int G = p.gran_q + (slab < p.gran_rem ? 1 : 0);
     const int r0 = b * p.rows_q + min(b, p.rows_rem);
     const int nrows = p.rows_q + (b < p.rows_rem ? 1 : 0);
     const int ntiles = (nrows + TILE_ROWS - 1) / TILE_ROWS;
@@ -144,7 +157,8 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_res_kernel(const ResParams p) {
     // a warp fetches four rows of each half (mma row g <-> tile row perm(g), below): with row_bytes a multiple of
     // 128 the two halves then sit in complementary 64-byte windows and the 8 rows x 64 B touch every bank exactly
     // four times (no conflicts) -- without one copy per padded row.
-    const uint32_t tile_bytes = (uint32_t)(TILE_ROWS * row_bytes + 128);
+    // With a K split a row's slab is not contiguous with the next row's: one copy per row, rows p.pitch apart.
+    const uint32_t tile_bytes = SPLIT ? (uint32_t)(TILE_ROWS * p.pitch) : (uint32_t)(TILE_ROWS * row_bytes + 128);
     const uint32_t half_off = (uint32_t)(8 * row_bytes + 64);
     float* s_amax = reinterpret_cast<float*>(smem + OFF_AMAX);
     int* s_ex = reinterpret_cast<int*>(smem + OFF_EX);
@@ -166,7 +180,7 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_res_kernel(const ResParams p) {
     stamp(1);
 
     // mma row (0..15) -> row of the tile, see the tile layout above
-    auto tile_row = [](int er) { return ((er & 1) << 3) + ((er & 8) >> 1) + ((er & 7) >> 1); };
+    auto tile_row = [&](int er) { return SPLIT ? er : ((er & 1) << 3) + ((er & 8) >> 1) + ((er & 7) >> 1); };
     const bool skip_loads = (p.debug & 2) != 0;
     // the two copies of tile i are issued by lane 0 of warps 2i and 2i + 1 (mod 16); the first also arms the tile's
     // barrier with the byte count of both (complete_tx may run ahead of expect_tx: the phase cannot complete before
@@ -176,7 +190,11 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_res_kernel(const ResParams p) {
         const int rows = min(TILE_ROWS, nrows - i * TILE_ROWS);
         const uint32_t bar = sbase + 8u * i, dst = sbase + p.tile_off + i * tile_bytes;
         const uint8_t* src = p.packed + (int64_t)(r0 + i * TILE_ROWS) * row_bytes;
-        if (warp == ((2 * i) & (NW - 1))) {
+        if (SPLIT) {                                          // row `warp` of the tile: this slab's bytes of it
+            if (warp == 0) mbar_arrive_expect_tx(bar, (uint32_t)(rows * G * GRAN_B));
+            if (warp < rows)
+                bulk_g2s_hint(dst + warp * p.pitch, src + (int64_t)warp * row_bytes + g0 * GRAN_B, (uint32_t)(G * GRAN_B), bar, pol);
+        } else if (warp == ((2 * i) & (NW - 1))) {
             mbar_arrive_expect_tx(bar, (uint32_t)(rows * row_bytes));
             bulk_g2s_hint(dst, src, (uint32_t)(min(rows, 8) * row_bytes), bar, pol);
         } else if (warp == ((2 * i + 1) & (NW - 1)) && rows > 8) {
@@ -217,7 +235,7 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_res_kernel(const ResParams p) {
     // ---- pass 1: amax of every batch row (coalesced 32-byte loads, all threads).  With one n-tile and at most
     // two items (8 activations each) per thread, the values stay in registers for pass 2.
     const int K8 = p.K >> 3;
-    const bool keep = NT == 1 && p.M * K8 <= 2 * NTHR;
+    const bool keep = NT == 1 && !SPLIT && p.M * K8 <= 2 * NTHR;
     float xv[2][8];
     if (keep) {
         float am0 = 0.0f, am1 = 0.0f;
@@ -275,7 +293,6 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_res_kernel(const ResParams p) {
     // ---- pass 2: x image of one n-tile at a time, then every lane pulls its B fragments
     // lane (g, t) holds mma column g = 4h + l: limb l of batch row 2*nt + h
     const int l = g & 3, h = g >> 2;
-    const int G = p.G;
     uint32_t bf[GPW][NT][4][2];
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
@@ -323,7 +340,7 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_res_kernel(const ResParams p) {
             for (int it = tid; it < items; it += NTHR) {
                 const int hh = it >= G * 16 ? 1 : 0;
                 float v[8];
-                load8f(p.x, p.x_dtype, (int64_t)(2 * nt + hh) * p.K + (it - hh * G * 16) * 8, v);
+                load8f(p.x, p.x_dtype, (int64_t)(2 * nt + hh) * p.K + (int64_t)(g0 * 16 + it - hh * G * 16) * 8, v);
                 convert(it, v);
             }
         }
@@ -375,7 +392,9 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_res_kernel(const ResParams p) {
     // ---- main loop: one 16-row tile per iteration, this warp's granules warp, warp + 16, ...
     // mma rows g (a0 / a2) and g + 8 (a1 / a3) of this lane <-> tile rows perm(g) and perm(g) + 4:
     // even g -> first half, row g / 2; odd g -> second half, row 8 + g / 2
-    const uint32_t lane_off = (uint32_t)((g & 1) * half_off + (g >> 1) * row_bytes + warp * GRAN_B + t * 16);
+    const uint32_t lane_off = SPLIT ? (uint32_t)(g * p.pitch + warp * GRAN_B + t * 16)
+                                        : (uint32_t)((g & 1) * half_off + (g >> 1) * row_bytes + warp * GRAN_B + t * 16);
+    const uint32_t hi_off = SPLIT ? (uint32_t)(8 * p.pitch) : (uint32_t)(4 * row_bytes);
     const uint32_t acc_lane = sbase + p.acc_off + (uint32_t)(((warp % R) * rep_ints + 2 * t * ACC_CS + g) * 4);
     const bool cols_live = p.M > 1 || t < 2;                   // M == 1: mma columns 4..7 are empty
     const int slot_ints = (p.M == 1 ? 4 : 8) * ACC_CS;         // slots mode: ints per (tile, warp)
@@ -397,7 +416,7 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_res_kernel(const ResParams p) {
             hi[q] = lo[q];
             if (warp + q * NW < G) {
                 lo[q] = lds128(tb + q * NW * GRAN_B);
-                hi[q] = lds128(tb + q * NW * GRAN_B + 4 * row_bytes);
+                hi[q] = lds128(tb + q * NW * GRAN_B + hi_off);
             }
         }
 #pragma unroll
@@ -457,6 +476,11 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_res_kernel(const ResParams p) {
         }
         store_out(p.y, p.y_dtype, (int64_t)em * p.N + row, v);
     };
+    // with a K split the exact s64 partial of output o goes to slot [slab][o] of the leader's exchange buffer
+    auto emit = [&](long long a, int o, int em, int row, float sc, float zp) {
+        if (!SPLIT) finish(a, em, row, sc, zp);
+        else st_cluster_b64(mapa(sbase + p.xbuf_off + (uint32_t)((slab * p.outs_cap + o) * 8), 0), a);
+    };
     if (NT == 1 && p.slots) {
         // four threads per output (one per limb) add the 16 warp slots; the quad combines through shuffles
         const int total = outs * 4;
@@ -479,7 +503,7 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_res_kernel(const ResParams p) {
                 float sc, zp;
                 if (idx0 == 0) { sc = pre_sc; zp = pre_zp; }
                 else { sc = __ldg(p.scales + row); zp = __ldg(p.zps + row); }
-                finish(a, em, row, sc, zp);
+                emit(a, (ti * p.M + em) * TILE_ROWS + er, em, row, sc, zp);
             }
         }
     } else
@@ -500,7 +524,35 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_res_kernel(const ResParams p) {
             l0 += a4[r * rep_ints]; l1 += a4[r * rep_ints + ACC_CS]; l2 += a4[r * rep_ints + 2 * ACC_CS]; l3 += a4[r * rep_ints + 3 * ACC_CS];
         }
         const long long a = (long long)l0 + ((long long)l1 << 8) + ((long long)l2 << 16) + ((long long)l3 << 24);
-        finish(a, em, row, sc, zp);
+        emit(a, o, em, row, sc, zp);
+    }
+    if (SPLIT) {
+        // ---- K split: sum_k X of every slab and the partials above meet in the leader, which finishes the rows
+        const uint32_t xtx = sbase + p.xbuf_off + (uint32_t)(nslab * p.outs_cap * 8);
+        if (tid < p.M)
+            st_cluster_b64(mapa(xtx + (uint32_t)((slab * 8 + tid) * 8), 0),
+                           (long long)s_txs[tid * 2] + ((long long)s_txs[tid * 2 + 1] << 16));
+        cluster_sync_all();
+        if (slab == 0) {
+            const long long* xb = reinterpret_cast<const long long*>(smem + p.xbuf_off);
+            const long long* xt = xb + nslab * p.outs_cap;
+            if (tid < p.M) {
+                long long tsum = 0;
+                for (int sl = 0; sl < nslab; ++sl) tsum += xt[sl * 8 + tid];
+                s_txs[tid * 2] = (int)(tsum & 0xffff);
+                s_txs[tid * 2 + 1] = (int)(tsum >> 16);
+            }
+            named_bar_sync(1, NTHR);
+            for (int o = tid; o < outs; o += NTHR) {
+                const int er = o & 15, rest = o >> 4;
+                const int em = rest % p.M, ti = rest / p.M;
+                const int row = r0 + ti * TILE_ROWS + tile_row(er);
+                if (row >= r0 + nrows) continue;
+                long long a = 0;
+                for (int sl = 0; sl < nslab; ++sl) a += xb[sl * p.outs_cap + o];
+                finish(a, em, row, __ldg(p.scales + row), __ldg(p.zps + row));
+            }
+        }
     }
     stamp(9);
     if (prof) {
@@ -517,37 +569,62 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_res_kernel(const ResParams p) {
 struct ResPlan {
     int grid, gpw, nt, ntiles;
     int acc_off, img_off, tile_off, slots, slots_alias;
+    int nslab, nrb, pitch, xbuf_off, outs_cap;
     size_t smem;
 };
 
-bool plan_res(int sm_count, int max_smem, int64_t M, int64_t N, int64_t K, ResPlan* c) {
-    if (M < 1 || M > 8 || K <= 0 || K % GRAN_K != 0 || N < 1 || N > 0x7fffffff) return false;
+// one candidate: K cut into nslab slabs (cluster of nslab CTAs), the SMs dealt out over the row blocks
+bool plan_res_slabs(int sm_count, int max_smem, int64_t M, int64_t N, int64_t K, int nslab, ResPlan* c) {
     const int G = (int)(K / GRAN_K);
-    if (G > 3 * NW) return false;                                   // GPW <= 3
-    int grid = sm_count;
-    const int min_grid = (int)((N + TILE_ROWS * MAX_TILES - 1) / (TILE_ROWS * MAX_TILES));
-    if (grid > (N + TILE_ROWS - 1) / TILE_ROWS) grid = (int)((N + TILE_ROWS - 1) / TILE_ROWS);   // >= one tile per CTA
-    if (grid < min_grid) return false;
-    const int rows = (int)((N + grid - 1) / grid);
+    const int Gmax = (G + nslab - 1) / nslab;                      // granules of the largest slab
+    if (Gmax > 3 * NW || nslab > G) return false;                   // GPW <= 3
+    int nrb = sm_count / nslab;
+    if (nrb < 1) return false;
+    const int min_rb = (int)((N + TILE_ROWS * MAX_TILES - 1) / (TILE_ROWS * MAX_TILES));
+    if (nrb > (N + TILE_ROWS - 1) / TILE_ROWS) nrb = (int)((N + TILE_ROWS - 1) / TILE_ROWS);   // >= one tile per CTA
+    if (nrb < min_rb) return false;
+    const int rows = (int)((N + nrb - 1) / nrb);
     const int ntiles = (rows + TILE_ROWS - 1) / TILE_ROWS;
     if (ntiles > MAX_TILES) return false;
     const int nt = M <= 2 ? 1 : (M <= 4 ? 2 : 4);
-    c->grid = grid; c->gpw = (G + NW - 1) / NW; c->nt = nt; c->ntiles = ntiles;
+    c->nslab = nslab; c->nrb = nrb; c->grid = nrb * nslab; c->gpw = (Gmax + NW - 1) / NW; c->nt = nt; c->ntiles = ntiles;
     if (c->gpw * nt > 8) return false;                              // B fragments must stay in registers
-    c->acc_off = OFF_END;
-    c->img_off = (c->acc_off + ACC_REPS_X_NT * ntiles * ACC_PLANE * 4 + 127) / 128 * 128;
-    c->tile_off = (c->img_off + 2 * G * 512 + 127) / 128 * 128;    // image: 2 rows x G granules x 4 limbs x 16 x 8 B
-    // M <= 2: per-warp partial slots live in the acc region and, for M == 2, on into the x image (dead by then)
+    c->pitch = ((Gmax * GRAN_B + 63) / 128) * 128 + 64;             // >= the slab's bytes of a row, = 64 mod 128
+    const int tiles_bytes = nslab > 1 ? ntiles * TILE_ROWS * c->pitch : ntiles * (TILE_ROWS * (int)(K / 2) + 128);
+    const int img_rows = M == 1 ? 1 : 2;
+    const int img_bytes = img_rows * Gmax * 512;                    // rows x granules x 4 limbs x 16 (t, word) x 8 B
+    const int acc_bytes = ACC_REPS_X_NT * ntiles * ACC_PLANE * 4;
     const int slot_bytes = NW * ntiles * (M == 1 ? 4 : 8) * ACC_CS * 4;
-    c->slots = nt == 1 && slot_bytes <= c->tile_off - c->acc_off;
-    c->slots_alias = c->slots && slot_bytes > c->img_off - c->acc_off;
-    c->smem = (size_t)c->tile_off + (size_t)ntiles * (TILE_ROWS * (K / 2) + 128);
-    return c->smem <= (size_t)max_smem;
+    c->outs_cap = ntiles * TILE_ROWS * (int)M;
+    const int xbuf_bytes = nslab > 1 ? nslab * (c->outs_cap * 8 + 64) : 0;
+    c->acc_off = OFF_END;
+    // layouts, roomiest first: (1) acc / slots, then the image; (2) M <= 2: the slots run on into the image (dead by
+    // then, one extra barrier); (3) M <= 2: slots and image share one region
+    for (int layout = 1; layout <= 3; ++layout) {
+        if (layout > 1 && nt != 1) break;
+        int region;
+        if (layout == 1) { c->img_off = (c->acc_off + (nt == 1 ? slot_bytes : acc_bytes) + 127) / 128 * 128; region = c->img_off + img_bytes; c->slots = nt == 1; c->slots_alias = 0; }
+        else if (layout == 2) { c->img_off = (c->acc_off + acc_bytes + 127) / 128 * 128; region = c->img_off + img_bytes; if (region < c->acc_off + slot_bytes) region = c->acc_off + slot_bytes; c->slots = 1; c->slots_alias = 1; }
+        else { c->img_off = c->acc_off; region = c->acc_off + (slot_bytes > img_bytes ? slot_bytes : img_bytes); c->slots = 1; c->slots_alias = 1; }
+        c->xbuf_off = (region + 127) / 128 * 128;
+        c->tile_off = (c->xbuf_off + xbuf_bytes + 127) / 128 * 128;
+        c->smem = (size_t)c->tile_off + (size_t)tiles_bytes;
+        if (c->smem <= (size_t)max_smem) return true;
+    }
+    return false;
 }
 
-template <int GPW, int NT>
+bool plan_res(int sm_count, int max_smem, int64_t M, int64_t N, int64_t K, ResPlan* c) {
+    if (M < 1 || M > 8 || K <= 0 || K % GRAN_K != 0 || N < 1 || N > 0x7fffffff) return false;
+    const int only = tuning().gemv_slabs;                           // bench hook: force the number of K slabs
+    for (int nslab = 1; nslab <= 4; ++nslab)
+        if ((only <= 0 || only == nslab) && plan_res_slabs(sm_count, max_smem, M, N, K, nslab, c)) return true;
+    return false;
+}
+
+template <int GPW, int NT, bool SPLIT>
 int launch_res_inst(const ResPlan& c, const ResParams& p, bool pdl, cudaStream_t st) {
-    auto kfn = gemv_res_kernel<GPW, NT>;
+    auto kfn = gemv_res_kernel<GPW, NT, SPLIT>;
     static thread_local int attr_dev_smem[64] = {0};
     int dev = 0;
     B200Q_CUDA(cudaGetDevice(&dev));
@@ -560,11 +637,22 @@ int launch_res_inst(const ResPlan& c, const ResParams& p, bool pdl, cudaStream_t
     cfg.blockDim = dim3(NTHR);
     cfg.dynamicSmemBytes = c.smem;
     cfg.stream = st;
-    cudaLaunchAttribute attrs[1];
-    attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attrs[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attrs[2];
+    int na = 0;
+    if (pdl) {
+        attrs[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attrs[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    if (c.nslab > 1) {
+        attrs[na].id = cudaLaunchAttributeClusterDimension;
+        attrs[na].val.clusterDim.x = (unsigned)c.nslab;
+        attrs[na].val.clusterDim.y = 1;
+        attrs[na].val.clusterDim.z = 1;
+        ++na;
+    }
     cfg.attrs = attrs;
-    cfg.numAttrs = pdl ? 1 : 0;
+    cfg.numAttrs = na;
     return check_cuda(cudaLaunchKernelEx(&cfg, kfn, p), "gemv_res launch");
 }
 
@@ -587,8 +675,10 @@ int launch_gemv_res(const DeviceInfo& dev, const void* x, int x_dtype, const uin
     p.x = x; p.packed = packed; p.scales = scales; p.zps = zps; p.y = y;
     p.x_dtype = x_dtype; p.y_dtype = y_dtype;
     p.M = (int)M; p.N = (int)N; p.K = (int)K;
-    p.rows_q = (int)(N / c.grid); p.rows_rem = (int)(N % c.grid);
-    p.G = (int)(K / GRAN_K);
+    p.rows_q = (int)(N / c.nrb); p.rows_rem = (int)(N % c.nrb);
+    p.nslab = c.nslab;
+    p.gran_q = (int)(K / GRAN_K) / c.nslab; p.gran_rem = (int)(K / GRAN_K) % c.nslab;
+    p.pitch = c.pitch; p.xbuf_off = c.xbuf_off; p.outs_cap = c.outs_cap;
     p.acc_off = c.acc_off; p.img_off = c.img_off; p.tile_off = c.tile_off;
     p.slots = c.slots; p.slots_alias = c.slots_alias;
     p.wait_weights = (flags & B200Q_FLAG_STATIC_WEIGHTS) ? 0 : 1;
@@ -604,7 +694,7 @@ int launch_gemv_res(const DeviceInfo& dev, const void* x, int x_dtype, const uin
     }
     const bool pdl = tuning().gemv_pdl != 0;
 #define B200Q_RES_CASE(GPW_, NT_) \
-    if (c.gpw == GPW_ && c.nt == NT_) return launch_res_inst<GPW_, NT_>(c, p, pdl, st);
+    if (c.gpw == GPW_ && c.nt == NT_) return c.nslab > 1 ? launch_res_inst<GPW_, NT_, true>(c, p, pdl, st) : launch_res_inst<GPW_, NT_, false>(c, p, pdl, st);
     B200Q_RES_CASE(1, 1) B200Q_RES_CASE(2, 1) B200Q_RES_CASE(3, 1)
     B200Q_RES_CASE(1, 2) B200Q_RES_CASE(2, 2) B200Q_RES_CASE(3, 2)
     B200Q_RES_CASE(1, 4) B200Q_RES_CASE(2, 4)

@@ -82,8 +82,7 @@ def main():
     for (K, N) in shapes:
         layers = make_pool(N, K, int(os.environ.get("POOL", "24")), dev)
         nbytes = lambda M: N * K // 2 + 8 * N + 4 * M * K + 4 * M * N
-        configs = [({"gemv_pf": pf, "gemv_early": e}, 1, True) for pf in (1,)
-                   for e in (91, 92, 93, 94, 95, 2, 3, 30, 31, 21, 12, 22, 41, 32, 91)]
+        configs = [({}, 1, True)] if K == 4096 else [({"gemv_slabs": ns, "gemv_early": e}, 1, True) for ns in (2, 3, 4) for e in (92, 91, 9, 32)]
         for tune, M, graph in configs:
             for k in KEYS:
                 _lib.tune(k, -1)
