@@ -268,15 +268,23 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_res_kernel(const ResParams p) {
         issue_late();
         for (int m = 0; m < p.M; ++m) {
             float am = 0.0f;
-            for (int i = tid; i < K8; i += NTHR) {
-                float v[8];
-                load8f(p.x, p.x_dtype, (int64_t)m * p.K + i * 8, v);
+            // four loads in flight per thread (a plain strided loop made one trip to L2 per iteration: 2.7 us for the
+            // 43 KB of a K = 11008 row while the weight requests are queued in front)
+            for (int i0 = tid; i0 < K8; i0 += 4 * NTHR) {
+                float v[4][8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) am = fmaxf(am, fabsf(v[e]));
+                for (int u = 0; u < 4; ++u) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[u][e] = 0.0f;
+                    if (i0 + u * NTHR < K8) load8f(p.x, p.x_dtype, (int64_t)m * p.K + (int64_t)(i0 + u * NTHR) * 8, v[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) am = fmaxf(am, fabsf(v[u][e]));
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, o));
-            if (lane == 0) s_amax[m * NW + warp] = am;
+            const unsigned int ua = __reduce_max_sync(0xffffffffu, __float_as_uint(am));
+            if (lane == 0) s_amax[m * NW + warp] = __uint_as_float(ua);
         }
     }
     __syncthreads();

@@ -12,7 +12,7 @@ dbg_prof = lib.b200q_debug_read_prof_res if RES else lib.b200q_debug_read_prof
 dbg_wall.argtypes = [ctypes.c_void_p, ctypes.c_int]
 dbg_prof.argtypes = [ctypes.c_void_p]
 dev = torch.device("cuda", 0)
-K, N, M = 4096, 11008, 1
+K, N, M = int(os.environ.get("K", "4096")), int(os.environ.get("N", "11008")), int(os.environ.get("M", "1"))
 layers = []
 for i in range(24):
     g = torch.Generator(device=dev); g.manual_seed(i)
