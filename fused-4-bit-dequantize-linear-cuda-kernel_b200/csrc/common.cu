@@ -101,6 +101,7 @@ int b200q_tune_set(const char* key, int value) {
     else if (!strcmp(key, "gemv_ctas")) g_tuning.gemv_ctas = value;
     else if (!strcmp(key, "gemv_debug")) g_tuning.gemv_debug = value;
     else if (!strcmp(key, "gemm_bn")) g_tuning.gemm_bn = value;
+    else if (!strcmp(key, "gemm_debug")) g_tuning.gemm_debug = value;
     else if (!strcmp(key, "gemm_sk")) g_tuning.gemm_sk = value;
     else if (!strcmp(key, "gemv_res")) g_tuning.gemv_res = value < 0 ? 1 : value;
     else if (!strcmp(key, "gemv_early")) g_tuning.gemv_early = value;

@@ -40,20 +40,24 @@ constexpr int BM = 128;            // weight rows per tile (UMMA M, TMEM lanes)
 // BN <= 192 two accumulators fit next to the A ring (2*BN + 128 <= 512 TMEM columns) and the epilogue of
 // tile i overlaps the MMAs of tile i+1; BN = 256 has one accumulator.
 constexpr int BK = 64;             // k-block: one 128-byte swizzle row of fp16
-constexpr int A_SLOTS = 4;         // TMEM A ring: 4 k-blocks x 32 columns
+// TMEM A ring: A_SLOTS k-blocks x 32 columns.  The ring is a latency loop (dequant -> tcgen05.st -> wait::st ->
+// mbarrier -> MMA -> commit -> mbarrier -> dequant, ~3 k clk per lap): with 4 slots a k-block cannot take less than
+// ~850 clk whatever the MMAs cost (gemm_debug ablation: removing every TMA load changed nothing), with 8 slots the
+// MMAs (716 clk per k-block at 256 tokens) are the limit again.  192 tokens x 2 accumulators leave room for 4 only.
+__host__ __device__ constexpr int a_slots(int bn) { return bn == 192 ? 4 : 8; }
 constexpr int TMEM_COLS = 512;
 constexpr int GEMM_THREADS = 16 * 32;
 constexpr int W_TILE_BYTES = BM * (BK / 2);    // 4 KB
-constexpr int MAX_STAGES = 6;
+constexpr int MAX_STAGES = 24;     // small token tiles (8 KB stages) need many stages to keep enough bytes in flight
 
 // shared memory map
 constexpr int OFF_FULL = 0;        // [MAX_STAGES]
-constexpr int OFF_EMPTY = 64;      // [MAX_STAGES]
-constexpr int OFF_AFULL = 128;     // [A_SLOTS]
-constexpr int OFF_AEMPTY = 192;    // [A_SLOTS]
-constexpr int OFF_DFULL = 256;     // [2]
-constexpr int OFF_DEMPTY = 272;    // [2]
-constexpr int OFF_TMEMPTR = 288;
+constexpr int OFF_EMPTY = 256;     // [MAX_STAGES]
+constexpr int OFF_AFULL = 512;     // [A_SLOTS]
+constexpr int OFF_AEMPTY = 576;    // [A_SLOTS]
+constexpr int OFF_DFULL = 640;     // [2]
+constexpr int OFF_DEMPTY = 656;    // [2]
+constexpr int OFF_TMEMPTR = 672;
 constexpr int OFF_TOK = 1024;      // float descale[256], rowsum[256]
 constexpr int OFF_STAGES = 4096;   // 1024-byte aligned stage buffers
 
@@ -76,6 +80,7 @@ struct GemmParams {
     // stream-K (plain linear with a badly quantised last wave): CTA c owns k-blocks [c*skq + min(c, skr), ...) of the
     // linearised (tile, k-block) space; a tile cut between CTAs is finished by the CTA that holds its last k-block,
     // the others publish their fp32 partial accumulator (workspace slot = CTA index) and raise a flag
+    int debug;               // bench-only ablations, see the TMA producer
     int sk;                  // 0: whole tiles, round-robin
     int skq, skr;
     float* part;             // [grid][BN][BM] fp32
@@ -166,6 +171,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
                const __grid_constant__ CUtensorMap map_w, const GemmParams p) {
     constexpr int X_TILE_BYTES = BN * BK * 2;
+    constexpr int A_SLOTS = a_slots(BN);
     constexpr int DBUF = 2 * BN + A_SLOTS * 32 <= TMEM_COLS ? 2 : 1;     // accumulators in TMEM
     constexpr int A_BASE = DBUF * BN;                                    // first column of the A ring
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -224,10 +230,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
                 const TileInfo& ti = w.ti;
                 for (int kb = w.kb0; kb < w.kb1; ++kb, ++it) {
                     if (it >= S) mbar_wait(empty(s), ph ^ 1);
-                    mbar_arrive_expect_tx(full(s), (uint32_t)(PARTS * X_TILE_BYTES + W_TILE_BYTES));
-                    tma_load_2d(xh_smem(s), &map_xh, kb * BK, ti.m0, full(s));
-                    if (PARTS == 2) tma_load_2d(xl_smem(s), &map_xl, kb * BK, ti.m0, full(s));
-                    tma_load_2d(w_smem(s), &map_w, kb * (BK / 2), ti.e * p.N + ti.n0, full(s));
+                    // bench-only ablation (tuning key gemm_debug): 1 = no weight loads, 2 = no activation loads
+                    const uint32_t xb = (p.debug & 2) ? 0u : (uint32_t)(PARTS * X_TILE_BYTES);
+                    const uint32_t wb = (p.debug & 1) ? 0u : (uint32_t)W_TILE_BYTES;
+                    mbar_arrive_expect_tx(full(s), xb + wb);
+                    if (xb) {
+                        tma_load_2d(xh_smem(s), &map_xh, kb * BK, ti.m0, full(s));
+                        if (PARTS == 2) tma_load_2d(xl_smem(s), &map_xl, kb * BK, ti.m0, full(s));
+                    }
+                    if (wb) tma_load_2d(w_smem(s), &map_w, kb * (BK / 2), ti.e * p.N + ti.n0, full(s));
                     if (++s == S) { s = 0; ph ^= 1; }
                 }
             });
@@ -252,6 +263,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
                     const uint32_t a_tmem = tmem + A_BASE + 32 * a;
 #pragma unroll
                     for (int kk = 0; kk < BK / 16; ++kk) {
+                        if (p.debug & 4) break;                     // ablation: no MMAs, only the commits
                         const uint64_t bh = smem_desc(xh_smem(s) + kk * 32, 16, 1024, SWIZZLE_128B);
                         mma_ts_f16(d_tmem, a_tmem + 8 * kk, bh, idesc, (kb > w.kb0 || kk) ? 1u : 0u);
                         if (PARTS == 2) {
@@ -306,9 +318,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
                         rr[4 * j + 2] = w2 & 0x000f000fu;
                         rr[4 * j + 3] = w2 & 0x00f000f0u;
                     }
-                    tmem_st16(dst + 16 * half, rr);
+                    if (!(p.debug & 8)) tmem_st16(dst + 16 * half, rr);     // ablation 8: no tcgen05.st
                 }
-                tmem_wait_st();
+                if (!(p.debug & 8)) tmem_wait_st();
                 tc_fence_before_sync();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(afull(a));
@@ -656,7 +668,13 @@ int launch_gemm_tc(const DeviceInfo& dev, const void* x, int x_dtype, const uint
             const double cost = (double)waves * (cand[i] == 256 ? 1.0 : 0.704);
             if (cost < best) { best = cost; bn = cand[i]; }
         }
-        if (tuning().gemm_bn == 128 || tuning().gemm_bn == 192 || tuning().gemm_bn == 256) bn = tuning().gemm_bn;
+        // few rows in total (decode-sized batches, M = 9..64, and MoE layers with a handful of tokens): a 256-token
+        // tile would spend 179 clk per MMA on empty columns; with 32 / 64 columns an MMA costs the 64 clk it takes to
+        // feed the A operand from tensor memory, i.e. the kernel runs at the weight-streaming rate of that floor
+        if (M <= 32) bn = 32;
+        else if (M <= 64) bn = 64;
+        const int fb = tuning().gemm_bn;
+        if (fb == 32 || fb == 64 || fb == 128 || fb == 192 || fb == 256) bn = fb;
     }
     // stream-K instead of whole tiles when the only wave is less than half full (plain linear): 256-token tiles,
     // the k-blocks of all tiles dealt out evenly over the SMs.  Measured (tools/run_gemm_sk.py, bench_gemm.py):
@@ -664,13 +682,14 @@ int launch_gemm_tc(const DeviceInfo& dev, const void* x, int x_dtype, const uint
     // un-overlapped accumulator drains per CTA cost more than the balance gains (4096 -> 11008 M = 512: -37 %).
     int sk = 0, skq = 0, skr = 0, sk_grid = 0;
     if (!starts && tuning().gemm_sk != 0) {
-        const long long tiles256 = ((M + 255) / 256) * n_tiles_h;
+        const int bnsk = M <= 64 ? bn : 256;                        // small batches keep their small token tile
+        const long long tiles256 = ((M + bnsk - 1) / bnsk) * n_tiles_h;
         const long long waves = (tiles256 + dev.sm_count - 1) / dev.sm_count;
         const double fill = (double)tiles256 / (double)(waves * dev.sm_count);
         const long long total_kb = tiles256 * (K / BK);
         const int g = dev.sm_count < SK_MAX_CTAS ? dev.sm_count : SK_MAX_CTAS;
         if ((tuning().gemm_sk > 0 || (fill < 0.5 && waves == 1)) && total_kb / g >= 8 && tiles256 <= 100000) {
-            sk = 1; bn = 256; sk_grid = g;
+            sk = 1; bn = bnsk; sk_grid = g;
             skq = (int)(total_kb / g); skr = (int)(total_kb % g);
         }
     }
@@ -692,15 +711,17 @@ int launch_gemm_tc(const DeviceInfo& dev, const void* x, int x_dtype, const uint
     if (stages < 2) return set_error(B200Q_EINVAL, "gemm_tc: not enough shared memory");
     p.stages = stages;
     p.sk = sk; p.skq = skq; p.skr = skr;
+    p.debug = tuning().gemm_debug > 0 ? tuning().gemm_debug : 0;
     p.part = reinterpret_cast<float*>(w8 + 2 * xbytes + 2 * sbytes);
     p.flags = reinterpret_cast<unsigned int*>(ws);
     const size_t smem = (size_t)OFF_STAGES + (size_t)stages * p.stage_bytes;
     typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmParams);
-    const int bi = bn == 128 ? 0 : (bn == 192 ? 1 : 2);
-    const KernelFn table[2][3] = {{gemm_tc_kernel<1, 128>, gemm_tc_kernel<1, 192>, gemm_tc_kernel<1, 256>},
-                                  {gemm_tc_kernel<2, 128>, gemm_tc_kernel<2, 192>, gemm_tc_kernel<2, 256>}};
+    const int bi = bn == 32 ? 0 : (bn == 64 ? 1 : (bn == 128 ? 2 : (bn == 192 ? 3 : 4)));
+    const KernelFn table[2][5] = {
+        {gemm_tc_kernel<1, 32>, gemm_tc_kernel<1, 64>, gemm_tc_kernel<1, 128>, gemm_tc_kernel<1, 192>, gemm_tc_kernel<1, 256>},
+        {gemm_tc_kernel<2, 32>, gemm_tc_kernel<2, 64>, gemm_tc_kernel<2, 128>, gemm_tc_kernel<2, 192>, gemm_tc_kernel<2, 256>}};
     KernelFn kfn = table[parts - 1][bi];
-    static thread_local int attr_done[64][2][3] = {{{0}}};
+    static thread_local int attr_done[64][2][5] = {{{0}}};
     int devi = 0;
     B200Q_CUDA(cudaGetDevice(&devi));
     if (devi >= 0 && devi < 64 && attr_done[devi][parts - 1][bi] < (int)smem) {

@@ -35,6 +35,7 @@ struct Tuning {
     int gemv_pdl = -1;      // 0 disables programmatic dependent launch
     int gemv_ctas = -1;     // cap on the number of CTAs (default: SM count)
     int gemm_bn = -1;       // token-tile height of the tcgen05 GEMM (128 / 192 / 256), default: heuristic
+    int gemm_debug = -1;    // bench-only ablations of the tcgen05 GEMM (1: no weight loads, 2: no activation loads)
     int gemm_sk = -1;       // stream-K in the tcgen05 GEMM: -1 heuristic, 0 off, 1 whenever possible
     int gemv_res = 1;       // 0: never use the resident-slab decode kernel
     int gemv_early = -1;    // tiles requested before the x loads (-1: all)
