@@ -44,7 +44,10 @@ constexpr int BK = 64;             // k-block: one 128-byte swizzle row of fp16
 // mbarrier -> MMA -> commit -> mbarrier -> dequant, ~3 k clk per lap): with 4 slots a k-block cannot take less than
 // ~850 clk whatever the MMAs cost (gemm_debug ablation: removing every TMA load changed nothing), with 8 slots the
 // MMAs (716 clk per k-block at 256 tokens) are the limit again.  192 tokens x 2 accumulators leave room for 4 only.
-__host__ __device__ constexpr int a_slots(int bn) { return bn == 192 ? 4 : 8; }
+// A pipeline stage holds KSUB (1 or 2) such 64-column sub-blocks: every stage costs ~300 - 550 clk of mbarrier /
+// tcgen05.commit hand-shakes whatever it carries (ablation with loads, stores and MMAs removed,
+// tools/gemm_ablate.py), so two sub-blocks per stage halve that overhead per byte.
+__host__ __device__ constexpr int a_slots(int bn, int ksub) { return ksub == 2 ? 4 : (bn == 192 ? 4 : 8); }
 constexpr int TMEM_COLS = 512;
 constexpr int GEMM_THREADS = 16 * 32;
 constexpr int W_TILE_BYTES = BM * (BK / 2);    // 4 KB
@@ -166,13 +169,14 @@ __device__ __forceinline__ void for_each_item(const GemmParams& p, int KB, int t
     }
 }
 
-template <int PARTS, int BN>   // PARTS 1: fp16 activations (hi only); 2: hi + lo (fp32 activations)
+template <int PARTS, int BN, int KSUB>   // PARTS 1: fp16 activations (hi only); 2: hi + lo (fp32 activations)
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
                const __grid_constant__ CUtensorMap map_w, const GemmParams p) {
     constexpr int X_TILE_BYTES = BN * BK * 2;
-    constexpr int A_SLOTS = a_slots(BN);
-    constexpr int DBUF = 2 * BN + A_SLOTS * 32 <= TMEM_COLS ? 2 : 1;     // accumulators in TMEM
+    constexpr int A_SLOTS = a_slots(BN, KSUB);
+    constexpr int A_COLS = 32 * KSUB;                                    // TMEM columns of one A slot
+    constexpr int DBUF = 2 * BN + A_SLOTS * A_COLS <= TMEM_COLS ? 2 : 1; // accumulators in TMEM
     constexpr int A_BASE = DBUF * BN;                                    // first column of the A ring
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sb = smem_u32(smem);
@@ -187,9 +191,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
     volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + OFF_TMEMPTR);
     float* tok = reinterpret_cast<float*>(smem + OFF_TOK);
     auto xh_smem = [&](int s) { return sb + OFF_STAGES + (uint32_t)s * p.stage_bytes; };
-    auto xl_smem = [&](int s) { return xh_smem(s) + X_TILE_BYTES; };
-    auto w_smem = [&](int s) { return xh_smem(s) + PARTS * X_TILE_BYTES; };
-    const int KB = p.K / BK;
+    auto xl_smem = [&](int s) { return xh_smem(s) + KSUB * X_TILE_BYTES; };
+    auto w_smem = [&](int s) { return xh_smem(s) + PARTS * KSUB * X_TILE_BYTES; };
+    const int KB = p.K / (BK * KSUB);                                    // stages per tile
     const int total_tiles = p.n_tiles * p.mt_bound;
 
     if (threadIdx.x == 0) {
@@ -231,14 +235,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
                 for (int kb = w.kb0; kb < w.kb1; ++kb, ++it) {
                     if (it >= S) mbar_wait(empty(s), ph ^ 1);
                     // bench-only ablation (tuning key gemm_debug): 1 = no weight loads, 2 = no activation loads
-                    const uint32_t xb = (p.debug & 2) ? 0u : (uint32_t)(PARTS * X_TILE_BYTES);
-                    const uint32_t wb = (p.debug & 1) ? 0u : (uint32_t)W_TILE_BYTES;
+                    const uint32_t xb = (p.debug & 2) ? 0u : (uint32_t)(PARTS * KSUB * X_TILE_BYTES);
+                    const uint32_t wb = (p.debug & 1) ? 0u : (uint32_t)(KSUB * W_TILE_BYTES);
                     mbar_arrive_expect_tx(full(s), xb + wb);
                     if (xb) {
-                        tma_load_2d(xh_smem(s), &map_xh, kb * BK, ti.m0, full(s));
-                        if (PARTS == 2) tma_load_2d(xl_smem(s), &map_xl, kb * BK, ti.m0, full(s));
+#pragma unroll
+                        for (int sub = 0; sub < KSUB; ++sub) {         // one 128-byte-swizzle atom [BN][64] per sub-block
+                            tma_load_2d(xh_smem(s) + sub * X_TILE_BYTES, &map_xh, (kb * KSUB + sub) * BK, ti.m0, full(s));
+                            if (PARTS == 2) tma_load_2d(xl_smem(s) + sub * X_TILE_BYTES, &map_xl, (kb * KSUB + sub) * BK, ti.m0, full(s));
+                        }
                     }
-                    if (wb) tma_load_2d(w_smem(s), &map_w, kb * (BK / 2), ti.e * p.N + ti.n0, full(s));
+                    if (wb) tma_load_2d(w_smem(s), &map_w, kb * KSUB * (BK / 2), ti.e * p.N + ti.n0, full(s));   // [128][32 KSUB] bytes
                     if (++s == S) { s = 0; ph ^= 1; }
                 }
             });
@@ -260,15 +267,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
                     mbar_wait(full(s), ph);
                     mbar_wait(afull(a), (ait / A_SLOTS) & 1);
                     tc_fence_after_sync();
-                    const uint32_t a_tmem = tmem + A_BASE + 32 * a;
+                    const uint32_t a_tmem = tmem + A_BASE + A_COLS * a;
 #pragma unroll
-                    for (int kk = 0; kk < BK / 16; ++kk) {
-                        if (p.debug & 4) break;                     // ablation: no MMAs, only the commits
-                        const uint64_t bh = smem_desc(xh_smem(s) + kk * 32, 16, 1024, SWIZZLE_128B);
-                        mma_ts_f16(d_tmem, a_tmem + 8 * kk, bh, idesc, (kb > w.kb0 || kk) ? 1u : 0u);
-                        if (PARTS == 2) {
-                            const uint64_t bl = smem_desc(xl_smem(s) + kk * 32, 16, 1024, SWIZZLE_128B);
-                            mma_ts_f16(d_tmem, a_tmem + 8 * kk, bl, idesc, 1u);
+                    for (int sub = 0; sub < KSUB; ++sub) {
+#pragma unroll
+                        for (int kk = 0; kk < BK / 16; ++kk) {
+                            if (p.debug & 4) break;                     // ablation: no MMAs, only the commits
+                            const uint64_t bh = smem_desc(xh_smem(s) + sub * X_TILE_BYTES + kk * 32, 16, 1024, SWIZZLE_128B);
+                            mma_ts_f16(d_tmem, a_tmem + 32 * sub + 8 * kk, bh, idesc, (kb > w.kb0 || sub || kk) ? 1u : 0u);
+                            if (PARTS == 2) {
+                                const uint64_t bl = smem_desc(xl_smem(s) + sub * X_TILE_BYTES + kk * 32, 16, 1024, SWIZZLE_128B);
+                                mma_ts_f16(d_tmem, a_tmem + 32 * sub + 8 * kk, bl, idesc, 1u);
+                            }
                         }
                     }
                     tc_commit(empty(s));
@@ -294,8 +304,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
                     continue;
                 }
                 mbar_wait(full(s), ph);
-                const uint4 w0 = lds128(w_smem(s) + r * (BK / 2));
-                const uint4 w1 = lds128(w_smem(s) + r * (BK / 2) + 16);
+                uint4 wv[2 * KSUB];
+#pragma unroll
+                for (int i = 0; i < 2 * KSUB; ++i) wv[i] = lds128(w_smem(s) + r * (KSUB * BK / 2) + 16 * i);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(empty(s));               // the packed bytes are in registers
                 const int a = ait % A_SLOTS;
@@ -303,16 +314,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
                     mbar_wait(aempty(a), ((ait / A_SLOTS) - 1) & 1);
                     tc_fence_after_sync();
                 }
-                const uint32_t dst = tmem + ((uint32_t)(32 * q) << 16) + A_BASE + 32 * a;
-                const uint32_t ws[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                const uint32_t dst = tmem + ((uint32_t)(32 * q) << 16) + A_BASE + A_COLS * a;
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
+                for (int half = 0; half < 2 * KSUB; ++half) {
+                    const uint32_t ws[4] = {wv[half].x, wv[half].y, wv[half].z, wv[half].w};
                     uint32_t rr[16];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         // nibble n left in the low mantissa bits of a zero-exponent fp16 is the subnormal
                         // n * 2^-24 (bits 0-3) or n * 2^-20 (bits 4-7): exact, no arithmetic
-                        const uint32_t w = ws[4 * half + j], w2 = w >> 8;
+                        const uint32_t w = ws[j], w2 = w >> 8;
                         rr[4 * j + 0] = w & 0x000f000fu;
                         rr[4 * j + 1] = w & 0x00f000f0u;
                         rr[4 * j + 2] = w2 & 0x000f000fu;
@@ -652,8 +663,12 @@ int launch_gemm_tc(const DeviceInfo& dev, const void* x, int x_dtype, const uint
     else { if (int rc = launch_xprep<__nv_bfloat16>(xp, M, K, st)) return rc; }
 
     CUtensorMap map_xh, map_xl, map_w;
+    // Stages of two 64-column sub-blocks (template parameter KSUB = 2) were tried to halve the per-stage
+    // hand-shakes: +3 % at 256-token tiles, -5 % at 192 (one accumulator left), and a hang at M = 32768 that was not
+    // tracked down -- not instantiated.
+    const int ksub = 1;
     // token-tile height: fewest (waves x time per wave).  Measured per-wave time (tools/sweep_gemm_bn.py):
-    // BN = 192 (two accumulators, epilogue overlapped) takes 0.70 of a BN = 256 wave; BN = 128 is never
+    // BN = 192 (two accumulators, epilogue overlapped, 4 A slots) takes 0.74 of a BN = 256 (8 A slots) wave; BN = 128 is never
     // better (64-clk MMAs run into the per-instruction floor) and is only reachable through gemm_bn.
     const int groups_n = starts ? E : 1;
     const int n_tiles_h = (int)((N + BM - 1) / BM);
@@ -665,7 +680,7 @@ int launch_gemm_tc(const DeviceInfo& dev, const void* x, int x_dtype, const uint
             const long long mt = (M + cand[i] - 1) / cand[i] + (starts ? groups_n / 2 : 0);
             const long long tiles = mt * n_tiles_h;
             const long long waves = (tiles + dev.sm_count - 1) / dev.sm_count;
-            const double cost = (double)waves * (cand[i] == 256 ? 1.0 : 0.704);
+            const double cost = (double)waves * (cand[i] == 256 ? 1.0 : 0.74);
             if (cost < best) { best = cost; bn = cand[i]; }
         }
         // few rows in total (decode-sized batches, M = 9..64, and MoE layers with a handful of tokens): a 256-token
@@ -686,7 +701,7 @@ int launch_gemm_tc(const DeviceInfo& dev, const void* x, int x_dtype, const uint
         const long long tiles256 = ((M + bnsk - 1) / bnsk) * n_tiles_h;
         const long long waves = (tiles256 + dev.sm_count - 1) / dev.sm_count;
         const double fill = (double)tiles256 / (double)(waves * dev.sm_count);
-        const long long total_kb = tiles256 * (K / BK);
+        const long long total_kb = tiles256 * (K / (BK * ksub));
         const int g = dev.sm_count < SK_MAX_CTAS ? dev.sm_count : SK_MAX_CTAS;
         if ((tuning().gemm_sk > 0 || (fill < 0.5 && waves == 1)) && total_kb / g >= 8 && tiles256 <= 100000) {
             sk = 1; bn = bnsk; sk_grid = g;
@@ -696,7 +711,7 @@ int launch_gemm_tc(const DeviceInfo& dev, const void* x, int x_dtype, const uint
     if (int rc = make_map_2d(&map_xh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, xh, (uint64_t)K, (uint64_t)M, BK, bn, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
     if (int rc = make_map_2d(&map_xl, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, parts == 2 ? xl : xh, (uint64_t)K, (uint64_t)M, BK, bn, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
     const int groups = starts ? E : 1;
-    if (int rc = make_map_2d(&map_w, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, packed, (uint64_t)(K / 2), (uint64_t)groups * N, BK / 2, BM, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
+    if (int rc = make_map_2d(&map_w, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, packed, (uint64_t)(K / 2), (uint64_t)groups * N, ksub * BK / 2, BM, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
 
     GemmParams p{};
     p.scales = scales; p.zps = zps; p.y = y; p.descale = descale; p.rowsum = rowsum;
@@ -705,7 +720,7 @@ int launch_gemm_tc(const DeviceInfo& dev, const void* x, int x_dtype, const uint
     p.bn = bn;
     p.mt_bound = (int)((M + bn - 1) / bn) + (starts ? E : 0);
     p.n_tiles = n_tiles_h;
-    p.stage_bytes = parts * bn * BK * 2 + W_TILE_BYTES;
+    p.stage_bytes = ksub * (parts * bn * BK * 2 + W_TILE_BYTES);
     int stages = (dev.max_smem_optin - OFF_STAGES) / p.stage_bytes;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (stages < 2) return set_error(B200Q_EINVAL, "gemm_tc: not enough shared memory");
@@ -718,15 +733,16 @@ int launch_gemm_tc(const DeviceInfo& dev, const void* x, int x_dtype, const uint
     typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmParams);
     const int bi = bn == 32 ? 0 : (bn == 64 ? 1 : (bn == 128 ? 2 : (bn == 192 ? 3 : 4)));
     const KernelFn table[2][5] = {
-        {gemm_tc_kernel<1, 32>, gemm_tc_kernel<1, 64>, gemm_tc_kernel<1, 128>, gemm_tc_kernel<1, 192>, gemm_tc_kernel<1, 256>},
-        {gemm_tc_kernel<2, 32>, gemm_tc_kernel<2, 64>, gemm_tc_kernel<2, 128>, gemm_tc_kernel<2, 192>, gemm_tc_kernel<2, 256>}};
-    KernelFn kfn = table[parts - 1][bi];
+        {gemm_tc_kernel<1, 32, 1>, gemm_tc_kernel<1, 64, 1>, gemm_tc_kernel<1, 128, 1>, gemm_tc_kernel<1, 192, 1>, gemm_tc_kernel<1, 256, 1>},
+        {gemm_tc_kernel<2, 32, 1>, gemm_tc_kernel<2, 64, 1>, gemm_tc_kernel<2, 128, 1>, gemm_tc_kernel<2, 192, 1>, gemm_tc_kernel<2, 256, 1>}};
+    const int ti_ = parts - 1;
+    KernelFn kfn = table[ti_][bi];
     static thread_local int attr_done[64][2][5] = {{{0}}};
     int devi = 0;
     B200Q_CUDA(cudaGetDevice(&devi));
-    if (devi >= 0 && devi < 64 && attr_done[devi][parts - 1][bi] < (int)smem) {
+    if (devi >= 0 && devi < 64 && attr_done[devi][ti_][bi] < (int)smem) {
         B200Q_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done[devi][parts - 1][bi] = (int)smem;
+        attr_done[devi][ti_][bi] = (int)smem;
     }
     const long long total_tiles = (long long)p.n_tiles * p.mt_bound;
     int grid = dev.sm_count;
