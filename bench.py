@@ -153,12 +153,38 @@ def run_reference(args):
         return
     steps = max(1, min(args.steps, 200))
     warmup = max(1, min(args.warmup, 5))
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    if (args.workload or ("gemv" if world == 1 else "moe")) == "moe":
+        # same metric / config as the product arm at this N: the Mixtral layer, composed from the reference's
+        # primitives on the host cores (bounded sample: one expert's three projections on 8 rows, scaled per token)
+        from bench_moe import cpu_moe_baseline, T_GLOBAL, E as MOE_E
+        best, cores, sample = 0.0, 1, ""
+        t0 = time.perf_counter()
+        for _ in range(min(steps, 5)):
+            v, cores, sample = cpu_moe_baseline()
+            best = max(best, v)
+        dt = (time.perf_counter() - t0) / min(steps, 5)
+        line = {
+            "impl": "reference", "metric": "mixtral_moe_int4_layer_tokens_per_s", "value": best, "unit": "tokens/s",
+            "n_gpus": args.gpus, "steps": min(steps, 5), "warmup": 0, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "Mixtral-8x7B INT4 MoE layer (8 experts, top-2, d=4096, ffn=14336), "
+                                   f"{T_GLOBAL} tokens/step, random routing" + (", expert-parallel" if world > 1 else ""),
+                       "arm": "the reference's CPU path composed per expert: dequantize_weights + matmul (C restatement, all host cores)",
+                       "tokens_per_step": T_GLOBAL, "experts_per_rank": MOE_E // max(world, 1)},
+            "cpu_baseline": {"value": best, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": best, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return
     gbs, dt, cores, what = cpu_reference_gemv(steps, warmup)
     line = {
         "impl": "reference", "metric": "int4_gemv_hbm_gbps", "value": gbs, "unit": "GB/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"Llama-7B MLP INT4 decode GEMV M=1 ({K_IN}->{N_OUT}), CPU dequantize + matmul",
+        "config": {"workload": f"Llama-7B MLP INT4 decode GEMV M=1 ({K_IN}->{N_OUT}), configs[1]",
+                   "arm": "the reference's CPU path: dequantize_weights + F.linear (C restatement, all host cores)",
                    "M": 1, "K": K_IN, "N": N_OUT},
         "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": cores, "kind": "port",
                          "sample": f"{steps} x one {K_IN}->{N_OUT} layer forward, M=1: {what} of "
