@@ -33,6 +33,9 @@
 
 namespace b200q {
 
+// bench-only trace (gemm_debug bit 4): SM clock of CTA 0 at the points named in tools/gemm_trace.py, first 96 k-blocks
+__device__ long long g_gemm_trace[8 * 96];
+
 namespace {
 
 constexpr int BM = 128;            // weight rows per tile (UMMA M, TMEM lanes)
@@ -234,6 +237,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
                 const TileInfo& ti = w.ti;
                 for (int kb = w.kb0; kb < w.kb1; ++kb, ++it) {
                     if (it >= S) mbar_wait(empty(s), ph ^ 1);
+                    if ((p.debug & 16) && blockIdx.x == 0 && it < 96) g_gemm_trace[0 * 96 + it] = clock64();
                     // bench-only ablation (tuning key gemm_debug): 1 = no weight loads, 2 = no activation loads
                     const uint32_t xb = (p.debug & 2) ? 0u : (uint32_t)(PARTS * KSUB * X_TILE_BYTES);
                     const uint32_t wb = (p.debug & 1) ? 0u : (uint32_t)(KSUB * W_TILE_BYTES);
@@ -265,7 +269,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
                 for (int kb = w.kb0; kb < w.kb1; ++kb, ++ait) {
                     const int a = ait % A_SLOTS;
                     mbar_wait(full(s), ph);
+                    if ((p.debug & 16) && blockIdx.x == 0 && ait < 96) g_gemm_trace[1 * 96 + ait] = clock64();
                     mbar_wait(afull(a), (ait / A_SLOTS) & 1);
+                    if ((p.debug & 16) && blockIdx.x == 0 && ait < 96) g_gemm_trace[2 * 96 + ait] = clock64();
                     tc_fence_after_sync();
                     const uint32_t a_tmem = tmem + A_BASE + A_COLS * a;
 #pragma unroll
@@ -283,6 +289,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
                     }
                     tc_commit(empty(s));
                     tc_commit(aempty(a));
+                    if ((p.debug & 16) && blockIdx.x == 0 && ait < 96) g_gemm_trace[3 * 96 + ait] = clock64();
                     if (++s == S) { s = 0; ph ^= 1; }
                 }
                 tc_commit(dfull(ab));
@@ -304,6 +311,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
                     continue;
                 }
                 mbar_wait(full(s), ph);
+                const bool tr = (p.debug & 16) && blockIdx.x == 0 && q == 0 && lane == 0 && ait < 96;
+                if (tr) g_gemm_trace[4 * 96 + ait] = clock64();
                 uint4 wv[2 * KSUB];
 #pragma unroll
                 for (int i = 0; i < 2 * KSUB; ++i) wv[i] = lds128(w_smem(s) + r * (KSUB * BK / 2) + 16 * i);
@@ -314,6 +323,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
                     mbar_wait(aempty(a), ((ait / A_SLOTS) - 1) & 1);
                     tc_fence_after_sync();
                 }
+                if (tr) g_gemm_trace[5 * 96 + ait] = clock64();
                 const uint32_t dst = tmem + ((uint32_t)(32 * q) << 16) + A_BASE + A_COLS * a;
 #pragma unroll
                 for (int half = 0; half < 2 * KSUB; ++half) {
@@ -335,6 +345,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
                 tc_fence_before_sync();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(afull(a));
+                if (tr) g_gemm_trace[6 * 96 + ait] = clock64();
                 if (++s == S) { s = 0; ph ^= 1; }
             }
         });
@@ -763,3 +774,8 @@ int launch_gemm_tc(const DeviceInfo& dev, const void* x, int x_dtype, const uint
 }
 
 }  // namespace b200q
+
+/* bench-only: per-k-block SM-clock trace of CTA 0 (gemm_debug bit 4), 8 x 96 int64 */
+extern "C" int b200q_debug_gemm_trace(long long* h_out) {
+    return b200q::check_cuda(cudaMemcpyFromSymbol(h_out, b200q::g_gemm_trace, sizeof(long long) * 8 * 96), "read gemm trace");
+}
