@@ -301,3 +301,57 @@ def test_decode_non_integer_zero_points(oracle, pkg):
     ref = oracle.reference_quantized_linear(x, packed, scales, zps, acc=np.float64)
     out = pkg._lib.linear_fwd(cuda(x), cuda(packed), cuda(scales), cuda(zps)).cpu().numpy()
     assert np.abs(ref - out).max() <= 2e-5 * np.abs(ref).max()
+
+
+# ---- tcgen05 GEMM: stream-K and small token tiles ----------------------------------------------------------
+@pytest.mark.parametrize("M,N,K", [(300, 4096, 11008), (70, 1000, 1024), (520, 2048, 2048), (1100, 640, 4096)])
+def test_stream_k_gemm_matches_whole_tiles_and_is_deterministic(oracle, pkg, M, N, K):
+    """Stream-K (forced with gemm_sk=1, also on shapes the heuristic would leave alone: several contributors per
+    tile, tiles finished by a CTA that also publishes) against the float64 oracle and against the whole-tile schedule;
+    a second run must be bit-identical (partials are added in CTA order) and must find the flags zeroed."""
+    rng = np.random.default_rng(M + N + K)
+    packed = rng.integers(0, 256, size=(N, K // 2), dtype=np.uint8)
+    scales = (rng.random(N, dtype=np.float32) * 0.01 + 0.001).astype(np.float32)
+    zps = rng.integers(0, 16, size=N).astype(np.float32)
+    x = rng.standard_normal((M, K), dtype=np.float32)
+    P, S, Z = cuda(packed), cuda(scales), cuda(zps)
+    X = cuda(x).to(torch.bfloat16)
+    ref = oracle.reference_quantized_linear(X.float().cpu().numpy(), packed, scales, zps, acc=np.float64)
+    outs = {}
+    for sk in (0, 1):
+        pkg._lib.tune("force_path", 3)
+        pkg._lib.tune("gemm_sk", sk)
+        try:
+            a = pkg._lib.linear_fwd(X, P, S, Z, out_dtype=torch.float32).cpu().numpy()
+            b = pkg._lib.linear_fwd(X, P, S, Z, out_dtype=torch.float32).cpu().numpy()
+        finally:
+            pkg._lib.tune("gemm_sk", -1)
+            pkg._lib.tune("force_path", -1)
+        assert np.array_equal(a, b), f"gemm_sk={sk}: not deterministic"
+        assert np.abs(a - ref).max() <= 1e-4 * np.abs(ref).max()
+        outs[sk] = a
+    # different summation split of the fp32 accumulation: equal to rounding, not bit-equal
+    assert np.abs(outs[0] - outs[1]).max() <= 2e-5 * np.abs(ref).max()
+    # the decode kernels share the first 4 KB of the workspace with the stream-K flags: they must still be zero
+    y1 = pkg._lib.linear_fwd(X[:1].float().contiguous(), P, S, Z).cpu().numpy()
+    assert np.abs(y1 - ref[:1]).max() <= 2e-5 * np.abs(ref[:1]).max()
+
+
+@pytest.mark.parametrize("bn", [32, 64, 128, 192, 256])
+def test_gemm_token_tile_heights(oracle, pkg, bn):
+    """Every token-tile height of the tcgen05 GEMM on one ragged shape (M, N not multiples of the tile)."""
+    rng = np.random.default_rng(bn)
+    M, N, K = 333, 777, 1536
+    packed = rng.integers(0, 256, size=(N, K // 2), dtype=np.uint8)
+    scales = (rng.random(N, dtype=np.float32) * 0.01 + 0.001).astype(np.float32)
+    zps = rng.integers(0, 16, size=N).astype(np.float32)
+    x = rng.standard_normal((M, K), dtype=np.float32)
+    ref = oracle.reference_quantized_linear(x, packed, scales, zps, acc=np.float64)
+    pkg._lib.tune("force_path", 3)
+    pkg._lib.tune("gemm_bn", bn)
+    try:
+        y = pkg._lib.linear_fwd(cuda(x), cuda(packed), cuda(scales), cuda(zps)).cpu().numpy()
+    finally:
+        pkg._lib.tune("gemm_bn", -1)
+        pkg._lib.tune("force_path", -1)
+    assert np.abs(y - ref).max() <= 1e-4 * np.abs(ref).max()
