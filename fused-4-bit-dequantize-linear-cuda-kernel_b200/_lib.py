@@ -45,6 +45,7 @@ SIGNATURES = {
     "b200q_moe_gather_rows": (_i32, [_vp, _i32, _vp, _i64, _i32, _i64, _vp, _vp]),
     "b200q_moe_grouped_ws_bytes": (_sz, [_i64, _i32, _i64, _i64]),
     "b200q_moe_grouped_fwd": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _i64, _i64, _i64, _vp, _sz, _vp]),
+    "b200q_moe_grouped_gated_fwd": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _i64, _i64, _i64, _vp, _sz, _vp]),
     "b200q_moe_grouped_fwd_ranges": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _i64, _i64, _i64, _vp, _sz, _vp]),
     "b200q_moe_silu_mul": (_i32, [_vp, _i32, _i64, _i64, _vp, _vp]),
     "b200q_moe_combine": (_i32, [_vp, _i32, _vp, _vp, _i64, _i32, _i64, _vp, _i32, _vp]),
@@ -261,6 +262,26 @@ def moe_grouped_fwd(xs: torch.Tensor, packed: torch.Tensor, scales: torch.Tensor
                                         ws.numel() if ws is not None else 0, stream_ptr(xs.device)),
               "b200q_moe_grouped_fwd")
     return y
+
+
+def moe_grouped_gated_fwd(xs: torch.Tensor, packed13: torch.Tensor, scales13: torch.Tensor, zps13: torch.Tensor,
+                          offsets: torch.Tensor, out_dtype=None) -> torch.Tensor:
+    """h [R,F] = silu(xs w1^T) * (xs w3^T) per expert group in one grouped GEMM; packed13 [E,2F,K/2] with the rows
+    of w1 and w3 interleaved (2f: w1[f], 2f+1: w3[f]).  Needs K % 128 == 0."""
+    lib = load()
+    R, K = xs.shape
+    E, N2 = packed13.shape[0], packed13.shape[1]
+    out_dtype = out_dtype or xs.dtype
+    with torch.cuda.device(xs.device):
+        h = torch.empty((R, N2 // 2), dtype=out_dtype, device=xs.device)
+        nb = lib.b200q_moe_grouped_ws_bytes(R, E, N2, K)
+        ws = workspace(xs.device, nb, "grouped") if nb else None
+        check(lib.b200q_moe_grouped_gated_fwd(xs.data_ptr(), dtype_code(xs), packed13.data_ptr(), scales13.data_ptr(),
+                                              zps13.data_ptr(), offsets.data_ptr(), E, h.data_ptr(), dtype_code(h),
+                                              R, N2 // 2, K, ws.data_ptr() if ws is not None else None,
+                                              ws.numel() if ws is not None else 0, stream_ptr(xs.device)),
+              "b200q_moe_grouped_gated_fwd")
+    return h
 
 
 def moe_grouped_fwd_ranges(xs: torch.Tensor, packed: torch.Tensor, scales: torch.Tensor, zps: torch.Tensor,

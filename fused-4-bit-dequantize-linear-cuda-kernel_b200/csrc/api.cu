@@ -151,6 +151,22 @@ int b200q_moe_grouped_fwd(const void* xs, int x_dtype, const uint8_t* packed, co
                         y, y_dtype, R, N, K, ws, ws_bytes, stream);
 }
 
+int b200q_moe_grouped_gated_fwd(const void* xs, int x_dtype, const uint8_t* packed13, const float* scales13,
+                                const float* zps13, const int32_t* offsets, int E, void* h, int h_dtype,
+                                int64_t R, int64_t F, int64_t K, void* ws, size_t ws_bytes, void* stream) {
+    if (R < 0 || F < 0 || K < 0 || E <= 0) return set_error(B200Q_EINVAL, "moe_grouped_gated_fwd: need R,F,K >= 0, E > 0");
+    if (!elem_size(x_dtype) || !elem_size(h_dtype)) return set_error(B200Q_EINVAL, "moe_grouped_gated_fwd: unsupported dtype");
+    if (R == 0 || F == 0) return 0;
+    if (!h || !scales13 || !zps13 || !offsets || !xs || !packed13) return set_error(B200Q_EINVAL, "moe_grouped_gated_fwd: null pointer");
+    DeviceInfo d;
+    if (int rc = current_device(&d)) return rc;
+    if (!(aligned(xs, 16) && aligned(packed13, 16) && aligned(h, 16)) || !gemm_tc_supported(R, 2 * F, K, x_dtype, h_dtype))
+        return set_error(B200Q_EINVAL, "moe_grouped_gated_fwd: needs K %% 128 == 0 and 16-byte aligned buffers "
+                                       "(otherwise: b200q_moe_grouped_fwd on w1||w3, then b200q_moe_silu_mul)");
+    return launch_gemm_tc(d, xs, x_dtype, packed13, scales13, zps13, h, h_dtype, R, 2 * F, K, offsets, offsets + 1, E, ws, ws_bytes,
+                          0u, static_cast<cudaStream_t>(stream), 1);
+}
+
 int b200q_moe_grouped_fwd_ranges(const void* xs, int x_dtype, const uint8_t* packed,
                                  const float* scales, const float* zps, const int32_t* starts,
                                  const int32_t* counts_end, int E, void* y, int y_dtype, int64_t R,

@@ -86,6 +86,8 @@ struct GemmParams {
     // stream-K (plain linear with a badly quantised last wave): CTA c owns k-blocks [c*skq + min(c, skr), ...) of the
     // linearised (tile, k-block) space; a tile cut between CTAs is finished by the CTA that holds its last k-block,
     // the others publish their fp32 partial accumulator (workspace slot = CTA index) and raise a flag
+    int gated;               // 1: weight rows are interleaved (2f: gate, 2f + 1: up); the epilogue writes
+                             //    h[m, f] = silu(gate) * up into y [R, N / 2] (fused SiLU-gate of the MoE layer)
     int debug;               // bench-only ablations, see the TMA producer
     int sk;                  // 0: whole tiles, round-robin
     int skq, skr;
@@ -419,15 +421,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
 #pragma unroll
                     for (int j = 0; j < 32; ++j) d[j] = __float_as_uint(__uint_as_float(d[j]) + __ldcg(src + (32 * c + j) * BM));
                 }
+                if (p.gated) {
+                    // fused SiLU-gate: lanes 2i (gate row) and 2i + 1 (up row) hold the two projections of h column
+                    // ti.n0 / 2 + 16 q + i; the even lane fetches its neighbour's value and writes the product
+                    const int64_t F = p.N >> 1;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int m = ti.m0 + 32 * c + j;
-                    if (n_ok && m < ti.mend) {
+                    for (int j = 0; j < 32; ++j) {
+                        const int m = ti.m0 + 32 * c + j;
                         const float v = sc * (__uint_as_float(d[j]) * tok[32 * c + j] - zp * tok[BN + 32 * c + j]);
-                        const int64_t o = (int64_t)m * p.N + n;
-                        if (p.y_dtype == B200Q_F32) static_cast<float*>(p.y)[o] = v;
-                        else if (p.y_dtype == B200Q_F16) static_cast<__half*>(p.y)[o] = __float2half_rn(v);
-                        else static_cast<__nv_bfloat16*>(p.y)[o] = __float2bfloat16_rn(v);
+                        const float u = __shfl_down_sync(0xffffffffu, v, 1);
+                        if (!(lane & 1) && n_ok && m < ti.mend) {
+                            const float hv = v / (1.0f + __expf(-v)) * u;
+                            const int64_t o = (int64_t)m * F + (n >> 1);
+                            if (p.y_dtype == B200Q_F32) static_cast<float*>(p.y)[o] = hv;
+                            else if (p.y_dtype == B200Q_F16) static_cast<__half*>(p.y)[o] = __float2half_rn(hv);
+                            else static_cast<__nv_bfloat16*>(p.y)[o] = __float2bfloat16_rn(hv);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int m = ti.m0 + 32 * c + j;
+                        if (n_ok && m < ti.mend) {
+                            const float v = sc * (__uint_as_float(d[j]) * tok[32 * c + j] - zp * tok[BN + 32 * c + j]);
+                            const int64_t o = (int64_t)m * p.N + n;
+                            if (p.y_dtype == B200Q_F32) static_cast<float*>(p.y)[o] = v;
+                            else if (p.y_dtype == B200Q_F16) static_cast<__half*>(p.y)[o] = __float2half_rn(v);
+                            else static_cast<__nv_bfloat16*>(p.y)[o] = __float2bfloat16_rn(v);
+                        }
                     }
                 }
             }
@@ -654,9 +675,10 @@ size_t gemm_tc_ws_bytes(int64_t M, int64_t N, int64_t K) {
 int launch_gemm_tc(const DeviceInfo& dev, const void* x, int x_dtype, const uint8_t* packed,
                    const float* scales, const float* zps, void* y, int y_dtype, int64_t M,
                    int64_t N, int64_t K, const int32_t* starts, const int32_t* ends, int E,
-                   void* ws, size_t ws_bytes, unsigned flags, cudaStream_t st) {
+                   void* ws, size_t ws_bytes, unsigned flags, cudaStream_t st, int gated) {
     (void)flags;
     if (!gemm_tc_supported(M, N, K, x_dtype, y_dtype)) return set_error(B200Q_EINVAL, "gemm_tc: unsupported shape");
+    if (gated && (N & 1)) return set_error(B200Q_EINVAL, "gemm_tc: the gated epilogue needs an even number of weight rows");
     const size_t need = gemm_tc_ws_bytes(M, N, K);
     if (!ws || ws_bytes < need) return set_error(B200Q_EWORKSPACE, "gemm_tc: workspace too small (%zu < %zu)", ws_bytes, need);
     // the tensor maps want 1024-byte aligned bases: align inside the (1 KB larger) workspace
@@ -707,7 +729,7 @@ int launch_gemm_tc(const DeviceInfo& dev, const void* x, int x_dtype, const uint
     // 11008 -> 4096 (32 weight-row tiles) M = 256 +28 %, M = 512 +17 %; with fuller waves the two extra
     // un-overlapped accumulator drains per CTA cost more than the balance gains (4096 -> 11008 M = 512: -37 %).
     int sk = 0, skq = 0, skr = 0, sk_grid = 0;
-    if (!starts && tuning().gemm_sk != 0) {
+    if (!starts && !gated && tuning().gemm_sk != 0) {
         const int bnsk = M <= 64 ? bn : 256;                        // small batches keep their small token tile
         const long long tiles256 = ((M + bnsk - 1) / bnsk) * n_tiles_h;
         const long long waves = (tiles256 + dev.sm_count - 1) / dev.sm_count;
@@ -738,6 +760,7 @@ int launch_gemm_tc(const DeviceInfo& dev, const void* x, int x_dtype, const uint
     p.stages = stages;
     p.sk = sk; p.skq = skq; p.skr = skr;
     p.debug = tuning().gemm_debug > 0 ? tuning().gemm_debug : 0;
+    p.gated = gated;
     p.part = reinterpret_cast<float*>(w8 + 2 * xbytes + 2 * sbytes);
     p.flags = reinterpret_cast<unsigned int*>(ws);
     const size_t smem = (size_t)OFF_STAGES + (size_t)stages * p.stage_bytes;

@@ -93,6 +93,6 @@ size_t gemm_tc_ws_bytes(int64_t M, int64_t N, int64_t K);
 int launch_gemm_tc(const DeviceInfo& dev, const void* x, int x_dtype, const uint8_t* packed,
                    const float* scales, const float* zps, void* y, int y_dtype, int64_t M,
                    int64_t N, int64_t K, const int32_t* starts, const int32_t* ends, int E,
-                   void* ws, size_t ws_bytes, unsigned flags, cudaStream_t st);
+                   void* ws, size_t ws_bytes, unsigned flags, cudaStream_t st, int gated = 0);
 
 }  // namespace b200q

@@ -114,15 +114,28 @@ class QuantizedMoE(nn.Module):
         self._stacked = None
         return super()._apply(fn, *args, **kwargs)
 
+    @property
+    def fused_gate(self) -> bool:
+        """The SiLU-gate runs in the epilogue of the first grouped GEMM (rows of w1 and w3 interleaved) whenever the
+        tcgen05 path takes the shape; otherwise w1||w3 are concatenated and b200q_moe_silu_mul follows."""
+        return self.gated and self.experts[0].in_features % 128 == 0
+
     def stacked_weights(self):
-        """[E,N,K/2] / [E,N] tensors for the grouped kernels: w1||w3 concatenated along N, and w2."""
+        """[E,N,K/2] / [E,N] tensors for the grouped kernels: w1 and w3 stacked along N (interleaved row by row when
+        `fused_gate`, else concatenated), and w2."""
         dev = self.experts[0].packed_weights.device
         if self._stacked is None or self._stacked[0] != dev:
             if self.gated:
                 p1, s1, z1 = _stack_experts(self.experts)
                 p3, s3, z3 = _stack_experts(self.experts_up)
-                w13 = (torch.cat([p1, p3], dim=1).contiguous(), torch.cat([s1, s3], dim=1).contiguous(),
-                       torch.cat([z1, z3], dim=1).contiguous())
+                if self.fused_gate:
+                    E, F = p1.shape[0], p1.shape[1]
+                    w13 = (torch.stack([p1, p3], dim=2).reshape(E, 2 * F, -1).contiguous(),
+                           torch.stack([s1, s3], dim=2).reshape(E, 2 * F).contiguous(),
+                           torch.stack([z1, z3], dim=2).reshape(E, 2 * F).contiguous())
+                else:
+                    w13 = (torch.cat([p1, p3], dim=1).contiguous(), torch.cat([s1, s3], dim=1).contiguous(),
+                           torch.cat([z1, z3], dim=1).contiguous())
                 w2 = _stack_experts(self.experts_down)
             else:
                 w13 = _stack_experts(self.experts)
@@ -149,10 +162,13 @@ class QuantizedMoE(nn.Module):
     def forward_grouped(self, xs: torch.Tensor, offsets: torch.Tensor) -> torch.Tensor:
         """Rows of xs grouped by expert (offsets [E+1] int32 on the device) -> expert outputs."""
         w13, w2 = self.stacked_weights()
-        gu = _lib.moe_grouped_fwd(xs, w13[0], w13[1], w13[2], offsets)
-        if not self.gated:
-            return gu
-        h = _lib.moe_silu_mul(gu)
+        if self.fused_gate:
+            h = _lib.moe_grouped_gated_fwd(xs, w13[0], w13[1], w13[2], offsets)
+        else:
+            gu = _lib.moe_grouped_fwd(xs, w13[0], w13[1], w13[2], offsets)
+            if not self.gated:
+                return gu
+            h = _lib.moe_silu_mul(gu)
         return _lib.moe_grouped_fwd(h, w2[0], w2[1], w2[2], offsets)
 
     @property

@@ -17,7 +17,8 @@
  *   b200q_moe_grouped_fwd   <- moe_int4_cuda.forward                csrc/moe_int4_kernel.cu:93-141
  *                              + QuantizedMoE.forward               benchmark/moe_grouped_gemm/moe_int4_module.py:123-125
  *   b200q_moe_grouped_fwd_ranges <- moe_int4_cuda.forward (input_offsets, tokens_per_expert)   csrc/moe_int4_kernel.cu:112-123
- *   b200q_moe_silu_mul      <- (north_star extension: gated MLP, silu(x w1^T) * (x w3^T))
+ *   b200q_moe_silu_mul, b200q_moe_grouped_gated_fwd
+ *                           <- (north_star extension: gated MLP, silu(x w1^T) * (x w3^T))
  *   b200q_moe_combine       <- combine_expert_outputs               routing.py:152-189
  *
  * Conventions
@@ -181,6 +182,16 @@ int b200q_moe_grouped_fwd_ranges(const void* xs, int x_dtype, const uint8_t* pac
                                  const float* scales, const float* zps, const int32_t* starts,
                                  const int32_t* ends, int E, void* y, int y_dtype, int64_t R,
                                  int64_t N, int64_t K, void* ws, size_t ws_bytes, void* stream);
+
+/* Gated first half of the expert MLP in ONE grouped GEMM (north-star extension; semantics composed from the
+ * reference's primitives):  h[p,f] = silu(xs[p,:] . w1_e[f,:]) * (xs[p,:] . w3_e[f,:])  for
+ * offsets[e] <= p < offsets[e+1].  packed13 [E,2F,K/2], scales13 / zps13 [E,2F] hold the rows of w1 and w3
+ * INTERLEAVED (row 2f = w1[f], row 2f+1 = w3[f]) so that a tile's epilogue has both projections of an h column;
+ * h [R,F].  Needs K % 128 == 0 and 16-byte aligned buffers (B200Q_EINVAL otherwise: use b200q_moe_grouped_fwd on
+ * the concatenated w1||w3 followed by b200q_moe_silu_mul).  ws: >= b200q_moe_grouped_ws_bytes(R,E,2F,K). */
+int b200q_moe_grouped_gated_fwd(const void* xs, int x_dtype, const uint8_t* packed13, const float* scales13,
+                                const float* zps13, const int32_t* offsets, int E, void* h, int h_dtype,
+                                int64_t R, int64_t F, int64_t K, void* ws, size_t ws_bytes, void* stream);
 
 /* h[p,f] = silu(a[p,f]) * b[p,f] where a = gu[p, 0:F], b = gu[p, F:2F]  (gated-MLP extension). */
 int b200q_moe_silu_mul(const void* gu, int dtype, int64_t R, int64_t F, void* h, void* stream);

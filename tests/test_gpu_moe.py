@@ -201,3 +201,39 @@ def test_mixtral_routed_layer_properties(pkg):
     diff = (y2 - y).abs().max().item()
     print(f"fused vs per-expert: max abs diff {diff:.3e}, |y|max {y.abs().max().item():.3f}")
     assert diff <= 3e-4 * y.abs().max().item()
+
+
+def test_fused_silu_gate_epilogue_matches_unfused(oracle, pkg):
+    """b200q_moe_grouped_gated_fwd (rows of w1 / w3 interleaved, SiLU-gate in the GEMM epilogue) against the
+    two-kernel form (grouped GEMM on w1||w3, then b200q_moe_silu_mul) and against the float64 oracle, ragged groups
+    (one of them empty)."""
+    import torch
+    rng = np.random.default_rng(3)
+    E, K, F = 4, 256, 384
+    counts = [37, 0, 130, 5]
+    R = sum(counts)
+    offs = torch.tensor(np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)).cuda()
+    w1 = [(rng.standard_normal((F, K)) * 0.05).astype(np.float32) for _ in range(E)]
+    w3 = [(rng.standard_normal((F, K)) * 0.05).astype(np.float32) for _ in range(E)]
+    q1, q3 = [oracle.quantize_weights(w) for w in w1], [oracle.quantize_weights(w) for w in w3]
+    x = rng.standard_normal((R, K), dtype=np.float32)
+    cu = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    st = lambda qs, i: np.stack([q[i] for q in qs])
+    # concatenated (two kernels) and interleaved (fused) weight layouts
+    cat = [np.concatenate([st(q1, i), st(q3, i)], axis=1) for i in range(3)]
+    il = [np.stack([st(q1, i), st(q3, i)], axis=2).reshape((E, 2 * F) + st(q1, i).shape[2:]) for i in range(3)]
+    X = cu(x)
+    gu = pkg._lib.moe_grouped_fwd(X, cu(cat[0]), cu(cat[1]), cu(cat[2]), offs)
+    h_two = pkg._lib.moe_silu_mul(gu).cpu().numpy()
+    h_fused = pkg._lib.moe_grouped_gated_fwd(X, cu(il[0]), cu(il[1]), cu(il[2]), offs).cpu().numpy()
+    ref = np.zeros((R, F))
+    for e in range(E):
+        lo, hi = int(offs[e]), int(offs[e + 1])
+        if hi > lo:
+            g = oracle.reference_quantized_linear(x[lo:hi], *q1[e], acc=np.float64)
+            u = oracle.reference_quantized_linear(x[lo:hi], *q3[e], acc=np.float64)
+            ref[lo:hi] = g / (1.0 + np.exp(-g)) * u
+    scale = np.abs(ref).max()
+    assert np.abs(h_fused - ref).max() <= 2e-4 * scale
+    assert np.abs(h_two - ref).max() <= 2e-4 * scale
+    assert np.abs(h_fused - h_two).max() <= 2e-4 * scale
