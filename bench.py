@@ -384,7 +384,8 @@ def run_gemv(args):
                      "algorithmic_bytes_per_launch": bytes_per_launch},
         "e2e": {"value": e2e_gbs, "unit": "GB/s", "h2d_bytes_per_step": POOL * M * K_IN * 4,
                 "d2h_bytes_per_step": POOL * M * N_OUT * 4, "steps": e2e_steps,
-                "api": "QuantizedLinear.forward_host -> b200q_linear_fwd_host (pinned host x and y, weights resident), "
+                "api": "QuantizedLinear.forward_host -> b200q_linear_fwd_host (pinned host x and y, weights resident; x is pulled "
+                       "over PCIe by a staging kernel and the GEMV epilogue stores y straight into the pinned buffer), "
                        "24 calls per step replayed as a CUDA graph", "us_per_call": ms2 * 1e3 / (e2e_steps * POOL)},
         "gpu_launches": launches,
         "clocks": clocks.summary(),

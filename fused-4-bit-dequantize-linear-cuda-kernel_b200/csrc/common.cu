@@ -61,6 +61,31 @@ int current_device(DeviceInfo* out) {
 static Tuning g_tuning;
 const Tuning& tuning() { return g_tuning; }
 
+// ---- pinned host memory -> device staging by a kernel (b200q_linear_fwd_host, decode-sized activations)
+__global__ void __launch_bounds__(256) stage_host_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int n16) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // dst may still be read by the preceding kernel
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+int launch_stage_host(const void* src_mapped, void* dst, size_t bytes, cudaStream_t st) {
+    const int n16 = (int)(bytes / 16);
+    int blocks = (n16 + 255) / 256;
+    if (blocks > 8) blocks = 8;
+    if (blocks < 1) blocks = 1;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)blocks);
+    cfg.blockDim = dim3(256);
+    cfg.stream = st;
+    cudaLaunchAttribute attrs[1];
+    attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attrs;
+    cfg.numAttrs = 1;
+    return check_cuda(cudaLaunchKernelEx(&cfg, stage_host_kernel, static_cast<const uint4*>(src_mapped), static_cast<uint4*>(dst), n16),
+                      "stage_host launch");
+}
+
 }  // namespace b200q
 
 using namespace b200q;
@@ -101,6 +126,7 @@ int b200q_tune_set(const char* key, int value) {
     else if (!strcmp(key, "gemv_ctas")) g_tuning.gemv_ctas = value;
     else if (!strcmp(key, "gemv_debug")) g_tuning.gemv_debug = value;
     else if (!strcmp(key, "gemm_bn")) g_tuning.gemm_bn = value;
+    else if (!strcmp(key, "host_direct")) g_tuning.host_direct = value;
     else if (!strcmp(key, "gemm_debug")) g_tuning.gemm_debug = value;
     else if (!strcmp(key, "gemm_sk")) g_tuning.gemm_sk = value;
     else if (!strcmp(key, "gemv_res")) g_tuning.gemv_res = value < 0 ? 1 : value;

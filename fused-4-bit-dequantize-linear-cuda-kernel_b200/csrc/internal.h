@@ -35,6 +35,7 @@ struct Tuning {
     int gemv_pdl = -1;      // 0 disables programmatic dependent launch
     int gemv_ctas = -1;     // cap on the number of CTAs (default: SM count)
     int gemm_bn = -1;       // token-tile height of the tcgen05 GEMM (128 / 192 / 256), default: heuristic
+    int host_direct = -1;   // 0: b200q_linear_fwd_host always copies the result back instead of storing into pinned memory
     int gemm_debug = -1;    // bench-only ablations of the tcgen05 GEMM (1: no weight loads, 2: no activation loads)
     int gemm_sk = -1;       // stream-K in the tcgen05 GEMM: -1 heuristic, 0 off, 1 whenever possible
     int gemv_res = 1;       // 0: never use the resident-slab decode kernel
@@ -71,6 +72,9 @@ int launch_gemv(const DeviceInfo& dev, const void* x, int x_dtype, const uint8_t
                 const float* scales, const float* zps, void* y, int y_dtype, int64_t M, int64_t N,
                 int64_t K, void* ws, size_t ws_bytes, unsigned flags, cudaStream_t st,
                 const uint8_t* next_packed = nullptr, size_t next_bytes = 0);
+
+// device-addressable pinned host memory -> device buffer, `bytes` % 16 == 0 (one small kernel instead of a copy node)
+int launch_stage_host(const void* src_mapped, void* dst, size_t bytes, cudaStream_t st);
 
 // decode GEMV, resident-slab variant (gemv_res.cu): M <= 8, K % 128 == 0, K <= 6144 and the CTA's rows fit in
 // shared memory; no workspace

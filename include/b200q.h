@@ -130,7 +130,9 @@ int b200q_linear_fwd_next(const void* x, int x_dtype, const uint8_t* packed, con
 /* Same with HOST activations: enqueues H2D copy of x (h_x -> the caller's device staging buffer d_x), the
  * fused dequantize-linear, and the D2H copy of the result (d_y -> h_y) on `stream`; h_x / h_y should be
  * pinned.  This is the call a host-resident caller of the reference's QuantizedLinear.forward maps to
- * (python/module.py:100-118 with x on the CPU and the module on the GPU).  Capturable in a CUDA graph. */
+ * (python/module.py:100-118 with x on the CPU and the module on the GPU).  Capturable in a CUDA graph.
+ * For M <= 8 and a device-addressable pinned h_y the kernel stores the result straight into h_y (no copy node);
+ * d_y is then unused. */
 int b200q_linear_fwd_host(const void* h_x, int x_dtype, void* d_x, const uint8_t* packed, const float* scales,
                           const float* zps, void* d_y, void* h_y, int y_dtype, int64_t M, int64_t N, int64_t K,
                           void* ws, size_t ws_bytes, unsigned flags, void* stream);
