@@ -40,7 +40,7 @@ def measure(layers, M, N, K, dev, steps=100, graph=True, flags=_lib.FLAG_STATIC_
     use_next = os.environ.get("NEXT", "1") == "1"
 
     def launch_all(sp):
-        for i in range(max(24, len(layers))):               # always 24+ launches per graph replay
+        for i in range(max(int(os.environ.get('GRAPH_LEN', '24')), len(layers))):               # always 24+ launches per graph replay
             p, s, z = layers[i % len(layers)]
             nxt = layers[(i + (0 if os.environ.get("NEXT_SELF") else 1)) % len(layers)][0]
             _lib.check(lib.b200q_linear_fwd_next(x.data_ptr(), 0, p.data_ptr(), s.data_ptr(), z.data_ptr(), y.data_ptr(), 0,
@@ -67,7 +67,7 @@ def measure(layers, M, N, K, dev, steps=100, graph=True, flags=_lib.FLAG_STATIC_
         run()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) * 1e3 / (steps * max(24, len(layers)))
+    return e0.elapsed_time(e1) * 1e3 / (steps * max(int(os.environ.get('GRAPH_LEN', '24')), len(layers)))
 
 
 def main():
@@ -82,7 +82,7 @@ def main():
     for (K, N) in shapes:
         layers = make_pool(N, K, int(os.environ.get("POOL", "24")), dev)
         nbytes = lambda M: N * K // 2 + 8 * N + 4 * M * K + 4 * M * N
-        configs = [({}, 1, True)] if K == 4096 else [({"gemv_slabs": ns, "gemv_early": e}, 1, True) for ns in (2, 3, 4) for e in (92, 91, 9, 32)]
+        configs = [({}, 1, True)]
         for tune, M, graph in configs:
             for k in KEYS:
                 _lib.tune(k, -1)
