@@ -355,3 +355,33 @@ def test_gemm_token_tile_heights(oracle, pkg, bn):
         pkg._lib.tune("gemm_bn", -1)
         pkg._lib.tune("force_path", -1)
     assert np.abs(y - ref).max() <= 1e-4 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("M,N,K", [(1, 4096, 11008), (2, 4100, 11008), (1, 37, 8192), (2, 1000, 7168)])
+def test_k_split_cluster_decode(oracle, pkg, dtype, M, N, K):
+    """K > 6144: the resident-slab kernel splits K over a cluster of two CTAs and adds the exact partials through
+    distributed shared memory; ragged row counts, 16-bit activations, and the ring kernel as a second opinion."""
+    rng = np.random.default_rng(N + K + M)
+    packed = rng.integers(0, 256, size=(N, K // 2), dtype=np.uint8)
+    scales = (rng.random(N, dtype=np.float32) * 0.01 + 0.001).astype(np.float32)
+    zps = rng.integers(0, 16, size=N).astype(np.float32)
+    X = cuda(rng.standard_normal((M, K), dtype=np.float32)).to(dtype)
+    P, S, Z = cuda(packed), cuda(scales), cuda(zps)
+    ref = oracle.reference_quantized_linear(X.float().cpu().numpy(), packed, scales, zps, acc=np.float64)
+    outs = {}
+    for path in (5, 2):
+        pkg._lib.tune("force_path", path)
+        try:
+            outs[path] = pkg._lib.linear_fwd(X, P, S, Z, out_dtype=torch.float32).cpu().numpy()
+        finally:
+            pkg._lib.tune("force_path", -1)
+        assert np.abs(outs[path] - ref).max() <= 1e-6 * np.abs(ref).max()
+    assert np.array_equal(pkg._lib.linear_fwd(X, P, S, Z, out_dtype=torch.float32).cpu().numpy(), outs[5])
+    # determinism of the cluster reduction
+    pkg._lib.tune("force_path", 5)
+    try:
+        again = pkg._lib.linear_fwd(X, P, S, Z, out_dtype=torch.float32).cpu().numpy()
+    finally:
+        pkg._lib.tune("force_path", -1)
+    assert np.array_equal(again, outs[5])
