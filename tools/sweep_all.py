@@ -68,7 +68,7 @@ def decode(K, N):
 def prefill(K, N):
     p, s, z = pool(N, K, 1)[0]
     for dt in (torch.bfloat16, torch.float32):
-        for M in (512, 1024, 2048, 4096):
+        for M in (256, 512, 1024, 2048, 4096):
             x = torch.randn(M, K, device=dev).to(dt)
             ms = timed(lambda: _lib.linear_fwd(x, p, s, z), 20)
             tf = 2.0 * M * N * K / (ms * 1e-3) / 1e12
@@ -97,9 +97,9 @@ def moe():
 
 if __name__ == "__main__":
     what = sys.argv[1:] or ["decode", "prefill", "moe"]
+    if "prefill" in what:       # first: the multi-millisecond MoE / fp32 blocks leave the part power-capped for a while
+        prefill(4096, 11008); prefill(11008, 4096)
     if "decode" in what:
         decode(4096, 11008); decode(11008, 4096)
-    if "prefill" in what:
-        prefill(4096, 11008); prefill(11008, 4096)
     if "moe" in what:
         moe()
