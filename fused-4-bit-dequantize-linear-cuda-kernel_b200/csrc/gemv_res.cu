@@ -266,25 +266,47 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_res_kernel(const ResParams p) {
         }
     } else {
         issue_late();
-        for (int m = 0; m < p.M; ++m) {
-            float am = 0.0f;
-            // four loads in flight per thread (a plain strided loop made one trip to L2 per iteration: 2.7 us for the
-            // 43 KB of a K = 11008 row while the weight requests are queued in front)
-            for (int i0 = tid; i0 < K8; i0 += 4 * NTHR) {
+        if (K8 <= NTHR) {
+            // a row is at most one item per thread: four ROWS in flight per thread (row after row cost one trip to L2
+            // each: 4.5 us for 8 rows while the weight requests are queued in front)
+            for (int m0 = 0; m0 < p.M; m0 += 4) {
                 float v[4][8];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
 #pragma unroll
                     for (int e = 0; e < 8; ++e) v[u][e] = 0.0f;
-                    if (i0 + u * NTHR < K8) load8f(p.x, p.x_dtype, (int64_t)m * p.K + (int64_t)(i0 + u * NTHR) * 8, v[u]);
+                    if (m0 + u < p.M && tid < K8) load8f(p.x, p.x_dtype, (int64_t)(m0 + u) * p.K + (int64_t)tid * 8, v[u]);
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
+                for (int u = 0; u < 4; ++u) {
+                    float am = 0.0f;
 #pragma unroll
                     for (int e = 0; e < 8; ++e) am = fmaxf(am, fabsf(v[u][e]));
+                    const unsigned int ua = __reduce_max_sync(0xffffffffu, __float_as_uint(am));
+                    if (lane == 0 && m0 + u < p.M) s_amax[(m0 + u) * NW + warp] = __uint_as_float(ua);
+                }
             }
-            const unsigned int ua = __reduce_max_sync(0xffffffffu, __float_as_uint(am));
-            if (lane == 0) s_amax[m * NW + warp] = __uint_as_float(ua);
+        } else {
+            for (int m = 0; m < p.M; ++m) {
+                float am = 0.0f;
+                // four loads in flight per thread (a plain strided loop made one trip to L2 per iteration: 2.7 us for
+                // the 43 KB of a K = 11008 row)
+                for (int i0 = tid; i0 < K8; i0 += 4 * NTHR) {
+                    float v[4][8];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v[u][e] = 0.0f;
+                        if (i0 + u * NTHR < K8) load8f(p.x, p.x_dtype, (int64_t)m * p.K + (int64_t)(i0 + u * NTHR) * 8, v[u]);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) am = fmaxf(am, fabsf(v[u][e]));
+                }
+                const unsigned int ua = __reduce_max_sync(0xffffffffu, __float_as_uint(am));
+                if (lane == 0) s_amax[m * NW + warp] = __uint_as_float(ua);
+            }
         }
     }
     __syncthreads();
@@ -345,11 +367,19 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_res_kernel(const ResParams p) {
             if (tid < items) convert(tid, xv[0]);
             if (tid + NTHR < items) convert(tid + NTHR, xv[1]);
         } else {
-            for (int it = tid; it < items; it += NTHR) {
-                const int hh = it >= G * 16 ? 1 : 0;
-                float v[8];
-                load8f(p.x, p.x_dtype, (int64_t)(2 * nt + hh) * p.K + (int64_t)(g0 * 16 + it - hh * G * 16) * 8, v);
-                convert(it, v);
+            for (int it0 = tid; it0 < items; it0 += 2 * NTHR) {       // two loads in flight per thread
+                float v[2][8];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int it = it0 + u * NTHR;
+                    if (it < items) {
+                        const int hh = it >= G * 16 ? 1 : 0;
+                        load8f(p.x, p.x_dtype, (int64_t)(2 * nt + hh) * p.K + (int64_t)(g0 * 16 + it - hh * G * 16) * 8, v[u]);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u)
+                    if (it0 + u * NTHR < items) convert(it0 + u * NTHR, v[u]);
             }
         }
         if (live_rows > 0) {
