@@ -165,6 +165,9 @@ def run_moe(args):
         "clocks": clocks.summary(),
         "ep": stats,
     }
+    # the same sub-object the N = 1 (GEMV-headline) line carries: `moe.value` is one consistent series over N = 1, 2, 4, 8
+    line["moe"] = {k: line[k] for k in ("metric", "value", "unit", "n_gpus", "ms_per_step", "dtype", "roofline")}
+    line["moe"]["workload"] = line["config"]["workload"]
     if not args.no_cpu:
         v, threads, sample = cpu_moe_baseline()
         line["cpu_baseline"] = {"value": v, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": sample}
