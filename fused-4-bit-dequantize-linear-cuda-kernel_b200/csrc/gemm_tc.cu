@@ -730,7 +730,8 @@ int launch_gemm_tc(const DeviceInfo& dev, const void* x, int x_dtype, const uint
     // un-overlapped accumulator drains per CTA cost more than the balance gains (4096 -> 11008 M = 512: -37 %).
     int sk = 0, skq = 0, skr = 0, sk_grid = 0;
     if (!starts && !gated && tuning().gemm_sk != 0) {
-        const int bnsk = M <= 64 ? bn : 256;                        // small batches keep their small token tile
+        const int fbs = tuning().gemm_bn;
+        const int bnsk = (fbs == 128 || fbs == 192 || fbs == 256) ? fbs : (M <= 64 ? bn : 256);   // small batches keep their small token tile
         const long long tiles256 = ((M + bnsk - 1) / bnsk) * n_tiles_h;
         const long long waves = (tiles256 + dev.sm_count - 1) / dev.sm_count;
         const double fill = (double)tiles256 / (double)(waves * dev.sm_count);
