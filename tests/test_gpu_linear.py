@@ -385,3 +385,43 @@ def test_k_split_cluster_decode(oracle, pkg, dtype, M, N, K):
     finally:
         pkg._lib.tune("force_path", -1)
     assert np.array_equal(again, outs[5])
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_forward_host_direct_and_copy_paths_agree(oracle, pkg, dtype):
+    """b200q_linear_fwd_host for decode-sized calls: staging kernel + stores straight into the pinned result buffer
+    (default) against the two-cudaMemcpyAsync form (host_direct=0); also inside a CUDA graph, replayed with new x."""
+    torch.manual_seed(5)
+    lin = torch.nn.Linear(4096, 1000, bias=False)
+    ql = pkg.QuantizedLinear.from_linear(lin.cuda())
+    outs = {}
+    for M in (1, 8):
+        x = torch.randn(M, 4096).to(dtype).pin_memory()
+        for hd in (1, 0):
+            pkg._lib.tune("host_direct", hd)
+            try:
+                y = ql.forward_host(x)
+                torch.cuda.synchronize()
+                outs[hd] = y.float().numpy().copy()
+            finally:
+                pkg._lib.tune("host_direct", -1)
+        assert np.array_equal(outs[0], outs[1])
+        ref = ql(x.cuda()).float().cpu().numpy()
+        assert np.array_equal(outs[1], ref)
+    # graph capture of the direct path: replays must pick up the CURRENT contents of the pinned input
+    x = torch.randn(1, 4096).to(dtype).pin_memory()
+    out = torch.empty(1, 1000, dtype=dtype).pin_memory()
+    ql.forward_host(x, out=out)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        ql.forward_host(x, out=out)
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        ql.forward_host(x, out=out)
+    x.copy_(torch.randn(1, 4096).to(dtype))
+    g.replay()
+    torch.cuda.synchronize()
+    assert np.array_equal(out.float().numpy(), ql(x.cuda()).float().cpu().numpy())
