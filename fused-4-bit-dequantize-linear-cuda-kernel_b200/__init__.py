@@ -5,7 +5,7 @@ and benchmark/moe_grouped_gemm): same names, same buffers, same results -- compu
 sm_100a kernels in ``libb200q.so`` (C ABI: include/b200q.h).
 """
 from .quantize import quantize_weights, dequantize_weights, reference_quantized_linear
-from .module import QuantizedLinear
+from .module import QuantizedLinear, link_decode_order
 from .moe import QuantizedMoEExpert, QuantizedMoE, MoEINT4, quantize_weights_moe
 from .routing import (RoutingResult, DeviceRouting, simulate_routing, create_expert_inputs,
                       combine_expert_outputs, get_expert_sizes_for_benchmark, route, make_logits)
@@ -14,6 +14,7 @@ from .ep import ExpertParallelMoE, dispatch_plan, shard_experts
 from . import _lib
 
 __all__ = [
+    "link_decode_order",
     "quantize_weights", "dequantize_weights", "reference_quantized_linear", "QuantizedLinear",
     "QuantizedMoEExpert", "QuantizedMoE", "MoEINT4", "quantize_weights_moe",
     "RoutingResult", "DeviceRouting", "simulate_routing", "create_expert_inputs",

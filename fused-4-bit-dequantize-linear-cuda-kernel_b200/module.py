@@ -95,3 +95,16 @@ class QuantizedLinear(nn.Module):
         return (f"in_features={self.in_features}, "
                 f"out_features={self.out_features}, "
                 f"bits=4")
+
+
+def link_decode_order(layers, cyclic: bool = True):
+    """Wire the next-layer L2 prefetch hints of the fused linears of a decode loop, in the order they run:
+    layers[i].set_next(layers[i + 1]); with `cyclic` the last one points at the first (the next token's first
+    layer).  Returns `layers`."""
+    layers = list(layers)
+    for i, layer in enumerate(layers):
+        if i + 1 < len(layers):
+            layer.set_next(layers[i + 1])
+        elif cyclic and len(layers) > 1:
+            layer.set_next(layers[0])
+    return layers

@@ -278,8 +278,7 @@ def test_next_layer_hint_does_not_change_results(oracle, pkg):
     x = cuda(rng.standard_normal((1, K), dtype=np.float32))
     plain = [m(x).cpu().numpy() for m in layers]
     plain = [m(x).cpu().numpy() for m in layers]            # second pass: static-weights fast path
-    for i, m in enumerate(layers):
-        m.set_next(layers[(i + 1) % 3])
+    pkg.link_decode_order(layers)                       # layers[i].set_next(layers[i + 1]), last -> first
     hinted = [m(x).cpu().numpy() for m in layers]
     for a, b in zip(plain, hinted):
         assert np.array_equal(a, b)
