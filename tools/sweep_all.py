@@ -39,9 +39,9 @@ def pool(N, K, n):
     return out
 
 
-def decode(K, N):
+def decode(K, N, batch=(1, 2, 4, 8, 16)):
     layers = pool(N, K, 24)
-    for M in (1, 2, 4, 8, 16):
+    for M in batch:
         x = torch.randn(M, K, device=dev)
         y = torch.empty(M, N, device=dev)
         ws = torch.zeros(max(lib.b200q_linear_ws_bytes(M, N, K), 16), dtype=torch.uint8, device=dev)
@@ -101,5 +101,6 @@ if __name__ == "__main__":
         prefill(4096, 11008); prefill(11008, 4096)
     if "decode" in what:
         decode(4096, 11008); decode(11008, 4096)
+        decode(4096, 14336, (1,)); decode(14336, 4096, (1,))        # one Mixtral expert's projections
     if "moe" in what:
         moe()

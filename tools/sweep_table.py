@@ -7,6 +7,7 @@ out = ["# SURVEY 8(d) configurations, one B200, `python tools/sweep_all.py` (dev
 for r in rows:
     if r["config"] == "decode":
         if r["M"] > 8: kern = "tcgen05 GEMM, 32-token tiles"
+        elif r["N"] * r["K"] > 46_000_000: kern = "ring (198 KB of weights per SM do not fit the resident scheme)"
         elif r["K"] > 6144: kern = "resident slab, K split over a 2-CTA cluster" if r["M"] <= 2 else "ring"
         else: kern = "resident slab"
         out.append(f'| {r["K"]} -> {r["N"]} | {r["M"]} | {r["us_per_launch"]:.2f} | {r["GBps"]:.0f} | {100*r["frac_hbm_peak"]:.1f} | {kern} |')
