@@ -82,7 +82,9 @@ def main():
     for (K, N) in shapes:
         layers = make_pool(N, K, int(os.environ.get("POOL", "24")), dev)
         nbytes = lambda M: N * K // 2 + 8 * N + 4 * M * K + 4 * M * N
-        configs = [({}, 1, True)]
+        configs = [({}, 1, True), ({}, 2, True), ({}, 4, True), ({}, 8, True),
+                   ({"gemv_pf": 0}, 1, True), ({"gemv_early": 31}, 1, True), ({"gemv_early": 9}, 1, True),
+                   ({"force_path": 2}, 1, True), ({"force_path": 2, "gemv_xprep": 1}, 1, True)]
         for tune, M, graph in configs:
             for k in KEYS:
                 _lib.tune(k, -1)
