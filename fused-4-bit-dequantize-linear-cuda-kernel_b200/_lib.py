@@ -72,7 +72,7 @@ def load() -> ctypes.CDLL:
                 fn.restype = res
                 fn.argtypes = args
             _lib = lib
-            # bench hook: B200Q_TUNE="gemm_ksub=1,gemv_early=91" applies b200q_tune_set keys at load time
+            # bench hook: B200Q_TUNE="gemm_bn=256,gemv_early=91" applies b200q_tune_set keys at load time
             for item in filter(None, os.environ.get("B200Q_TUNE", "").split(",")):
                 key, _, val = item.partition("=")
                 lib.b200q_tune_set(key.strip().encode(), int(val))

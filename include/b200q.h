@@ -137,9 +137,11 @@ int b200q_linear_fwd_host(const void* h_x, int x_dtype, void* d_x, const uint8_t
                           const float* zps, void* d_y, void* h_y, int y_dtype, int64_t M, int64_t N, int64_t K,
                           void* ws, size_t ws_bytes, unsigned flags, void* stream);
 
-/* Bench / tuning hook: override a launch heuristic process-wide (key = "gemv_warps" | "gemv_slabs"
- * | "gemv_stages" | "gemv_pdl" | "gemv_ctas" | "gemv_occ2" | "gemv_debug" | "gemm_bn" | "force_path"; value < 0
- * restores the default).  Not needed by callers. */
+/* Bench / tuning hook: override a launch heuristic process-wide; value < 0 restores the default.  Keys:
+ *   force_path (1 generic SIMT, 2 ring decode kernel, 3 tcgen05 GEMM, 4 tcgen05 decode experiment, 5 resident-slab
+ *   decode kernel), gemv_res, gemv_early, gemv_pf, gemv_xprep, gemv_warps, gemv_slabs, gemv_stages, gemv_pdl,
+ *   gemv_ctas, gemv_occ2, gemv_debug, gemm_bn (32 / 64 / 128 / 192 / 256), gemm_sk, gemm_debug, host_direct.
+ * Their meaning is documented next to the Tuning struct in csrc/internal.h.  Not needed by callers. */
 int b200q_tune_set(const char* key, int value);
 
 /* ---- MoE ---------------------------------------------------------------------------------- */
