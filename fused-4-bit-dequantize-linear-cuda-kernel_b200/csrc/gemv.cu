@@ -1,24 +1,24 @@
-// Decode path: y[M,N] = x[M,K] @ dequant(W)^T for M <= 8.  HBM-bound: every packed byte is read
-// exactly once, by the TMA engine, into shared memory; everything else is on-chip.
+// Decode path, ring kernel: y[M,N] = x[M,K] @ dequant(W)^T for M <= 8 on the shapes the resident-slab kernel
+// (gemv_res.cu) does not take -- a CTA's share of W does not fit in shared memory even with K split over a cluster
+// (e.g. 14336 -> 4096), or M > 2 with K > 6144.  HBM-bound: every packed byte is read exactly once, by the TMA
+// engine, into a shared-memory ring; everything else is on-chip.
 //
-// Decomposition (DESIGN.md "GEMV"):
+// Decomposition:
 //   * K is cut into `nslab` slabs of whole 128-column granules, N into `nrb` row blocks;
 //     CTA (rb, slab) streams rows [r0,r1) x slab bytes.  nslab * nrb ~= SM count, one CTA per SM.
-//   * a stage of the shared-memory ring = 16 weight rows x one chunk of NW granules.  Warp w issues
-//     the cp.async.bulk (UBLKCP) of row w of every stage, so the whole slab of the Llama shapes is
-//     requested within the first microsecond of the kernel, 16 issuers in parallel.
-//   * arithmetic is EXACT INTEGER: nibbles are widened to u8 with 3 ALU ops per 8 weights
-//     (w & 0x0f0f0f0f, (w >> 4) & 0x0f0f0f0f) and fed to IMMA m16n8k32 (u8 x s8 -> s32); x is a
-//     per-row fixed-point number round(x * 2^e) < 2^30 cut into four signed base-256 limbs, one mma
-//     column per (batch row, limb).  sum_k q*X and sum_k X are exact, so the result differs from the
-//     fp32 reference only by the 2^-30 fixed-point step of x and the final fp32 rounding, and it is
-//     bit-reproducible whatever the summation order.
-//   * warp w owns granules w, w+NW, ... of the slab for the whole kernel, so its x operand (mma B
-//     fragments) sits in registers; the CTA builds it cooperatively, once, through shared memory.
-//   * per-warp tile partials (s32) go to shared memory without a barrier; once per round of `rt`
-//     tiles: one named barrier, cross-warp sum, epilogue y = s * 2^-e * (sum q*X - zp * sum X); with
-//     nslab > 1 the slab partials go to a workspace and the last CTA of a row block (ticket counter)
-//     adds them in slab order: deterministic.
+//   * a stage of the ring = 16 weight rows x the slab's bytes of a row (one contiguous bulk copy per tile when
+//     nslab == 1, else one copy per row with an odd 64-byte pitch); slots are recycled through empty barriers.
+//   * arithmetic is EXACT INTEGER, as in gemv_res.cu: x is a per-row fixed-point number (even columns
+//     Xe = round(x 2^e), odd columns Xo = round(x 2^(e-4))) cut into four signed base-256 limbs, one IMMA m16n8k32
+//     (u8 x s8 -> s32) column per (batch row, limb); the raw packed byte meets Xe, the masked byte 16 q_hi meets
+//     Xo - Xe, so the nibbles are never widened.  sum q*X and sum X are exact: bit-reproducible whatever the order.
+//   * warp w owns granules w, w+NW, ... of the slab for the whole kernel, so its x operand (mma B fragments) sits in
+//     registers; it is built inside the CTA (block amax, then a warp-local conversion through a 512-byte staging
+//     slot) -- or, with the bench key gemv_xprep = 1, once per launch by xprep_kernel (an extra kernel in the
+//     dependency chain: slower, kept as a measured alternative).
+//   * per-warp tile partials (s32) go to shared memory without a barrier; once per round of `rt` tiles: one named
+//     barrier, cross-warp sum, epilogue y = s * 2^-e * (sum q*X - zp * sum X); with nslab > 1 the slab partials go
+//     to a workspace and the last CTA of a row block (ticket counter) adds them in slab order: deterministic.
 //
 // Reference being replaced: csrc/quantized_linear_kernel.cu:90-279 (one thread per output).
 #include <cmath>

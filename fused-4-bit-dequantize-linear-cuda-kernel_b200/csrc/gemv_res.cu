@@ -1,20 +1,28 @@
-// Decode path, "resident slab" variant: y[M,N] = x[M,K] @ dequant(W)^T for M <= 8 when a CTA's whole
-// share of W (its rows x K/2 packed bytes) fits in shared memory next to the x operand.
+// Decode path, "resident slab" kernel (the default for M <= 8): y[M,N] = x[M,K] @ dequant(W)^T when a CTA's whole
+// share of W (its rows x K/2 packed bytes, or half of that with K split over a 2-CTA cluster) fits in shared memory
+// next to the x operand.  HBM-bound by design: every packed byte is read once, by the TMA engine.
 //
-// Same kind of arithmetic as gemv.cu (exact integers: u8 weight bytes x signed base-256 limbs of a fixed-point
-// x on IMMA m16n8k32, s32 accumulation, fp64 epilogue: results do not depend on the summation order); what
-// differs is the amount of code every warp executes and that the nibbles are never widened (main loop).  gemv.cu spends ~1.1 k - 1.8 k instructions per warp per launch,
-// most of them outside the 5-tile main loop (profiles/r01_gemv_notes.md): with 16 warps on 4 schedulers
-// that is 2 - 4 us of pure issue time.  This kernel
-//   * has no ring: tile i is ONE bulk copy into its own slot with its own single-use mbarrier;
-//   * builds the x operand cooperatively: every thread converts 8 consecutive activations once
-//     (coalesced loads, 8 F2I) into the four limb planes of a shared-memory image laid out in mma
-//     B-fragment order, so a lane fetches the operand of a granule with two 16-byte loads;
-//   * reduces the 16 warp partials of a tile with shared-memory integer atomics (exact and order
-//     independent) into a 512-byte plane per (tile, n-tile): no partial buffers, no reduction rounds,
-//     one thread per output in the epilogue;
-//   * needs no workspace and no second kernel: consecutive decode layers are main -> main, which
-//     programmatic dependent launch overlaps CTA by CTA.
+// Arithmetic: exact integers.  x is a per-row fixed-point number (even columns Xe = round(x 2^e), odd columns
+// Xo = round(x 2^(e-4))) cut into four signed base-256 limbs = four columns of IMMA m16n8k32 (u8 x s8 -> s32) per batch
+// row.  The nibbles are never widened: the raw packed byte q_lo + 16 q_hi meets the limbs of Xe, the masked byte
+// 16 q_hi meets the limbs of Z = Xo - Xe.  s32 partial sums, s64 when the limbs are combined,
+// y = s * 2^-e * (sum q X - zp * sum X) with one fp32 rounding: results do not depend on the summation order.
+//
+// Structure (profiles/r01_gemv_notes.md has the measurements behind each choice):
+//   * no ring: tile i (16 rows) lands in its own slot with its own single-use mbarrier.  Two bulk copies per
+//     tile, the second half skewed by 64 bytes, make the 8-row LDS.128 of a warp conflict-free; with K split
+//     over a cluster: one copy per row, rows 64 bytes off a 128-byte multiple apart;
+//   * requests are staged (two tiles before griddepcontrol.wait, the rest behind the x loads) so that the
+//     16 KB of x do not queue behind 22 MB of weight requests; optionally the NEXT layer's weights are
+//     prefetched into L2 (cp.async.bulk.prefetch.L2) behind the own ones;
+//   * the x operand is built inside the CTA: one coalesced 32-byte load per thread (kept in registers for
+//     M <= 2), block amax with REDUX + one barrier, 8 F2I per thread, byte transposes (PRMT) into a shared-memory
+//     image in mma B-fragment order; a lane then fetches the operand of a granule with two 16-byte loads;
+//   * cross-warp reduction: per-warp partial slots (plain stores) and a 4-threads-per-output epilogue for
+//     M <= 2; replicated shared-memory integer atomics for M = 3..8; with K split, the exact s64 partials of
+//     the second CTA reach the leader through distributed shared memory;
+//   * no workspace and no second kernel: consecutive decode layers are main -> main, which programmatic
+//     dependent launch overlaps CTA by CTA.
 //
 // Reference being replaced: csrc/quantized_linear_kernel.cu:90-279 (one thread per output).
 #include <cmath>
