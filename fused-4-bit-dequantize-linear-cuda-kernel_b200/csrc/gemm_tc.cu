@@ -2,8 +2,12 @@
 //     Y[m, n] = sum_k X[m, k] * dequant(W)[n, k]        for M >= 9 rows (and every grouped call)
 //
 // "Swap-AB" tcgen05 GEMM: the 128 x K slab of INT4 weights is the A operand and lives in TENSOR
-// MEMORY; the activations are the B operand in shared memory (TMA, 128-byte swizzle), up to 256
-// token rows per tile, so one CTA tile is D[128 weight rows x 256 tokens] in TMEM (fp32).
+// MEMORY; the activations are the B operand in shared memory (TMA, 128-byte swizzle), BN = 32 .. 256
+// token rows per tile, so one CTA tile is D[128 weight rows x BN tokens] in TMEM (fp32).  BN <= 192 leaves
+// room for two accumulators (the epilogue of tile i overlaps the MMAs of tile i + 1); 32 / 64 serve decode-sized
+// batches.  Persistent grid; whole tiles round-robin, or stream-K (k-blocks dealt out evenly, partial
+// accumulators through the workspace) when the only wave is less than half full; grouped mode for the MoE
+// layer, optionally with the SiLU-gate in the epilogue (rows of w1 / w3 interleaved).
 //
 //   warp 0      TMA producer: per 64-column k-block one activation tile (256 x 64 fp16, plus the
 //               low-part tile for fp32 inputs) and one packed-weight tile (128 rows x 32 bytes)
