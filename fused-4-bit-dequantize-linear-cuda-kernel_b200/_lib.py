@@ -18,7 +18,7 @@ FLAG_NONE, FLAG_STATIC_WEIGHTS = 0, 1
 _DTYPE_CODE = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
 
 _here = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_here, "libb200q.so")
+LIB_PATH = os.environ.get("B200Q_LIB") or os.path.join(_here, "libb200q.so")   # B200Q_LIB: tools/ pick the -DB200Q_PROF build
 
 _c = ctypes
 _vp, _i64, _i32, _sz, _u32 = _c.c_void_p, _c.c_int64, _c.c_int, _c.c_size_t, _c.c_uint
@@ -37,6 +37,7 @@ SIGNATURES = {
     "b200q_linear_ws_bytes": (_sz, [_i64, _i64, _i64]),
     "b200q_linear_fwd": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _i32, _i64, _i64, _i64, _vp, _sz, _u32, _vp]),
     "b200q_linear_fwd_next": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _i32, _i64, _i64, _i64, _vp, _sz, _u32, _vp, _vp, _sz]),
+    "b200q_linear_bias_fwd": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i64, _i64, _vp, _sz, _u32, _vp, _vp, _sz]),
     "b200q_linear_fwd_host": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i64, _i64, _vp, _sz, _u32, _vp]),
     "b200q_tune_set": (_i32, [_c.c_char_p, _i32]),
     "b200q_moe_topk": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _vp]),
@@ -123,8 +124,8 @@ def tune(key: str, value: int) -> None:
 # ------------------------------------------------------------------------------------ wrappers
 def linear_fwd(x: torch.Tensor, packed: torch.Tensor, scales: torch.Tensor, zps: torch.Tensor,
                out_dtype=None, flags: int = FLAG_NONE, out: torch.Tensor | None = None,
-               next_packed: torch.Tensor | None = None) -> torch.Tensor:
-    """y[M,N] = x[M,K] @ dequant(packed, scales, zps)^T on the current stream of x's device.
+               next_packed: torch.Tensor | None = None, bias: torch.Tensor | None = None) -> torch.Tensor:
+    """y[M,N] = x[M,K] @ dequant(packed, scales, zps)^T (+ bias [N] f32) on the current stream of x's device.
     next_packed: packed weights of the fused linear that follows on this stream (L2 prefetch hint)."""
     lib = load()
     M, K = x.shape
@@ -134,8 +135,9 @@ def linear_fwd(x: torch.Tensor, packed: torch.Tensor, scales: torch.Tensor, zps:
         y = out if out is not None else torch.empty((M, N), dtype=out_dtype, device=x.device)
         ws_bytes = lib.b200q_linear_ws_bytes(M, N, K)
         ws = workspace(x.device, ws_bytes, "linear") if ws_bytes else None
-        check(lib.b200q_linear_fwd_next(x.data_ptr(), dtype_code(x), packed.data_ptr(), scales.data_ptr(),
-                                        zps.data_ptr(), y.data_ptr(), dtype_code(y), M, N, K,
+        check(lib.b200q_linear_bias_fwd(x.data_ptr(), dtype_code(x), packed.data_ptr(), scales.data_ptr(),
+                                        zps.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                        y.data_ptr(), dtype_code(y), M, N, K,
                                         ws.data_ptr() if ws is not None else None, ws.numel() if ws is not None else 0,
                                         flags, stream_ptr(x.device),
                                         next_packed.data_ptr() if next_packed is not None else None,

@@ -66,15 +66,13 @@ int b200q_dequantize_rows(const uint8_t* packed, const float* scales, const floa
 size_t b200q_linear_ws_bytes(int64_t M, int64_t N, int64_t K) {
     size_t a = gemv_ws_bytes(M, N, K);
     size_t b = gemm_tc_ws_bytes(M, N, K);
-    size_t c = gemv_tc_ws_bytes(M, N, K);
-    if (b > a) a = b;
-    return c > a ? c : a;
+    return b > a ? b : a;
 }
 
 int b200q_linear_fwd(const void* x, int x_dtype, const uint8_t* packed, const float* scales,
                      const float* zps, void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
                      void* ws, size_t ws_bytes, unsigned flags, void* stream) {
-    return b200q_linear_fwd_next(x, x_dtype, packed, scales, zps, y, y_dtype, M, N, K, ws, ws_bytes, flags, stream,
+    return b200q_linear_bias_fwd(x, x_dtype, packed, scales, zps, nullptr, y, y_dtype, M, N, K, ws, ws_bytes, flags, stream,
                                  nullptr, 0);
 }
 
@@ -82,29 +80,45 @@ int b200q_linear_fwd_next(const void* x, int x_dtype, const uint8_t* packed, con
                           const float* zps, void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
                           void* ws, size_t ws_bytes, unsigned flags, void* stream,
                           const uint8_t* next_packed, size_t next_bytes) {
+    return b200q_linear_bias_fwd(x, x_dtype, packed, scales, zps, nullptr, y, y_dtype, M, N, K, ws, ws_bytes, flags, stream,
+                                 next_packed, next_bytes);
+}
+
+int b200q_linear_bias_fwd(const void* x, int x_dtype, const uint8_t* packed, const float* scales,
+                          const float* zps, const float* bias, void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
+                          void* ws, size_t ws_bytes, unsigned flags, void* stream,
+                          const uint8_t* next_packed, size_t next_bytes) {
     if (M < 0 || N < 0 || K < 0 || (K & 1)) return set_error(B200Q_EINVAL, "linear_fwd: need M,N >= 0 and even K >= 0 (M=%lld N=%lld K=%lld)", (long long)M, (long long)N, (long long)K);
     if (!elem_size(x_dtype) || !elem_size(y_dtype)) return set_error(B200Q_EINVAL, "linear_fwd: unsupported dtype (x=%d y=%d)", x_dtype, y_dtype);
     if (M == 0 || N == 0) return 0;
     if (!y || !scales || !zps || (K > 0 && (!x || !packed))) return set_error(B200Q_EINVAL, "linear_fwd: null pointer");
     if (!aligned(x, elem_size(x_dtype)) || !aligned(y, elem_size(y_dtype))) return set_error(B200Q_EALIGN, "linear_fwd: x / y not aligned to their element size");
+    if (bias && !aligned(bias, 4)) return set_error(B200Q_EALIGN, "linear_fwd: bias must be 4-byte aligned");
     DeviceInfo d;
     if (int rc = current_device(&d)) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int force = tuning().force_path;
     const bool vec_ok = aligned(x, 16) && aligned(packed, 16) && aligned(y, 16);
-    // decode: register-fed IMMA kernel (gemv.cu); the tcgen05 TS-mode variant (gemv_tc.cu) is exact but
-    // slower for M <= 8 (A-from-TMEM feed rate, profiles/r01_gemv_notes.md) and only runs when forced
-    if (force == 4 && vec_ok && gemv_tc_supported(M, N, K))
-        return launch_gemv_tc(d, x, x_dtype, packed, scales, zps, y, y_dtype, M, N, K, ws, ws_bytes, flags, st);
-    if ((force <= 0 || force == 5) && (tuning().gemv_res != 0 || force == 5) && vec_ok && gemv_res_supported(M, N, K))
-        return launch_gemv_res(d, x, x_dtype, packed, scales, zps, y, y_dtype, M, N, K, flags, st, next_packed, next_bytes);
-    if (force != 1 && force != 3 && force != 4 && force != 5 && vec_ok && gemv_supported(M, N, K, x_dtype))
-        return launch_gemv(d, x, x_dtype, packed, scales, zps, y, y_dtype, M, N, K, ws, ws_bytes, flags, st,
-                           next_packed, next_bytes);
-    if (force != 1 && force != 2 && force != 4 && force != 5 && vec_ok && gemm_tc_supported(M, N, K, x_dtype, y_dtype))
-        return launch_gemm_tc(d, x, x_dtype, packed, scales, zps, y, y_dtype, M, N, K, nullptr, nullptr, 1, ws, ws_bytes, flags, st);
-    if (force == 2 || force == 3 || force == 4 || force == 5) return set_error(B200Q_EINVAL, "linear_fwd: forced path %d does not support this shape / alignment", force);
-    return launch_linear_generic(x, x_dtype, packed, scales, zps, y, y_dtype, M, N, K, nullptr, nullptr, 1, 0, st);
+    // decode (M <= 16): the CTA-resident IMMA kernel (gemv_dec.cu) whenever ceil(N / SMs) rows fit in shared memory
+    if ((force <= 0 || force == 6) && vec_ok && gemv_dec_supported(d, M, N, K))
+        return launch_gemv_dec(d, x, x_dtype, packed, scales, zps, bias, y, y_dtype, M, N, K, flags, st, next_packed, next_bytes);
+    int rc = 0;
+    bool done = false;
+    // ... else the ring kernel (M <= 8: e.g. Mixtral's 14336-wide projections, 198 KB of weights per SM)
+    if (!done && (force <= 0 || force == 2) && vec_ok && gemv_supported(M, N, K, x_dtype)) {
+        rc = launch_gemv(d, x, x_dtype, packed, scales, zps, y, y_dtype, M, N, K, ws, ws_bytes, flags, st, next_packed, next_bytes);
+        if (!rc) rc = launch_nonfinite_fixup(x, x_dtype, packed, scales, zps, nullptr, y, y_dtype, M, N, K, nullptr, nullptr, 1, 0, st);
+        done = true;
+    }
+    // prefill: tcgen05 GEMM (rows with NaN / Inf are recomputed by its fix-up pass)
+    if (!done && (force <= 0 || force == 3) && vec_ok && gemm_tc_supported(M, N, K, x_dtype, y_dtype)) {
+        rc = launch_gemm_tc(d, x, x_dtype, packed, scales, zps, y, y_dtype, M, N, K, nullptr, nullptr, 1, ws, ws_bytes, flags, st);
+        done = true;
+    }
+    if (!done && force > 1) return set_error(B200Q_EINVAL, "linear_fwd: forced path %d does not support this shape / alignment", force);
+    if (!done) rc = launch_linear_generic(x, x_dtype, packed, scales, zps, y, y_dtype, M, N, K, nullptr, nullptr, 1, 0, st);
+    if (!rc && bias) rc = launch_bias_add(y, y_dtype, bias, M, N, st);
+    return rc;
 }
 
 int b200q_linear_fwd_host(const void* h_x, int x_dtype, void* d_x, const uint8_t* packed, const float* scales,
@@ -119,7 +133,7 @@ int b200q_linear_fwd_host(const void* h_x, int x_dtype, void* d_x, const uint8_t
     // into d_x (a copy node costs ~8 us of launch latency for 16 KB); everything else goes through cudaMemcpyAsync.
     const size_t xbytes = (size_t)M * K * elem_size(x_dtype);
     bool staged = false;
-    if (M <= 8 && tuning().host_direct != 0 && xbytes <= (256u << 10) && xbytes % 16 == 0 && aligned(d_x, 16)) {
+    if (M <= 16 && tuning().host_direct != 0 && xbytes <= (1u << 20) && xbytes % 16 == 0 && aligned(d_x, 16)) {
         cudaPointerAttributes at{};
         if (cudaPointerGetAttributes(&at, h_x) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer &&
             aligned(at.devicePointer, 16)) {
@@ -133,7 +147,7 @@ int b200q_linear_fwd_host(const void* h_x, int x_dtype, void* d_x, const uint8_t
     // Decode-sized results (M <= 8: tens of KB): when h_y is pinned memory that the device can address (any
     // cudaHostAlloc / cudaHostRegister allocation under unified addressing), the kernel's epilogue stores straight
     // into it over PCIe -- posted writes, ~1 us -- instead of a separate ~10 us copy node behind the kernel.
-    if (M <= 8 && tuning().host_direct != 0) {
+    if (M <= 16 && tuning().host_direct != 0) {
         cudaPointerAttributes at{};
         if (cudaPointerGetAttributes(&at, h_y) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer &&
             aligned(at.devicePointer, 16))
@@ -163,8 +177,12 @@ static int grouped_impl(const void* xs, int x_dtype, const uint8_t* packed, cons
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int force = tuning().force_path;
     const bool vec_ok = aligned(xs, 16) && aligned(packed, 16) && aligned(y, 16);
-    if (force != 1 && vec_ok && gemm_tc_supported(R, N, K, x_dtype, y_dtype))
+    if (force != 1 && vec_ok && gemm_tc_supported(R, N, K, x_dtype, y_dtype)) {
+        // the GEMM only writes rows inside a group: honour "rows outside every group are zero-filled" first
+        if (zero_outside)
+            if (int rc = launch_zero_rows_outside(y, y_dtype, R, N, starts, ends + (E - 1), st)) return rc;
         return launch_gemm_tc(d, xs, x_dtype, packed, scales, zps, y, y_dtype, R, N, K, starts, ends, E, ws, ws_bytes, 0u, st);
+    }
     return launch_linear_generic(xs, x_dtype, packed, scales, zps, y, y_dtype, R, N, K, starts, ends, E, zero_outside, st);
 }
 

@@ -37,8 +37,16 @@
 
 namespace b200q {
 
-// bench-only trace (gemm_debug bit 4): SM clock of CTA 0 at the points named in tools/gemm_trace.py, first 96 k-blocks
+// bench-only (-DB200Q_PROF builds of tools/): ablation switches (tuning key gemm_debug) and a per-k-block SM-clock
+// trace of CTA 0 (bit 4, tools/gemm_trace.py).  The product build compiles all of it out.
+#ifdef B200Q_PROF
+#define B200Q_GEMM_DBG(p) ((p).debug)
 __device__ long long g_gemm_trace[8 * 96];
+#define B200Q_TRACE(row, idx) g_gemm_trace[(row) * 96 + (idx)] = clock64()
+#else
+#define B200Q_GEMM_DBG(p) 0
+#define B200Q_TRACE(row, idx) ((void)0)
+#endif
 
 namespace {
 
@@ -203,6 +211,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
     auto xl_smem = [&](int s) { return xh_smem(s) + KSUB * X_TILE_BYTES; };
     auto w_smem = [&](int s) { return xh_smem(s) + PARTS * KSUB * X_TILE_BYTES; };
     const int KB = p.K / (BK * KSUB);                                    // stages per tile
+    const int dbg = B200Q_GEMM_DBG(p);
+    (void)dbg;
     const int total_tiles = p.n_tiles * p.mt_bound;
 
     if (threadIdx.x == 0) {
@@ -243,10 +253,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
                 const TileInfo& ti = w.ti;
                 for (int kb = w.kb0; kb < w.kb1; ++kb, ++it) {
                     if (it >= S) mbar_wait(empty(s), ph ^ 1);
-                    if ((p.debug & 16) && blockIdx.x == 0 && it < 96) g_gemm_trace[0 * 96 + it] = clock64();
+                    if ((dbg & 16) && blockIdx.x == 0 && it < 96) B200Q_TRACE(0, it);
                     // bench-only ablation (tuning key gemm_debug): 1 = no weight loads, 2 = no activation loads
-                    const uint32_t xb = (p.debug & 2) ? 0u : (uint32_t)(PARTS * KSUB * X_TILE_BYTES);
-                    const uint32_t wb = (p.debug & 1) ? 0u : (uint32_t)(KSUB * W_TILE_BYTES);
+                    const uint32_t xb = (dbg & 2) ? 0u : (uint32_t)(PARTS * KSUB * X_TILE_BYTES);
+                    const uint32_t wb = (dbg & 1) ? 0u : (uint32_t)(KSUB * W_TILE_BYTES);
                     mbar_arrive_expect_tx(full(s), xb + wb);
                     if (xb) {
 #pragma unroll
@@ -275,16 +285,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
                 for (int kb = w.kb0; kb < w.kb1; ++kb, ++ait) {
                     const int a = ait % A_SLOTS;
                     mbar_wait(full(s), ph);
-                    if ((p.debug & 16) && blockIdx.x == 0 && ait < 96) g_gemm_trace[1 * 96 + ait] = clock64();
+                    if ((dbg & 16) && blockIdx.x == 0 && ait < 96) B200Q_TRACE(1, ait);
                     mbar_wait(afull(a), (ait / A_SLOTS) & 1);
-                    if ((p.debug & 16) && blockIdx.x == 0 && ait < 96) g_gemm_trace[2 * 96 + ait] = clock64();
+                    if ((dbg & 16) && blockIdx.x == 0 && ait < 96) B200Q_TRACE(2, ait);
                     tc_fence_after_sync();
                     const uint32_t a_tmem = tmem + A_BASE + A_COLS * a;
 #pragma unroll
                     for (int sub = 0; sub < KSUB; ++sub) {
 #pragma unroll
                         for (int kk = 0; kk < BK / 16; ++kk) {
-                            if (p.debug & 4) break;                     // ablation: no MMAs, only the commits
+                            if (dbg & 4) break;                     // ablation: no MMAs, only the commits
                             const uint64_t bh = smem_desc(xh_smem(s) + sub * X_TILE_BYTES + kk * 32, 16, 1024, SWIZZLE_128B);
                             mma_ts_f16(d_tmem, a_tmem + 32 * sub + 8 * kk, bh, idesc, (kb > w.kb0 || sub || kk) ? 1u : 0u);
                             if (PARTS == 2) {
@@ -295,7 +305,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
                     }
                     tc_commit(empty(s));
                     tc_commit(aempty(a));
-                    if ((p.debug & 16) && blockIdx.x == 0 && ait < 96) g_gemm_trace[3 * 96 + ait] = clock64();
+                    if ((dbg & 16) && blockIdx.x == 0 && ait < 96) B200Q_TRACE(3, ait);
                     if (++s == S) { s = 0; ph ^= 1; }
                 }
                 tc_commit(dfull(ab));
@@ -317,8 +327,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
                     continue;
                 }
                 mbar_wait(full(s), ph);
-                const bool tr = (p.debug & 16) && blockIdx.x == 0 && q == 0 && lane == 0 && ait < 96;
-                if (tr) g_gemm_trace[4 * 96 + ait] = clock64();
+                const bool tr = (dbg & 16) && blockIdx.x == 0 && q == 0 && lane == 0 && ait < 96;
+                if (tr) B200Q_TRACE(4, ait);
                 uint4 wv[2 * KSUB];
 #pragma unroll
                 for (int i = 0; i < 2 * KSUB; ++i) wv[i] = lds128(w_smem(s) + r * (KSUB * BK / 2) + 16 * i);
@@ -329,7 +339,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
                     mbar_wait(aempty(a), ((ait / A_SLOTS) - 1) & 1);
                     tc_fence_after_sync();
                 }
-                if (tr) g_gemm_trace[5 * 96 + ait] = clock64();
+                if (tr) B200Q_TRACE(5, ait);
                 const uint32_t dst = tmem + ((uint32_t)(32 * q) << 16) + A_BASE + A_COLS * a;
 #pragma unroll
                 for (int half = 0; half < 2 * KSUB; ++half) {
@@ -345,13 +355,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
                         rr[4 * j + 2] = w2 & 0x000f000fu;
                         rr[4 * j + 3] = w2 & 0x00f000f0u;
                     }
-                    if (!(p.debug & 8)) tmem_st16(dst + 16 * half, rr);     // ablation 8: no tcgen05.st
+                    if (!(dbg & 8)) tmem_st16(dst + 16 * half, rr);     // ablation 8: no tcgen05.st
                 }
-                if (!(p.debug & 8)) tmem_wait_st();
+                if (!(dbg & 8)) tmem_wait_st();
                 tc_fence_before_sync();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(afull(a));
-                if (tr) g_gemm_trace[6 * 96 + ait] = clock64();
+                if (tr) B200Q_TRACE(6, ait);
                 if (++s == S) { s = 0; ph ^= 1; }
             }
         });
@@ -399,8 +409,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
             }
             if (w.nadd > 0 && et < w.nadd) {
                 // ---- stream-K: wait (bounded) for the partials of the CTAs that hold the head of this tile
+                // (all CTAs are resident and every CTA publishes before it waits, so this cannot dead-lock; a partial
+                // that does not show up within ~1 s means a broken launch: trap -> sticky CUDA error, never a wrong sum)
                 volatile unsigned int* f = p.flags + w.c0 + et;
-                for (unsigned spin = 0; *f == 0u && spin < (1u << 24); ++spin) __nanosleep(64);
+                unsigned spin = 0;
+                while (*f == 0u) {
+                    __nanosleep(64);
+                    if (++spin > (1u << 24)) __trap();
+                }
                 __threadfence();
             }
             named_bar_sync(1, 128);
@@ -480,6 +496,7 @@ struct XprepGemmParams {
     __half* xl;       // nullptr for 16-bit inputs
     float* descale;
     float* rowsum;
+    int* nf;          // [R] 1: the row holds NaN / Inf (recomputed by the fix-up pass)
     int x_dtype, R, K;
 };
 
@@ -507,20 +524,22 @@ __global__ void __launch_bounds__(256) xprep_gemm_kernel(const XprepGemmParams p
     const int64_t m = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (m >= p.R) return;
     const T* xr = static_cast<const T*>(p.x) + m * p.K;
-    float am = 0.0f, sum = 0.0f;
+    // amax through the bit patterns (non-negative floats order like unsigned integers; NaN / Inf sort above
+    // every finite value instead of being dropped by fmaxf)
+    unsigned int ub = 0u;
+    float sum = 0.0f;
     for (int k = lane * 8; k < p.K; k += 256) {
         float v[8];
         ld8<T>(xr + k, v);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { am = fmaxf(am, fabsf(v[i])); sum += v[i]; }
+        for (int i = 0; i < 8; ++i) { ub = max(ub, __float_as_uint(v[i]) & 0x7fffffffu); sum += v[i]; }
     }
+    ub = __reduce_max_sync(0xffffffffu, ub);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, o));
-        sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    }
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     int ex = 0;
-    if (am > 0.0f && am < INFINITY) ex = max(-100, min(100, 140 - (int)((__float_as_uint(am) >> 23) & 0xffu)));
+    if (ub > 0u && ub < 0x7f800000u) ex = max(-100, min(100, 140 - (int)(ub >> 23)));
+    if (lane == 0) p.nf[m] = ub >= 0x7f800000u ? 1 : 0;
     const float up = __uint_as_float((uint32_t)(127 + ex) << 23), up_hi = up * 0.0625f;
     if (lane == 0) {
         p.descale[m] = __uint_as_float((uint32_t)(127 + 24 - ex) << 23);
@@ -553,14 +572,16 @@ __global__ void __launch_bounds__(256) xprep_gemm_kernel(const XprepGemmParams p
 // (the warp-per-row kernel above walks the row twice with one load in flight: 8 us for 256 rows).
 template <typename T, int NCH>
 __global__ void __launch_bounds__(256) xprep_gemm_rows_kernel(const XprepGemmParams p) {
-    __shared__ float s_am[2][4], s_sum[2][4];
+    __shared__ unsigned int s_am[2][4];
+    __shared__ float s_sum[2][4];
     pdl_launch_dependents();                        // the GEMM's CTAs may set themselves up meanwhile
     const int rt = threadIdx.x & 127, rw = threadIdx.x >> 7, lane = threadIdx.x & 31, w4 = (threadIdx.x >> 5) & 3;
     const int64_t m = (int64_t)blockIdx.x * 2 + rw;
     const bool row_ok = m < p.R;
     const T* xr = static_cast<const T*>(p.x) + (row_ok ? m : 0) * p.K;
     float v[NCH][8];
-    float am = 0.0f, sum = 0.0f;
+    unsigned int ub = 0u;
+    float sum = 0.0f;
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {
         const int k = i * 1024 + rt * 8;
@@ -573,19 +594,18 @@ __global__ void __launch_bounds__(256) xprep_gemm_rows_kernel(const XprepGemmPar
 #pragma unroll
     for (int i = 0; i < NCH; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { am = fmaxf(am, fabsf(v[i][j])); sum += v[i][j]; }
+        for (int j = 0; j < 8; ++j) { ub = max(ub, __float_as_uint(v[i][j]) & 0x7fffffffu); sum += v[i][j]; }
+    ub = __reduce_max_sync(0xffffffffu, ub);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, o));
-        sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    }
-    if (lane == 0) { s_am[rw][w4] = am; s_sum[rw][w4] = sum; }
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) { s_am[rw][w4] = ub; s_sum[rw][w4] = sum; }
     __syncthreads();
-    am = fmaxf(fmaxf(s_am[rw][0], s_am[rw][1]), fmaxf(s_am[rw][2], s_am[rw][3]));
+    ub = max(max(s_am[rw][0], s_am[rw][1]), max(s_am[rw][2], s_am[rw][3]));
     sum = (s_sum[rw][0] + s_sum[rw][1]) + (s_sum[rw][2] + s_sum[rw][3]);
     if (!row_ok) return;
     int ex = 0;
-    if (am > 0.0f && am < INFINITY) ex = max(-100, min(100, 140 - (int)((__float_as_uint(am) >> 23) & 0xffu)));
+    if (ub > 0u && ub < 0x7f800000u) ex = max(-100, min(100, 140 - (int)(ub >> 23)));
+    if (rt == 0) p.nf[m] = ub >= 0x7f800000u ? 1 : 0;
     const float up = __uint_as_float((uint32_t)(127 + ex) << 23), up_hi = up * 0.0625f;
     if (rt == 0) {
         p.descale[m] = __uint_as_float((uint32_t)(127 + 24 - ex) << 23);
@@ -673,7 +693,7 @@ constexpr int SK_MAX_CTAS = 160;
 constexpr size_t SK_PART_BYTES = (size_t)SK_MAX_CTAS * 256 * BM * 4;
 size_t gemm_tc_ws_bytes(int64_t M, int64_t N, int64_t K) {
     if (!gemm_tc_supported(M, N, K, B200Q_F32, B200Q_F32)) return 0;
-    return WS_RESERVED + 2 * align_up((size_t)M * K * 2, 1024) + 2 * align_up((size_t)M * 4, 1024) + 1024 + SK_PART_BYTES;
+    return WS_RESERVED + 2 * align_up((size_t)M * K * 2, 1024) + 3 * align_up((size_t)M * 4, 1024) + 1024 + SK_PART_BYTES;
 }
 
 int launch_gemm_tc(const DeviceInfo& dev, const void* x, int x_dtype, const uint8_t* packed,
@@ -692,9 +712,10 @@ int launch_gemm_tc(const DeviceInfo& dev, const void* x, int x_dtype, const uint
     __half* xl = reinterpret_cast<__half*>(w8 + xbytes);
     float* descale = reinterpret_cast<float*>(w8 + 2 * xbytes);
     float* rowsum = reinterpret_cast<float*>(w8 + 2 * xbytes + sbytes);
+    int* nf = reinterpret_cast<int*>(w8 + 2 * xbytes + 2 * sbytes);
     const int parts = x_dtype == B200Q_F32 ? 2 : 1;
 
-    XprepGemmParams xp{x, xh, parts == 2 ? xl : nullptr, descale, rowsum, x_dtype, (int)M, (int)K};
+    XprepGemmParams xp{x, xh, parts == 2 ? xl : nullptr, descale, rowsum, nf, x_dtype, (int)M, (int)K};
     if (x_dtype == B200Q_F32) { if (int rc = launch_xprep<float>(xp, M, K, st)) return rc; }
     else if (x_dtype == B200Q_F16) { if (int rc = launch_xprep<__half>(xp, M, K, st)) return rc; }
     else { if (int rc = launch_xprep<__nv_bfloat16>(xp, M, K, st)) return rc; }
@@ -766,7 +787,7 @@ int launch_gemm_tc(const DeviceInfo& dev, const void* x, int x_dtype, const uint
     p.sk = sk; p.skq = skq; p.skr = skr;
     p.debug = tuning().gemm_debug > 0 ? tuning().gemm_debug : 0;
     p.gated = gated;
-    p.part = reinterpret_cast<float*>(w8 + 2 * xbytes + 2 * sbytes);
+    p.part = reinterpret_cast<float*>(w8 + 2 * xbytes + 3 * sbytes);
     p.flags = reinterpret_cast<unsigned int*>(ws);
     const size_t smem = (size_t)OFF_STAGES + (size_t)stages * p.stage_bytes;
     typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmParams);
@@ -798,12 +819,16 @@ int launch_gemm_tc(const DeviceInfo& dev, const void* x, int x_dtype, const uint
     attrs[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attrs;
     cfg.numAttrs = 1;
-    return check_cuda(cudaLaunchKernelEx(&cfg, kfn, map_xh, map_xl, map_w, p), "gemm_tc launch");
+    if (int rc = check_cuda(cudaLaunchKernelEx(&cfg, kfn, map_xh, map_xl, map_w, p), "gemm_tc launch")) return rc;
+    // token rows with NaN / Inf (flagged by the preparation kernel): recomputed in the reference's order
+    return launch_nonfinite_fixup(x, x_dtype, packed, scales, zps, nf, y, y_dtype, M, N, K, starts, ends, groups, gated, st);
 }
 
 }  // namespace b200q
 
+#ifdef B200Q_PROF
 /* bench-only: per-k-block SM-clock trace of CTA 0 (gemm_debug bit 4), 8 x 96 int64 */
 extern "C" int b200q_debug_gemm_trace(long long* h_out) {
     return b200q::check_cuda(cudaMemcpyFromSymbol(h_out, b200q::g_gemm_trace, sizeof(long long) * 8 * 96), "read gemm trace");
 }
+#endif

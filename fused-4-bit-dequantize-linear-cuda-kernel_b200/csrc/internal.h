@@ -41,10 +41,12 @@ struct Tuning {
     int gemv_res = 1;       // 0: never use the resident-slab decode kernel
     int gemv_early = -1;    // tiles requested before the x loads (-1: all)
     int gemv_xprep = 0;     // 0: x operand built inside every CTA (default); 1: by a separate preparation kernel
-    int gemv_pf = 1;        // next-layer L2 prefetch: 0 off, 1 bulk by the producer lane, 2 per-thread lines, 3 bulk by the last warp
+    int gemv_pf = 3;        // next-layer L2 prefetch: 0 off; resident kernel: 1 behind the last own request, 2 before the own requests, 3 after the operand build (default: the prologue is sensitive to memory traffic)
     int gemv_occ2 = 0;      // 1: 8-warp CTAs sized so that two launches share an SM (cross-layer prefetch)
     int gemv_debug = -1;    // bench-only ablations: 1 = skip the mma work, 2 = skip the weight loads
-    int force_path = -1;    // 0 auto, 1 generic SIMT, 2 gemv (mma.sync), 3 tcgen05 gemm, 4 gemv (tcgen05), 5 gemv (resident slab)
+    int force_path = -1;    // 0 auto, 1 generic SIMT, 2 ring decode kernel, 3 tcgen05 gemm, 6 resident decode kernel (gemv_dec)
+    int gemv_warm = 0;      // resident decode kernel: 1 = dummy (instruction-cache warming) phases before the real ones (measured: a net loss, profiles/r02_decode_notes.md)
+    int gemv_slots = 1;     // resident decode kernel, M <= 2: 0 = pipelined cross-warp reduction instead of per-warp slots
 };
 const Tuning& tuning();
 
@@ -73,22 +75,30 @@ int launch_gemv(const DeviceInfo& dev, const void* x, int x_dtype, const uint8_t
                 int64_t K, void* ws, size_t ws_bytes, unsigned flags, cudaStream_t st,
                 const uint8_t* next_packed = nullptr, size_t next_bytes = 0);
 
+// y[m, n] += bias[n] (paths without a fused bias)
+int launch_bias_add(void* y, int y_dtype, const float* bias, int64_t M, int64_t N, cudaStream_t st);
+
+// Rows of x that contain NaN / Inf are recomputed in the reference's order (w = (q - zp) * s, then fp32 multiply-add;
+// python/quantize.py:172, 202) so that non-finite inputs propagate as in dequantize + F.linear.  nf_flags: per-row
+// flags written by the activation preparation (nullptr: the kernel scans x itself).  Grouped: starts / ends / E as in
+// launch_gemm_tc; gated: y is h [R, N/2] = silu(row 2f) * (row 2f+1).
+int launch_nonfinite_fixup(const void* x, int x_dtype, const uint8_t* packed, const float* scales, const float* zps,
+                           const int* nf_flags, void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
+                           const int32_t* starts, const int32_t* ends, int E, int gated, cudaStream_t st);
+
+// rows [0, *first) and [*last, R) of y <- 0 (the offsets[E+1] form of b200q_moe_grouped_fwd: first = offsets, last = offsets + E)
+int launch_zero_rows_outside(void* y, int y_dtype, int64_t R, int64_t N, const int32_t* first, const int32_t* last,
+                             cudaStream_t st);
+
 // device-addressable pinned host memory -> device buffer, `bytes` % 16 == 0 (one small kernel instead of a copy node)
 int launch_stage_host(const void* src_mapped, void* dst, size_t bytes, cudaStream_t st);
 
-// decode GEMV, resident-slab variant (gemv_res.cu): M <= 8, K % 128 == 0, K <= 6144 and the CTA's rows fit in
-// shared memory; no workspace
-bool gemv_res_supported(int64_t M, int64_t N, int64_t K);
-int launch_gemv_res(const DeviceInfo& dev, const void* x, int x_dtype, const uint8_t* packed, const float* scales,
-                    const float* zps, void* y, int y_dtype, int64_t M, int64_t N, int64_t K, unsigned flags,
-                    cudaStream_t st, const uint8_t* next_packed, size_t next_bytes);
-
-// decode GEMV on tcgen05 (weights -> TMEM A operand), M <= 8, K % 128 == 0
-bool gemv_tc_supported(int64_t M, int64_t N, int64_t K);
-size_t gemv_tc_ws_bytes(int64_t M, int64_t N, int64_t K);
-int launch_gemv_tc(const DeviceInfo& dev, const void* x, int x_dtype, const uint8_t* packed,
-                   const float* scales, const float* zps, void* y, int y_dtype, int64_t M, int64_t N,
-                   int64_t K, void* ws, size_t ws_bytes, unsigned flags, cudaStream_t st);
+// decode GEMV with the CTA's rows resident in shared memory (gemv_dec.cu): M <= 16, K % 128 == 0, K <= 16384 and
+// ceil(N / SMs) rows x K / 2 bytes fit in shared memory; no workspace; optional bias [N] f32
+bool gemv_dec_supported(const DeviceInfo& dev, int64_t M, int64_t N, int64_t K);
+int launch_gemv_dec(const DeviceInfo& dev, const void* x, int x_dtype, const uint8_t* packed, const float* scales,
+                    const float* zps, const float* bias, void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
+                    unsigned flags, cudaStream_t st, const uint8_t* next_packed, size_t next_bytes);
 
 // prefill / grouped path on tcgen05 tensor cores (M >= 17 rows, K % 128 == 0, N % 16 == 0).
 // starts == nullptr: plain linear; else grouped over E experts (packed [E,N,K/2]).

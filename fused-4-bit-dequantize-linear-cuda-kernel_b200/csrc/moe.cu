@@ -45,11 +45,18 @@ moe_topk_kernel(const float* __restrict__ logits, int64_t T, int E, int k,
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     const float inv = 1.0f / sum;
+    // A NaN / +Inf logit makes every probability of the token NaN (as torch.softmax does).  The selection below must
+    // still return k valid, distinct experts (the permutation / gather kernels index with them): NaN probabilities
+    // are ranked as equal keys (ties -> lowest expert index), and the NaN is carried by the routing weights, so it
+    // reaches the layer output exactly as in the reference (routing.py:72-76, 186-187).
+    bool bad = false;
 #pragma unroll
     for (int j = 0; j < MAX_E_PER_LANE; ++j) {
         int e = lane + 32 * j;
         v[j] = e < E ? v[j] * inv : -1.0f;   // probabilities are >= 0; -1 marks "absent / taken"
+        if (v[j] != v[j]) { bad = true; v[j] = 2.0f; }
     }
+    bad = __any_sync(0xffffffffu, bad);
     // routing.py:73 top-k (descending probability), then :76 renormalise over the k winners
     float wsel = 0.0f, wsum = 0.0f;
     int isel = 0;
@@ -77,7 +84,7 @@ moe_topk_kernel(const float* __restrict__ logits, int64_t T, int E, int k,
     }
     if (lane < k) {
         idx[t * k + lane] = isel;
-        weights[t * k + lane] = wsel / wsum;
+        weights[t * k + lane] = bad ? __int_as_float(0x7fc00000) : wsel / wsum;
     }
 }
 
@@ -108,7 +115,7 @@ perm_hist_kernel(const int32_t* __restrict__ idx, int64_t A, int E, int32_t* __r
 
 __global__ void __launch_bounds__(PERM_THREADS)
 perm_scan_kernel(int32_t* __restrict__ ws, int nblocks, int E, int32_t* __restrict__ counts,
-                 int32_t* __restrict__ offsets) {
+                 int32_t* __restrict__ offsets, int32_t* __restrict__ sorted_slot, int64_t A) {
     extern __shared__ int32_t s_cnt[];   // [E] totals then exclusive offsets
     for (int e = threadIdx.x; e < E; e += PERM_THREADS) {
         int tot = 0;
@@ -126,8 +133,13 @@ perm_scan_kernel(int32_t* __restrict__ ws, int nblocks, int E, int32_t* __restri
             run += c;
         }
         offsets[E] = run;
+        s_cnt[E] = run;
     }
     __syncthreads();
+    // assignments with an expert id outside [0, E) (only possible with caller-made routing) are dropped: the tail
+    // of sorted_slot they leave unused is marked -1 (gather writes zero rows, combine skips them)
+    if (sorted_slot)
+        for (int64_t i = s_cnt[E] + (int64_t)threadIdx.x; i < A; i += PERM_THREADS) sorted_slot[i] = -1;
     for (int e = threadIdx.x; e < E; e += PERM_THREADS) {
         int run = s_cnt[e];
         for (int b = 0; b < nblocks; ++b) {
@@ -167,6 +179,8 @@ perm_scatter_kernel(const int32_t* __restrict__ idx, int64_t A, int E,
             for (int w = 0; w < warp; ++w) pos += s_warp[w * E + e];
             sorted_slot[pos] = (int32_t)a;
             inv_perm[a] = pos;
+        } else if (a < A) {
+            inv_perm[a] = -1;
         }
         __syncthreads();
         for (int ee = threadIdx.x; ee < E; ee += PERM_THREADS) {
@@ -186,9 +200,13 @@ gather_rows_kernel(const uint4* __restrict__ x, const int32_t* __restrict__ sort
                    int64_t rows, int k, int64_t vec_per_row, uint4* __restrict__ xs) {
     const int64_t p = blockIdx.x;
     if (p >= rows) return;
-    const int64_t src = sorted_slot[p] / k;
-    const uint4* s = x + src * vec_per_row;
+    const int slot = sorted_slot[p];
     uint4* d = xs + p * vec_per_row;
+    if (slot < 0) {                                       // unused tail position (dropped assignment)
+        for (int64_t i = threadIdx.x; i < vec_per_row; i += blockDim.x) d[i] = make_uint4(0u, 0u, 0u, 0u);
+        return;
+    }
+    const uint4* s = x + (int64_t)(slot / k) * vec_per_row;
     for (int64_t i = threadIdx.x; i < vec_per_row; i += blockDim.x) d[i] = __ldg(s + i);
 }
 
@@ -243,7 +261,7 @@ combine_kernel(const YT* __restrict__ y, const int32_t* __restrict__ inv_perm,
         float acc = 0.0f;
         for (int s = 0; s < k; ++s) {
             const int64_t p = inv_perm[t * k + s];
-            const float prod = __fmul_rn(to_f32<YT>(y[p * F + f]), weights[t * k + s]);
+            const float prod = p < 0 ? 0.0f : __fmul_rn(to_f32<YT>(y[p * F + f]), weights[t * k + s]);
             acc = s == 0 ? prod : __fadd_rn(acc, prod);
         }
         out[t * F + f] = from_f32<OT>(acc);
@@ -312,7 +330,7 @@ int b200q_moe_permute(const int32_t* idx, int64_t T, int E, int k, int32_t* coun
     if (nblocks < 1) nblocks = 1;
     int32_t* w = static_cast<int32_t*>(ws);
     perm_hist_kernel<<<nblocks, PERM_THREADS, E * sizeof(int32_t), st>>>(idx, A, E, w);
-    perm_scan_kernel<<<1, PERM_THREADS, E * sizeof(int32_t), st>>>(w, nblocks, E, counts, offsets);
+    perm_scan_kernel<<<1, PERM_THREADS, (E + 1) * sizeof(int32_t), st>>>(w, nblocks, E, counts, offsets, sorted_slot, A);
     if (A > 0)
         perm_scatter_kernel<<<nblocks, PERM_THREADS, (1 + PERM_THREADS / 32) * E * sizeof(int32_t), st>>>(idx, A, E, w, sorted_slot, inv_perm);
     return check_cuda(cudaGetLastError(), "moe_permute launch");

@@ -3,7 +3,8 @@
 Same constructor, ``from_linear`` classmethod, buffer names / shapes / dtypes (so reference
 ``state_dict``s load), ``forward`` and ``extra_repr``.  ``forward`` always runs the fused sm_100a
 kernel; a CPU tensor raises instead of silently taking a slow path.
-Superset: any leading dims ``[..., K]``, fp16 / bf16 activations.
+Superset: any leading dims ``[..., K]``, fp16 / bf16 activations, an optional fp32 ``bias`` buffer (the reference
+asserts ``linear.bias is None``, python/module.py:84; a module without bias has exactly the reference's state_dict).
 """
 from __future__ import annotations
 
@@ -15,7 +16,7 @@ from .quantize import quantize_weights
 
 
 class QuantizedLinear(nn.Module):
-    def __init__(self, in_features: int, out_features: int):
+    def __init__(self, in_features: int, out_features: int, bias: bool = False):
         super().__init__()
         self.in_features = in_features
         self.out_features = out_features
@@ -24,6 +25,10 @@ class QuantizedLinear(nn.Module):
                              torch.zeros(out_features, in_features // 2, dtype=torch.uint8))
         self.register_buffer("scales", torch.zeros(out_features, dtype=torch.float32))
         self.register_buffer("zero_points", torch.zeros(out_features, dtype=torch.float32))
+        if bias:
+            self.register_buffer("bias", torch.zeros(out_features, dtype=torch.float32))
+        else:
+            self.bias = None
         # Weights written by a kernel that may still be running (from_linear) must not be
         # prefetched ahead of it; the first forward therefore runs without the static-weights flag.
         self._weights_settled = False
@@ -38,8 +43,10 @@ class QuantizedLinear(nn.Module):
 
     @classmethod
     def from_linear(cls, linear: nn.Linear) -> "QuantizedLinear":
-        assert linear.bias is None, "Bias not supported yet"   # python/module.py:84
-        module = cls(linear.in_features, linear.out_features)
+        # python/module.py:84 asserts `linear.bias is None`; here the bias is kept in fp32 and added by the kernel
+        module = cls(linear.in_features, linear.out_features, bias=linear.bias is not None)
+        if linear.bias is not None:
+            module.bias = linear.bias.data.detach().to(torch.float32).clone()
         packed, scales, zp = quantize_weights(linear.weight.data)
         module.packed_weights = packed
         module.scales = scales
@@ -65,7 +72,8 @@ class QuantizedLinear(nn.Module):
             x2 = x2.contiguous()
         flags = _lib.FLAG_STATIC_WEIGHTS if self._weights_settled else _lib.FLAG_NONE
         nxt = self._next.packed_weights if self._next is not None else None
-        y = _lib.linear_fwd(x2, self.packed_weights, self.scales, self.zero_points, flags=flags, next_packed=nxt)
+        y = _lib.linear_fwd(x2, self.packed_weights, self.scales, self.zero_points, flags=flags, next_packed=nxt,
+                            bias=self.bias)
         self._weights_settled = True
         return y.reshape(*lead, self.out_features)
 

@@ -48,18 +48,21 @@ class QuantizedMoEExpert(nn.Module):
             return torch.empty(0, self.out_features, device=x.device, dtype=torch.float16)
         _lib.require_cuda(x, "x")
         # reference: x @ dequant(W).T.to(x.dtype) -> result in x.dtype (moe_int4_module.py:71-72)
-        return _lib.linear_fwd(x.contiguous(), self.packed_weights, self.scales, self.zero_points,
-                               out_dtype=x.dtype)
+        # (buffers of a gated QuantizedMoE are strided views of the interleaved w1 / w3 stack: compact them for this call)
+        return _lib.linear_fwd(x.contiguous(), self.packed_weights.contiguous(), self.scales.contiguous(),
+                               self.zero_points.contiguous(), out_dtype=x.dtype)
 
     @property
     def weight_memory_bytes(self) -> int:
         return self.packed_weights.numel() + self.scales.numel() * 4 + self.zero_points.numel() * 4
 
 
-def _stack_experts(experts: Sequence[QuantizedMoEExpert]):
-    return (torch.stack([e.packed_weights for e in experts]).contiguous(),
-            torch.stack([e.scales for e in experts]).contiguous(),
-            torch.stack([e.zero_points for e in experts]).contiguous())
+_BUFS = ("packed_weights", "scales", "zero_points")
+
+
+def _aliases(t: torch.Tensor, view: torch.Tensor) -> bool:
+    return (t.device == view.device and t.data_ptr() == view.data_ptr() and t.shape == view.shape
+            and t.stride() == view.stride() and t.dtype == view.dtype)
 
 
 class QuantizedMoE(nn.Module):
@@ -69,6 +72,11 @@ class QuantizedMoE(nn.Module):
     ``forward(list) -> list`` applies them.  Gated mode (``from_gated_fp16_weights``): ``experts``
     holds w1 (gate), ``experts_up`` w3 and ``experts_down`` w2, and ``forward_routed`` runs the
     whole layer ``sum_k p_k * w2_e( silu(w1_e x) * (w3_e x) )``.
+
+    Weights exist ONCE on the device: the grouped kernels want all experts in one ``[E, N, K/2]`` tensor (w1 and w3
+    interleaved row by row for the fused SiLU-gate), so that tensor is the storage and the per-expert buffers
+    (``experts.{i}.packed_weights`` ... -- the reference's state_dict keys, moe_int4_module.py:38-45) are views into
+    it.  ``load_state_dict`` copies through the views; replacing an expert or moving the module re-stacks lazily.
     """
 
     def __init__(self, num_experts: int, hidden_dim: int, ffn_dim: int, gated: bool = False):
@@ -84,7 +92,7 @@ class QuantizedMoE(nn.Module):
                 [QuantizedMoEExpert(hidden_dim, ffn_dim) for _ in range(num_experts)])
             self.experts_down = nn.ModuleList(
                 [QuantizedMoEExpert(ffn_dim, hidden_dim) for _ in range(num_experts)])
-        self._stacked = None   # (device, w13 triple, w2 triple), rebuilt when the device changes
+        self._stacked = None   # (w13 triple, w2 triple or None): the storage the expert buffers are views of
 
     @classmethod
     def from_fp16_weights(cls, weights: List[torch.Tensor]) -> "QuantizedMoE":
@@ -110,38 +118,56 @@ class QuantizedMoE(nn.Module):
         return [expert(x) for expert, x in zip(self.experts, expert_inputs)]   # moe_int4_module.py:123-125
 
     # ------------------------------------------------------------------ fused routed layer
-    def _apply(self, fn, *args, **kwargs):
-        self._stacked = None
-        return super()._apply(fn, *args, **kwargs)
-
     @property
     def fused_gate(self) -> bool:
         """The SiLU-gate runs in the epilogue of the first grouped GEMM (rows of w1 and w3 interleaved) whenever the
         tcgen05 path takes the shape; otherwise w1||w3 are concatenated and b200q_moe_silu_mul follows."""
         return self.gated and self.experts[0].in_features % 128 == 0
 
+    def _views(self, w13, w2):
+        """(module, buffer name, view into the stacked storage) for every per-expert buffer."""
+        out = []
+        F = self.ffn_dim
+        for e in range(self.num_experts):
+            for j, name in enumerate(_BUFS):
+                if not self.gated:
+                    out.append((self.experts[e], name, w13[j][e]))
+                elif self.fused_gate:
+                    out.append((self.experts[e], name, w13[j][e, 0::2]))
+                    out.append((self.experts_up[e], name, w13[j][e, 1::2]))
+                else:
+                    out.append((self.experts[e], name, w13[j][e, :F]))
+                    out.append((self.experts_up[e], name, w13[j][e, F:]))
+                if self.gated:
+                    out.append((self.experts_down[e], name, w2[j][e]))
+        return out
+
+    def _restack(self):
+        """Move every expert's buffers into the stacked tensors and turn them into views of those."""
+        first = self.experts[0]
+        dev = first.packed_weights.device
+        E, F, d = self.num_experts, self.ffn_dim, self.hidden_dim
+        n13 = 2 * F if self.gated else F
+        w13 = (torch.empty((E, n13, d // 2), dtype=torch.uint8, device=dev),
+               torch.empty((E, n13), dtype=torch.float32, device=dev),
+               torch.empty((E, n13), dtype=torch.float32, device=dev))
+        w2 = None
+        if self.gated:
+            w2 = (torch.empty((E, d, F // 2), dtype=torch.uint8, device=dev),
+                  torch.empty((E, d), dtype=torch.float32, device=dev),
+                  torch.empty((E, d), dtype=torch.float32, device=dev))
+        for mod, name, view in self._views(w13, w2):
+            view.copy_(mod._buffers[name].to(dev))
+            mod._buffers[name] = view                       # the old tensor is released: one copy on the device
+        self._stacked = (w13, w2)
+
     def stacked_weights(self):
         """[E,N,K/2] / [E,N] tensors for the grouped kernels: w1 and w3 stacked along N (interleaved row by row when
-        `fused_gate`, else concatenated), and w2."""
-        dev = self.experts[0].packed_weights.device
-        if self._stacked is None or self._stacked[0] != dev:
-            if self.gated:
-                p1, s1, z1 = _stack_experts(self.experts)
-                p3, s3, z3 = _stack_experts(self.experts_up)
-                if self.fused_gate:
-                    E, F = p1.shape[0], p1.shape[1]
-                    w13 = (torch.stack([p1, p3], dim=2).reshape(E, 2 * F, -1).contiguous(),
-                           torch.stack([s1, s3], dim=2).reshape(E, 2 * F).contiguous(),
-                           torch.stack([z1, z3], dim=2).reshape(E, 2 * F).contiguous())
-                else:
-                    w13 = (torch.cat([p1, p3], dim=1).contiguous(), torch.cat([s1, s3], dim=1).contiguous(),
-                           torch.cat([z1, z3], dim=1).contiguous())
-                w2 = _stack_experts(self.experts_down)
-            else:
-                w13 = _stack_experts(self.experts)
-                w2 = None
-            self._stacked = (dev, w13, w2)
-        return self._stacked[1], self._stacked[2]
+        `fused_gate`, else concatenated), and w2.  These ARE the weights; the per-expert buffers alias them."""
+        st = self._stacked
+        if st is None or not all(_aliases(mod._buffers[name], view) for mod, name, view in self._views(*st)):
+            self._restack()
+        return self._stacked
 
     def forward_routed(self, x: torch.Tensor, router_logits: torch.Tensor, top_k: int = 2,
                        routing: Optional[DeviceRouting] = None) -> torch.Tensor:

@@ -108,9 +108,10 @@ int b200q_dequantize_rows(const uint8_t* packed, const float* scales, const floa
 /* y[M,N] = x[M,K] @ dequant(packed[N,K/2], scales[N], zps[N])^T
  *   x_dtype / y_dtype: B200Q_F32 | B200Q_F16 | B200Q_BF16 (the reference API is f32/f32).
  *   x, y row-major and contiguous; x 16-byte aligned, packed 16-byte aligned, K even.
- *   M may be any value >= 0.  K % 128 == 0 with 16-byte aligned pointers: M <= 8 takes the decode
- *   kernel (TMA bulk copies, exact-integer IMMA), M >= 9 the tcgen05 GEMM; anything else a generic
- *   SIMT kernel.
+ *   M may be any value >= 0.  K % 128 == 0 with 16-byte aligned pointers: M <= 16 takes the decode
+ *   kernel (TMA tensor boxes, exact-integer IMMA) whenever ceil(N / SMs) weight rows fit in shared memory,
+ *   larger batches the tcgen05 GEMM; anything else a generic SIMT kernel.
+ *   Rows of x that contain NaN / Inf give the values dequantize + F.linear gives (python/quantize.py:172, 202).
  *   ws: >= b200q_linear_ws_bytes(M,N,K) bytes (may be NULL when that is 0). */
 size_t b200q_linear_ws_bytes(int64_t M, int64_t N, int64_t K);
 int b200q_linear_fwd(const void* x, int x_dtype, const uint8_t* packed, const float* scales,
@@ -127,6 +128,14 @@ int b200q_linear_fwd_next(const void* x, int x_dtype, const uint8_t* packed, con
                           void* ws, size_t ws_bytes, unsigned flags, void* stream,
                           const uint8_t* next_packed, size_t next_bytes);
 
+/* Same, plus a per-output bias: y[m,n] += bias[n] (bias [N] f32, NULL = none).  The reference asserts
+ * `linear.bias is None` (python/module.py:84); this lifts that restriction.  The decode kernel adds the
+ * bias in its epilogue; the other paths run a small element-wise pass behind the GEMM. */
+int b200q_linear_bias_fwd(const void* x, int x_dtype, const uint8_t* packed, const float* scales,
+                          const float* zps, const float* bias, void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
+                          void* ws, size_t ws_bytes, unsigned flags, void* stream,
+                          const uint8_t* next_packed, size_t next_bytes);
+
 /* Same with HOST activations: enqueues H2D copy of x (h_x -> the caller's device staging buffer d_x), the
  * fused dequantize-linear, and the D2H copy of the result (d_y -> h_y) on `stream`; h_x / h_y should be
  * pinned.  This is the call a host-resident caller of the reference's QuantizedLinear.forward maps to
@@ -138,9 +147,9 @@ int b200q_linear_fwd_host(const void* h_x, int x_dtype, void* d_x, const uint8_t
                           void* ws, size_t ws_bytes, unsigned flags, void* stream);
 
 /* Bench / tuning hook: override a launch heuristic process-wide; value < 0 restores the default.  Keys:
- *   force_path (1 generic SIMT, 2 ring decode kernel, 3 tcgen05 GEMM, 4 tcgen05 decode experiment, 5 resident-slab
- *   decode kernel), gemv_res, gemv_early, gemv_pf, gemv_xprep, gemv_warps, gemv_slabs, gemv_stages, gemv_pdl,
- *   gemv_ctas, gemv_occ2, gemv_debug, gemm_bn (32 / 64 / 128 / 192 / 256), gemm_sk, gemm_debug, host_direct.
+ *   force_path (1 generic SIMT, 2 ring decode kernel, 3 tcgen05 GEMM, 6 resident decode kernel), gemv_early, gemv_pf,
+ *   gemv_tma3d, gemv_xprep, gemv_warps, gemv_slabs, gemv_stages, gemv_pdl, gemv_ctas, gemv_occ2, gemv_debug,
+ *   gemm_bn (32 / 64 / 128 / 192 / 256), gemm_sk, gemm_debug (needs a -DB200Q_PROF build), host_direct.
  * Their meaning is documented next to the Tuning struct in csrc/internal.h.  Not needed by callers. */
 int b200q_tune_set(const char* key, int value);
 

@@ -83,8 +83,9 @@ def test_module_surface_matches_reference(pkg):
     assert sd["scales"].shape == (64,) and sd["scales"].dtype == torch.float32
     assert sd["zero_points"].shape == (64,) and sd["zero_points"].dtype == torch.float32
     assert "bits=4" in repr(ql)
-    with pytest.raises(AssertionError):
-        pkg.QuantizedLinear.from_linear(torch.nn.Linear(8, 8, bias=True))
+    # superset of python/module.py:84 (which asserts `bias is None`): an optional fp32 bias buffer
+    qb = pkg.QuantizedLinear(128, 64, bias=True)
+    assert list(qb.state_dict()) == ["packed_weights", "scales", "zero_points", "bias"] and qb.bias.shape == (64,)
     moe = pkg.QuantizedMoE(4, 64, 128)
     assert len(moe.experts) == 4 and moe.experts[0].packed_weights.shape == (128, 32)
     assert moe.total_memory_bytes == 4 * (128 * 32 + 128 * 4 * 2)

@@ -98,9 +98,9 @@ def test_llama_mixtral_decode_shapes(oracle, K, N, M):
     err = np.abs(ref - y[:, rows]).max()
     scale = np.abs(ref).max()
     print(f"K={K} N={N} M={M}: max abs err {err:.3e}, |y|max {scale:.2f}, rel {err / scale:.2e}")
-    # M <= 8: exact-integer IMMA path (error = final fp32 rounding); M > 8: tcgen05 path, fp16 hi/lo split of
-    # x with fp32 accumulation in tensor memory over up to 14336 terms
-    assert err < 1e-2 and err / scale < (2e-5 if M <= 8 else 1e-4)
+    # exact-integer IMMA path (error = final fp32 rounding) for M <= 16 on the Llama shapes and M <= 8 on Mixtral's
+    # (ring kernel); Mixtral M = 16: tcgen05 path, fp16 hi/lo split of x, fp32 accumulation over up to 14336 terms
+    assert err < 1e-2 and err / scale < (2e-5 if (M <= 8 or 14336 not in (K, N)) else 1e-4)
     # linearity: f(2x) == 2 f(x) exactly (power-of-two scaling commutes with every rounding step)
     y2 = ext.forward(cuda(2 * x), P, S, Z).cpu().numpy()
     assert np.array_equal(y2, 2 * y)
@@ -227,13 +227,14 @@ def test_forward_host_pinned(oracle, pkg):
         ql(torch.randn(2, 1024))                      # pageable host memory: no silent slow path
 
 
-# ---- decode kernels: resident-slab (gemv_res.cu, force_path 5) and ring (gemv.cu, force_path 2) ----------
-@pytest.mark.parametrize("M", [1, 2, 3, 5, 8])
+# ---- decode kernels: CTA-resident (gemv_dec.cu, force_path 6) and ring (gemv.cu, force_path 2, M <= 8) ----------
+@pytest.mark.parametrize("M", [1, 2, 3, 4, 5, 8, 9, 13, 16])
 @pytest.mark.parametrize("N,K", [(1, 128), (7, 128), (9, 256), (16, 384), (200, 1024), (2371, 2048), (11008, 4096),
-                                 (3000, 6144)])
-def test_resident_slab_kernel_edge_shapes(oracle, pkg, M, N, K):
-    """Ragged row counts (last tile with <= 8 and > 8 rows, fewer tiles than SMs), every batch size of the decode
-    path, one to three granules per warp; both decode kernels against the float64 oracle and against each other."""
+                                 (3000, 6144), (4096, 11008), (1500, 8192), (600, 16384)])
+def test_resident_decode_kernel_edge_shapes(oracle, pkg, M, N, K):
+    """Ragged row counts (fewer tiles than SMs, last tile partly foreign / out of bounds), every batch size of the
+    decode path (passes of two or four batch rows), one to four column pairs per warp, K = 128 mod 256 (half-empty
+    last TMA box); the resident kernel against the float64 oracle and, for M <= 8, against the ring kernel."""
     rng = np.random.default_rng(1000 * M + N + K)
     packed = rng.integers(0, 256, size=(N, K // 2), dtype=np.uint8)
     scales = (rng.random(N, dtype=np.float32) * 0.01 + 0.001).astype(np.float32)
@@ -243,25 +244,52 @@ def test_resident_slab_kernel_edge_shapes(oracle, pkg, M, N, K):
     rows = np.arange(N) if N <= 512 else rng.choice(N, size=512, replace=False)
     ref = oracle.reference_quantized_linear(x, packed[rows], scales[rows], zps[rows], acc=np.float64)
     outs = {}
-    for path in (5, 2):
+    for path in (6, 2) if M <= 8 else (6,):
         pkg._lib.tune("force_path", path)
         try:
             outs[path] = pkg._lib.linear_fwd(X, P, S, Z).cpu().numpy()
         except RuntimeError:
-            # the resident-slab kernel keeps the B fragments of a warp in registers: (K / 2048) * ceil(M / 2) <= 8
-            assert path == 5 and -(-K // 2048) * (1 if M <= 2 else 2 if M <= 4 else 4) > 8
+            # the ring kernel does not take every shape; the resident kernel wants whole 256-column TMA boxes
+            assert path == 2 or K % 256 != 0
             continue
         finally:
             pkg._lib.tune("force_path", -1)
         for m in range(M):          # rows have very different magnitudes: the bar is per batch row
             err = np.abs(ref[m] - outs[path][m, rows]).max()
             assert err <= 1e-6 * np.abs(ref[m]).max() + 1e-30, f"path {path} row {m}: {err} vs |y|max {np.abs(ref[m]).max()}"
-    if 5 in outs:
+    if 2 in outs and 6 in outs:
         # the two kernels quantise the odd columns of x on different grids: equal to ~1e-7, not bit-equal
         for m in range(M):
-            assert np.abs(outs[5][m] - outs[2][m]).max() <= 1e-6 * np.abs(outs[2][m]).max() + 1e-30
-        # default dispatch picks the resident-slab kernel for these shapes: bit-identical with the forced run
-        assert np.array_equal(pkg._lib.linear_fwd(X, P, S, Z).cpu().numpy(), outs[5])
+            assert np.abs(outs[6][m] - outs[2][m]).max() <= 1e-6 * np.abs(outs[2][m]).max() + 1e-30
+    # default dispatch (resident kernel when K % 256 == 0, else ring kernel / tcgen05): deterministic, within the bar
+    y = pkg._lib.linear_fwd(X, P, S, Z).cpu().numpy()
+    assert np.array_equal(pkg._lib.linear_fwd(X, P, S, Z).cpu().numpy(), y)
+    if 6 in outs:
+        assert np.array_equal(y, outs[6])
+    for m in range(M):
+        assert np.abs(ref[m] - y[m, rows]).max() <= 1e-4 * np.abs(ref[m]).max() + 1e-30
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 11008, 4096), (2, 4096, 11008), (2, 700, 2048), (1, 2368, 4096), (1, 2369, 4096)])
+def test_resident_decode_kernel_slot_and_pipelined_reductions_agree(oracle, pkg, M, N, K):
+    """M <= 2 in one pass: per-(tile, warp) slots folded after the loop (default) against the pipelined double-buffer
+    reduction the larger batches use (tuning key gemv_slots = 0).  Integer sums: bit-identical.  N = 2368 = 148 x 16:
+    the row of 0x11 bytes that yields sum_k X needs a tile of its own."""
+    rng = np.random.default_rng(M + N + K)
+    packed = rng.integers(0, 256, size=(N, K // 2), dtype=np.uint8)
+    scales = (rng.random(N, dtype=np.float32) * 0.01 + 0.001).astype(np.float32)
+    zps = rng.integers(0, 16, size=N).astype(np.float32)
+    x = rng.standard_normal((M, K), dtype=np.float32)
+    ref = oracle.reference_quantized_linear(x, packed, scales, zps, acc=np.float64)
+    outs = []
+    for slots in (1, 0):
+        pkg._lib.tune("gemv_slots", slots)
+        try:
+            outs.append(pkg._lib.linear_fwd(cuda(x), cuda(packed), cuda(scales), cuda(zps)).cpu().numpy())
+        finally:
+            pkg._lib.tune("gemv_slots", -1)
+        assert np.abs(outs[-1] - ref).max() <= 1e-6 * np.abs(ref).max()
+    assert np.array_equal(outs[0], outs[1])
 
 
 def test_next_layer_hint_does_not_change_results(oracle, pkg):
@@ -356,11 +384,12 @@ def test_gemm_token_tile_heights(oracle, pkg, bn):
     assert np.abs(y - ref).max() <= 1e-4 * np.abs(ref).max()
 
 
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("M,N,K", [(1, 4096, 11008), (2, 4100, 11008), (1, 37, 8192), (2, 1000, 7168)])
-def test_k_split_cluster_decode(oracle, pkg, dtype, M, N, K):
-    """K > 6144: the resident-slab kernel splits K over a cluster of two CTAs and adds the exact partials through
-    distributed shared memory; ragged row counts, 16-bit activations, and the ring kernel as a second opinion."""
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("M,N,K", [(1, 4096, 11008), (2, 4100, 11008), (1, 37, 8192), (2, 1000, 7168), (7, 4096, 11008),
+                                   (16, 4096, 11008), (12, 11008, 4096)])
+def test_wide_k_and_16bit_decode(oracle, pkg, dtype, M, N, K):
+    """K up to 11008 without a K split (three column pairs per warp; M > 2 in passes of two batch rows), ragged row
+    counts, 16-bit activations, determinism; the ring kernel as a second opinion where it applies (M <= 8)."""
     rng = np.random.default_rng(N + K + M)
     packed = rng.integers(0, 256, size=(N, K // 2), dtype=np.uint8)
     scales = (rng.random(N, dtype=np.float32) * 0.01 + 0.001).astype(np.float32)
@@ -369,21 +398,17 @@ def test_k_split_cluster_decode(oracle, pkg, dtype, M, N, K):
     P, S, Z = cuda(packed), cuda(scales), cuda(zps)
     ref = oracle.reference_quantized_linear(X.float().cpu().numpy(), packed, scales, zps, acc=np.float64)
     outs = {}
-    for path in (5, 2):
+    for path in (6, 2) if M <= 8 else (6,):
         pkg._lib.tune("force_path", path)
         try:
             outs[path] = pkg._lib.linear_fwd(X, P, S, Z, out_dtype=torch.float32).cpu().numpy()
+        except RuntimeError:
+            assert path == 2
+            continue
         finally:
             pkg._lib.tune("force_path", -1)
         assert np.abs(outs[path] - ref).max() <= 1e-6 * np.abs(ref).max()
-    assert np.array_equal(pkg._lib.linear_fwd(X, P, S, Z, out_dtype=torch.float32).cpu().numpy(), outs[5])
-    # determinism of the cluster reduction
-    pkg._lib.tune("force_path", 5)
-    try:
-        again = pkg._lib.linear_fwd(X, P, S, Z, out_dtype=torch.float32).cpu().numpy()
-    finally:
-        pkg._lib.tune("force_path", -1)
-    assert np.array_equal(again, outs[5])
+    assert np.array_equal(pkg._lib.linear_fwd(X, P, S, Z, out_dtype=torch.float32).cpu().numpy(), outs[6])
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])

@@ -1,0 +1,27 @@
+"""ncu target: a few launches of the resident decode kernel over the 24-layer pool (no graph).  M K N from argv."""
+import os, sys
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from b200q_pkg import pkg
+_lib = pkg._lib
+lib = _lib.load()
+M = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+K = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
+N = int(sys.argv[3]) if len(sys.argv) > 3 else 11008
+dev = torch.device("cuda", 0)
+layers = []
+for i in range(24):
+    g = torch.Generator(device=dev); g.manual_seed(i)
+    layers.append((torch.randint(0, 256, (N, K // 2), generator=g, device=dev, dtype=torch.uint8),
+                   torch.rand(N, generator=g, device=dev) * 0.01 + 0.001, torch.randint(0, 16, (N,), generator=g, device=dev).float()))
+x = torch.randn(M, K, device=dev); y = torch.empty(M, N, device=dev)
+ws = torch.zeros(max(lib.b200q_linear_ws_bytes(M, N, K), 16), dtype=torch.uint8, device=dev)
+sp = torch.cuda.current_stream(dev).cuda_stream
+for r in range(2):
+    for i, (p, s, z) in enumerate(layers):
+        nxt = layers[(i + 1) % 24][0]
+        _lib.check(lib.b200q_linear_fwd_next(x.data_ptr(), 0, p.data_ptr(), s.data_ptr(), z.data_ptr(), y.data_ptr(), 0, M, N, K,
+                                             ws.data_ptr(), ws.numel(), 1, sp, nxt.data_ptr(), nxt.numel()), "fwd")
+torch.cuda.synchronize()
+print("ok")
