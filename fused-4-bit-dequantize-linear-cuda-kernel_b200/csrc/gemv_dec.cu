@@ -66,8 +66,8 @@ constexpr int OFF_EMPTY = 528;       // [2]
 constexpr int OFF_FLAG = 544;        // bit m: batch row m holds NaN / Inf
 constexpr int OFF_EX = 832;          // [16] exponent of every batch row
 constexpr int OFF_AMAX = 1024;       // [2 (pass parity)][4 rows][16 warps] u32
-constexpr int OFF_DYN = 2048;        // operand exchange (1 KB per warp), partial-tile double buffer, accumulator, tiles
-constexpr int SCR_BYTES = NW * 1024;
+constexpr int OFF_DYN = 2048;        // partial-tile buffers (their owner's slots double as its operand exchange space), accumulator, tiles
+constexpr int WARP_RED = 1024;       // bytes of a warp in one partial-tile buffer (pipelined reduction)
 
 struct DecParams {
     const void* x;
@@ -88,13 +88,11 @@ struct DecParams {
     int ntiles_max;
     int tile_bytes;
     int tile_off;                    // byte offset of tile 0 in dynamic shared memory (1024-aligned)
-    int scr_off, red_off, fin_off;   // exchange buffers, partial-tile double buffer, accumulator
-    int alias;                       // 1: exchange buffers and partial-tile buffers share memory (two more barriers per pass)
+    int red_off, fin_off;            // partial-tile buffers, accumulator
     int slots;                       // 1 (single pass, M <= 2): one slot per (tile, warp) at red_off, folded after the loop
     int npasses;
     int wait_weights;                // 1: weights may be written by the preceding kernel
     int early_tiles;                 // a + 10 b: a tiles requested before griddepcontrol.wait, b more behind the x loads
-    int warm;                        // 1: dummy phases that pull the code into the instruction cache while the kernel would only wait
     int pf_mode;                     // next-layer L2 prefetch: 1 behind the last own request, 2 before the own requests, 3 after the operand build
     int debug;                       // B200Q_PROF builds: record phase stamps
 };
@@ -181,24 +179,24 @@ __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
-// weight requests of tiles [from, to): one 3-D box [16 rows][chunk pairs][128 B] per (tile, pair group), one elected
+// weight requests [from, to) (request = (tile, pair group), ~32 KB): one 3-D box [16 rows][chunk pairs][128 B] per (tile, pair group), one elected
 // thread.  Not inlined: three call sites (before griddepcontrol.wait, behind the x loads, after the operand build),
 // and code that runs once costs ~10 clk per instruction whatever it does (profiles/r02_decode_notes.md).
 __device__ __noinline__ void dec_issue_tiles(const CUtensorMap* tmap, uint32_t bar0, uint32_t dst0, int row0, int from, int to,
                                              int nbars, int chunk, int tile_bytes) {
     const uint64_t pol = policy_evict_first();
-    for (int i = from; i < to; ++i)
-        for (int grp = 0; grp < nbars; ++grp) {
-            const uint32_t bar = bar0 + 8u * (uint32_t)(i * nbars + grp);
-            mbar_arrive_expect_tx(bar, (uint32_t)(chunk * PAIR_BYTES));
-            tma_box_3d(dst0 + (uint32_t)(i * tile_bytes + grp * chunk * PAIR_BYTES), tmap, 0, row0 + i * TILE_ROWS, grp * chunk, bar, pol);
-        }
+    for (int op = from; op < to; ++op) {                      // op = tile * nbars + pair group
+        const int i = op / nbars, grp = op - i * nbars;
+        const uint32_t bar = bar0 + 8u * (uint32_t)op;
+        mbar_arrive_expect_tx(bar, (uint32_t)(chunk * PAIR_BYTES));
+        tma_box_3d(dst0 + (uint32_t)(i * tile_bytes + grp * chunk * PAIR_BYTES), tmap, 0, row0 + i * TILE_ROWS, grp * chunk, bar, pol);
+    }
 }
 
 template <int GPW2, int NT>          // pairs per warp, n-tiles (two batch rows each) per pass
 __global__ void __launch_bounds__(NTHR, 1) gemv_dec_kernel(const __grid_constant__ CUtensorMap tmap, const DecParams p) {
     constexpr int MB = 2 * NT;       // batch rows per pass
-    constexpr int RB = NW * NT * 512;   // bytes of one partial-tile buffer
+    constexpr int RB = NW * WARP_RED;   // bytes of one partial-tile buffer
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -237,8 +235,9 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_dec_kernel(const __grid_constant
     // Staged (tuning key gemv_early = a + 10 * b): a tiles before griddepcontrol.wait, b more once the x loads are
     // in flight, the rest when the x operand is built -- bounds what queues ahead of the x loads.
     const bool issuer = warp == NW - 1 && lane == 0 && !B200Q_ABL(4);
-    const int early = min(p.early_tiles % 10, ntma);
-    const int mid = min(early + p.early_tiles / 10, ntma);
+    const int nops = ntma * p.nbars;                         // requests of ~32 KB: (tile, pair group)
+    const int early = min(p.early_tiles % 10, nops);
+    const int mid = min(early + p.early_tiles / 10, nops);
     auto prefetch_next = [&]() {
         if (!p.next_bytes) return;
         const unsigned long long per = (((unsigned long long)p.next_chunk) + 127ull) & ~127ull;
@@ -253,7 +252,7 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_dec_kernel(const __grid_constant
         tma_prefetch_desc(&tmap);
         if (p.pf_mode == 2) prefetch_next();
         dec_issue_tiles(&tmap, sbase + OFF_BARS, sbase + p.tile_off, r0, 0, early, p.nbars, p.chunk, p.tile_bytes);
-        if (early == ntma && p.pf_mode == 1) prefetch_next();
+        if (early == nops && p.pf_mode == 1) prefetch_next();
     }
     B200Q_STAMP(2);
 
@@ -265,8 +264,12 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_dec_kernel(const __grid_constant
 #pragma unroll
         for (int c = 0; c < 4; ++c) offc[c] = (uint32_t)((ri + 8 * (mi & 1)) * 128 + (((2 * c + (mi >> 1)) ^ ri) << 4));
     }
-    const uint32_t scr = sbase + p.scr_off + (uint32_t)(warp * 1024);      // this warp's exchange buffer
     const uint32_t red = sbase + p.red_off;
+    // Operand exchange space of this warp: four 512-byte parts = its OWN partial-tile slots (slots of tiles 0..3, or its
+    // kilobyte in both buffers of the pipelined reduction) -- nobody else touches them before the main loop.
+    const uint32_t xbase = red + (uint32_t)(warp * (p.slots ? 512 : WARP_RED));
+    const uint32_t xs1 = p.slots ? (uint32_t)(NW * 512) : 512u, xs2 = p.slots ? (uint32_t)(2 * NW * 512) : (uint32_t)RB;
+    auto xpart = [&](int k) { return xbase + (uint32_t)(k & 1) * xs1 + (uint32_t)(k >> 1) * xs2; };
     const int hsel = g >> 2, lsel = g & 3;                   // lane (g, t) holds mma column g: digit lsel of batch row 2 nt + hsel
     // scale / zero point of this thread's output row (one row per thread: at most 256 rows per CTA), fetched early
     // (latency hidden by the main loop)
@@ -279,61 +282,40 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_dec_kernel(const __grid_constant
         mbar_wait(full_bar(bb), (uint32_t)((itx >> 1) & 1));
         constexpr int WORDS = NT * 128, SRC = NTHR / WORDS, PER = NW / SRC;
         const int rho = tid % WORDS, sq = tid / WORDS;
-        const uint32_t src = red + (uint32_t)(bb * RB + sq * PER * NT * 512 + rho * 4);
+        const uint32_t src = red + (uint32_t)(bb * RB + sq * PER * WARP_RED + rho * 4);
         int s = 0;
 #pragma unroll
-        for (int w = 0; w < PER; ++w) s += lds32(src + (uint32_t)(w * NT * 512));
+        for (int w = 0; w < PER; ++w) s += lds32(src + (uint32_t)(w * WARP_RED));
         red_add_s32(sbase + p.fin_off + (uint32_t)((((pass * p.ntiles_max + tile) * NT) * 128 + rho) * 4), s);
         __syncwarp();
         if (lane == 0) mbar_arrive(empty_bar(bb));
     };
 
-    // ---- phases.  Code that runs once costs ~10 clk per instruction on this part (one exposed instruction-cache
-    // miss per 128-byte line), and this kernel is little else.  So the two windows in which every warp would only
-    // wait are used to run the SAME instructions once on dummy data (profiles/r02_decode_notes.md):
-    //   ph = -2  before griddepcontrol.wait (the predecessor is still draining): the operand build, on zeros;
-    //   ph = -1  while the loads of x are in flight: one tile of the main loop, the fold and the epilogue
-    //            (no barrier waits, results land in buffers the real pass overwrites, global stores predicated off);
-    //   ph >= 0  the real passes.
+    pdl_wait();              // x (and y) belong to the stream-ordered predecessor
+    B200Q_STAMP(3);
     float xv[GPW2][MB][8];
     uint32_t bf[GPW2][4][NT][4];                              // per 32-byte step: {e-word b0, e-word b1, z-word b0, z-word b1}
 #pragma unroll 1
-    for (int ph = p.warm ? -2 : 0; ph < p.npasses; ++ph) {
-        const bool real = ph >= 0;
-        const int pass = real ? ph : 0;
+    for (int pass = 0; pass < p.npasses; ++pass) {
         const int m0 = pass * MB;
-        if (ph == (p.warm ? -1 : 0)) {
-            pdl_wait();      // x (and y) belong to the stream-ordered predecessor
-            B200Q_STAMP(3);
-        }
         // ---- x of this pass: this warp's columns only, all loads in flight at once
-        if (ph == -2) {
 #pragma unroll
-            for (int q = 0; q < GPW2; ++q)
+        for (int q = 0; q < GPW2; ++q) {
+            const int col = (warp + NW * q) * 256 + lane * 8;
 #pragma unroll
-                for (int hr = 0; hr < MB; ++hr)
+            for (int hr = 0; hr < MB; ++hr) {
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) xv[q][hr][e] = 0.0f;
-        } else if (ph != 0 || !p.warm) {
-#pragma unroll
-            for (int q = 0; q < GPW2; ++q) {
-                const int col = (warp + NW * q) * 256 + lane * 8;
-#pragma unroll
-                for (int hr = 0; hr < MB; ++hr) {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) xv[q][hr][e] = 0.0f;
-                    if (col < p.K && m0 + hr < p.M) load8f(p.x, p.x_dtype, (int64_t)(m0 + hr) * p.K + col, xv[q][hr]);
-                }
+                for (int e = 0; e < 8; ++e) xv[q][hr][e] = 0.0f;
+                if (col < p.K && m0 + hr < p.M) load8f(p.x, p.x_dtype, (int64_t)(m0 + hr) * p.K + col, xv[q][hr]);
             }
-            if (pass == 0 && issuer && early < mid) {
-                dec_issue_tiles(&tmap, sbase + OFF_BARS, sbase + p.tile_off, r0, early, mid, p.nbars, p.chunk, p.tile_bytes);
-                if (mid == ntma && p.pf_mode == 1) prefetch_next();
-            }
+        }
+        if (pass == 0 && issuer && early < mid) {
+            dec_issue_tiles(&tmap, sbase + OFF_BARS, sbase + p.tile_off, r0, early, mid, p.nbars, p.chunk, p.tile_bytes);
+            if (mid == nops && p.pf_mode == 1) prefetch_next();
         }
         int ex[MB];
 #pragma unroll
         for (int hr = 0; hr < MB; ++hr) ex[hr] = 0;
-        if (real) {
         // ---- row amax (non-negative floats order like their bit patterns: one REDUX per row); NaN / Inf show up
         // as an exponent field of 0xff
 #pragma unroll
@@ -362,30 +344,20 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_dec_kernel(const __grid_constant
                 if (tid == 0) s_ex[m0 + hr] = ex[hr];
             }
         }
-        }   // real
 
         // ---- operand: digits of Xe / Z, exchanged inside the warp.  Source lane i (0..31) of a pair holds columns
         // 8 i .. 8 i + 7 = packed bytes 4 i .. 4 i + 3: word (i & 3) of the 16-byte column i >> 2, i.e. the bytes lane quad
         // t = i & 3 multiplies in step c = i >> 3, first (b0) or second (b1) half (i >> 2) & 1.
-        if (ph != -1) {
-        const uint32_t sdst = scr + (uint32_t)((((lane >> 3) * 4 + (lane & 3)) * 16) + ((lane >> 2) & 1) * 4);
-        const uint32_t ssrc = scr + (uint32_t)(lsel * 256 + t * 16);
+        const uint32_t soff = (uint32_t)((((lane >> 3) * 4 + (lane & 3)) * 16) + ((lane >> 2) & 1) * 4);
+        const uint32_t ssrc = xpart(2 * hsel + (lsel >> 1)) + (uint32_t)((lsel & 1) * 256 + t * 16);
 #pragma unroll
         for (int q = 0; q < GPW2; ++q) {
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) {
 #pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
+                for (int hh = 0; hh < 2; ++hh) {                  // the two batch rows of this n-tile: independent chains
                     const int hr = 2 * nt + hh;
-                    if (m0 + hr >= p.M) {                         // uniform: no such batch row (odd M)
-                        if (hsel == hh) {
-#pragma unroll
-                            for (int c = 0; c < 4; ++c)
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) bf[q][c][nt][j] = 0u;
-                        }
-                        continue;
-                    }
+                    if (m0 + hr >= p.M) continue;                 // uniform: no such batch row (odd M)
                     const float up = __uint_as_float((uint32_t)(127 + ex[hr]) << 23), up16 = up * 0.0625f;
                     uint32_t D[8];
 #pragma unroll
@@ -401,36 +373,38 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_dec_kernel(const __grid_constant
                     const uint32_t e2 = __byte_perm(D[0], D[2], 0x7362), e3 = __byte_perm(D[4], D[6], 0x7362);
                     const uint32_t o0 = __byte_perm(D[1], D[3], 0x5140), o1 = __byte_perm(D[5], D[7], 0x5140);
                     const uint32_t o2 = __byte_perm(D[1], D[3], 0x7362), o3 = __byte_perm(D[5], D[7], 0x7362);
-                    sts32(sdst, __byte_perm(e0, e1, 0x5410));       sts32(sdst + 8, __byte_perm(o0, o1, 0x5410));
-                    sts32(sdst + 256, __byte_perm(e0, e1, 0x7632)); sts32(sdst + 264, __byte_perm(o0, o1, 0x7632));
-                    sts32(sdst + 512, __byte_perm(e2, e3, 0x5410)); sts32(sdst + 520, __byte_perm(o2, o3, 0x5410));
-                    sts32(sdst + 768, __byte_perm(e2, e3, 0x7632)); sts32(sdst + 776, __byte_perm(o2, o3, 0x7632));
-                    __syncwarp();
-                    if (hsel == hh) {                             // lanes whose mma column belongs to this batch row
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            const uint4 v = lds128(ssrc + (uint32_t)(c * 64));
-                            bf[q][c][nt][0] = v.x; bf[q][c][nt][1] = v.y; bf[q][c][nt][2] = v.z; bf[q][c][nt][3] = v.w;
-                        }
-                    }
-                    __syncwarp();
+                    const uint32_t d01 = xpart(2 * hh) + soff, d23 = xpart(2 * hh + 1) + soff;      // digits 0, 1 / 2, 3 of row hh
+                    sts32(d01, __byte_perm(e0, e1, 0x5410));       sts32(d01 + 8, __byte_perm(o0, o1, 0x5410));
+                    sts32(d01 + 256, __byte_perm(e0, e1, 0x7632)); sts32(d01 + 264, __byte_perm(o0, o1, 0x7632));
+                    sts32(d23, __byte_perm(e2, e3, 0x5410));       sts32(d23 + 8, __byte_perm(o2, o3, 0x5410));
+                    sts32(d23 + 256, __byte_perm(e2, e3, 0x7632)); sts32(d23 + 264, __byte_perm(o2, o3, 0x7632));
                 }
+                __syncwarp();
+                if (m0 + 2 * nt + hsel < p.M) {                   // this lane's mma column belongs to a batch row that exists
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const uint4 v = lds128(ssrc + (uint32_t)(c * 64));
+                        bf[q][c][nt][0] = v.x; bf[q][c][nt][1] = v.y; bf[q][c][nt][2] = v.z; bf[q][c][nt][3] = v.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) bf[q][c][nt][j] = 0u;
+                }
+                __syncwarp();
             }
         }
-        }   // ph != -1
-        if (ph == 0 && issuer) {
-            if (mid < ntma) dec_issue_tiles(&tmap, sbase + OFF_BARS, sbase + p.tile_off, r0, mid, ntma, p.nbars, p.chunk, p.tile_bytes);
-            if (p.pf_mode == 3 || (p.pf_mode == 1 && mid < ntma)) prefetch_next();
+        if (pass == 0 && issuer) {
+            if (mid < nops) dec_issue_tiles(&tmap, sbase + OFF_BARS, sbase + p.tile_off, r0, mid, nops, p.nbars, p.chunk, p.tile_bytes);
+            if (p.pf_mode == 3 || (p.pf_mode == 1 && mid < nops)) prefetch_next();
         }
-        if (ph == 0) B200Q_STAMP(5);
-        // shared exchange / partial-tile memory (many passes): every warp must be done with its exchange buffer
-        if (p.alias) __syncthreads();
+        if (pass == 0) B200Q_STAMP(5);
 
-        // ---- main loop: one 16-row tile per iteration, this warp's pairs of it (dummy phase: one tile, no waits)
-        if (ph != -2) {
-        const int nloop = real ? ntl : 1;
-        for (int i = 0; i < nloop; ++i) {
-            int c0[NT][4], c1[NT][4];                         // raw bytes x digits of Xe, masked bytes x digits of Z
+        // ---- main loop: one 16-row tile per iteration, this warp's pairs of it
+        for (int i = 0; i < ntl; ++i) {
+            // raw bytes x digits of Xe, masked bytes x digits of Z (two chains of dependent IMMAs; four were not faster)
+            int c0[NT][4], c1[NT][4];
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
@@ -440,9 +414,9 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_dec_kernel(const __grid_constant
             for (int q = 0; q < GPW2; ++q) {
                 const int P = warp + NW * q;
                 if (P < p.npairs) {                           // uniform
-                    if (ph == 0 && i < ntma && !B200Q_ABL(4)) mbar_wait(tile_bar(i, P / p.chunk), 0);
+                    if (pass == 0 && i < ntma && !B200Q_ABL(4)) mbar_wait(tile_bar(i, P / p.chunk), 0);
                     const uint32_t pb = tb + (uint32_t)(P * PAIR_BYTES);
-                    if (ph == 0 && i == tf) {                 // the row of 0x11 bytes behind the last weight row
+                    if (pass == 0 && i == tf) {               // the row of 0x11 bytes behind the last weight row
                         if (lane < 8) sts128(pb + (uint32_t)(rf * 128 + lane * 16), make_uint4(0x11111111u, 0x11111111u, 0x11111111u, 0x11111111u));
                         __syncwarp();
                     }
@@ -465,41 +439,43 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_dec_kernel(const __grid_constant
                 sts128(red + (uint32_t)((i * NW + warp) * 512 + lane * 16),
                        make_uint4((uint32_t)(c0[0][0] + c1[0][0]), (uint32_t)(c0[0][1] + c1[0][1]),
                                   (uint32_t)(c0[0][2] + c1[0][2]), (uint32_t)(c0[0][3] + c1[0][3])));
-                if (real && i < 6) B200Q_STAMP(6 + i);
+                if (i < 6) B200Q_STAMP(6 + i);
                 continue;
             }
-            if (!real) continue;                              // dummy phase: the partial tile goes nowhere
             // hand the partial tile over (double buffer; the buffer was last read for tile it - 2)
             const int bb = it & 1;
             if (it >= 2) mbar_wait(empty_bar(bb), (uint32_t)(((it >> 1) - 1) & 1));
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt)
-                sts128(red + (uint32_t)(bb * RB + (warp * NT + nt) * 512 + lane * 16),
+                sts128(red + (uint32_t)(bb * RB + warp * WARP_RED + nt * 512 + lane * 16),
                        make_uint4((uint32_t)(c0[nt][0] + c1[nt][0]), (uint32_t)(c0[nt][1] + c1[nt][1]),
                                   (uint32_t)(c0[nt][2] + c1[nt][2]), (uint32_t)(c0[nt][3] + c1[nt][3])));
             __syncwarp();
             if (lane == 0) mbar_arrive(full_bar(bb));
             if (i >= 1) reduce_tile(it - 1, pass, i - 1);
-            if (ph == 0 && i < 6) B200Q_STAMP(6 + i);
+            if (pass == 0 && i < 6) B200Q_STAMP(6 + i);
             ++it;
         }
-        if (real && !p.slots) reduce_tile(it - 1, pass, ntl - 1);
-        if (ph == 0) B200Q_STAMP(12);
-        }   // ph != -2
-        // shared exchange / partial-tile memory: wait until every warp has folded the last tile
-        if (p.alias && real && pass + 1 < p.npasses) __syncthreads();
-        if (ph != -1 && ph != p.npasses - 1) continue;
+        if (!p.slots) reduce_tile(it - 1, pass, ntl - 1);
+        if (pass == 0) B200Q_STAMP(12);
+        // (the exchange space of the next pass is the warp's own partial-tile slots: the amax barrier of that pass comes
+        // after every warp has folded the last tile of this one, so they are free again)
+    }
 
-    // ======== after the last pass (and once in the dummy phase): fold, epilogue
+    // ======== after the last pass: fold, epilogue
     __syncthreads();
     if (p.slots) {
         // fold the 16 warp slots of every tile (integer adds: exact, order independent)
-        for (int w = tid; w < ntl * 128; w += NTHR) {
-            const uint32_t src = red + (uint32_t)(((w >> 7) * NW) * 512 + (w & 127) * 4);
+        // (M = 1: only mma columns 0..3 are live, i.e. the words of lane quads t = 0, 1)
+        const int sh = p.M == 1 ? 6 : 7;
+        for (int v = tid; v < (ntl << sh); v += NTHR) {
+            const int tile = v >> sh, rem = v & ((1 << sh) - 1);
+            const int word = p.M == 1 ? ((rem >> 3) * 16 + (rem & 7)) : rem;
+            const uint32_t src = red + (uint32_t)((tile * NW) * 512 + word * 4);
             int s = 0;
 #pragma unroll
             for (int k = 0; k < NW; ++k) s += lds32(src + (uint32_t)(k * 512));
-            fin[w] = s;
+            fin[tile * 128 + word] = s;
         }
         __syncthreads();
     }
@@ -507,7 +483,7 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_dec_kernel(const __grid_constant
 
     // ---- epilogue: one thread per output (tile, batch row, row): digits -> sum_k q*X (exact s64),
     // y = s * 2^-e * (sum_k q*X - zp * sum_k X) (+ bias)
-    const unsigned int flagged = real ? *s_flag : 0u;
+    const unsigned int flagged = *s_flag;
     // word of (mma row r, column col) in a 16 x 8 tile stored as [lane = 4 (r & 7) + col / 2][reg = 2 (r >> 3) + (col & 1)]
     auto word_of = [](int r, int col) { return (((r & 7) * 4 + (col >> 1)) * 4) + ((r >> 3) * 2 + (col & 1)); };
     if (tid < nrows) {
@@ -537,7 +513,7 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_dec_kernel(const __grid_constant
                 const double down = __longlong_as_double((long long)(1023 - ex) << 52);                // 2^-e
                 v = sc * (float)(((double)a - (double)zp * (double)txl) * down);
             }
-            if (real) store_out(p.y, p.y_dtype, (int64_t)m * p.N + row, v + bias);
+            store_out(p.y, p.y_dtype, (int64_t)m * p.N + row, v + bias);
         }
     }
     // ---- batch rows with NaN / Inf: the reference's arithmetic (dequantise, then fp32 multiply-add), so that
@@ -566,13 +542,12 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_dec_kernel(const __grid_constant
             }
         }
     }
-    }   // phases
     B200Q_STAMP(14);
 }
 
 struct DecPlan {
     int grid, gpw2, nt, npasses, ntiles, npairs, nbars, chunk, tile_bytes, tile_off, rows_q, rows_rem;
-    int scr_off, red_off, fin_off, alias, slots;
+    int red_off, fin_off, slots;
     size_t smem;
 };
 
@@ -597,16 +572,13 @@ bool plan_dec(int sm_count, int max_smem, int64_t M, int64_t N, int64_t K, DecPl
     if (c->ntiles * c->nbars > MAX_BARS) return false;
     c->tile_bytes = c->nbars * c->chunk * PAIR_BYTES;             // >= npairs * 2 KB: a 3-D box always has room
     const int fin_bytes = c->npasses * c->ntiles * c->nt * 512;
-    const int red_bytes = 2 * NW * c->nt * 512;
-    const int slot_bytes = c->ntiles * NW * 512;
-    // (1) single pass of <= 2 batch rows: slots; (2) separate exchange and partial-tile buffers; (3) they share memory
-    for (int form = (c->nt == 1 && c->npasses == 1 && tuning().gemv_slots != 0) ? 0 : 1; form < 3; ++form) {
+    const int red_bytes = 2 * NW * WARP_RED;
+    const int slot_bytes = (c->ntiles > 4 ? c->ntiles : 4) * NW * 512;      // >= 4 slots per warp: its exchange space
+    // (1) single pass of <= 2 batch rows: one slot per (tile, warp); (2) double-buffered pipelined reduction
+    for (int form = (c->nt == 1 && c->npasses == 1 && tuning().gemv_slots != 0) ? 0 : 1; form < 2; ++form) {
         c->slots = form == 0;
-        c->alias = form == 2;
-        c->scr_off = OFF_DYN;
-        c->red_off = c->alias ? OFF_DYN : OFF_DYN + SCR_BYTES;
-        const int rb = c->slots ? slot_bytes : red_bytes;
-        c->fin_off = c->red_off + (c->alias && rb < SCR_BYTES ? SCR_BYTES : rb);
+        c->red_off = OFF_DYN;
+        c->fin_off = c->red_off + (c->slots ? slot_bytes : red_bytes);
         c->tile_off = (c->fin_off + fin_bytes + 1023) / 1024 * 1024;
         c->smem = (size_t)c->tile_off + (size_t)c->ntiles * c->tile_bytes;
         if (c->smem <= (size_t)max_smem) return true;
@@ -710,12 +682,11 @@ int launch_gemv_dec(const DeviceInfo& dev, const void* x, int x_dtype, const uin
     p.rows_q = c.rows_q; p.rows_rem = c.rows_rem;
     p.npairs = c.npairs; p.nbars = c.nbars; p.chunk = c.chunk;
     p.ntiles_max = c.ntiles; p.tile_bytes = c.tile_bytes; p.tile_off = c.tile_off; p.npasses = c.npasses;
-    p.scr_off = c.scr_off; p.red_off = c.red_off; p.fin_off = c.fin_off; p.alias = c.alias; p.slots = c.slots;
+    p.red_off = c.red_off; p.fin_off = c.fin_off; p.slots = c.slots;
     p.wait_weights = (flags & B200Q_FLAG_STATIC_WEIGHTS) ? 0 : 1;
     p.early_tiles = tuning().gemv_early >= 0 ? tuning().gemv_early : 92;     // two tiles up front, the rest behind the x loads
     p.next_packed = next_packed;
     p.pf_mode = tuning().gemv_pf;
-    p.warm = tuning().gemv_warm;
     p.next_bytes = (tuning().gemv_pf != 0 && next_packed && (reinterpret_cast<uintptr_t>(next_packed) & 15) == 0) ? next_bytes : 0;
     p.next_chunk = (unsigned int)(p.next_bytes / (unsigned long long)c.grid);
     p.debug = tuning().gemv_debug > 0 ? tuning().gemv_debug : 0;

@@ -45,7 +45,6 @@ struct Tuning {
     int gemv_occ2 = 0;      // 1: 8-warp CTAs sized so that two launches share an SM (cross-layer prefetch)
     int gemv_debug = -1;    // bench-only ablations: 1 = skip the mma work, 2 = skip the weight loads
     int force_path = -1;    // 0 auto, 1 generic SIMT, 2 ring decode kernel, 3 tcgen05 gemm, 6 resident decode kernel (gemv_dec)
-    int gemv_warm = 0;      // resident decode kernel: 1 = dummy (instruction-cache warming) phases before the real ones (measured: a net loss, profiles/r02_decode_notes.md)
     int gemv_slots = 1;     // resident decode kernel, M <= 2: 0 = pipelined cross-warp reduction instead of per-warp slots
 };
 const Tuning& tuning();
