@@ -100,7 +100,8 @@ int b200q_linear_bias_fwd(const void* x, int x_dtype, const uint8_t* packed, con
     const int force = tuning().force_path;
     const bool vec_ok = aligned(x, 16) && aligned(packed, 16) && aligned(y, 16);
     // decode (M <= 16): the CTA-resident IMMA kernel (gemv_dec.cu) whenever ceil(N / SMs) rows fit in shared memory
-    if ((force <= 0 || force == 6) && vec_ok && gemv_dec_supported(d, M, N, K))
+    // (wide K with many batch rows would need > 4 passes of two rows: the tcgen05 GEMM is faster there)
+    if ((force <= 0 || force == 6) && vec_ok && gemv_dec_supported(d, M, N, K) && (force == 6 || M <= 8 || K <= 8192))
         return launch_gemv_dec(d, x, x_dtype, packed, scales, zps, bias, y, y_dtype, M, N, K, flags, st, next_packed, next_bytes);
     int rc = 0;
     bool done = false;

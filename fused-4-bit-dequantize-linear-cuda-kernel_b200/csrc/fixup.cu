@@ -54,6 +54,10 @@ __device__ __forceinline__ float ref_dot(const FixParams& p, int e, int64_t n, i
 }
 
 __global__ void __launch_bounds__(256) nonfinite_fixup_kernel(const FixParams p) {
+    // launched with programmatic stream serialisation: the kernel after this one may set itself up meanwhile; this
+    // one only touches memory once the kernel whose rows it repairs has completed
+    pdl_launch_dependents();
+    pdl_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int64_t m = blockIdx.x; m < p.M; m += gridDim.x) {
         int bad;
@@ -111,9 +115,16 @@ int launch_nonfinite_fixup(const void* x, int x_dtype, const uint8_t* packed, co
                            const int32_t* starts, const int32_t* ends, int E, int gated, cudaStream_t st) {
     if (M <= 0 || N <= 0 || K <= 0) return 0;
     FixParams p{x, packed, scales, zps, nf_flags, y, starts, ends, E, gated, x_dtype, y_dtype, M, N, K};
-    const unsigned grid = (unsigned)(M < 1184 ? M : 1184);
-    nonfinite_fixup_kernel<<<grid, 256, 0, st>>>(p);
-    return check_cuda(cudaGetLastError(), "nonfinite_fixup launch");
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(M < 1184 ? M : 1184));
+    cfg.blockDim = dim3(256);
+    cfg.stream = st;
+    cudaLaunchAttribute attrs[1];
+    attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attrs;
+    cfg.numAttrs = 1;
+    return check_cuda(cudaLaunchKernelEx(&cfg, nonfinite_fixup_kernel, p), "nonfinite_fixup launch");
 }
 
 int launch_bias_add(void* y, int y_dtype, const float* bias, int64_t M, int64_t N, cudaStream_t st) {

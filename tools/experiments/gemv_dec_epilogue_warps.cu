@@ -1,0 +1,708 @@
+// Decode path (M = 1..16): y[M,N] = x[M,K] @ dequant(W)^T (+ bias) with the CTA's whole share of W resident in
+// shared memory.  HBM-bound by design: every packed byte is read once, by the TMA engine.
+//
+// Arithmetic: exact integers (unchanged from round 1).  x is a per-row fixed-point number (even columns
+// Xe = round(x 2^e), odd columns Xo = round(x 2^(e-4))) cut into four signed base-256 digits = four columns of IMMA
+// m16n8k32 (u8 x s8 -> s32) per batch row.  The nibbles are never widened: the raw packed byte q_lo + 16 q_hi meets
+// the digits of Xe, the masked byte 16 q_hi meets the digits of Z = Xo - Xe.  s32 partial sums, s64 when the digits
+// are combined, y = s * 2^-e * (sum q X - zp * sum X) with one fp32 rounding: results do not depend on the
+// summation order.  A batch row that contains NaN / Inf is recomputed in the reference's order (w = (q - zp) * s,
+// fp32 FMA), so non-finite inputs propagate exactly like dequantize + F.linear (python/quantize.py:172, 202).
+//
+// Structure:
+//   * weights: tile i = 16 rows x K/2 bytes arrives as TMA tensor boxes [16 rows x 128 bytes] with the 128-byte
+//     swizzle (one box per 256-column "pair", or one 3-D box per group of pairs), so that the 8-row LDS.128 of a
+//     warp is conflict-free for ANY row stride -- no K split, no skewed copies, K only has to be a multiple of 128.
+//     One single-use mbarrier per (tile, pair group);
+//   * warp w owns the column pairs w, w + 16, ... of every tile: it loads, converts and keeps the B fragments of
+//     exactly those columns (warp-private exchange buffer, __syncwarp only); the one block barrier of a pass is
+//     the row amax;
+//   * sum X for the zero-point term comes from the digit words (IDP4A), not from a second pass;
+//   * cross-warp reduction is pipelined: after tile i every warp parks its 16 x 8 partial tile in a double
+//     buffer (mbarrier full / empty), and all 512 threads fold the 16 partials of tile i - 1 into the
+//     accumulator (integer adds: exact, order independent) while the tensor cores work on tile i + 1;
+//   * M = 3..16: passes of up to four batch rows (two n-tiles) over the resident tiles -- the weights are read
+//     from HBM once whatever M is.
+//
+// Reference being replaced: csrc/quantized_linear_kernel.cu:90-279 (one thread per output, M x weight traffic).
+#include <cuda.h>
+#include <cmath>
+#include <mutex>
+#include "internal.h"
+#include "ptx.cuh"
+#include "tc.cuh"
+
+namespace b200q {
+
+// bench-only (-DB200Q_PROF build, tools/prof_dec.py): per-CTA wall-clock stamps of the phases of the last launch
+#ifdef B200Q_PROF
+__device__ long long g_dec_prof[256 * 16];
+#define B200Q_STAMP(i) B200Q_STAMP_IF(tid == 0, i)
+#define B200Q_STAMP_IF(who, i)                                                       \
+    do {                                                                             \
+        if (p.debug && (who) && blockIdx.x < 256) {                                  \
+            long long t_;                                                            \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                   \
+            g_dec_prof[blockIdx.x * 16 + (i)] = t_;                                  \
+        }                                                                            \
+    } while (0)
+#define B200Q_ABL(bit) ((p.debug & (bit)) != 0)     // 2: no IMMA, 4: no weight traffic / waits, 8: no weight LDS, 16: no hand-over / reduce
+#else
+#define B200Q_STAMP(i) ((void)0)
+#define B200Q_STAMP_IF(who, i) ((void)0)
+#define B200Q_ABL(bit) false
+#endif
+
+namespace {
+
+constexpr int NW = 16;               // MMA warps per CTA (one 256-column pair of every tile each, + 16, ...)
+constexpr int EW = 4;                // epilogue warps: fold the 16 partial tiles of tile i and write y while the MMA warps run tile i + 1
+constexpr int NTHR_MMA = NW * 32, NTHR_EPI = EW * 32, NTHR = NTHR_MMA + NTHR_EPI;
+constexpr int TILE_ROWS = 16;
+constexpr int PAIR_BYTES = TILE_ROWS * 128;      // one pair (256 columns) of one tile in shared memory
+constexpr int MAX_BARS = 64;                     // (tile, pair group) barriers
+constexpr int MAX_BUF = 32;                      // partial-tile buffers
+constexpr int MAX_ROWS = 256;                    // weight rows per CTA
+
+// shared memory map (bytes)
+constexpr int OFF_BARS = 0;          // [MAX_BARS] tile barriers
+constexpr int OFF_FULL = 512;        // [MAX_BUF]
+constexpr int OFF_EMPTY = 768;       // [MAX_BUF]
+constexpr int OFF_FLAG = 1024;       // bit m: batch row m holds NaN / Inf
+constexpr int OFF_EX = 1040;         // [16] exponent of every batch row
+constexpr int OFF_TX = 1152;         // [16] s64: sum_k X of every batch row
+constexpr int OFF_AMAX = 1280;       // [2 (pass parity)][4 rows][16 warps] u32
+constexpr int OFF_SC = 2048;         // [MAX_ROWS] scales, zero points, bias of this CTA's rows
+constexpr int OFF_ZP = 3072;
+constexpr int OFF_BI = 4096;
+constexpr int OFF_DYN = 5120;        // partial-tile buffers (their owner's slots double as its operand exchange space), tiles
+
+struct DecParams {
+    const void* x;
+    const uint8_t* packed;
+    const float* scales;
+    const float* zps;
+    const float* bias;               // may be null
+    void* y;
+    const uint8_t* next_packed;      // L2 prefetch hint (weights of the next fused linear), may be null
+    unsigned long long next_bytes;
+    unsigned int next_chunk;         // next_bytes / gridDim.x
+    int x_dtype, y_dtype;
+    int M, N, K;
+    int rows_q, rows_rem;            // CTA b owns rows_q (+1 if b < rows_rem) rows
+    int npairs;                      // K / 256
+    int nbars;                       // pair groups (barriers) per tile
+    int chunk;                       // pairs per group
+    int tile_bytes;
+    int tile_off;                    // byte offset of tile 0 in dynamic shared memory (1024-aligned)
+    int red_off;                     // partial-tile buffers
+    int nbuf;                        // ... how many (>= tiles x passes: every tile has its own, nobody waits)
+    int npasses;
+    int wait_weights;                // 1: weights may be written by the preceding kernel
+    int early_ops;                   // weight requests issued before griddepcontrol.wait (the rest once the x loads are in flight)
+    int pf_mode;                     // next-layer L2 prefetch: 0 off, 1 behind the last own request, 2 before the own requests, 3 after the first tile
+    int debug;                       // B200Q_PROF builds: record phase stamps
+};
+
+__device__ __forceinline__ void load8f(const void* x, int dtype, int64_t idx, float (&v)[8]) {
+    if (dtype == B200Q_F32) {
+        const float4 a = *reinterpret_cast<const float4*>(static_cast<const float*>(x) + idx);
+        const float4 b = *reinterpret_cast<const float4*>(static_cast<const float*>(x) + idx + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else if (dtype == B200Q_F16) {
+        const uint4 r = *reinterpret_cast<const uint4*>(static_cast<const __half*>(x) + idx);
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+            v[2 * i] = f.x; v[2 * i + 1] = f.y;
+        }
+    } else {
+        const uint4 r = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(x) + idx);
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+            v[2 * i] = f.x; v[2 * i + 1] = f.y;
+        }
+    }
+}
+
+__device__ __forceinline__ float load1f(const void* x, int dtype, int64_t idx) {
+    if (dtype == B200Q_F32) return static_cast<const float*>(x)[idx];
+    if (dtype == B200Q_F16) return __half2float(static_cast<const __half*>(x)[idx]);
+    return __bfloat162float(static_cast<const __nv_bfloat16*>(x)[idx]);
+}
+
+__device__ __forceinline__ void store_out(void* y, int dtype, int64_t idx, float v) {
+    if (dtype == B200Q_F32) static_cast<float*>(y)[idx] = v;
+    else if (dtype == B200Q_F16) static_cast<__half*>(y)[idx] = __float2half_rn(v);
+    else static_cast<__nv_bfloat16*>(y)[idx] = __float2bfloat16_rn(v);
+}
+
+// D(16x8,s32) += A(16x32,u8,row) * B(32x8,s8,col)      SASS: IMMA.16832.U8.S8
+__device__ __forceinline__ void imma(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                     uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ void red_add_s32(uint32_t addr, int v) {
+    asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ int lds32(uint32_t addr) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b) {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+
+// TMA tensor-box loads with an L2 eviction hint (the weights are read once)
+__device__ __forceinline__ void tma_box_2d(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
+        ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar), "l"(pol)
+        : "memory");
+}
+__device__ __forceinline__ void tma_box_3d(uint32_t dst, const void* tmap, int c0, int c1, int c2, uint32_t bar, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;"
+        ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar), "l"(pol)
+        : "memory");
+}
+
+// A fragment of IMMA m16n8k32 straight from the swizzled tile: four 8 x 16-byte matrices (rows 0-7 / 8-15 of two
+// adjacent 16-byte columns) land in a0..a3 of every lane.  SASS: LDSM.16.M88.4
+__device__ __forceinline__ void ldsm_x4(uint32_t (&a)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3])
+                 : "r"(addr));
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+// weight requests [from, to) (request = (tile, pair group), ~32 KB): one 3-D box [16 rows][chunk pairs][128 B] each, one
+// elected thread.  Tile 0 holds rows 0..14 of the CTA (its last row is replaced by the 0x11 row, see below), tile
+// i >= 1 rows 16 i - 1 .. 16 i + 14.
+__device__ __noinline__ void dec_issue_tiles(const CUtensorMap* tmap, uint32_t bar0, uint32_t dst0, int row0, int from, int to,
+                                             int nbars, int chunk, int tile_bytes) {
+    const uint64_t pol = policy_evict_first();
+    for (int op = from; op < to; ++op) {                      // op = tile * nbars + pair group
+        const int i = op / nbars, grp = op - i * nbars;
+        const uint32_t bar = bar0 + 8u * (uint32_t)op;
+        mbar_arrive_expect_tx(bar, (uint32_t)(chunk * PAIR_BYTES));
+        tma_box_3d(dst0 + (uint32_t)(i * tile_bytes + grp * chunk * PAIR_BYTES), tmap, 0, row0 + (i ? i * TILE_ROWS - 1 : 0), grp * chunk, bar, pol);
+    }
+}
+
+__device__ __forceinline__ void bar_sync_id(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive_id(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+
+template <int GPW2, int NT>          // pairs per warp, n-tiles (two batch rows each) per pass
+__global__ void __launch_bounds__(NTHR, 1) gemv_dec_kernel(const __grid_constant__ CUtensorMap tmap, const DecParams p) {
+    constexpr int MB = 2 * NT;       // batch rows per pass
+    constexpr int BUFB = NW * NT * 512;   // bytes of one partial-tile buffer: [warp][n-tile][lane][4] s32
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t sbase = smem_u32(smem);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+
+    B200Q_STAMP(0);
+    const int b = (int)blockIdx.x;
+    const int r0 = b * p.rows_q + min(b, p.rows_rem);
+    const int nrows = p.rows_q + (b < p.rows_rem ? 1 : 0);
+    // Row 15 of tile 0 is a row of bytes 0x11 (q_lo = q_hi = 1): the tensor cores then deliver sum_k X (the zero-point
+    // term) as one more output row, with no extra arithmetic in the operand build.
+    const int ntl = nrows <= 15 ? 1 : 1 + (nrows - 15 + TILE_ROWS - 1) / TILE_ROWS;
+    int* s_ex = reinterpret_cast<int*>(smem + OFF_EX);
+    long long* s_tx = reinterpret_cast<long long*>(smem + OFF_TX);
+    unsigned int* s_flag = reinterpret_cast<unsigned int*>(smem + OFF_FLAG);
+    unsigned int* s_amax = reinterpret_cast<unsigned int*>(smem + OFF_AMAX);
+    float* s_sc = reinterpret_cast<float*>(smem + OFF_SC);
+    float* s_zp = reinterpret_cast<float*>(smem + OFF_ZP);
+    float* s_bi = reinterpret_cast<float*>(smem + OFF_BI);
+    auto tile_bar = [&](int i, int grp) { return sbase + OFF_BARS + 8u * (uint32_t)(i * p.nbars + grp); };
+    auto full_bar = [&](int bb) { return sbase + OFF_FULL + 8u * (uint32_t)bb; };
+    auto empty_bar = [&](int bb) { return sbase + OFF_EMPTY + 8u * (uint32_t)bb; };
+    const int nops = ntl * p.nbars;                          // weight requests of ~32 KB: (tile, pair group)
+    const int nbuf = p.nbuf;
+    const uint32_t red = sbase + p.red_off;
+
+    if (tid < nops) mbar_init(sbase + OFF_BARS + 8u * tid, 1);
+    if (tid >= 64 && tid < 64 + nbuf) { mbar_init(full_bar(tid - 64), NW); mbar_init(empty_bar(tid - 64), EW); }
+    if (tid == 0) *s_flag = 0u;
+    fence_mbar_init();
+    __syncthreads();
+    pdl_launch_dependents();
+    B200Q_STAMP(1);
+
+    if (warp >= NW) {
+        // =========================================================== epilogue warps (and the weight requests)
+        const int e = tid - NTHR_MMA;
+        auto prefetch_next = [&]() {
+            if (!p.next_bytes) return;
+            const unsigned long long per = (((unsigned long long)p.next_chunk) + 127ull) & ~127ull;
+            const unsigned long long beg = min(per * blockIdx.x, p.next_bytes), end = min(beg + per, p.next_bytes);
+            for (unsigned long long off = beg; off < end; off += 32768ull) {
+                const unsigned int n = (unsigned int)min(32768ull, end - off) & ~15u;
+                if (n) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.next_packed + off), "r"(n) : "memory");
+            }
+        };
+        // staged requests: early_ops before griddepcontrol.wait, the rest once the MMA warps have their x loads in
+        // flight (22 MB of requests queued ahead of those loads cost ~1 us)
+        const bool issuer = e == 0 && !B200Q_ABL(4);
+        const int early = min(p.early_ops, nops);
+        if (p.wait_weights) pdl_wait();
+        if (issuer) {
+            tma_prefetch_desc(&tmap);
+            if (p.pf_mode == 2) prefetch_next();
+            dec_issue_tiles(&tmap, sbase + OFF_BARS, sbase + p.tile_off, r0, 0, early, p.nbars, p.chunk, p.tile_bytes);
+        }
+        // scales / zero points / bias of this CTA's rows -> shared memory (read once per row and batch row later)
+        for (int r = e; r < nrows; r += NTHR_EPI) {
+            s_sc[r] = __ldg(p.scales + r0 + r);
+            s_zp[r] = __ldg(p.zps + r0 + r);
+            s_bi[r] = p.bias ? __ldg(p.bias + r0 + r) : 0.0f;
+        }
+        if (warp == NW) {
+            bar_sync_id(2, NTHR_MMA + 32);                    // the x loads of pass 0 are in flight
+            if (issuer) {
+                dec_issue_tiles(&tmap, sbase + OFF_BARS, sbase + p.tile_off, r0, early, nops, p.nbars, p.chunk, p.tile_bytes);
+                if (p.pf_mode == 1) prefetch_next();
+            }
+        }
+        pdl_wait();          // y belongs to the stream-ordered predecessor
+        bar_sync_id(3, NTHR_EPI);
+        // thread e: quarter qd = e & 3 of the 16 partials of output (mma row r, batch row h of the n-tile)
+        const int qd = e & 3, r = (e >> 2) & 15, h = e >> 6;
+        const uint32_t w01 = (uint32_t)((((r & 7) * 4 + 2 * h) * 4 + (r >> 3) * 2) * 4);       // digits 0, 1 (adjacent words); 2, 3 at + 16
+        int it = 0;
+        for (int pass = 0; pass < p.npasses; ++pass) {
+            for (int i = 0; i < ntl; ++i, ++it) {
+                const int bb = it % nbuf;
+                mbar_wait(full_bar(bb), (uint32_t)((it / nbuf) & 1));
+                const unsigned int flagged = *s_flag;
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    const uint32_t src = red + (uint32_t)(bb * BUFB + (qd * 4) * NT * 512 + nt * 512) + w01;
+                    int d0 = 0, d1 = 0, d2 = 0, d3 = 0;
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) {
+                        const uint2 lo = lds64(src + (uint32_t)(w * NT * 512)), hi = lds64(src + (uint32_t)(w * NT * 512 + 16));
+                        d0 += (int)lo.x; d1 += (int)lo.y; d2 += (int)hi.x; d3 += (int)hi.y;
+                    }
+                    long long a = (long long)d0 + ((long long)d1 << 8) + ((long long)d2 << 16) + ((long long)d3 << 24);
+                    a += __shfl_xor_sync(0xffffffffu, a, 1);
+                    a += __shfl_xor_sync(0xffffffffu, a, 2);
+                    const int m = pass * MB + 2 * nt + h;
+                    if (i == 0) {                              // uniform: tile 0 carries the 0x11 row = sum_k X of every batch row
+                        if (r == 15 && qd == 0 && m < p.M) s_tx[m] = a;
+                        bar_sync_id(3, NTHR_EPI);
+                    }
+                    const int rc = i ? i * TILE_ROWS - 1 + r : r;
+                    if (qd == 0 && m < p.M && rc < nrows && (i || r < 15) && !((flagged >> m) & 1u)) {
+                        const long long txl = s_tx[m];
+                        const float sc = s_sc[rc], zp = s_zp[rc];
+                        const int ex = s_ex[m];
+                        const int zi = __float2int_rn(zp);
+                        float v;
+                        if ((float)zi == zp && zi >= -32768 && zi <= 32767 && ex >= -126) {
+                            // quantiser-made zero points are integers: a - zp * sum X exactly in s64, ONE rounding to fp32 (the
+                            // same value the fp64 expression below rounds to), then the exact power of two and the scale
+                            v = sc * (__ll2float_rn(a - (long long)zi * txl) * __uint_as_float((uint32_t)(127 - ex) << 23));
+                        } else {
+                            const double down = __longlong_as_double((long long)(1023 - ex) << 52);                // 2^-e
+                            v = sc * (float)(((double)a - (double)zp * (double)txl) * down);
+                        }
+                        store_out(p.y, p.y_dtype, (int64_t)m * p.N + r0 + rc, v + s_bi[rc]);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty_bar(bb));
+                if (it == 0 && issuer && p.pf_mode == 3) prefetch_next();
+                if (pass == 0 && i < 6) B200Q_STAMP_IF(e == 0, 6 + i);
+            }
+        }
+    } else {
+    // =========================================================== MMA warps
+    // per-lane constants of the main loop: ldmatrix row address of this lane for the four 32-byte steps of a pair
+    // (lane i supplies row (i & 7) + 8 ((i >> 3) & 1) of the 16-byte column 2 c + (i >> 4); 128-byte swizzle: column ^ row)
+    uint32_t offc[4];
+    {
+        const int ri = lane & 7, mi = lane >> 3;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) offc[c] = (uint32_t)((ri + 8 * (mi & 1)) * 128 + (((2 * c + (mi >> 1)) ^ ri) << 4));
+    }
+    // Operand exchange space of this warp: four 512-byte parts = its OWN slots in the first partial-tile buffers --
+    // nobody else touches them before the main loop of a pass.
+    const uint32_t xbase = red + (uint32_t)(warp * NT * 512);
+    auto xpart = [&](int k) { return NT == 2 ? xbase + (uint32_t)((k >> 1) * BUFB + (k & 1) * 512) : xbase + (uint32_t)(k * BUFB); };
+    const int hsel = g >> 2, lsel = g & 3;                   // lane (g, t) holds mma column g: digit lsel of batch row 2 nt + hsel
+
+    if (p.wait_weights) pdl_wait();
+    B200Q_STAMP(2);
+    pdl_wait();              // x belongs to the stream-ordered predecessor
+    B200Q_STAMP(3);
+    float xv[GPW2][MB][8];
+    uint32_t bf[GPW2][4][NT][4];                              // per 32-byte step: {e-word b0, e-word b1, z-word b0, z-word b1}
+    int it = 0;                                               // partial tiles handed over so far (all passes)
+#pragma unroll 1
+    for (int pass = 0; pass < p.npasses; ++pass) {
+        const int m0 = pass * MB;
+        // ---- x of this pass: this warp's columns only, all loads in flight at once
+#pragma unroll
+        for (int q = 0; q < GPW2; ++q) {
+            const int col = (warp + NW * q) * 256 + lane * 8;
+#pragma unroll
+            for (int hr = 0; hr < MB; ++hr) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) xv[q][hr][e] = 0.0f;
+                if (col < p.K && m0 + hr < p.M) load8f(p.x, p.x_dtype, (int64_t)(m0 + hr) * p.K + col, xv[q][hr]);
+            }
+        }
+        if (pass == 0) bar_arrive_id(2, NTHR_MMA + 32);       // tells the issuer that the x loads are in flight
+        // ---- row amax (non-negative floats order like their bit patterns: one REDUX per row); NaN / Inf show up
+        // as an exponent field of 0xff
+#pragma unroll
+        for (int hr = 0; hr < MB; ++hr) {
+            if (m0 + hr < p.M) {                              // uniform
+                unsigned int u = 0u;
+#pragma unroll
+                for (int q = 0; q < GPW2; ++q)
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) u = max(u, __float_as_uint(xv[q][hr][e]) & 0x7fffffffu);
+                u = __reduce_max_sync(0xffffffffu, u);
+                if (lane == 0) s_amax[((pass & 1) * 4 + hr) * NW + warp] = u;
+            }
+        }
+        bar_sync_id(1, NTHR_MMA);
+        if (pass == 0) B200Q_STAMP(4);
+        int ex[MB];
+#pragma unroll
+        for (int hr = 0; hr < MB; ++hr) {
+            ex[hr] = 0;
+            if (m0 + hr < p.M) {                              // uniform
+                const unsigned int u = __reduce_max_sync(0xffffffffu, lane < NW ? s_amax[((pass & 1) * 4 + hr) * NW + lane] : 0u);
+                if (u >= 0x7f800000u) {
+                    if (tid == 0) atomicOr(s_flag, 1u << (m0 + hr));
+                } else if (u > 0u) {
+                    ex[hr] = max(-96, min(126, 155 - (int)(u >> 23)));
+                }
+                if (tid == 0) s_ex[m0 + hr] = ex[hr];
+            }
+        }
+        // the exchange space below is this warp's slots in the first buffers: wait until the epilogue warps have folded
+        // whatever the previous pass left there (first pass: nothing)
+        if (pass > 0) {
+            const int nb = min(nbuf, 4);
+            for (int k = 0; k < nb; ++k) {
+                const int last = ((it - 1 - k) / nbuf) * nbuf + k;           // last hand-over that used buffer k ...
+                const int j = last <= it - 1 ? last : last - nbuf;
+                if (j >= 0) mbar_wait(empty_bar(k), (uint32_t)((j / nbuf) & 1));
+            }
+        }
+
+        // ---- operand: digits of Xe / Z, exchanged inside the warp.  Source lane i (0..31) of a pair holds columns
+        // 8 i .. 8 i + 7 = packed bytes 4 i .. 4 i + 3: word (i & 3) of the 16-byte column i >> 2, i.e. the bytes lane quad
+        // t = i & 3 multiplies in step c = i >> 3, first (b0) or second (b1) half (i >> 2) & 1.
+        const uint32_t soff = (uint32_t)((((lane >> 3) * 4 + (lane & 3)) * 16) + ((lane >> 2) & 1) * 4);
+        const uint32_t ssrc = xpart(2 * hsel + (lsel >> 1)) + (uint32_t)((lsel & 1) * 256 + t * 16);
+#pragma unroll
+        for (int q = 0; q < GPW2; ++q) {
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {                  // the two batch rows of this n-tile: independent chains
+                    const int hr = 2 * nt + hh;
+                    if (m0 + hr >= p.M) continue;                 // uniform: no such batch row (odd M)
+                    const float up = __uint_as_float((uint32_t)(127 + ex[hr]) << 23), up16 = up * 0.0625f;
+                    uint32_t D[8];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        // even column: Xe = round(x 2^e); odd column: Xo = round(x 2^(e-4)), carried as Z = Xo - Xe
+                        const int Xe = __float2int_rn(xv[q][hr][2 * i] * up);
+                        const int Xo = __float2int_rn(xv[q][hr][2 * i + 1] * up16);
+                        D[2 * i] = (uint32_t)(Xe + 0x00808080) ^ 0x00808080u;      // byte l = signed base-256 digit l
+                        D[2 * i + 1] = (uint32_t)(Xo - Xe + 0x00808080) ^ 0x00808080u;
+                    }
+                    // 4x4 byte transposes: digit l of the four Xe -> e-word l (meets the raw bytes), of the four Z -> z-word l
+                    const uint32_t e0 = __byte_perm(D[0], D[2], 0x5140), e1 = __byte_perm(D[4], D[6], 0x5140);
+                    const uint32_t e2 = __byte_perm(D[0], D[2], 0x7362), e3 = __byte_perm(D[4], D[6], 0x7362);
+                    const uint32_t o0 = __byte_perm(D[1], D[3], 0x5140), o1 = __byte_perm(D[5], D[7], 0x5140);
+                    const uint32_t o2 = __byte_perm(D[1], D[3], 0x7362), o3 = __byte_perm(D[5], D[7], 0x7362);
+                    const uint32_t d01 = xpart(2 * hh) + soff, d23 = xpart(2 * hh + 1) + soff;      // digits 0, 1 / 2, 3 of row hh
+                    sts32(d01, __byte_perm(e0, e1, 0x5410));       sts32(d01 + 8, __byte_perm(o0, o1, 0x5410));
+                    sts32(d01 + 256, __byte_perm(e0, e1, 0x7632)); sts32(d01 + 264, __byte_perm(o0, o1, 0x7632));
+                    sts32(d23, __byte_perm(e2, e3, 0x5410));       sts32(d23 + 8, __byte_perm(o2, o3, 0x5410));
+                    sts32(d23 + 256, __byte_perm(e2, e3, 0x7632)); sts32(d23 + 264, __byte_perm(o2, o3, 0x7632));
+                }
+                __syncwarp();
+                if (m0 + 2 * nt + hsel < p.M) {                   // this lane's mma column belongs to a batch row that exists
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const uint4 v = lds128(ssrc + (uint32_t)(c * 64));
+                        bf[q][c][nt][0] = v.x; bf[q][c][nt][1] = v.y; bf[q][c][nt][2] = v.z; bf[q][c][nt][3] = v.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) bf[q][c][nt][j] = 0u;
+                }
+                __syncwarp();
+            }
+        }
+        if (pass == 0) B200Q_STAMP(5);
+
+        // ---- main loop: one 16-row tile per iteration, this warp's pairs of it; the partial tile goes to the epilogue warps
+        for (int i = 0; i < ntl; ++i, ++it) {
+            int c0[NT][4], c1[NT][4];                         // raw bytes x digits of Xe, masked bytes x digits of Z
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) { c0[nt][r] = 0; c1[nt][r] = 0; }
+            const uint32_t tb = sbase + p.tile_off + (uint32_t)(i * p.tile_bytes);
+#pragma unroll
+            for (int q = 0; q < GPW2; ++q) {
+                const int P = warp + NW * q;
+                if (P < p.npairs) {                           // uniform
+                    if (pass == 0 && !B200Q_ABL(4)) mbar_wait(tile_bar(i, P / p.chunk), 0);
+                    const uint32_t pb = tb + (uint32_t)(P * PAIR_BYTES);
+                    if (pass == 0 && i == 0) {                // the row of 0x11 bytes: row 15 of tile 0
+                        if (lane < 8) sts128(pb + (uint32_t)(15 * 128 + lane * 16), make_uint4(0x11111111u, 0x11111111u, 0x11111111u, 0x11111111u));
+                        __syncwarp();
+                    }
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        // no nibble extraction: sum_k (q_lo + 16 q_hi) Xe + (16 q_hi) (Xo - Xe) = sum_k q_lo Xe + q_hi 16 Xo
+                        uint32_t a[4];
+                        ldsm_x4(a, pb + offc[c]);
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt) imma(c0[nt], a[0], a[1], a[2], a[3], bf[q][c][nt][0], bf[q][c][nt][1]);
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) a[r] &= 0xf0f0f0f0u;
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt) imma(c1[nt], a[0], a[1], a[2], a[3], bf[q][c][nt][2], bf[q][c][nt][3]);
+                    }
+                }
+            }
+            const int bb = it % nbuf;
+            if (it >= nbuf) mbar_wait(empty_bar(bb), (uint32_t)(((it / nbuf) - 1) & 1));     // (never with one buffer per tile)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+                sts128(red + (uint32_t)(bb * BUFB + (warp * NT + nt) * 512 + lane * 16),
+                       make_uint4((uint32_t)(c0[nt][0] + c1[nt][0]), (uint32_t)(c0[nt][1] + c1[nt][1]),
+                                  (uint32_t)(c0[nt][2] + c1[nt][2]), (uint32_t)(c0[nt][3] + c1[nt][3])));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_bar(bb));
+        }
+        if (pass == 0) B200Q_STAMP(12);
+    }
+    }   // roles
+    __syncthreads();
+    B200Q_STAMP(13);
+
+    // ---- batch rows with NaN / Inf: the reference's arithmetic (dequantise, then fp32 multiply-add), so that
+    // non-finite values propagate as in F.linear; one warp per output, weights re-read from global memory
+    const unsigned int flagged = *s_flag;
+    if (flagged) {
+        const int64_t row_bytes = p.K >> 1;
+        for (int m = 0; m < p.M; ++m) {
+            if (!((flagged >> m) & 1u)) continue;
+            for (int rc = warp; rc < nrows; rc += NW + EW) {
+                const int row = r0 + rc;
+                const float sc = __ldg(p.scales + row), zp = __ldg(p.zps + row);
+                const uint8_t* wr = p.packed + (int64_t)row * row_bytes;
+                float acc = 0.0f;
+                for (int kb = lane; kb < row_bytes; kb += 32) {
+                    const unsigned int byte = wr[kb];
+                    const float w0 = ((float)(byte & 15u) - zp) * sc, w1 = ((float)(byte >> 4) - zp) * sc;
+                    acc = fmaf(w0, load1f(p.x, p.x_dtype, (int64_t)m * p.K + 2 * kb), acc);
+                    acc = fmaf(w1, load1f(p.x, p.x_dtype, (int64_t)m * p.K + 2 * kb + 1), acc);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if (lane == 0) {
+                    if (p.bias) acc += __ldg(p.bias + row);
+                    store_out(p.y, p.y_dtype, (int64_t)m * p.N + row, acc);
+                }
+            }
+        }
+    }
+    B200Q_STAMP(14);
+}
+
+struct DecPlan {
+    int grid, gpw2, nt, npasses, ntiles, npairs, nbars, chunk, tile_bytes, tile_off, rows_q, rows_rem;
+    int red_off, nbuf;
+    size_t smem;
+};
+
+bool plan_dec(int sm_count, int max_smem, int64_t M, int64_t N, int64_t K, DecPlan* c) {
+    if (M < 1 || M > 16 || K < 256 || K % 256 != 0 || K > 16384 || N < 1 || N > 0x7fffffff) return false;
+    c->npairs = (int)(K / 256);
+    c->gpw2 = (c->npairs + NW - 1) / NW;                          // <= 4
+    c->nt = (M >= 3 && c->gpw2 <= 2) ? 2 : 1;                     // B fragments: 16 gpw2 nt registers
+    const int mb = 2 * c->nt;
+    c->npasses = (int)((M + mb - 1) / mb);
+    int cap = tuning().gemv_ctas > 0 ? tuning().gemv_ctas : sm_count;
+    if (cap > sm_count) cap = sm_count;
+    int64_t grid = (N + TILE_ROWS - 2) / (TILE_ROWS - 1);       // few rows: at most 15 per CTA (+ the 0x11 row = one tile)
+    if (grid > cap) grid = cap;
+    c->grid = (int)grid;
+    c->rows_q = (int)(N / grid); c->rows_rem = (int)(N % grid);
+    const int br = c->rows_q + (c->rows_rem ? 1 : 0);
+    if (br > MAX_ROWS) return false;
+    c->ntiles = br <= 15 ? 1 : 1 + (br - 15 + TILE_ROWS - 1) / TILE_ROWS;      // tile 0: 15 rows + the 0x11 row that yields sum_k X
+    c->nbars = c->gpw2;
+    c->chunk = (c->npairs + c->nbars - 1) / c->nbars;
+    if (c->ntiles * c->nbars > MAX_BARS) return false;
+    c->tile_bytes = c->nbars * c->chunk * PAIR_BYTES;             // >= npairs * 2 KB: a 3-D box always has room
+    const int bufb = NW * c->nt * 512;
+    c->red_off = OFF_DYN;
+    // partial-tile buffers: one per (pass, tile) when that fits (nobody ever waits for a free one); at least four
+    // 512-byte slots per warp (its operand exchange space)
+    const int want = c->ntiles * c->npasses < MAX_BUF ? c->ntiles * c->npasses : MAX_BUF;
+    const int least = c->nt == 2 ? 2 : 4;
+    for (int nbuf = want > least ? want : least; nbuf >= least; --nbuf) {
+        if (tuning().gemv_slots > 0 && nbuf > tuning().gemv_slots && nbuf > least) continue;       // bench hook: cap the ring
+        c->nbuf = nbuf;
+        c->tile_off = (c->red_off + nbuf * bufb + 1023) / 1024 * 1024;
+        c->smem = (size_t)c->tile_off + (size_t)c->ntiles * c->tile_bytes;
+        if (c->smem <= (size_t)max_smem) return true;
+    }
+    return false;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn dec_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    });
+    return fn;
+}
+
+// tensor maps only depend on (address, N, K, form): a decode loop calls the same layers again and again
+struct MapKey { const void* ptr; int64_t N, K; int form; };
+struct MapSlot { MapKey key; CUtensorMap map; bool ok; };
+
+int weight_map(const uint8_t* packed, int64_t N, int64_t K, int chunk, CUtensorMap* out) {
+    constexpr int SLOTS = 64;
+    static thread_local MapSlot cache[SLOTS];
+    static thread_local bool init = false;
+    if (!init) { for (auto& s : cache) s.ok = false; init = true; }
+    const size_t h = ((reinterpret_cast<uintptr_t>(packed) >> 8) * 0x9E3779B97F4A7C15ull >> 40) % SLOTS;
+    MapSlot& s = cache[h];
+    if (s.ok && s.key.ptr == packed && s.key.N == N && s.key.K == K && s.key.form == chunk) { *out = s.map; return 0; }
+    EncodeTiledFn fn = dec_encode_fn();
+    if (!fn) return set_error(B200Q_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    // packed [N][K/2] viewed as [row][column of 128 bytes][byte]: the box [16 rows][chunk columns][128 B] lands in shared
+    // memory as [column][row][128 B] with the 128-byte swizzle keyed by the row -- the layout ldmatrix wants
+    cuuint64_t dims[3] = {128, (cuuint64_t)N, (cuuint64_t)(K / 256)};
+    cuuint64_t strides[2] = {(cuuint64_t)(K / 2), 128};
+    cuuint32_t box[3] = {128, TILE_ROWS, (cuuint32_t)chunk};
+    cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = fn(&s.map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(packed), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { s.ok = false; return set_error(B200Q_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r); }
+    s.key = MapKey{packed, N, K, chunk};
+    s.ok = true;
+    *out = s.map;
+    return 0;
+}
+
+template <int GPW2, int NT>
+int launch_dec_inst(const DecPlan& c, const CUtensorMap& map, const DecParams& p, bool pdl, cudaStream_t st) {
+    auto kfn = gemv_dec_kernel<GPW2, NT>;
+    static thread_local int attr_dev_smem[64] = {0};
+    int dev = 0;
+    B200Q_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && attr_dev_smem[dev] < (int)c.smem) {
+        B200Q_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
+        attr_dev_smem[dev] = (int)c.smem;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)c.grid);
+    cfg.blockDim = dim3(NTHR);
+    cfg.dynamicSmemBytes = c.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attrs[1];
+    int na = 0;
+    if (pdl) {
+        attrs[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attrs[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attrs;
+    cfg.numAttrs = na;
+    return check_cuda(cudaLaunchKernelEx(&cfg, kfn, map, p), "gemv_dec launch");
+}
+
+}  // namespace
+
+bool gemv_dec_supported(const DeviceInfo& dev, int64_t M, int64_t N, int64_t K) {
+    DecPlan c;
+    return plan_dec(dev.sm_count, dev.max_smem_optin, M, N, K, &c);
+}
+
+int launch_gemv_dec(const DeviceInfo& dev, const void* x, int x_dtype, const uint8_t* packed, const float* scales,
+                    const float* zps, const float* bias, void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
+                    unsigned flags, cudaStream_t st, const uint8_t* next_packed, size_t next_bytes) {
+    DecPlan c;
+    if (!plan_dec(dev.sm_count, dev.max_smem_optin, M, N, K, &c))
+        return set_error(B200Q_EINVAL, "gemv_dec: unsupported shape M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
+    if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(packed) & 15))
+        return set_error(B200Q_EALIGN, "gemv_dec: x and packed must be 16-byte aligned");
+    DecParams p{};
+    p.x = x; p.packed = packed; p.scales = scales; p.zps = zps; p.bias = bias; p.y = y;
+    p.x_dtype = x_dtype; p.y_dtype = y_dtype;
+    p.M = (int)M; p.N = (int)N; p.K = (int)K;
+    p.rows_q = c.rows_q; p.rows_rem = c.rows_rem;
+    p.npairs = c.npairs; p.nbars = c.nbars; p.chunk = c.chunk;
+    p.tile_bytes = c.tile_bytes; p.tile_off = c.tile_off; p.npasses = c.npasses;
+    p.red_off = c.red_off; p.nbuf = c.nbuf;
+    p.wait_weights = (flags & B200Q_FLAG_STATIC_WEIGHTS) ? 0 : 1;
+    p.early_ops = tuning().gemv_early >= 0 ? tuning().gemv_early : 2;        // two requests (~64 KB per SM) up front, the rest behind the x loads
+    p.next_packed = next_packed;
+    p.pf_mode = tuning().gemv_pf;
+    p.next_bytes = (tuning().gemv_pf != 0 && next_packed && (reinterpret_cast<uintptr_t>(next_packed) & 15) == 0) ? next_bytes : 0;
+    p.next_chunk = (unsigned int)(p.next_bytes / (unsigned long long)c.grid);
+    p.debug = tuning().gemv_debug > 0 ? tuning().gemv_debug : 0;
+    CUtensorMap map;
+    if (int rc = weight_map(packed, N, K, c.chunk, &map)) return rc;
+    const bool pdl = tuning().gemv_pdl != 0;
+#define B200Q_DEC_CASE(GPW2_, NT_) \
+    if (c.gpw2 == GPW2_ && c.nt == NT_) return launch_dec_inst<GPW2_, NT_>(c, map, p, pdl, st);
+    B200Q_DEC_CASE(1, 1) B200Q_DEC_CASE(2, 1) B200Q_DEC_CASE(3, 1) B200Q_DEC_CASE(4, 1)
+    B200Q_DEC_CASE(1, 2) B200Q_DEC_CASE(2, 2)
+#undef B200Q_DEC_CASE
+    return set_error(B200Q_EINVAL, "gemv_dec: no kernel instance for gpw2=%d nt=%d", c.gpw2, c.nt);
+}
+
+}  // namespace b200q
+
+#ifdef B200Q_PROF
+extern "C" int b200q_debug_read_prof_dec(long long* h_out) {
+    return b200q::check_cuda(cudaMemcpyFromSymbol(h_out, b200q::g_dec_prof, sizeof(long long) * 256 * 16), "read prof");
+}
+#endif
