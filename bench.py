@@ -110,103 +110,222 @@ def oracle_module():
     return int4_oracle
 
 
-def blas_threads():
-    try:
-        from threadpoolctl import threadpool_info
-        n = [p.get("num_threads", 1) for p in threadpool_info() if p.get("user_api") == "blas"]
-        return max(n) if n else 1
-    except Exception:
-        return os.cpu_count() or 1
+REF_ROOT = os.path.join(ROOT, "oracle", "_ref", "reference")      # staged copy of the reference (oracle/make_ref.py)
 
 
 def cpu_reference_gemv(steps, warmup, M=1):
-    """The reference CPU path (dequantize_weights to a full fp32 matrix, then F.linear:
-    python/quantize.py:127-202) timed on the host cores, one 4096->11008 layer per step.  Uses the C
-    restatement (oracle/oracle.c, pthreads over all online cores) when it is built, else the numpy one.
-    Returns (GB/s, seconds per layer, threads, description)."""
+    """The reference's CPU path timed on the host cores, one 4096->11008 layer per step: the REAL reference
+    (oracle/_ref/reference: python/module.py QuantizedLinear.forward on a CPU tensor -> quantize.py dequantize_weights +
+    F.linear, :127-202) when it is staged, else the C restatement (oracle/oracle.c).
+    Returns (GB/s, seconds per layer, threads, kind, description)."""
     import numpy as np
-    oracle = oracle_module()
-    rng = np.random.default_rng(42)
-    packed = rng.integers(0, 256, size=(N_OUT, K_IN // 2), dtype=np.uint8)
-    scales = (rng.random(N_OUT, dtype=np.float32) * 0.004 + 0.002).astype(np.float32)
-    zps = rng.integers(0, 16, size=N_OUT).astype(np.float32)
-    x = rng.standard_normal((M, K_IN), dtype=np.float32)
-    try:
-        import c_oracle
-        lin = c_oracle.Linear(packed, scales, zps)
-        fn, threads, what = (lambda: lin(x)), c_oracle.max_threads(), "C restatement (oracle/oracle.c, pthreads)"
-    except Exception:
-        fn = lambda: oracle.reference_quantized_linear(x, packed, scales, zps)
-        threads, what = blas_threads(), "numpy restatement (oracle/int4_oracle.py)"
+    if os.path.isdir(os.path.join(REF_ROOT, "python")):
+        import torch
+        sys.path.insert(0, REF_ROOT)
+        from python.module import QuantizedLinear as RefQuantizedLinear
+        torch.manual_seed(42)
+        ql = RefQuantizedLinear.from_linear(torch.nn.Linear(K_IN, N_OUT, bias=False))       # BASELINE.json configs[0]
+        x = torch.randn(M, K_IN) if M > 1 else torch.randn(K_IN)
+        fn = lambda: ql(x)
+        threads, kind = torch.get_num_threads(), "reference"
+        what = "the reference itself (python/module.py forward on CPU = quantize.py dequantize_weights + F.linear, torch CPU threads)"
+    else:
+        oracle = oracle_module()
+        rng = np.random.default_rng(42)
+        packed = rng.integers(0, 256, size=(N_OUT, K_IN // 2), dtype=np.uint8)
+        scales = (rng.random(N_OUT, dtype=np.float32) * 0.004 + 0.002).astype(np.float32)
+        zps = rng.integers(0, 16, size=N_OUT).astype(np.float32)
+        x = rng.standard_normal((M, K_IN), dtype=np.float32)
+        kind = "port"
+        try:
+            import c_oracle
+            lin = c_oracle.Linear(packed, scales, zps)
+            fn, threads, what = (lambda: lin(x)), c_oracle.max_threads(), "C restatement (oracle/oracle.c, pthreads) of dequantize_weights + F.linear"
+        except Exception:
+            fn = lambda: oracle.reference_quantized_linear(x, packed, scales, zps)
+            threads, what = os.cpu_count() or 1, "numpy restatement (oracle/int4_oracle.py) of dequantize_weights + F.linear"
     for _ in range(warmup):
         fn()
     t0 = time.perf_counter()
     for _ in range(steps):
         fn()
     dt = (time.perf_counter() - t0) / steps
-    return gemv_bytes(M, N_OUT, K_IN) / dt / 1e9, dt, threads, what
+    return gemv_bytes(M, N_OUT, K_IN) / dt / 1e9, dt, threads, kind, what
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 200))
-    warmup = max(1, min(args.warmup, 5))
+    steps = max(1, min(args.steps, 50))
+    warmup = max(1, min(args.warmup, 3))
     world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
-    if (args.workload or ("gemv" if world == 1 else "moe")) == "moe":
-        # same metric / config as the product arm at this N: the Mixtral layer, composed from the reference's
-        # primitives on the host cores (bounded sample: one expert's three projections on 8 rows, scaled per token)
-        from bench_moe import cpu_moe_baseline, T_GLOBAL, E as MOE_E
-        best, cores, sample = 0.0, 1, ""
+    if (args.workload or default_workload(args)) == "moe":
+        # same metric / config as the product arm at this N: the Mixtral layer composed from the reference's own
+        # primitives on the host cores; bounded sample = 512 tokens of the same layer (every call dequantises all 24
+        # projections, as the reference's QuantizedMoE.forward does)
+        from bench_moe import cpu_moe_reference, T_GLOBAL, E as MOE_E
+        nsteps = max(1, min(steps, 3))
         t0 = time.perf_counter()
-        for _ in range(min(steps, 5)):
-            v, cores, sample = cpu_moe_baseline()
-            best = max(best, v)
-        dt = (time.perf_counter() - t0) / min(steps, 5)
+        v, cores, kind, sample = cpu_moe_reference(steps=nsteps, tokens=512)
+        dt = (time.perf_counter() - t0) / (nsteps + 1)
         line = {
-            "impl": "reference", "metric": "mixtral_moe_int4_layer_tokens_per_s", "value": best, "unit": "tokens/s",
-            "n_gpus": args.gpus, "steps": min(steps, 5), "warmup": 0, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "impl": "reference", "metric": "mixtral_moe_int4_layer_tokens_per_s", "value": v, "unit": "tokens/s",
+            "n_gpus": args.gpus, "steps": nsteps, "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "Mixtral-8x7B INT4 MoE layer (8 experts, top-2, d=4096, ffn=14336), "
                                    f"{T_GLOBAL} tokens/step, random routing" + (", expert-parallel" if world > 1 else ""),
-                       "arm": "the reference's CPU path composed per expert: dequantize_weights + matmul (C restatement, all host cores)",
-                       "tokens_per_step": T_GLOBAL, "experts_per_rank": MOE_E // max(world, 1)},
-            "cpu_baseline": {"value": best, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": best, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                       "arm": "the reference's CPU path composed per expert (dequantize_weights + matmul, routing.py dispatch / combine); "
+                              "each step is a bounded sample of the workload: 512 of its tokens",
+                       "tokens_per_step": T_GLOBAL, "sample_tokens_per_step": 512, "experts_per_rank": MOE_E // max(world, 1)},
+            "cpu_baseline": {"value": v, "unit": "tokens/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
         print(json.dumps(line))
         return
-    gbs, dt, cores, what = cpu_reference_gemv(steps, warmup)
+    gbs, dt, cores, kind, what = cpu_reference_gemv(steps, warmup)
     line = {
         "impl": "reference", "metric": "int4_gemv_hbm_gbps", "value": gbs, "unit": "GB/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"Llama-7B MLP INT4 decode GEMV M=1 ({K_IN}->{N_OUT}), configs[1]",
-                   "arm": "the reference's CPU path: dequantize_weights + F.linear (C restatement, all host cores)",
-                   "M": 1, "K": K_IN, "N": N_OUT},
-        "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": cores, "kind": "port",
-                         "sample": f"{steps} x one {K_IN}->{N_OUT} layer forward, M=1: {what} of "
-                                   "python/quantize.py dequantize_weights + F.linear"},
+                   "arm": what, "M": 1, "K": K_IN, "N": N_OUT},
+        "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": cores, "kind": kind,
+                         "sample": f"{steps} x one {K_IN}->{N_OUT} layer forward, M=1: {what}"},
         "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
 
 
-def make_pool(torch, pkg, n_layers, device):
-    """POOL independently-seeded Llama up-projection layers, quantised on the GPU (bit-exact with
-    the reference's quantize_weights)."""
+def make_pool(torch, pkg, n_layers, device, K=K_IN, N=N_OUT):
+    """POOL independently-seeded layers, quantised on the GPU (bit-exact with the reference's quantize_weights)."""
     layers = []
     for i in range(n_layers):
         g = torch.Generator(device=device)
         g.manual_seed(42 + i)
-        # nn.Linear's default init range for in_features=4096: U(-1/64, 1/64)
-        w = (torch.rand(N_OUT, K_IN, generator=g, device=device) * 2 - 1) / 64.0
+        # nn.Linear's default init range: U(-1/sqrt(K), 1/sqrt(K))
+        w = (torch.rand(N, K, generator=g, device=device) * 2 - 1) / (K ** 0.5)
         layers.append(pkg.quantize_weights(w))
         del w
     return layers
+
+
+def time_decode(torch, _lib, lib, layers, M, K, N, dev, hint=True, graph=True, reps=4, iters=20):
+    """us per fused dequantize-linear launch over the layer pool (every launch streams its weights from HBM)."""
+    x = torch.randn(M, K, device=dev)
+    y = torch.empty(M, N, device=dev)
+    ws = torch.zeros(max(lib.b200q_linear_ws_bytes(M, N, K), 16), dtype=torch.uint8, device=dev)
+
+    def launch_all(sp):
+        for _ in range(reps):
+            for i, (p, s, z) in enumerate(layers):
+                nxt = layers[(i + 1) % len(layers)][0] if hint else None
+                _lib.check(lib.b200q_linear_fwd_next(x.data_ptr(), _lib.F32, p.data_ptr(), s.data_ptr(), z.data_ptr(), y.data_ptr(),
+                                                     _lib.F32, M, N, K, ws.data_ptr(), ws.numel(), _lib.FLAG_STATIC_WEIGHTS, sp,
+                                                     nxt.data_ptr() if nxt is not None else None,
+                                                     nxt.numel() if nxt is not None else 0), "b200q_linear_fwd_next")
+
+    g = None
+    if graph:
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            launch_all(side.cuda_stream)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            launch_all(torch.cuda.current_stream(dev).cuda_stream)
+    run = g.replay if g is not None else (lambda: launch_all(torch.cuda.current_stream(dev).cuda_stream))
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        run()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    return e0.elapsed_time(e1) * 1e3 / (iters * reps * len(layers))
+
+
+def decode_sweep(torch, pkg, dev, peak, first_pool=None):
+    """BASELINE.json configs[1]: M = 1, 2, 4, 8, 16 on both Llama-7B MLP shapes, fp32 activations, next-layer hint on."""
+    _lib = pkg._lib
+    lib = _lib.load()
+    out = []
+    for (K, N) in ((4096, 11008), (11008, 4096)):
+        layers = first_pool if (first_pool is not None and (K, N) == (K_IN, N_OUT)) else make_pool(torch, pkg, POOL, dev, K, N)
+        for M in (1, 2, 4, 8, 16):
+            us = time_decode(torch, _lib, lib, layers, M, K, N, dev)
+            nb = gemv_bytes(M, N, K)
+            out.append({"K": K, "N": N, "M": M, "us_per_launch": round(us, 3), "GBps": round(nb / us / 1e3, 1),
+                        "frac_hbm_peak": round(nb / us / 1e3 / peak, 4)})
+        if layers is not first_pool:
+            del layers
+            torch.cuda.empty_cache()
+    return out
+
+
+def prefill_sweep(torch, pkg, dev, peak_tf):
+    """BASELINE.json configs[2]: M = 512 .. 4096 through the tcgen05 GEMM, bf16 and fp32 activations (the reference API's
+    dtype; hi + lo split = twice the MMAs).  FLOPs = 2 M N K (dequantisation not counted); includes the activation
+    preparation pass.  One layer, repeated calls: the 22.5 MB of weights stay in L2, the tensor pipe is the bound."""
+    _lib = pkg._lib
+    out = []
+    for (K, N) in ((4096, 11008), (11008, 4096)):
+        p, s, z = make_pool(torch, pkg, 1, dev, K, N)[0]
+        for dt in (torch.bfloat16, torch.float32):
+            for M in (256, 512, 1024, 2048, 4096):
+                x = torch.randn(M, K, device=dev).to(dt)
+                for _ in range(3):
+                    _lib.linear_fwd(x, p, s, z)
+                torch.cuda.synchronize(dev)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(10):
+                    _lib.linear_fwd(x, p, s, z)
+                e1.record()
+                torch.cuda.synchronize(dev)
+                ms = e0.elapsed_time(e1) / 10
+                tf = 2.0 * M * N * K / (ms * 1e-3) / 1e12
+                out.append({"K": K, "N": N, "M": M, "x": str(dt).replace("torch.", ""), "ms": round(ms, 4), "TFLOPs": round(tf, 1),
+                            "frac_bf16_peak": round(tf / peak_tf, 4)})
+        del p, s, z
+    return out
+
+
+def ref_gpu_kernel(torch, dev, layers):
+    """The reference's own CUDA kernel (csrc/quantized_linear_kernel.cu:90-279) built for sm_100 from its sources by
+    oracle/make_ref.py (baseline/_ref/), timed on the same layer pool: us per launch at M = 1 and 16."""
+    import glob
+    import importlib.util
+    so = glob.glob(os.path.join(ROOT, "baseline", "_ref", "fused_quant_linear_cuda*.so"))
+    if not so:
+        return {"unavailable": "baseline/_ref/fused_quant_linear_cuda*.so not built (python oracle/make_ref.py --cuda)"}
+    try:
+        spec = importlib.util.spec_from_file_location("fused_quant_linear_cuda", so[0])
+        ext = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ext)
+        out = {"what": "reference kernel rebuilt for sm_100 (TORCH_CUDA_ARCH_LIST=10.0), its pybind forward(), stream 0, 24-layer pool"}
+        for M in (1, 16):
+            x = torch.randn(M, K_IN, device=dev)
+            for (p, s, z) in layers[:3]:
+                ext.forward(x, p, s, z)
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for (p, s, z) in layers:
+                ext.forward(x, p, s, z)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            us = e0.elapsed_time(e1) * 1e3 / len(layers)
+            out[f"M{M}_us_per_launch"] = round(us, 2)
+            out[f"M{M}_GBps"] = round(gemv_bytes(M, N_OUT, K_IN) / us / 1e3, 1)
+        return out
+    except Exception as e:
+        return {"unavailable": repr(e)[:200]}
 
 
 def run_gemv(args):
@@ -234,7 +353,7 @@ def run_gemv(args):
     ws = torch.zeros(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
 
     # a decode loop knows which fused linear follows: each call names the next layer's packed weights so the
-    # kernel can pull them into L2 behind its own weight stream (b200q_linear_fwd_next; --no-hint turns it off)
+    # kernel can pull them into L2 behind its own work (b200q_linear_fwd_next; --no-hint turns it off)
     def launch_all(stream_ptr):
         for i, (p, s, z) in enumerate(layers):
             nxt = None if args.no_hint else layers[(i + 1) % len(layers)][0]
@@ -291,15 +410,16 @@ def run_gemv(args):
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    launches = args.steps * POOL            # fused dequantize-linear calls; each is ONE kernel (gemv_res_kernel)
+    launches = args.steps * POOL            # fused dequantize-linear calls; each is ONE kernel (gemv_dec_kernel)
     per_launch_s = ms * 1e-3 / launches
     bytes_per_launch = gemv_bytes(M, N_OUT, K_IN)
     gbs_per_gpu = bytes_per_launch / per_launch_s / 1e9
     value = gbs_per_gpu * world
 
     # ---- end to end through the public API with HOST buffers: QuantizedLinear.forward_host (one C-ABI call,
-    # b200q_linear_fwd_host, enqueues the H2D copy of x, the kernels and the D2H copy of y).  The 24 calls of a
-    # step are captured in a CUDA graph, as a decode loop would; every replay copies x from and y to pinned memory.
+    # b200q_linear_fwd_host, enqueues the H2D copy of x, the kernels and the D2H copy of y).  Measured twice: the 24
+    # calls of a step captured in a CUDA graph, as a decode loop would, and EAGER -- every call pays the Python /
+    # ctypes cost of the API it names.
     mods = []
     for (p, s, z) in layers:
         m = pkg.QuantizedLinear(K_IN, N_OUT)
@@ -324,32 +444,34 @@ def run_gemv(args):
         with torch.cuda.graph(e2e_graph):
             e2e_all()
 
-    def e2e_step():
-        if e2e_graph is not None:
-            e2e_graph.replay()
-        else:
-            e2e_all()
+    def timed(fn, n):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        t_ms = e0.elapsed_time(e1)
+        if dist is not None:
+            tt = torch.tensor([t_ms], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t_ms = float(tt.item())
+        return t_ms
 
     e2e_steps = max(3, min(args.steps, 100))
-    for _ in range(3):
-        e2e_step()
-    torch.cuda.synchronize(dev)
+    ms2 = timed(e2e_graph.replay if e2e_graph is not None else e2e_all, e2e_steps)
     ref0 = oracle.reference_quantized_linear(xh.numpy(), p0[rows], s0[rows], z0[rows], acc=np.float64)
     e2e_err = float(np.abs(yhs[0].numpy()[:, rows] - ref0).max())
     assert e2e_err < 1e-3, f"e2e parity check failed: max abs err {e2e_err}"
-    if dist is not None:
-        dist.barrier()
-    e0.record()
-    for _ in range(e2e_steps):
-        e2e_step()
-    e1.record()
-    torch.cuda.synchronize(dev)
-    ms2 = e0.elapsed_time(e1)
-    if dist is not None:
-        t = torch.tensor([ms2], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms2 = float(t.item())
     e2e_gbs = bytes_per_launch / (ms2 * 1e-3 / (e2e_steps * POOL)) / 1e9 * world
+    eager_steps = max(3, min(args.steps, 20))
+    ms3 = timed(e2e_all, eager_steps)                                       # eager, host buffers
+    xd = torch.randn(M, K_IN, device=dev)
+    ms4 = timed(lambda: [m(xd) for m in mods], eager_steps)               # eager, device buffers: QuantizedLinear.forward
 
     if rank != 0:
         if dist is not None:
@@ -357,15 +479,18 @@ def run_gemv(args):
         return
     peaks, peak_src = measured_peaks()
     peak = float(peaks["hbm_gbs"])
-    traffic = None
+    traffic, traffic_note = None, None
     tpath = os.path.join(ROOT, "profiles", "gemv_traffic.json")
     if os.path.exists(tpath):
         try:
             with open(tpath) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch")
+                tj = json.load(f)
+            traffic = tj.get("dram_bytes_per_launch")
+            traffic_note = {k: tj[k] for k in tj if k != "dram_bytes_per_launch"}
         except Exception:
             traffic = None
-    cpu_gbs, cpu_dt, cpu_threads, cpu_what = cpu_reference_gemv(steps=20, warmup=2, M=M) if not args.no_cpu else (None, None, None, None)
+    if not args.no_cpu:
+        cpu_gbs, cpu_dt, cpu_threads, cpu_kind, cpu_what = cpu_reference_gemv(steps=20, warmup=2, M=M)
     line = {
         "metric": "int4_gemv_hbm_gbps", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -380,44 +505,69 @@ def run_gemv(args):
         },
         "us_per_launch": per_launch_s * 1e6,
         "roofline": {"bound": "hbm", "achieved": gbs_per_gpu, "peak": peak, "unit": "GB/s",
-                     "frac": gbs_per_gpu / peak, "traffic": traffic, "peak_source": peak_src,
+                     "frac": gbs_per_gpu / peak, "traffic": traffic, "traffic_capture": traffic_note, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": bytes_per_launch},
         "e2e": {"value": e2e_gbs, "unit": "GB/s", "h2d_bytes_per_step": POOL * M * K_IN * 4,
                 "d2h_bytes_per_step": POOL * M * N_OUT * 4, "steps": e2e_steps,
                 "api": "QuantizedLinear.forward_host -> b200q_linear_fwd_host (pinned host x and y, weights resident; x is pulled "
                        "over PCIe by a staging kernel and the GEMV epilogue stores y straight into the pinned buffer), "
-                       "24 calls per step replayed as a CUDA graph", "us_per_call": ms2 * 1e3 / (e2e_steps * POOL)},
+                       "24 calls per step replayed as a CUDA graph", "us_per_call": ms2 * 1e3 / (e2e_steps * POOL),
+                "eager_us_per_call": ms3 * 1e3 / (eager_steps * POOL),
+                "eager_value": bytes_per_launch / (ms3 * 1e-3 / (eager_steps * POOL)) / 1e9 * world,
+                "eager_note": "the same 24 forward_host calls per step issued from Python without a graph: includes the per-call "
+                              "Python / ctypes cost of the API",
+                "eager_device_us_per_call": ms4 * 1e3 / (eager_steps * POOL),
+                "eager_device_note": "QuantizedLinear.forward on a device tensor, no graph (host overhead per call when it exceeds the kernel)"},
         "gpu_launches": launches,
         "clocks": clocks.summary(),
         "parity": {"max_abs_err_vs_f64_oracle": err},
     }
-    if cpu_gbs is not None:
-        line["cpu_baseline"] = {"value": cpu_gbs, "unit": "GB/s", "cores": cpu_threads, "kind": "port",
-                                "sample": f"20 x one {K_IN}->{N_OUT} layer forward, M={M}: {cpu_what} of "
-                                          "dequantize_weights + F.linear", "ms_per_layer": cpu_dt * 1e3}
+    if not args.no_cpu:
+        line["cpu_baseline"] = {"value": cpu_gbs, "unit": "GB/s", "cores": cpu_threads, "kind": cpu_kind,
+                                "sample": f"20 x one {K_IN}->{N_OUT} layer forward, M={M}: {cpu_what}", "ms_per_layer": cpu_dt * 1e3}
+    if world == 1 and not args.no_sweeps:
+        # the other single-GPU configurations of BASELINE.json, driver-visible: configs[1] (all M, both shapes),
+        # configs[2] (prefill), the same-box reference GPU kernel
+        try:
+            line["ref_gpu_kernel"] = ref_gpu_kernel(torch, dev, layers)
+            line["decode_sweep"] = decode_sweep(torch, pkg, dev, peak, first_pool=layers)
+            del mods, graph, e2e_graph
+            line["prefill"] = prefill_sweep(torch, pkg, dev, float(peaks["bf16_tflops"]))
+        except Exception as e:
+            line["sweep_error"] = repr(e)[:300]
     # the second clause of BASELINE.json's metric (MoE layer tokens/s) at this GPU count, as a sub-object: the
     # 1-GPU point of the expert-parallel scaling curve that `--gpus 2/4/8` (default workload "moe") continues
     if world == 1 and not args.no_moe:
         try:
-            del layers, mods, graph, e2e_graph
+            del layers
             torch.cuda.empty_cache()
             import io
             import contextlib
-            from bench_moe import run_moe
+            from bench_moe import run_moe, moe_decode
             buf = io.StringIO()
-            margs = argparse.Namespace(steps=20, warmup=3, no_cpu=True)
+            margs = argparse.Namespace(steps=20, warmup=3, no_cpu=args.no_cpu)
             with contextlib.redirect_stdout(buf):
                 run_moe(margs)
             ml = json.loads(buf.getvalue().strip().splitlines()[-1])
-            line["moe"] = {k: ml[k] for k in ("metric", "value", "unit", "n_gpus", "ms_per_step", "dtype", "roofline")}
+            line["moe"] = {k: ml[k] for k in ("metric", "value", "unit", "n_gpus", "ms_per_step", "dtype", "roofline", "parity", "skewed") if k in ml}
             line["moe"]["workload"] = ml["config"]["workload"]
             line["moe"]["note"] = ("1-GPU base of the expert-parallel series: `bench.py --gpus 2|4|8` report this metric "
                                    "(same layer, same 16384 tokens per step, strong scaling) as their headline value")
+            if "cpu_baseline" in ml:
+                line["moe"]["cpu_baseline"] = ml["cpu_baseline"]
+            line["moe_decode"] = moe_decode(torch, pkg, dev, peak)
         except Exception as e:      # the headline line must not depend on the extra measurement
             line["moe"] = {"error": repr(e)[:200]}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def default_workload(args):
+    """N = 1 run directly: the GEMV line (with the MoE layer as a sub-object).  Under torch.distributed.run (any N,
+    also 1) or with --gpus > 1: the MoE layer, so that the points of a scaling series share one metric."""
+    under_launcher = "WORLD_SIZE" in os.environ or "TORCHELASTIC_RUN_ID" in os.environ
+    return "moe" if (args.gpus > 1 or under_launcher) else "gemv"
 
 
 def main():
@@ -432,10 +582,11 @@ def main():
     ap.add_argument("--no-hint", action="store_true", help="gemv workload: do not name the next layer's weights (no L2 prefetch)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-moe", action="store_true", help="skip the MoE-layer sub-measurement of the N=1 gemv line")
+    ap.add_argument("--no-sweeps", action="store_true", help="skip decode_sweep / prefill / ref_gpu_kernel of the N=1 gemv line")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
-    workload = args.workload or ("gemv" if args.gpus <= 1 and int(os.environ.get("WORLD_SIZE", "1")) <= 1 else "moe")
+    workload = args.workload or default_workload(args)
     if workload == "gemv":
         return run_gemv(args)
     from bench_moe import run_moe       # expert-parallel Mixtral layer

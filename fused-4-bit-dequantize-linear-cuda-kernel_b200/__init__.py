@@ -10,7 +10,7 @@ from .moe import QuantizedMoEExpert, QuantizedMoE, MoEINT4, quantize_weights_moe
 from .routing import (RoutingResult, DeviceRouting, simulate_routing, create_expert_inputs,
                       combine_expert_outputs, get_expert_sizes_for_benchmark, route, make_logits)
 from .config import MoEConfig, MIXTRAL_8x7B, DEBUG_CONFIG, LLAMA_7B_MLP
-from .ep import ExpertParallelMoE, dispatch_plan, shard_experts
+from .ep import ExpertParallelMoE, dispatch_plan, shard_experts, local_expert_list, virtual_ids, ep_plan_host
 from . import _lib
 
 __all__ = [
@@ -19,6 +19,6 @@ __all__ = [
     "QuantizedMoEExpert", "QuantizedMoE", "MoEINT4", "quantize_weights_moe",
     "RoutingResult", "DeviceRouting", "simulate_routing", "create_expert_inputs",
     "combine_expert_outputs", "get_expert_sizes_for_benchmark", "route", "make_logits",
-    "ExpertParallelMoE", "dispatch_plan", "shard_experts",
+    "ExpertParallelMoE", "dispatch_plan", "shard_experts", "local_expert_list", "virtual_ids", "ep_plan_host",
     "MoEConfig", "MIXTRAL_8x7B", "DEBUG_CONFIG", "LLAMA_7B_MLP",
 ]

@@ -48,6 +48,13 @@ SIGNATURES = {
     "b200q_moe_grouped_fwd": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _i64, _i64, _i64, _vp, _sz, _vp]),
     "b200q_moe_grouped_gated_fwd": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _i64, _i64, _i64, _vp, _sz, _vp]),
     "b200q_moe_grouped_fwd_ranges": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _i64, _i64, _i64, _vp, _sz, _vp]),
+    "b200q_moe_grouped_fwd_mapped": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _i32, _i64, _i64, _i64, _vp, _sz, _vp]),
+    "b200q_ep_plan": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200q_ep_unique_id": (_i32, [_vp]),
+    "b200q_ep_comm_create": (_i32, [_vp, _i32, _i32, _c.POINTER(_vp)]),
+    "b200q_ep_comm_destroy": (_i32, [_vp]),
+    "b200q_ep_allgather_i32": (_i32, [_vp, _vp, _vp, _i64, _vp]),
+    "b200q_ep_exchange": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _i64, _vp]),
     "b200q_moe_silu_mul": (_i32, [_vp, _i32, _i64, _i64, _vp, _vp]),
     "b200q_moe_combine": (_i32, [_vp, _i32, _vp, _vp, _i64, _i32, _i64, _vp, _i32, _vp]),
 }
@@ -301,6 +308,27 @@ def moe_grouped_fwd_ranges(xs: torch.Tensor, packed: torch.Tensor, scales: torch
                                                ws.numel() if ws is not None else 0, stream_ptr(xs.device)),
               "b200q_moe_grouped_fwd_ranges")
     return out
+
+
+def moe_grouped_fwd_mapped(xs: torch.Tensor, packed: torch.Tensor, scales: torch.Tensor, zps: torch.Tensor,
+                           starts: torch.Tensor, ends: torch.Tensor, range_expert: torch.Tensor, gated: bool,
+                           out_dtype=None) -> torch.Tensor:
+    """Rows [starts[v], ends[v]) of xs through expert range_expert[v] of packed [E,N,K/2]; gated: h [R, N/2]."""
+    lib = load()
+    R, K = xs.shape
+    E, N = packed.shape[0], packed.shape[1]
+    out_dtype = out_dtype or xs.dtype
+    with torch.cuda.device(xs.device):
+        y = torch.zeros((R, N // 2 if gated else N), dtype=out_dtype, device=xs.device)
+        nb = lib.b200q_moe_grouped_ws_bytes(R, E, N, K)
+        ws = workspace(xs.device, nb, "grouped") if nb else None
+        check(lib.b200q_moe_grouped_fwd_mapped(xs.data_ptr(), dtype_code(xs), packed.data_ptr(), scales.data_ptr(),
+                                               zps.data_ptr(), starts.data_ptr(), ends.data_ptr(), range_expert.data_ptr(),
+                                               starts.numel(), E, 1 if gated else 0, y.data_ptr(), dtype_code(y), R, N, K,
+                                               ws.data_ptr() if ws is not None else None,
+                                               ws.numel() if ws is not None else 0, stream_ptr(xs.device)),
+              "b200q_moe_grouped_fwd_mapped")
+    return y
 
 
 def moe_silu_mul(gu: torch.Tensor) -> torch.Tensor:

@@ -32,6 +32,7 @@ struct FixParams {
     void* y;
     const int32_t* starts;
     const int32_t* ends;
+    const int32_t* emap;       // weight expert of every range (nullptr: identity)
     int E, gated, x_dtype, y_dtype;
     int64_t M, N, K;
 };
@@ -76,7 +77,7 @@ __global__ void __launch_bounds__(256) nonfinite_fixup_kernel(const FixParams p)
         if (p.starts) {
             e = -1;
             for (int i = 0; i < p.E; ++i)
-                if (m >= p.starts[i] && m < p.ends[i]) { e = i; break; }
+                if (m >= p.starts[i] && m < p.ends[i]) { e = p.emap ? p.emap[i] : i; break; }
             if (e < 0) continue;
         }
         if (p.gated) {
@@ -112,9 +113,10 @@ __global__ void __launch_bounds__(256) zero_rows_outside_kernel(void* y, int y_d
 
 int launch_nonfinite_fixup(const void* x, int x_dtype, const uint8_t* packed, const float* scales, const float* zps,
                            const int* nf_flags, void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
-                           const int32_t* starts, const int32_t* ends, int E, int gated, cudaStream_t st) {
+                           const int32_t* starts, const int32_t* ends, int E, int gated, cudaStream_t st,
+                           const int32_t* emap) {
     if (M <= 0 || N <= 0 || K <= 0) return 0;
-    FixParams p{x, packed, scales, zps, nf_flags, y, starts, ends, E, gated, x_dtype, y_dtype, M, N, K};
+    FixParams p{x, packed, scales, zps, nf_flags, y, starts, ends, emap, E, gated, x_dtype, y_dtype, M, N, K};
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(M < 1184 ? M : 1184));
     cfg.blockDim = dim3(256);

@@ -87,6 +87,7 @@ struct GemmParams {
     const float* rowsum;     // [R] sum_k x[m, k]
     const int32_t* starts;   // grouped: [E] device, else nullptr
     const int32_t* ends;
+    const int32_t* emap;     // grouped: weight expert of every range (nullptr: range e uses expert e)
     int E;
     int y_dtype;
     int R, N, K;             // token rows, weight rows (per expert), columns
@@ -108,7 +109,7 @@ struct GemmParams {
 };
 
 struct TileInfo {
-    int e, m0, mend, n0;
+    int e, m0, mend, n0;     // e: weight expert of the tile's range
 };
 
 // tile index -> (expert, first token row, end of the group, first weight row); false = no such tile
@@ -129,7 +130,7 @@ __device__ __forceinline__ bool locate(const GemmParams& p, int t, TileInfo& ti)
         if (cnt <= 0) continue;
         const int tiles = (cnt + p.bn - 1) / p.bn;
         if (rem < tiles) {
-            ti.e = e;
+            ti.e = p.emap ? p.emap[e] : e;
             ti.m0 = lo + rem * p.bn;
             ti.mend = hi;
             return true;
@@ -699,7 +700,8 @@ size_t gemm_tc_ws_bytes(int64_t M, int64_t N, int64_t K) {
 int launch_gemm_tc(const DeviceInfo& dev, const void* x, int x_dtype, const uint8_t* packed,
                    const float* scales, const float* zps, void* y, int y_dtype, int64_t M,
                    int64_t N, int64_t K, const int32_t* starts, const int32_t* ends, int E,
-                   void* ws, size_t ws_bytes, unsigned flags, cudaStream_t st, int gated) {
+                   void* ws, size_t ws_bytes, unsigned flags, cudaStream_t st, int gated, const int32_t* emap,
+                   int n_wexperts) {
     (void)flags;
     if (!gemm_tc_supported(M, N, K, x_dtype, y_dtype)) return set_error(B200Q_EINVAL, "gemm_tc: unsupported shape");
     if (gated && (N & 1)) return set_error(B200Q_EINVAL, "gemm_tc: the gated epilogue needs an even number of weight rows");
@@ -770,11 +772,12 @@ int launch_gemm_tc(const DeviceInfo& dev, const void* x, int x_dtype, const uint
     if (int rc = make_map_2d(&map_xh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, xh, (uint64_t)K, (uint64_t)M, BK, bn, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
     if (int rc = make_map_2d(&map_xl, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, parts == 2 ? xl : xh, (uint64_t)K, (uint64_t)M, BK, bn, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
     const int groups = starts ? E : 1;
-    if (int rc = make_map_2d(&map_w, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, packed, (uint64_t)(K / 2), (uint64_t)groups * N, ksub * BK / 2, BM, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
+    const int wgroups = (starts && emap) ? n_wexperts : groups;           // experts in the weight tensor
+    if (int rc = make_map_2d(&map_w, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, packed, (uint64_t)(K / 2), (uint64_t)wgroups * N, ksub * BK / 2, BM, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
 
     GemmParams p{};
     p.scales = scales; p.zps = zps; p.y = y; p.descale = descale; p.rowsum = rowsum;
-    p.starts = starts; p.ends = ends; p.E = groups; p.y_dtype = y_dtype;
+    p.starts = starts; p.ends = ends; p.emap = starts ? emap : nullptr; p.E = groups; p.y_dtype = y_dtype;
     p.R = (int)M; p.N = (int)N; p.K = (int)K;
     p.bn = bn;
     p.mt_bound = (int)((M + bn - 1) / bn) + (starts ? E : 0);
@@ -821,7 +824,8 @@ int launch_gemm_tc(const DeviceInfo& dev, const void* x, int x_dtype, const uint
     cfg.numAttrs = 1;
     if (int rc = check_cuda(cudaLaunchKernelEx(&cfg, kfn, map_xh, map_xl, map_w, p), "gemm_tc launch")) return rc;
     // token rows with NaN / Inf (flagged by the preparation kernel): recomputed in the reference's order
-    return launch_nonfinite_fixup(x, x_dtype, packed, scales, zps, nf, y, y_dtype, M, N, K, starts, ends, groups, gated, st);
+    return launch_nonfinite_fixup(x, x_dtype, packed, scales, zps, nf, y, y_dtype, M, N, K, starts, ends, groups, gated, st,
+                                  starts ? emap : nullptr);
 }
 
 }  // namespace b200q

@@ -63,7 +63,7 @@ int launch_minmax(const float* v, int64_t count, float* out, void* ws, cudaStrea
 int launch_linear_generic(const void* x, int x_dtype, const uint8_t* packed, const float* scales,
                           const float* zps, void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
                           const int32_t* starts, const int32_t* ends, int E, int zero_outside,
-                          cudaStream_t st);
+                          cudaStream_t st, const int32_t* emap = nullptr);
 
 // decode GEMV, M <= 16, K % 128 == 0.  Returns B200Q_EINVAL if the shape is not supported so
 // the dispatcher can fall through.
@@ -83,7 +83,8 @@ int launch_bias_add(void* y, int y_dtype, const float* bias, int64_t M, int64_t 
 // launch_gemm_tc; gated: y is h [R, N/2] = silu(row 2f) * (row 2f+1).
 int launch_nonfinite_fixup(const void* x, int x_dtype, const uint8_t* packed, const float* scales, const float* zps,
                            const int* nf_flags, void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
-                           const int32_t* starts, const int32_t* ends, int E, int gated, cudaStream_t st);
+                           const int32_t* starts, const int32_t* ends, int E, int gated, cudaStream_t st,
+                           const int32_t* emap = nullptr);
 
 // rows [0, *first) and [*last, R) of y <- 0 (the offsets[E+1] form of b200q_moe_grouped_fwd: first = offsets, last = offsets + E)
 int launch_zero_rows_outside(void* y, int y_dtype, int64_t R, int64_t N, const int32_t* first, const int32_t* last,
@@ -106,6 +107,7 @@ size_t gemm_tc_ws_bytes(int64_t M, int64_t N, int64_t K);
 int launch_gemm_tc(const DeviceInfo& dev, const void* x, int x_dtype, const uint8_t* packed,
                    const float* scales, const float* zps, void* y, int y_dtype, int64_t M,
                    int64_t N, int64_t K, const int32_t* starts, const int32_t* ends, int E,
-                   void* ws, size_t ws_bytes, unsigned flags, cudaStream_t st, int gated = 0);
+                   void* ws, size_t ws_bytes, unsigned flags, cudaStream_t st, int gated = 0,
+                   const int32_t* emap = nullptr, int n_wexperts = 0);
 
 }  // namespace b200q

@@ -50,6 +50,7 @@ struct GroupArgs {
     const int32_t* ends;     // [E] one past the last row of every group
     int E;
     int zero_outside;        // offsets form: rows before the first / after the last group are zeroed
+    const int32_t* emap;     // weight expert of every group (nullptr: group e uses expert e)
     int64_t wstride;   // packed bytes per expert
     int64_t sstride;   // scales per expert
 };
@@ -100,6 +101,7 @@ linear_generic_kernel(const XT* __restrict__ x, const uint8_t* __restrict__ pack
         if (lane < rows) y[(m0 + lane) * N + n] = from_f32<YT>(0.0f);
         return;
     }
+    if (g.emap) expert = g.emap[expert];
     const uint8_t* pr = packed + expert * g.wstride + n * (K / 2);
     const float s = scales[expert * g.sstride + n], z = zps[expert * g.sstride + n];
     const XT* xb = x + m0 * K;
@@ -153,8 +155,8 @@ linear_generic_kernel(const XT* __restrict__ x, const uint8_t* __restrict__ pack
 template <typename XT, typename YT>
 int launch_typed(const void* x, const uint8_t* packed, const float* scales, const float* zps,
                  void* y, int64_t R, int64_t N, int64_t K, const int32_t* starts, const int32_t* ends,
-                 int E, int zero_outside, cudaStream_t st) {
-    GroupArgs g{starts, ends, E, zero_outside, N * (K / 2), N};
+                 int E, int zero_outside, cudaStream_t st, const int32_t* emap) {
+    GroupArgs g{starts, ends, E, zero_outside, emap, N * (K / 2), N};
     int64_t tiles = (R + MT - 1) / MT + (starts ? E + 2 : 0);
     if (tiles > 65535) return set_error(B200Q_EINVAL, "generic path: too many row tiles (%lld)", (long long)tiles);
     dim3 grid(static_cast<unsigned>((N + GW - 1) / GW), static_cast<unsigned>(tiles));
@@ -172,11 +174,11 @@ int launch_typed(const void* x, const uint8_t* packed, const float* scales, cons
 template <typename XT>
 int launch_x(const void* x, const uint8_t* packed, const float* scales, const float* zps, void* y,
              int y_dtype, int64_t R, int64_t N, int64_t K, const int32_t* starts, const int32_t* ends,
-             int E, int zero_outside, cudaStream_t st) {
+             int E, int zero_outside, cudaStream_t st, const int32_t* emap) {
     switch (y_dtype) {
-        case B200Q_F32: return launch_typed<XT, float>(x, packed, scales, zps, y, R, N, K, starts, ends, E, zero_outside, st);
-        case B200Q_F16: return launch_typed<XT, __half>(x, packed, scales, zps, y, R, N, K, starts, ends, E, zero_outside, st);
-        case B200Q_BF16: return launch_typed<XT, __nv_bfloat16>(x, packed, scales, zps, y, R, N, K, starts, ends, E, zero_outside, st);
+        case B200Q_F32: return launch_typed<XT, float>(x, packed, scales, zps, y, R, N, K, starts, ends, E, zero_outside, st, emap);
+        case B200Q_F16: return launch_typed<XT, __half>(x, packed, scales, zps, y, R, N, K, starts, ends, E, zero_outside, st, emap);
+        case B200Q_BF16: return launch_typed<XT, __nv_bfloat16>(x, packed, scales, zps, y, R, N, K, starts, ends, E, zero_outside, st, emap);
     }
     return set_error(B200Q_EINVAL, "bad y_dtype %d", y_dtype);
 }
@@ -186,12 +188,12 @@ int launch_x(const void* x, const uint8_t* packed, const float* scales, const fl
 int launch_linear_generic(const void* x, int x_dtype, const uint8_t* packed, const float* scales,
                           const float* zps, void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
                           const int32_t* starts, const int32_t* ends, int E, int zero_outside,
-                          cudaStream_t st) {
+                          cudaStream_t st, const int32_t* emap) {
     if (M == 0 || N == 0) return 0;
     switch (x_dtype) {
-        case B200Q_F32: return launch_x<float>(x, packed, scales, zps, y, y_dtype, M, N, K, starts, ends, E, zero_outside, st);
-        case B200Q_F16: return launch_x<__half>(x, packed, scales, zps, y, y_dtype, M, N, K, starts, ends, E, zero_outside, st);
-        case B200Q_BF16: return launch_x<__nv_bfloat16>(x, packed, scales, zps, y, y_dtype, M, N, K, starts, ends, E, zero_outside, st);
+        case B200Q_F32: return launch_x<float>(x, packed, scales, zps, y, y_dtype, M, N, K, starts, ends, E, zero_outside, st, emap);
+        case B200Q_F16: return launch_x<__half>(x, packed, scales, zps, y, y_dtype, M, N, K, starts, ends, E, zero_outside, st, emap);
+        case B200Q_BF16: return launch_x<__nv_bfloat16>(x, packed, scales, zps, y, y_dtype, M, N, K, starts, ends, E, zero_outside, st, emap);
     }
     return set_error(B200Q_EINVAL, "bad x_dtype %d", x_dtype);
 }

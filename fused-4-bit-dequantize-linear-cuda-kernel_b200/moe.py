@@ -24,6 +24,17 @@ from .routing import DeviceRouting, route
 class QuantizedMoEExpert(nn.Module):
     """One expert projection with packed INT4 weights (moe_int4_module.py:21-81)."""
 
+    _gen = 0    # bumped whenever a weight buffer is replaced or moved: a QuantizedMoE re-stacks lazily when it changes
+
+    def __setattr__(self, name, value):
+        if name in ("packed_weights", "scales", "zero_points"):
+            object.__setattr__(self, "_gen", self._gen + 1)
+        super().__setattr__(name, value)
+
+    def _apply(self, fn, *args, **kwargs):
+        object.__setattr__(self, "_gen", self._gen + 1)
+        return super()._apply(fn, *args, **kwargs)
+
     def __init__(self, in_features: int, out_features: int):
         super().__init__()
         self.in_features = in_features
@@ -93,6 +104,7 @@ class QuantizedMoE(nn.Module):
             self.experts_down = nn.ModuleList(
                 [QuantizedMoEExpert(ffn_dim, hidden_dim) for _ in range(num_experts)])
         self._stacked = None   # (w13 triple, w2 triple or None): the storage the expert buffers are views of
+        self._stamp = None
 
     @classmethod
     def from_fp16_weights(cls, weights: List[torch.Tensor]) -> "QuantizedMoE":
@@ -160,13 +172,23 @@ class QuantizedMoE(nn.Module):
             view.copy_(mod._buffers[name].to(dev))
             mod._buffers[name] = view                       # the old tensor is released: one copy on the device
         self._stacked = (w13, w2)
+        self._stamp = self._expert_stamp()
+
+    def _expert_stamp(self):
+        mods = list(self.experts) + (list(self.experts_up) + list(self.experts_down) if self.gated else [])
+        return tuple((id(m), m._gen) for m in mods)
 
     def stacked_weights(self):
         """[E,N,K/2] / [E,N] tensors for the grouped kernels: w1 and w3 stacked along N (interleaved row by row when
         `fused_gate`, else concatenated), and w2.  These ARE the weights; the per-expert buffers alias them."""
-        st = self._stacked
-        if st is None or not all(_aliases(mod._buffers[name], view) for mod, name, view in self._views(*st)):
-            self._restack()
+        # cheap check per call (identity and generation counter of every expert module); the full aliasing check only
+        # when that changed
+        if self._stacked is None or self._stamp != self._expert_stamp():
+            st = self._stacked
+            if st is None or not all(_aliases(mod._buffers[name], view) for mod, name, view in self._views(*st)):
+                self._restack()
+            else:
+                self._stamp = self._expert_stamp()
         return self._stacked
 
     def forward_routed(self, x: torch.Tensor, router_logits: torch.Tensor, top_k: int = 2,
@@ -196,6 +218,21 @@ class QuantizedMoE(nn.Module):
                 return gu
             h = _lib.moe_silu_mul(gu)
         return _lib.moe_grouped_fwd(h, w2[0], w2[1], w2[2], offsets)
+
+    def forward_ranges(self, rows: torch.Tensor, starts: torch.Tensor, ends: torch.Tensor,
+                       range_expert: torch.Tensor) -> torch.Tensor:
+        """Rows [starts[v], ends[v]) of `rows` go through expert range_expert[v] (int32 device tensors; ranges may be
+        empty and need not be sorted) -- what an expert-parallel rank runs on the rows it received, which arrive ordered
+        (source rank, expert).  Rows covered by no range come back as zeros."""
+        w13, w2 = self.stacked_weights()
+        if self.fused_gate:
+            h = _lib.moe_grouped_fwd_mapped(rows, w13[0], w13[1], w13[2], starts, ends, range_expert, gated=True)
+        else:
+            gu = _lib.moe_grouped_fwd_mapped(rows, w13[0], w13[1], w13[2], starts, ends, range_expert, gated=False)
+            if not self.gated:
+                return gu
+            h = _lib.moe_silu_mul(gu)
+        return _lib.moe_grouped_fwd_mapped(h, w2[0], w2[1], w2[2], starts, ends, range_expert, gated=False)
 
     @property
     def total_memory_bytes(self) -> int:

@@ -50,7 +50,7 @@
 extern "C" {
 #endif
 
-#define B200Q_VERSION 100 /* major*10000 + minor*100 + patch */
+#define B200Q_VERSION 200 /* major*10000 + minor*100 + patch */
 
 /* error codes */
 #define B200Q_OK 0
@@ -59,6 +59,7 @@ extern "C" {
 #define B200Q_EARCH (-3)      /* current device is not compute capability 10.x                     */
 #define B200Q_ECUDA (-4)      /* a CUDA runtime call failed; see b200q_last_error_string()          */
 #define B200Q_EWORKSPACE (-5) /* workspace too small                                                */
+#define B200Q_ENCCL (-6)      /* NCCL could not be loaded, or an NCCL call failed (b200q_ep_*)       */
 
 /* element types of activations / outputs */
 #define B200Q_F32 0
@@ -209,9 +210,45 @@ int b200q_moe_grouped_gated_fwd(const void* xs, int x_dtype, const uint8_t* pack
 /* h[p,f] = silu(a[p,f]) * b[p,f] where a = gu[p, 0:F], b = gu[p, F:2F]  (gated-MLP extension). */
 int b200q_moe_silu_mul(const void* gu, int dtype, int64_t R, int64_t F, void* h, void* stream);
 
+/* Same family, ranges with an explicit weight expert: rows [starts[v], ends[v]) use expert range_expert[v] of
+ * packed [n_experts,N,K/2] (all three arrays [n_ranges] i32 on the device; empty ranges are skipped; rows covered by
+ * no range are not written).  gated != 0: the fused SiLU-gate form (N = 2F interleaved rows, y is h [R, N/2]).
+ * This is what an expert-parallel rank runs on the rows it received, which arrive ordered (source rank, expert):
+ * one range per (local expert, source) pair instead of a re-sort (see b200q_ep_plan). */
+int b200q_moe_grouped_fwd_mapped(const void* xs, int x_dtype, const uint8_t* packed, const float* scales,
+                                 const float* zps, const int32_t* starts, const int32_t* ends,
+                                 const int32_t* range_expert, int n_ranges, int n_experts, int gated, void* y, int y_dtype,
+                                 int64_t R, int64_t N, int64_t K, void* ws, size_t ws_bytes, void* stream);
+
 /* out[t,:] = sum_s weights[t,s] * y[inv_perm[t*k+s], :]   (routing.py:175-187). */
 int b200q_moe_combine(const void* y, int dtype, const int32_t* inv_perm, const float* weights,
                       int64_t T, int k, int64_t F, void* out, int out_dtype, void* stream);
+
+/* ---- expert parallelism (not in the reference: it is single-GPU; north-star extension) -------------------------
+ * One process per GPU.  Rank r owns experts [r E/world, (r+1) E/world); experts flagged in `replicated` are held by
+ * every rank and serve their tokens where those live (hot-expert replication for skewed routing).  Every rank sorts
+ * its (token, slot) assignments by (destination rank, expert) -- b200q_moe_permute on remapped expert ids -- and:
+ *
+ * b200q_ep_plan: counts_all [world,E] i32 (the all-gathered tokens-per-expert histograms, original expert ids),
+ *   replicated [E] i32 or NULL, local_index [E] i32 (index of expert e in this rank's weight tensor, -1 if absent), all on
+ *   the device  ->  splits [2 world] i32 (rows sent to / received from every rank), and for the received rows (ordered
+ *   source rank, then expert) range_starts / range_ends / range_expert [E world] i32 = the arguments of
+ *   b200q_moe_grouped_fwd_mapped (entry local_index * world + source).  One small kernel, no host work.
+ * b200q_ep_unique_id / b200q_ep_comm_create / b200q_ep_comm_destroy: an NCCL communicator for the exchange (the id is
+ *   128 bytes of HOST memory made on one rank and handed to the others by the caller, e.g. a torch.distributed
+ *   broadcast).  libnccl.so.2 is resolved with dlopen; B200Q_ENCCL if it cannot be found or a call fails.
+ * b200q_ep_allgather_i32: recv [world * count] <- send [count] of every rank (the histogram exchange).
+ * b200q_ep_exchange: variable-split all-to-all of rows of row_bytes bytes: h_send_rows / h_recv_rows [world] i64 on the
+ *   HOST (NCCL's send / recv sizes are host arguments: the one place the plan's splits are needed on the host). */
+int b200q_ep_plan(const int32_t* counts_all, int world, int rank, int E, const int32_t* replicated,
+                  const int32_t* local_index, int32_t* splits, int32_t* range_starts, int32_t* range_ends,
+                  int32_t* range_expert, void* stream);
+int b200q_ep_unique_id(void* h_id128);
+int b200q_ep_comm_create(const void* h_id128, int rank, int world, void** comm);
+int b200q_ep_comm_destroy(void* comm);
+int b200q_ep_allgather_i32(void* comm, const int32_t* send, int32_t* recv, int64_t count, void* stream);
+int b200q_ep_exchange(void* comm, int world, const void* send, const int64_t* h_send_rows, void* recv,
+                      const int64_t* h_recv_rows, int64_t row_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(pkg):
 
 def test_version_and_error_string(pkg):
     lib = pkg._lib.load()
-    assert lib.b200q_version() == 100
+    assert lib.b200q_version() == 200
     assert isinstance(lib.b200q_last_error_string(), bytes)
 
 

@@ -264,7 +264,7 @@ def test_resident_decode_kernel_edge_shapes(oracle, pkg, M, N, K):
     # default dispatch (resident kernel when K % 256 == 0, else ring kernel / tcgen05): deterministic, within the bar
     y = pkg._lib.linear_fwd(X, P, S, Z).cpu().numpy()
     assert np.array_equal(pkg._lib.linear_fwd(X, P, S, Z).cpu().numpy(), y)
-    if 6 in outs:
+    if 6 in outs and (M <= 8 or K <= 8192):          # (wide K with M > 8 goes to the tcgen05 GEMM by default)
         assert np.array_equal(y, outs[6])
     for m in range(M):
         assert np.abs(ref[m] - y[m, rows]).max() <= 1e-4 * np.abs(ref[m]).max() + 1e-30
@@ -408,7 +408,8 @@ def test_wide_k_and_16bit_decode(oracle, pkg, dtype, M, N, K):
         finally:
             pkg._lib.tune("force_path", -1)
         assert np.abs(outs[path] - ref).max() <= 1e-6 * np.abs(ref).max()
-    assert np.array_equal(pkg._lib.linear_fwd(X, P, S, Z, out_dtype=torch.float32).cpu().numpy(), outs[6])
+    if M <= 8 or K <= 8192:
+        assert np.array_equal(pkg._lib.linear_fwd(X, P, S, Z, out_dtype=torch.float32).cpu().numpy(), outs[6])
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
