@@ -121,6 +121,7 @@ def cpu_reference_gemv(steps, warmup, M=1):
     import numpy as np
     if os.path.isdir(os.path.join(REF_ROOT, "python")):
         import torch
+        torch.set_num_threads(os.cpu_count() or 1)   # (torch.distributed.run exports OMP_NUM_THREADS=1)
         sys.path.insert(0, REF_ROOT)
         from python.module import QuantizedLinear as RefQuantizedLinear
         torch.manual_seed(42)

@@ -120,6 +120,7 @@ def cpu_moe_reference(steps=2, tokens=512):
     (as QuantizedMoE.forward does, moe_int4_module.py:71-72).  Returns (tokens/s, cores, kind, sample)."""
     import numpy as np
     import torch
+    torch.set_num_threads(os.cpu_count() or 1)       # (torch.distributed.run exports OMP_NUM_THREADS=1)
     ref_root = os.path.join(ROOT, "oracle", "_ref", "reference")
     kind = "reference"
     if os.path.isdir(os.path.join(ref_root, "python")):
@@ -255,6 +256,11 @@ def run_moe(args):
         with ClockSampler(local_rank) as clocks:
             ms = time_steps(torch, dist, dev, lambda: layer(x, logits), args.steps if routing == "random" else max(3, args.steps // 2), args.warmup)
         results[key] = {"ms_per_step": ms, "tokens_per_s": T_GLOBAL / (ms * 1e-3), "ep": dict(layer.last_stats)}
+        if world > 1:                              # one more call with CUDA events around the phases (not part of the timing)
+            layer.profile = True
+            layer(x, logits)
+            layer.profile = False
+            results[key]["ep"] = dict(layer.last_stats)
         if routing == "random":
             clocks_summary = clocks.summary()
             # end to end: activations and router logits start in pinned host memory, the result returns to the host
@@ -297,7 +303,7 @@ def run_moe(args):
         "clocks": clocks_summary,
         "ep": results["random"]["ep"],
         "parity": parity,
-        "skewed": {k: {"tokens_per_s": v["tokens_per_s"], "ms_per_step": v["ms_per_step"]} for k, v in results.items() if k != "random"},
+        "skewed": {k: {"tokens_per_s": v["tokens_per_s"], "ms_per_step": v["ms_per_step"], "ep": v["ep"]} for k, v in results.items() if k != "random"},
     }
     if world > 1:
         line["skewed"]["note"] = ("the reference's default routing recipe (47 % of the assignments to expert 0); "

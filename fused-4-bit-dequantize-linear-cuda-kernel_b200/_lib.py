@@ -43,6 +43,8 @@ SIGNATURES = {
     "b200q_moe_topk": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _vp]),
     "b200q_moe_permute_ws_bytes": (_sz, [_i64, _i32, _i32]),
     "b200q_moe_permute": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "b200q_moe_permute_mapped": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "b200q_moe_route": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "b200q_moe_gather_rows": (_i32, [_vp, _i32, _vp, _i64, _i32, _i64, _vp, _vp]),
     "b200q_moe_grouped_ws_bytes": (_sz, [_i64, _i32, _i64, _i64]),
     "b200q_moe_grouped_fwd": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _i64, _i64, _i64, _vp, _sz, _vp]),
@@ -85,6 +87,30 @@ def load() -> ctypes.CDLL:
                 key, _, val = item.partition("=")
                 lib.b200q_tune_set(key.strip().encode(), int(val))
     return _lib
+
+
+_torch_ext = None
+
+
+def torch_ext():
+    """The compiled torch binding (csrc/torch_binding.cpp -> b200q_torch.so: checks, allocation, stream lookup and the C-ABI
+    call in one C++ function), or None when it has not been built -- the ctypes wrappers below then do the same work."""
+    global _torch_ext
+    if _torch_ext is None:
+        path = os.path.join(_here, "b200q_torch.so")
+        if os.environ.get("B200Q_NO_TORCH_EXT") or os.environ.get("B200Q_LIB") or not os.path.exists(path):
+            _torch_ext = False
+        else:
+            try:
+                load()                                   # libb200q.so first (B200Q_TUNE is applied there)
+                import importlib.util
+                spec = importlib.util.spec_from_file_location("b200q_torch", path)
+                mod = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(mod)
+                _torch_ext = mod
+            except Exception:
+                _torch_ext = False
+    return _torch_ext or None
 
 
 def check(rc: int, what: str) -> None:
@@ -134,6 +160,9 @@ def linear_fwd(x: torch.Tensor, packed: torch.Tensor, scales: torch.Tensor, zps:
                next_packed: torch.Tensor | None = None, bias: torch.Tensor | None = None) -> torch.Tensor:
     """y[M,N] = x[M,K] @ dequant(packed, scales, zps)^T (+ bias [N] f32) on the current stream of x's device.
     next_packed: packed weights of the fused linear that follows on this stream (L2 prefetch hint)."""
+    ext = torch_ext()
+    if ext is not None and out is None:
+        return ext.linear_forward(x, packed, scales, zps, bias, out_dtype, flags, next_packed)
     lib = load()
     M, K = x.shape
     N = packed.shape[0]
@@ -243,6 +272,27 @@ def moe_permute(idx: torch.Tensor, E: int):
     return counts, offsets, sorted_slot, inv_perm
 
 
+def moe_route(logits: torch.Tensor, k: int, remap: torch.Tensor | None = None):
+    """top-k + stable permutation in one C call: logits [T,E] f32 -> (idx [T,k] i32, weights [T,k] f32, counts [E],
+    offsets [E+1], sorted_slot [T*k], inv_perm [T*k]); remap [E] i32: sort by remap[expert] (counts stay per expert)."""
+    lib = load()
+    T, E = logits.shape
+    dev = logits.device
+    with torch.cuda.device(dev):
+        idx = torch.empty((T, k), dtype=torch.int32, device=dev)
+        w = torch.empty((T, k), dtype=torch.float32, device=dev)
+        counts = torch.empty((E,), dtype=torch.int32, device=dev)
+        offsets = torch.empty((E + 1,), dtype=torch.int32, device=dev)
+        sorted_slot = torch.empty((T * k,), dtype=torch.int32, device=dev)
+        inv_perm = torch.empty((T * k,), dtype=torch.int32, device=dev)
+        nb = lib.b200q_moe_permute_ws_bytes(T, E, k)
+        ws = workspace(dev, nb, "permute")
+        check(lib.b200q_moe_route(logits.data_ptr(), remap.data_ptr() if remap is not None else None, T, E, k, idx.data_ptr(),
+                                  w.data_ptr(), counts.data_ptr(), offsets.data_ptr(), sorted_slot.data_ptr(), inv_perm.data_ptr(),
+                                  ws.data_ptr(), ws.numel(), stream_ptr(dev)), "b200q_moe_route")
+    return idx, w, counts, offsets, sorted_slot, inv_perm
+
+
 def moe_gather_rows(x: torch.Tensor, sorted_slot: torch.Tensor, k: int) -> torch.Tensor:
     lib = load()
     rows = sorted_slot.numel()
@@ -312,14 +362,15 @@ def moe_grouped_fwd_ranges(xs: torch.Tensor, packed: torch.Tensor, scales: torch
 
 def moe_grouped_fwd_mapped(xs: torch.Tensor, packed: torch.Tensor, scales: torch.Tensor, zps: torch.Tensor,
                            starts: torch.Tensor, ends: torch.Tensor, range_expert: torch.Tensor, gated: bool,
-                           out_dtype=None) -> torch.Tensor:
-    """Rows [starts[v], ends[v]) of xs through expert range_expert[v] of packed [E,N,K/2]; gated: h [R, N/2]."""
+                           out_dtype=None, zero_fill: bool = True) -> torch.Tensor:
+    """Rows [starts[v], ends[v]) of xs through expert range_expert[v] of packed [E,N,K/2]; gated: h [R, N/2].
+    zero_fill=False: rows covered by no range are left uninitialised (callers whose ranges cover every row)."""
     lib = load()
     R, K = xs.shape
     E, N = packed.shape[0], packed.shape[1]
     out_dtype = out_dtype or xs.dtype
     with torch.cuda.device(xs.device):
-        y = torch.zeros((R, N // 2 if gated else N), dtype=out_dtype, device=xs.device)
+        y = (torch.zeros if zero_fill else torch.empty)((R, N // 2 if gated else N), dtype=out_dtype, device=xs.device)
         nb = lib.b200q_moe_grouped_ws_bytes(R, E, N, K)
         ws = workspace(xs.device, nb, "grouped") if nb else None
         check(lib.b200q_moe_grouped_fwd_mapped(xs.data_ptr(), dtype_code(xs), packed.data_ptr(), scales.data_ptr(),

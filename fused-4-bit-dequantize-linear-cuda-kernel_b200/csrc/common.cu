@@ -129,6 +129,7 @@ int b200q_tune_set(const char* key, int value) {
     else if (!strcmp(key, "host_direct")) g_tuning.host_direct = value;
     else if (!strcmp(key, "gemm_debug")) g_tuning.gemm_debug = value;
     else if (!strcmp(key, "gemm_sk")) g_tuning.gemm_sk = value;
+    else if (!strcmp(key, "gemm_mt_major")) g_tuning.gemm_mt_major = value;
     else if (!strcmp(key, "gemv_res")) g_tuning.gemv_res = value < 0 ? 1 : value;
     else if (!strcmp(key, "gemv_early")) g_tuning.gemv_early = value;
     else if (!strcmp(key, "gemv_xprep")) g_tuning.gemv_xprep = value < 0 ? 0 : value;

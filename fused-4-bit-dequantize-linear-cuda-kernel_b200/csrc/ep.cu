@@ -60,6 +60,22 @@ __global__ void ep_plan_kernel(const int32_t* __restrict__ counts_all, int world
             }
             splits[world + s] = recv;
         }
+        // ranges of one expert that happen to be adjacent in the receive buffer (always the case with one expert per
+        // rank) are merged: the grouped GEMM tiles rows per range, and many short ranges mean many ragged last tiles
+        for (int li = 0; li < E; ++li) {
+            int cur = -1;
+            for (int s = 0; s < world; ++s) {
+                const int v = li * world + s;
+                if (range_ends[v] <= range_starts[v]) continue;
+                if (cur >= 0 && range_ends[cur] == range_starts[v]) {
+                    range_ends[cur] = range_ends[v];
+                    range_starts[v] = 0;
+                    range_ends[v] = 0;
+                } else {
+                    cur = v;
+                }
+            }
+        }
     }
 }
 

@@ -99,6 +99,9 @@ struct GemmParams {
     // stream-K (plain linear with a badly quantised last wave): CTA c owns k-blocks [c*skq + min(c, skr), ...) of the
     // linearised (tile, k-block) space; a tile cut between CTAs is finished by the CTA that holds its last k-block,
     // the others publish their fp32 partial accumulator (workspace slot = CTA index) and raise a flag
+    int mt_major;            // tile order: 0 = all token tiles of a weight tile first; 1 = all weight tiles of a token tile first
+                             //    (many, mostly empty ranges: the valid tiles are then a PREFIX of the index space, so the
+                             //    persistent CTAs stay balanced whatever the bound on the number of token tiles is)
     int gated;               // 1: weight rows are interleaved (2f: gate, 2f + 1: up); the epilogue writes
                              //    h[m, f] = silu(gate) * up into y [R, N / 2] (fused SiLU-gate of the MoE layer)
     int debug;               // bench-only ablations, see the TMA producer
@@ -114,8 +117,10 @@ struct TileInfo {
 
 // tile index -> (expert, first token row, end of the group, first weight row); false = no such tile
 __device__ __forceinline__ bool locate(const GemmParams& p, int t, TileInfo& ti) {
-    const int nt = t / p.mt_bound, mt = t - nt * p.mt_bound;
-    if (nt >= p.n_tiles) return false;
+    int nt, mt;
+    if (p.mt_major) { mt = t / p.n_tiles; nt = t - mt * p.n_tiles; }
+    else { nt = t / p.mt_bound; mt = t - nt * p.mt_bound; }
+    if (nt >= p.n_tiles || mt >= p.mt_bound) return false;
     ti.n0 = nt * BM;
     if (!p.starts) {
         ti.e = 0;
@@ -159,7 +164,10 @@ __device__ __forceinline__ void for_each_item(const GemmParams& p, int KB, int t
     Item it;
     if (!p.sk) {
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-            if (!locate(p, t, it.ti)) continue;
+            if (!locate(p, t, it.ti)) {
+                if (p.mt_major) break;          // the valid tiles are a prefix of the index space in this order
+                continue;
+            }
             it.kb0 = 0; it.kb1 = KB; it.publish = 0; it.nadd = 0; it.c0 = 0;
             body(it);
         }
@@ -790,6 +798,7 @@ int launch_gemm_tc(const DeviceInfo& dev, const void* x, int x_dtype, const uint
     p.sk = sk; p.skq = skq; p.skr = skr;
     p.debug = tuning().gemm_debug > 0 ? tuning().gemm_debug : 0;
     p.gated = gated;
+    p.mt_major = tuning().gemm_mt_major >= 0 ? (tuning().gemm_mt_major != 0 && starts != nullptr) : ((starts && emap) ? 1 : 0);
     p.part = reinterpret_cast<float*>(w8 + 2 * xbytes + 3 * sbytes);
     p.flags = reinterpret_cast<unsigned int*>(ws);
     const size_t smem = (size_t)OFF_STAGES + (size_t)stages * p.stage_bytes;

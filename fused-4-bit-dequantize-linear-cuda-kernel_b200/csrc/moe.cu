@@ -97,7 +97,7 @@ constexpr int PERM_THREADS = 256;
 constexpr int PERM_CHUNK = 2048;   // assignments per block
 
 __global__ void __launch_bounds__(PERM_THREADS)
-perm_hist_kernel(const int32_t* __restrict__ idx, int64_t A, int E, int32_t* __restrict__ ws) {
+perm_hist_kernel(const int32_t* __restrict__ idx, int64_t A, int E, int32_t* __restrict__ ws, const int32_t* __restrict__ remap) {
     extern __shared__ int32_t s_hist[];
     for (int e = threadIdx.x; e < E; e += PERM_THREADS) s_hist[e] = 0;
     __syncthreads();
@@ -106,7 +106,7 @@ perm_hist_kernel(const int32_t* __restrict__ idx, int64_t A, int E, int32_t* __r
         int64_t a = base + i;
         if (a < A) {
             int e = idx[a];
-            if (e >= 0 && e < E) atomicAdd(&s_hist[e], 1);
+            if (e >= 0 && e < E) atomicAdd(&s_hist[remap ? remap[e] : e], 1);
         }
     }
     __syncthreads();
@@ -115,14 +115,18 @@ perm_hist_kernel(const int32_t* __restrict__ idx, int64_t A, int E, int32_t* __r
 
 __global__ void __launch_bounds__(PERM_THREADS)
 perm_scan_kernel(int32_t* __restrict__ ws, int nblocks, int E, int32_t* __restrict__ counts,
-                 int32_t* __restrict__ offsets, int32_t* __restrict__ sorted_slot, int64_t A) {
+                 int32_t* __restrict__ offsets, int32_t* __restrict__ sorted_slot, int64_t A, const int32_t* __restrict__ remap) {
     extern __shared__ int32_t s_cnt[];   // [E] totals then exclusive offsets
     for (int e = threadIdx.x; e < E; e += PERM_THREADS) {
         int tot = 0;
         for (int b = 0; b < nblocks; ++b) tot += ws[(int64_t)b * E + e];
         s_cnt[e] = tot;
-        counts[e] = tot;
+        if (!remap) counts[e] = tot;
     }
+    __syncthreads();
+    // sorted by a remapped id (expert-parallel send order): the histogram is still reported per ORIGINAL expert id
+    if (remap)
+        for (int e = threadIdx.x; e < E; e += PERM_THREADS) counts[e] = s_cnt[remap[e]];
     __syncthreads();
     if (threadIdx.x == 0) {
         int run = 0;
@@ -153,7 +157,7 @@ perm_scan_kernel(int32_t* __restrict__ ws, int nblocks, int E, int32_t* __restri
 __global__ void __launch_bounds__(PERM_THREADS)
 perm_scatter_kernel(const int32_t* __restrict__ idx, int64_t A, int E,
                     const int32_t* __restrict__ ws, int32_t* __restrict__ sorted_slot,
-                    int32_t* __restrict__ inv_perm) {
+                    int32_t* __restrict__ inv_perm, const int32_t* __restrict__ remap) {
     extern __shared__ int32_t smem[];
     int32_t* s_run = smem;            // [E] next free position per expert
     int32_t* s_warp = smem + E;       // [8][E] per-warp counts of the current round
@@ -169,6 +173,7 @@ perm_scatter_kernel(const int32_t* __restrict__ idx, int64_t A, int E,
         if (a < A) {
             e = idx[a];
             if (e < 0 || e >= E) e = -1;
+            else if (remap) e = remap[e];
         }
         const unsigned peers = __match_any_sync(0xffffffffu, e);
         const int rank = __popc(peers & ((1u << lane) - 1u));
@@ -317,6 +322,19 @@ size_t b200q_moe_permute_ws_bytes(int64_t T, int E, int k) {
 int b200q_moe_permute(const int32_t* idx, int64_t T, int E, int k, int32_t* counts,
                       int32_t* offsets, int32_t* sorted_slot, int32_t* inv_perm, void* ws,
                       size_t ws_bytes, void* stream) {
+    return b200q_moe_permute_mapped(idx, nullptr, T, E, k, counts, offsets, sorted_slot, inv_perm, ws, ws_bytes, stream);
+}
+
+int b200q_moe_route(const float* logits, const int32_t* remap, int64_t T, int E, int k, int32_t* idx, float* weights,
+                    int32_t* counts, int32_t* offsets, int32_t* sorted_slot, int32_t* inv_perm, void* ws, size_t ws_bytes,
+                    void* stream) {
+    if (int rc = b200q_moe_topk(logits, T, E, k, idx, weights, stream)) return rc;
+    return b200q_moe_permute_mapped(idx, remap, T, E, k, counts, offsets, sorted_slot, inv_perm, ws, ws_bytes, stream);
+}
+
+int b200q_moe_permute_mapped(const int32_t* idx, const int32_t* remap, int64_t T, int E, int k, int32_t* counts,
+                             int32_t* offsets, int32_t* sorted_slot, int32_t* inv_perm, void* ws,
+                             size_t ws_bytes, void* stream) {
     if (T < 0 || E <= 0 || E > 1024 || k <= 0) return set_error(B200Q_EINVAL, "moe_permute: bad T/E/k");
     const int64_t A = T * k;
     if (A > 0x7fffffffLL) return set_error(B200Q_EINVAL, "moe_permute: T*k exceeds int32");
@@ -329,10 +347,10 @@ int b200q_moe_permute(const int32_t* idx, int64_t T, int E, int k, int32_t* coun
     int nblocks = static_cast<int>((A + PERM_CHUNK - 1) / PERM_CHUNK);
     if (nblocks < 1) nblocks = 1;
     int32_t* w = static_cast<int32_t*>(ws);
-    perm_hist_kernel<<<nblocks, PERM_THREADS, E * sizeof(int32_t), st>>>(idx, A, E, w);
-    perm_scan_kernel<<<1, PERM_THREADS, (E + 1) * sizeof(int32_t), st>>>(w, nblocks, E, counts, offsets, sorted_slot, A);
+    perm_hist_kernel<<<nblocks, PERM_THREADS, E * sizeof(int32_t), st>>>(idx, A, E, w, remap);
+    perm_scan_kernel<<<1, PERM_THREADS, (E + 1) * sizeof(int32_t), st>>>(w, nblocks, E, counts, offsets, sorted_slot, A, remap);
     if (A > 0)
-        perm_scatter_kernel<<<nblocks, PERM_THREADS, (1 + PERM_THREADS / 32) * E * sizeof(int32_t), st>>>(idx, A, E, w, sorted_slot, inv_perm);
+        perm_scatter_kernel<<<nblocks, PERM_THREADS, (1 + PERM_THREADS / 32) * E * sizeof(int32_t), st>>>(idx, A, E, w, sorted_slot, inv_perm, remap);
     return check_cuda(cudaGetLastError(), "moe_permute launch");
 }
 

@@ -78,6 +78,17 @@ def ep_plan_host(counts_all: np.ndarray, rank: int, world: int, replicated: Sequ
                 ends[li * world + s] = off + c
             off += c
             recv[s] += c
+    for li in range(E):                      # adjacent ranges of one expert are merged (fewer ragged last tiles)
+        cur = -1
+        for s in range(world):
+            v = li * world + s
+            if ends[v] <= starts[v]:
+                continue
+            if cur >= 0 and ends[cur] == starts[v]:
+                ends[cur] = ends[v]
+                starts[v] = ends[v] = 0
+            else:
+                cur = v
     return send, recv, starts, ends, (np.arange(E * world) // world).astype(np.int32)
 
 
@@ -121,12 +132,8 @@ class CudaOps(TorchCommOps):
         _lib.require_cuda(logits, "logits")
         logits = logits.to(torch.float32).contiguous()
         E = logits.shape[1]
-        idx, w = _lib.moe_topk(logits, top_k)
-        if vid is None:
-            counts, offsets, sorted_slot, inv_perm = _lib.moe_permute(idx, E)
-            return DeviceRouting(idx, w, counts, offsets, sorted_slot, inv_perm, E, top_k)
-        counts_v, offsets, sorted_slot, inv_perm = _lib.moe_permute(vid[idx.long()].to(torch.int32), E)
-        return DeviceRouting(idx, w, counts_v[vid], offsets, sorted_slot, inv_perm, E, top_k)
+        idx, w, counts, offsets, sorted_slot, inv_perm = _lib.moe_route(logits, top_k, vid)     # one C call
+        return DeviceRouting(idx, w, counts, offsets, sorted_slot, inv_perm, E, top_k)
 
     def gather(self, x, index, k):
         return _lib.moe_gather_rows(x, index, k)
@@ -135,7 +142,7 @@ class CudaOps(TorchCommOps):
         return moe.forward_grouped(xs, offsets)
 
     def experts_ranges(self, moe, rows, starts, ends, range_expert):
-        return moe.forward_ranges(rows, starts, ends, range_expert)
+        return moe.forward_ranges(rows, starts, ends, range_expert, all_rows_covered=True)   # every received row has an expert here
 
     def combine(self, y, inv_perm, weights, k):
         return _lib.moe_combine(y, inv_perm, weights, k, out_dtype=torch.float32)
@@ -228,12 +235,13 @@ class ExpertParallelMoE(torch.nn.Module):
         self.replicated = tuple(sorted(set(int(e) for e in replicated)))
         self.ops = ops if ops is not None else CudaOps(group)
         self.last_stats = {}
+        self.profile = False         # True: CUDA events around the phases of the next forward -> last_stats["phases_ms"]
         self._static = None          # (device, vid, replicated mask, local index) as device tensors
 
     def _tables(self, dev, rank, world):
         if self._static is None or self._static[0] != dev:
             E = self.num_experts
-            vid = torch.from_numpy(virtual_ids(E, rank, world, self.replicated)).to(dev)
+            vid = torch.from_numpy(virtual_ids(E, rank, world, self.replicated)).to(device=dev, dtype=torch.int32)
             rep = torch.zeros(E, dtype=torch.int32)
             rep[list(self.replicated)] = 1
             lidx = torch.full((E,), -1, dtype=torch.int32)
@@ -252,8 +260,18 @@ class ExpertParallelMoE(torch.nn.Module):
             y = ops.experts(self.local_moe, xs, dr.offsets)
             return ops.combine(y, dr.inv_perm, dr.expert_weights, k)
         _, vid, rep_t, lidx_t, rep_h, lidx_h = self._tables(x.device, rank, world)
+        marks = []
+
+        def mark(name):
+            if self.profile and x.is_cuda:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                marks.append((name, ev))
+
+        mark("start")
         dr = ops.route(router_logits, k, vid)                     # rows sorted by (destination rank, expert)
         xs = ops.gather(x, dr.sorted_slot, k)
+        mark("route+gather")
         counts_all = ops.allgather_counts(dr.counts, world)       # [world * E], original expert ids
         if hasattr(ops, "plan"):
             splits, starts, ends, rexp = ops.plan(counts_all, rank, world, E, rep_t, lidx_t)
@@ -261,9 +279,18 @@ class ExpertParallelMoE(torch.nn.Module):
         else:                                                     # CPU stand-in: the numpy statement of the same plan
             send_rows, recv_rows, starts, ends, rexp = ep_plan_host(counts_all.cpu().numpy().reshape(world, E), rank, world,
                                                                     self.replicated, lidx_h)
+        mark("histogram all-gather + plan + host sync")
         recv = ops.exchange(xs, send_rows, recv_rows)             # DISPATCH
+        mark("dispatch all-to-all")
         yg = ops.experts_ranges(self.local_moe, recv, starts, ends, rexp)
+        mark("expert GEMMs")
         back = ops.exchange(yg, recv_rows, send_rows)             # COMBINE
+        mark("combine all-to-all")
+        out = ops.combine(back, dr.inv_perm, dr.expert_weights, k)
+        mark("weighted combine")
         self.last_stats = {"sent_rows": int(sum(send_rows)), "recv_rows": int(sum(recv_rows)),
                            "bytes_out": int(sum(send_rows) - send_rows[rank]) * x.shape[1] * x.element_size()}
-        return ops.combine(back, dr.inv_perm, dr.expert_weights, k)
+        if marks:
+            torch.cuda.synchronize(x.device)
+            self.last_stats["phases_ms"] = {marks[i][0]: round(marks[i - 1][1].elapsed_time(marks[i][1]), 4) for i in range(1, len(marks))}
+        return out

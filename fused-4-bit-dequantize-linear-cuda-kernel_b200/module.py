@@ -67,6 +67,14 @@ class QuantizedLinear(nn.Module):
         lead = x.shape[:-1]
         if x.shape[-1] != self.in_features:
             raise RuntimeError(f"expected last dim {self.in_features}, got {x.shape[-1]}")
+        ext = _lib.torch_ext()
+        if ext is not None and x.is_contiguous():
+            # compiled binding: checks, output / workspace allocation, stream lookup and the C-ABI call in one C++ function
+            y = ext.linear_forward(x, self.packed_weights, self.scales, self.zero_points, self.bias, None,
+                                   _lib.FLAG_STATIC_WEIGHTS if self._weights_settled else _lib.FLAG_NONE,
+                                   self._next.packed_weights if self._next is not None else None)
+            self._weights_settled = True
+            return y
         x2 = x.reshape(-1, self.in_features)
         if not x2.is_contiguous():
             x2 = x2.contiguous()

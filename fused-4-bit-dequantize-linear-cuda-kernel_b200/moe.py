@@ -220,19 +220,21 @@ class QuantizedMoE(nn.Module):
         return _lib.moe_grouped_fwd(h, w2[0], w2[1], w2[2], offsets)
 
     def forward_ranges(self, rows: torch.Tensor, starts: torch.Tensor, ends: torch.Tensor,
-                       range_expert: torch.Tensor) -> torch.Tensor:
+                       range_expert: torch.Tensor, all_rows_covered: bool = False) -> torch.Tensor:
         """Rows [starts[v], ends[v]) of `rows` go through expert range_expert[v] (int32 device tensors; ranges may be
         empty and need not be sorted) -- what an expert-parallel rank runs on the rows it received, which arrive ordered
-        (source rank, expert).  Rows covered by no range come back as zeros."""
+        (source rank, expert).  Rows covered by no range come back as zeros (unless the caller vouches that there are
+        none: all_rows_covered skips the memset)."""
         w13, w2 = self.stacked_weights()
+        z = not all_rows_covered
         if self.fused_gate:
-            h = _lib.moe_grouped_fwd_mapped(rows, w13[0], w13[1], w13[2], starts, ends, range_expert, gated=True)
+            h = _lib.moe_grouped_fwd_mapped(rows, w13[0], w13[1], w13[2], starts, ends, range_expert, gated=True, zero_fill=False)
         else:
-            gu = _lib.moe_grouped_fwd_mapped(rows, w13[0], w13[1], w13[2], starts, ends, range_expert, gated=False)
+            gu = _lib.moe_grouped_fwd_mapped(rows, w13[0], w13[1], w13[2], starts, ends, range_expert, gated=False, zero_fill=z)
             if not self.gated:
                 return gu
             h = _lib.moe_silu_mul(gu)
-        return _lib.moe_grouped_fwd_mapped(h, w2[0], w2[1], w2[2], starts, ends, range_expert, gated=False)
+        return _lib.moe_grouped_fwd_mapped(h, w2[0], w2[1], w2[2], starts, ends, range_expert, gated=False, zero_fill=z)
 
     @property
     def total_memory_bytes(self) -> int:

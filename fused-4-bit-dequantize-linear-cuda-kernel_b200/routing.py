@@ -65,8 +65,7 @@ def route(logits: torch.Tensor, top_k: int) -> DeviceRouting:
     _lib.require_cuda(logits, "logits")
     logits = logits.to(torch.float32).contiguous()
     E = logits.shape[1]
-    idx, w = _lib.moe_topk(logits, top_k)
-    counts, offsets, sorted_slot, inv_perm = _lib.moe_permute(idx, E)
+    idx, w, counts, offsets, sorted_slot, inv_perm = _lib.moe_route(logits, top_k)      # one C call: top-k + permutation
     return DeviceRouting(idx, w, counts, offsets, sorted_slot, inv_perm, E, top_k)
 
 

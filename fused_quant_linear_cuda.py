@@ -21,6 +21,9 @@ def _check(cond, msg):
 
 def forward(input, packed_weights, scales, zero_points):
     """Fused INT4 dequantize + linear forward: input [K] or [M,K] f32 -> [N] or [M,N] f32."""
+    ext = _lib.torch_ext()
+    if ext is not None:          # compiled binding (csrc/torch_binding.cpp): the same checks and messages, in C++
+        return ext.forward(input, packed_weights, scales, zero_points)
     squeeze = False
     if input.dim() == 1:
         input = input.unsqueeze(0)

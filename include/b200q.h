@@ -174,6 +174,18 @@ int b200q_moe_permute(const int32_t* idx, int64_t T, int E, int k, int32_t* coun
                       int32_t* offsets, int32_t* sorted_slot, int32_t* inv_perm, void* ws,
                       size_t ws_bytes, void* stream);
 
+/* Same, sorted by remap[expert] instead of the expert id (remap [E] i32 on the device, a permutation of 0..E-1;
+ * NULL = identity): offsets / sorted_slot / inv_perm follow the remapped order, counts stay per ORIGINAL expert id.
+ * Expert-parallel ranks sort by (destination rank, expert) this way (see b200q_ep_plan). */
+int b200q_moe_permute_mapped(const int32_t* idx, const int32_t* remap, int64_t T, int E, int k, int32_t* counts,
+                             int32_t* offsets, int32_t* sorted_slot, int32_t* inv_perm, void* ws,
+                             size_t ws_bytes, void* stream);
+
+/* b200q_moe_topk followed by b200q_moe_permute_mapped in one call (one host transition for the whole router). */
+int b200q_moe_route(const float* logits, const int32_t* remap, int64_t T, int E, int k, int32_t* idx, float* weights,
+                    int32_t* counts, int32_t* offsets, int32_t* sorted_slot, int32_t* inv_perm, void* ws, size_t ws_bytes,
+                    void* stream);
+
 /* xs[p,:] = x[sorted_slot[p] / k, :]  (routing.py:137-147).  d % 4 == 0 (f32) / 8 (16-bit). */
 int b200q_moe_gather_rows(const void* x, int dtype, const int32_t* sorted_slot, int64_t rows,
                           int k, int64_t d, void* xs, void* stream);
