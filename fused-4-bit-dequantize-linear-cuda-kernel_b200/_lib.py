@@ -38,6 +38,8 @@ SIGNATURES = {
     "b200q_linear_fwd": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _i32, _i64, _i64, _i64, _vp, _sz, _u32, _vp]),
     "b200q_linear_fwd_next": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _i32, _i64, _i64, _i64, _vp, _sz, _u32, _vp, _vp, _sz]),
     "b200q_linear_bias_fwd": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i64, _i64, _vp, _sz, _u32, _vp, _vp, _sz]),
+    "b200q_linear_groupwise_fwd": (_i32, [_vp, _i32, _vp, _vp, _vp, _i64, _vp, _i32, _i64, _i64, _i64, _vp]),
+    "b200q_linear_gated_fwd": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _i32, _i64, _i64, _i64, _vp, _sz, _u32, _vp, _vp, _sz]),
     "b200q_linear_fwd_host": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i64, _i64, _vp, _sz, _u32, _vp]),
     "b200q_tune_set": (_i32, [_c.c_char_p, _i32]),
     "b200q_moe_topk": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _vp]),
@@ -179,6 +181,40 @@ def linear_fwd(x: torch.Tensor, packed: torch.Tensor, scales: torch.Tensor, zps:
                                         next_packed.data_ptr() if next_packed is not None else None,
                                         next_packed.numel() if next_packed is not None else 0), "b200q_linear_fwd")
     return y
+
+
+def linear_groupwise_fwd(x: torch.Tensor, packed: torch.Tensor, scales: torch.Tensor, zps: torch.Tensor, group_size: int,
+                         out_dtype=None) -> torch.Tensor:
+    """y = x @ dequant(packed, scales [N, K/G], zps [N, K/G])^T with one scale / zero point per G columns."""
+    lib = load()
+    M, K = x.shape
+    N = packed.shape[0]
+    out_dtype = out_dtype or x.dtype
+    with torch.cuda.device(x.device):
+        y = torch.empty((M, N), dtype=out_dtype, device=x.device)
+        check(lib.b200q_linear_groupwise_fwd(x.data_ptr(), dtype_code(x), packed.data_ptr(), scales.data_ptr(), zps.data_ptr(),
+                                             group_size, y.data_ptr(), dtype_code(y), M, N, K, stream_ptr(x.device)),
+              "b200q_linear_groupwise_fwd")
+    return y
+
+
+def linear_gated_fwd(x: torch.Tensor, packed13: torch.Tensor, scales13: torch.Tensor, zps13: torch.Tensor,
+                     out_dtype=None, flags: int = FLAG_NONE, next_packed: torch.Tensor | None = None) -> torch.Tensor:
+    """h[M,F] = silu(x w_gate^T) * (x w_up^T); packed13 [2F,K/2] with gate / up rows interleaved (2f: gate, 2f+1: up)."""
+    lib = load()
+    M, K = x.shape
+    F = packed13.shape[0] // 2
+    out_dtype = out_dtype or x.dtype
+    with torch.cuda.device(x.device):
+        h = torch.empty((M, F), dtype=out_dtype, device=x.device)
+        ws_bytes = lib.b200q_linear_ws_bytes(M, 2 * F, K)
+        ws = workspace(x.device, ws_bytes, "linear") if ws_bytes else None
+        check(lib.b200q_linear_gated_fwd(x.data_ptr(), dtype_code(x), packed13.data_ptr(), scales13.data_ptr(), zps13.data_ptr(),
+                                         h.data_ptr(), dtype_code(h), M, F, K, ws.data_ptr() if ws is not None else None,
+                                         ws.numel() if ws is not None else 0, flags, stream_ptr(x.device),
+                                         next_packed.data_ptr() if next_packed is not None else None,
+                                         next_packed.numel() if next_packed is not None else 0), "b200q_linear_gated_fwd")
+    return h
 
 
 def linear_fwd_host(x_host: torch.Tensor, x_dev: torch.Tensor, packed, scales, zps, y_dev: torch.Tensor,

@@ -122,6 +122,39 @@ int b200q_linear_bias_fwd(const void* x, int x_dtype, const uint8_t* packed, con
     return rc;
 }
 
+int b200q_linear_groupwise_fwd(const void* x, int x_dtype, const uint8_t* packed, const float* scales, const float* zps,
+                               int64_t group_size, void* y, int y_dtype, int64_t M, int64_t N, int64_t K, void* stream) {
+    if (M < 0 || N < 0 || K < 0 || (K & 1)) return set_error(B200Q_EINVAL, "linear_groupwise_fwd: need M,N >= 0 and even K >= 0");
+    if (group_size <= 0 || (group_size & 7) || K % group_size) return set_error(B200Q_EINVAL, "linear_groupwise_fwd: group_size must be a multiple of 8 that divides K (got %lld, K=%lld)", (long long)group_size, (long long)K);
+    if (!elem_size(x_dtype) || !elem_size(y_dtype)) return set_error(B200Q_EINVAL, "linear_groupwise_fwd: unsupported dtype");
+    if (M == 0 || N == 0) return 0;
+    if (!y || !scales || !zps || !x || !packed) return set_error(B200Q_EINVAL, "linear_groupwise_fwd: null pointer");
+    DeviceInfo d;
+    if (int rc = current_device(&d)) return rc;
+    return launch_linear_generic(x, x_dtype, packed, scales, zps, y, y_dtype, M, N, K, nullptr, nullptr, 1, 0,
+                                 static_cast<cudaStream_t>(stream), nullptr, (int)group_size);
+}
+
+int b200q_linear_gated_fwd(const void* x, int x_dtype, const uint8_t* packed13, const float* scales13, const float* zps13,
+                           void* h, int h_dtype, int64_t M, int64_t F, int64_t K, void* ws, size_t ws_bytes, unsigned flags,
+                           void* stream, const uint8_t* next_packed, size_t next_bytes) {
+    if (M < 0 || F < 0 || K < 0 || (K & 1)) return set_error(B200Q_EINVAL, "linear_gated_fwd: need M,F >= 0 and even K >= 0");
+    if (!elem_size(x_dtype) || !elem_size(h_dtype)) return set_error(B200Q_EINVAL, "linear_gated_fwd: unsupported dtype");
+    if (M == 0 || F == 0) return 0;
+    if (!h || !scales13 || !zps13 || !x || !packed13) return set_error(B200Q_EINVAL, "linear_gated_fwd: null pointer");
+    DeviceInfo d;
+    if (int rc = current_device(&d)) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!(aligned(x, 16) && aligned(packed13, 16) && aligned(h, 16)))
+        return set_error(B200Q_EALIGN, "linear_gated_fwd: x, packed13 and h must be 16-byte aligned");
+    const int force = tuning().force_path;
+    if ((force <= 0 || force == 6) && gemv_dec_supported(d, M, 2 * F, K, 1) && (force == 6 || M <= 8 || K <= 8192))
+        return launch_gemv_dec(d, x, x_dtype, packed13, scales13, zps13, nullptr, h, h_dtype, M, 2 * F, K, flags, st, next_packed, next_bytes, 1);
+    if (force != 6 && gemm_tc_supported(M, 2 * F, K, x_dtype, h_dtype))
+        return launch_gemm_tc(d, x, x_dtype, packed13, scales13, zps13, h, h_dtype, M, 2 * F, K, nullptr, nullptr, 1, ws, ws_bytes, flags, st, 1);
+    return set_error(B200Q_EINVAL, "linear_gated_fwd: needs K %% 128 == 0 (otherwise: b200q_linear_fwd on the concatenated rows, then b200q_moe_silu_mul)");
+}
+
 int b200q_linear_fwd_host(const void* h_x, int x_dtype, void* d_x, const uint8_t* packed, const float* scales,
                           const float* zps, void* d_y, void* h_y, int y_dtype, int64_t M, int64_t N, int64_t K,
                           void* ws, size_t ws_bytes, unsigned flags, void* stream) {

@@ -94,6 +94,7 @@ struct DecParams {
     int wait_weights;                // 1: weights may be written by the preceding kernel
     int early_tiles;                 // a + 10 b: a tiles requested before griddepcontrol.wait, b more behind the x loads
     int pf_mode;                     // next-layer L2 prefetch: 1 behind the last own request, 2 before the own requests, 3 after the operand build
+    int gated;                       // 1: rows 2f / 2f+1 are the gate / up projection of column f; y is h [M, N/2] = silu(gate) * up
     int debug;                       // B200Q_PROF builds: record phase stamps
 };
 
@@ -204,8 +205,10 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_dec_kernel(const __grid_constant
 
     B200Q_STAMP(0);
     const int b = (int)blockIdx.x;
-    const int r0 = b * p.rows_q + min(b, p.rows_rem);
-    const int nrows = p.rows_q + (b < p.rows_rem ? 1 : 0);
+    // (gated: rows are dealt out in gate / up pairs, so both projections of an output column meet in one CTA)
+    const int unit = p.gated ? 2 : 1;
+    const int r0 = unit * (b * p.rows_q + min(b, p.rows_rem));
+    const int nrows = unit * (p.rows_q + (b < p.rows_rem ? 1 : 0));
     const int ntma = (nrows + TILE_ROWS - 1) / TILE_ROWS;    // tiles with weight rows
     // One more row: a row of bytes 0x11 (q_lo = q_hi = 1) behind the last weight row makes the tensor cores deliver
     // sum_k X (the zero-point term) as one more output row -- no extra arithmetic in the operand build.
@@ -486,34 +489,43 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_dec_kernel(const __grid_constant
     const unsigned int flagged = *s_flag;
     // word of (mma row r, column col) in a 16 x 8 tile stored as [lane = 4 (r & 7) + col / 2][reg = 2 (r >> 3) + (col & 1)]
     auto word_of = [](int r, int col) { return (((r & 7) * 4 + (col >> 1)) * 4) + ((r >> 3) * 2 + (col & 1)); };
-    if (tid < nrows) {
+    {
+        const bool mine = tid < nrows;
         const int ti = tid >> 4, r = tid & 15, row = r0 + tid;
         const float sc = pre_sc, zp = pre_zp;
-        const float bias = p.bias ? __ldg(p.bias + row) : 0.0f;
+        const float bias = (mine && p.bias) ? __ldg(p.bias + row) : 0.0f;
         const int zi = __float2int_rn(zp);
         const bool zint = (float)zi == zp && zi >= -32768 && zi <= 32767;
         for (int m = 0; m < p.M; ++m) {
-            if ((flagged >> m) & 1u) continue;
-            const int pass = m / MB, mm = m - pass * MB, nt = mm >> 1, h = mm & 1;
-            const int* f = fin + ((pass * p.ntiles_max + ti) * NT + nt) * 128;
-            const int* ft = fin + ((pass * p.ntiles_max + tf) * NT + nt) * 128;     // the 0x11 row: sum_k X
-            long long a = 0, txl = 0;
+            if ((flagged >> m) & 1u) continue;               // uniform
+            float v = 0.0f;
+            if (mine) {
+                const int pass = m / MB, mm = m - pass * MB, nt = mm >> 1, h = mm & 1;
+                const int* f = fin + ((pass * p.ntiles_max + ti) * NT + nt) * 128;
+                const int* ft = fin + ((pass * p.ntiles_max + tf) * NT + nt) * 128;     // the 0x11 row: sum_k X
+                long long a = 0, txl = 0;
 #pragma unroll
-            for (int l = 0; l < 4; ++l) {
-                a += (long long)f[word_of(r, 4 * h + l)] << (8 * l);
-                txl += (long long)ft[word_of(rf, 4 * h + l)] << (8 * l);
+                for (int l = 0; l < 4; ++l) {
+                    a += (long long)f[word_of(r, 4 * h + l)] << (8 * l);
+                    txl += (long long)ft[word_of(rf, 4 * h + l)] << (8 * l);
+                }
+                const int ex = s_ex[m];
+                if (zint && ex >= -126) {
+                    // quantiser-made zero points are integers: a - zp * sum X exactly in s64, ONE rounding to fp32 (the
+                    // same value the fp64 expression below rounds to), then the exact power of two and the scale
+                    v = sc * (__ll2float_rn(a - (long long)zi * txl) * __uint_as_float((uint32_t)(127 - ex) << 23));
+                } else {
+                    const double down = __longlong_as_double((long long)(1023 - ex) << 52);                // 2^-e
+                    v = sc * (float)(((double)a - (double)zp * (double)txl) * down);
+                }
             }
-            const int ex = s_ex[m];
-            float v;
-            if (zint && ex >= -126) {
-                // quantiser-made zero points are integers: a - zp * sum X exactly in s64, ONE rounding to fp32 (the
-                // same value the fp64 expression below rounds to), then the exact power of two and the scale
-                v = sc * (__ll2float_rn(a - (long long)zi * txl) * __uint_as_float((uint32_t)(127 - ex) << 23));
-            } else {
-                const double down = __longlong_as_double((long long)(1023 - ex) << 52);                // 2^-e
-                v = sc * (float)(((double)a - (double)zp * (double)txl) * down);
+            if (p.gated) {
+                // fused gate + up pair: the even row (gate) fetches its neighbour's value (up) and writes silu(gate) * up
+                const float u = __shfl_down_sync(0xffffffffu, v, 1);
+                if (mine && !(tid & 1)) store_out(p.y, p.y_dtype, (int64_t)m * (p.N >> 1) + (row >> 1), v / (1.0f + __expf(-v)) * u);
+            } else if (mine) {
+                store_out(p.y, p.y_dtype, (int64_t)m * p.N + row, v + bias);
             }
-            store_out(p.y, p.y_dtype, (int64_t)m * p.N + row, v + bias);
         }
     }
     // ---- batch rows with NaN / Inf: the reference's arithmetic (dequantise, then fp32 multiply-add), so that
@@ -522,8 +534,7 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_dec_kernel(const __grid_constant
         const int64_t row_bytes = p.K >> 1;
         for (int m = 0; m < p.M; ++m) {
             if (!((flagged >> m) & 1u)) continue;
-            for (int rc = warp; rc < nrows; rc += NW) {
-                const int row = r0 + rc;
+            auto ref_row = [&](int row) {
                 const float sc = __ldg(p.scales + row), zp = __ldg(p.zps + row);
                 const uint8_t* wr = p.packed + (int64_t)row * row_bytes;
                 float acc = 0.0f;
@@ -535,7 +546,15 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_dec_kernel(const __grid_constant
                 }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-                if (lane == 0) {
+                return acc;
+            };
+            for (int rc = unit * warp; rc < nrows; rc += unit * NW) {
+                const int row = r0 + rc;
+                float acc = ref_row(row);
+                if (p.gated) {
+                    const float up = ref_row(row + 1);
+                    if (lane == 0) store_out(p.y, p.y_dtype, (int64_t)m * (p.N >> 1) + (row >> 1), acc / (1.0f + __expf(-acc)) * up);
+                } else if (lane == 0) {
                     if (p.bias) acc += __ldg(p.bias + row);
                     store_out(p.y, p.y_dtype, (int64_t)m * p.N + row, acc);
                 }
@@ -551,8 +570,11 @@ struct DecPlan {
     size_t smem;
 };
 
-bool plan_dec(int sm_count, int max_smem, int64_t M, int64_t N, int64_t K, DecPlan* c) {
+bool plan_dec(int sm_count, int max_smem, int64_t M, int64_t N, int64_t K, DecPlan* c, int gated = 0) {
     if (M < 1 || M > 16 || K < 256 || K % 256 != 0 || K > 16384 || N < 1 || N > 0x7fffffff) return false;
+    if (gated && (N & 1)) return false;
+    const int unit = gated ? 2 : 1;                                // rows are dealt out in gate / up pairs
+    N /= unit;
     c->npairs = (int)(K / 256);
     c->gpw2 = (c->npairs + NW - 1) / NW;                          // <= 4
     c->nt = (M >= 3 && c->gpw2 <= 2) ? 2 : 1;                     // B fragments: 16 gpw2 nt registers
@@ -560,11 +582,11 @@ bool plan_dec(int sm_count, int max_smem, int64_t M, int64_t N, int64_t K, DecPl
     c->npasses = (int)((M + mb - 1) / mb);
     int cap = tuning().gemv_ctas > 0 ? tuning().gemv_ctas : sm_count;
     if (cap > sm_count) cap = sm_count;
-    int64_t grid = (N + TILE_ROWS - 2) / (TILE_ROWS - 1);       // few rows: at most 15 per CTA (+ the 0x11 row = one tile)
+    int64_t grid = (N * unit + TILE_ROWS - 2 - (unit - 1)) / (TILE_ROWS - unit);       // few rows: at most 15 (14) per CTA (+ the 0x11 row = one tile)
     if (grid > cap) grid = cap;
     c->grid = (int)grid;
     c->rows_q = (int)(N / grid); c->rows_rem = (int)(N % grid);
-    const int br = c->rows_q + (c->rows_rem ? 1 : 0);
+    const int br = unit * (c->rows_q + (c->rows_rem ? 1 : 0));
     if (br > 256) return false;                                    // one output row per thread in the epilogue
     c->ntiles = (br + 1 + TILE_ROWS - 1) / TILE_ROWS;             // one more row: the 0x11 row that yields sum_k X
     c->nbars = c->gpw2;
@@ -662,21 +684,22 @@ int launch_dec_inst(const DecPlan& c, const CUtensorMap& map, const DecParams& p
 
 }  // namespace
 
-bool gemv_dec_supported(const DeviceInfo& dev, int64_t M, int64_t N, int64_t K) {
+bool gemv_dec_supported(const DeviceInfo& dev, int64_t M, int64_t N, int64_t K, int gated) {
     DecPlan c;
-    return plan_dec(dev.sm_count, dev.max_smem_optin, M, N, K, &c);
+    return plan_dec(dev.sm_count, dev.max_smem_optin, M, N, K, &c, gated);
 }
 
 int launch_gemv_dec(const DeviceInfo& dev, const void* x, int x_dtype, const uint8_t* packed, const float* scales,
                     const float* zps, const float* bias, void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
-                    unsigned flags, cudaStream_t st, const uint8_t* next_packed, size_t next_bytes) {
+                    unsigned flags, cudaStream_t st, const uint8_t* next_packed, size_t next_bytes, int gated) {
     DecPlan c;
-    if (!plan_dec(dev.sm_count, dev.max_smem_optin, M, N, K, &c))
+    if (!plan_dec(dev.sm_count, dev.max_smem_optin, M, N, K, &c, gated))
         return set_error(B200Q_EINVAL, "gemv_dec: unsupported shape M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
     if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(packed) & 15))
         return set_error(B200Q_EALIGN, "gemv_dec: x and packed must be 16-byte aligned");
     DecParams p{};
-    p.x = x; p.packed = packed; p.scales = scales; p.zps = zps; p.bias = bias; p.y = y;
+    p.x = x; p.packed = packed; p.scales = scales; p.zps = zps; p.bias = gated ? nullptr : bias; p.y = y;
+    p.gated = gated;
     p.x_dtype = x_dtype; p.y_dtype = y_dtype;
     p.M = (int)M; p.N = (int)N; p.K = (int)K;
     p.rows_q = c.rows_q; p.rows_rem = c.rows_rem;

@@ -64,7 +64,7 @@ int launch_minmax(const float* v, int64_t count, float* out, void* ws, cudaStrea
 int launch_linear_generic(const void* x, int x_dtype, const uint8_t* packed, const float* scales,
                           const float* zps, void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
                           const int32_t* starts, const int32_t* ends, int E, int zero_outside,
-                          cudaStream_t st, const int32_t* emap = nullptr);
+                          cudaStream_t st, const int32_t* emap = nullptr, int kgroup = 0);
 
 // decode GEMV, M <= 16, K % 128 == 0.  Returns B200Q_EINVAL if the shape is not supported so
 // the dispatcher can fall through.
@@ -96,10 +96,10 @@ int launch_stage_host(const void* src_mapped, void* dst, size_t bytes, cudaStrea
 
 // decode GEMV with the CTA's rows resident in shared memory (gemv_dec.cu): M <= 16, K % 128 == 0, K <= 16384 and
 // ceil(N / SMs) rows x K / 2 bytes fit in shared memory; no workspace; optional bias [N] f32
-bool gemv_dec_supported(const DeviceInfo& dev, int64_t M, int64_t N, int64_t K);
+bool gemv_dec_supported(const DeviceInfo& dev, int64_t M, int64_t N, int64_t K, int gated = 0);
 int launch_gemv_dec(const DeviceInfo& dev, const void* x, int x_dtype, const uint8_t* packed, const float* scales,
                     const float* zps, const float* bias, void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
-                    unsigned flags, cudaStream_t st, const uint8_t* next_packed, size_t next_bytes);
+                    unsigned flags, cudaStream_t st, const uint8_t* next_packed, size_t next_bytes, int gated = 0);
 
 // prefill / grouped path on tcgen05 tensor cores (M >= 17 rows, K % 128 == 0, N % 16 == 0).
 // starts == nullptr: plain linear; else grouped over E experts (packed [E,N,K/2]).

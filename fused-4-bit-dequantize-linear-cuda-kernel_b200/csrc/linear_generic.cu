@@ -51,6 +51,7 @@ struct GroupArgs {
     int E;
     int zero_outside;        // offsets form: rows before the first / after the last group are zeroed
     const int32_t* emap;     // weight expert of every group (nullptr: group e uses expert e)
+    int kgroup;              // 0: one scale / zero point per weight row; G > 0: one per G columns (scales [N, K/G])
     int64_t wstride;   // packed bytes per expert
     int64_t sstride;   // scales per expert
 };
@@ -103,7 +104,10 @@ linear_generic_kernel(const XT* __restrict__ x, const uint8_t* __restrict__ pack
     }
     if (g.emap) expert = g.emap[expert];
     const uint8_t* pr = packed + expert * g.wstride + n * (K / 2);
-    const float s = scales[expert * g.sstride + n], z = zps[expert * g.sstride + n];
+    const int64_t ngrp = g.kgroup ? K / g.kgroup : 1;
+    const float* srow = scales + (expert * g.sstride + n) * ngrp;
+    const float* zrow = zps + (expert * g.sstride + n) * ngrp;
+    float s = srow[0], z = zrow[0];
     const XT* xb = x + m0 * K;
 
     float acc[MT];
@@ -114,6 +118,7 @@ linear_generic_kernel(const XT* __restrict__ x, const uint8_t* __restrict__ pack
         const uint32_t* p4 = reinterpret_cast<const uint32_t*>(pr);
         for (int64_t i = lane; i < K / 8; i += 32) {
             const uint32_t wd = __ldg(p4 + i);
+            if (g.kgroup) { s = srow[(8 * i) / g.kgroup]; z = zrow[(8 * i) / g.kgroup]; }
             float wf[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j)
@@ -131,6 +136,7 @@ linear_generic_kernel(const XT* __restrict__ x, const uint8_t* __restrict__ pack
     } else {
         for (int64_t i = lane; i < K / 2; i += 32) {
             const uint32_t b = pr[i];
+            if (g.kgroup) { s = srow[(2 * i) / g.kgroup]; z = zrow[(2 * i) / g.kgroup]; }
             const float w0 = __fmul_rn(__fsub_rn(static_cast<float>(b & 15u), z), s);
             const float w1 = __fmul_rn(__fsub_rn(static_cast<float>(b >> 4), z), s);
 #pragma unroll
@@ -155,8 +161,8 @@ linear_generic_kernel(const XT* __restrict__ x, const uint8_t* __restrict__ pack
 template <typename XT, typename YT>
 int launch_typed(const void* x, const uint8_t* packed, const float* scales, const float* zps,
                  void* y, int64_t R, int64_t N, int64_t K, const int32_t* starts, const int32_t* ends,
-                 int E, int zero_outside, cudaStream_t st, const int32_t* emap) {
-    GroupArgs g{starts, ends, E, zero_outside, emap, N * (K / 2), N};
+                 int E, int zero_outside, cudaStream_t st, const int32_t* emap, int kgroup) {
+    GroupArgs g{starts, ends, E, zero_outside, emap, kgroup, N * (K / 2), N};
     int64_t tiles = (R + MT - 1) / MT + (starts ? E + 2 : 0);
     if (tiles > 65535) return set_error(B200Q_EINVAL, "generic path: too many row tiles (%lld)", (long long)tiles);
     dim3 grid(static_cast<unsigned>((N + GW - 1) / GW), static_cast<unsigned>(tiles));
@@ -174,11 +180,11 @@ int launch_typed(const void* x, const uint8_t* packed, const float* scales, cons
 template <typename XT>
 int launch_x(const void* x, const uint8_t* packed, const float* scales, const float* zps, void* y,
              int y_dtype, int64_t R, int64_t N, int64_t K, const int32_t* starts, const int32_t* ends,
-             int E, int zero_outside, cudaStream_t st, const int32_t* emap) {
+             int E, int zero_outside, cudaStream_t st, const int32_t* emap, int kgroup) {
     switch (y_dtype) {
-        case B200Q_F32: return launch_typed<XT, float>(x, packed, scales, zps, y, R, N, K, starts, ends, E, zero_outside, st, emap);
-        case B200Q_F16: return launch_typed<XT, __half>(x, packed, scales, zps, y, R, N, K, starts, ends, E, zero_outside, st, emap);
-        case B200Q_BF16: return launch_typed<XT, __nv_bfloat16>(x, packed, scales, zps, y, R, N, K, starts, ends, E, zero_outside, st, emap);
+        case B200Q_F32: return launch_typed<XT, float>(x, packed, scales, zps, y, R, N, K, starts, ends, E, zero_outside, st, emap, kgroup);
+        case B200Q_F16: return launch_typed<XT, __half>(x, packed, scales, zps, y, R, N, K, starts, ends, E, zero_outside, st, emap, kgroup);
+        case B200Q_BF16: return launch_typed<XT, __nv_bfloat16>(x, packed, scales, zps, y, R, N, K, starts, ends, E, zero_outside, st, emap, kgroup);
     }
     return set_error(B200Q_EINVAL, "bad y_dtype %d", y_dtype);
 }
@@ -188,12 +194,12 @@ int launch_x(const void* x, const uint8_t* packed, const float* scales, const fl
 int launch_linear_generic(const void* x, int x_dtype, const uint8_t* packed, const float* scales,
                           const float* zps, void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
                           const int32_t* starts, const int32_t* ends, int E, int zero_outside,
-                          cudaStream_t st, const int32_t* emap) {
+                          cudaStream_t st, const int32_t* emap, int kgroup) {
     if (M == 0 || N == 0) return 0;
     switch (x_dtype) {
-        case B200Q_F32: return launch_x<float>(x, packed, scales, zps, y, y_dtype, M, N, K, starts, ends, E, zero_outside, st, emap);
-        case B200Q_F16: return launch_x<__half>(x, packed, scales, zps, y, y_dtype, M, N, K, starts, ends, E, zero_outside, st, emap);
-        case B200Q_BF16: return launch_x<__nv_bfloat16>(x, packed, scales, zps, y, y_dtype, M, N, K, starts, ends, E, zero_outside, st, emap);
+        case B200Q_F32: return launch_x<float>(x, packed, scales, zps, y, y_dtype, M, N, K, starts, ends, E, zero_outside, st, emap, kgroup);
+        case B200Q_F16: return launch_x<__half>(x, packed, scales, zps, y, y_dtype, M, N, K, starts, ends, E, zero_outside, st, emap, kgroup);
+        case B200Q_BF16: return launch_x<__nv_bfloat16>(x, packed, scales, zps, y, y_dtype, M, N, K, starts, ends, E, zero_outside, st, emap, kgroup);
     }
     return set_error(B200Q_EINVAL, "bad x_dtype %d", x_dtype);
 }

@@ -12,19 +12,34 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .quantize import quantize_weights
+from .quantize import quantize_weights, quantize_weights_grouped
 
 
 class QuantizedLinear(nn.Module):
-    def __init__(self, in_features: int, out_features: int, bias: bool = False):
+    _gen = 0    # bumped whenever a weight buffer is replaced or moved (QuantizedGatedMLP re-stacks lazily when it changes)
+
+    def __setattr__(self, name, value):
+        if name in ("packed_weights", "scales", "zero_points"):
+            object.__setattr__(self, "_gen", self._gen + 1)
+        super().__setattr__(name, value)
+
+    def _apply(self, fn, *args, **kwargs):
+        object.__setattr__(self, "_gen", self._gen + 1)
+        return super()._apply(fn, *args, **kwargs)
+
+    def __init__(self, in_features: int, out_features: int, bias: bool = False, group_size: int = 0):
         super().__init__()
         self.in_features = in_features
         self.out_features = out_features
+        # group_size > 0: one scale / zero point per `group_size` columns (scales [N, K/G]).  0 = the
+        # reference's per-row format
+        self.group_size = group_size
         # python/module.py:59-64
         self.register_buffer("packed_weights",
                              torch.zeros(out_features, in_features // 2, dtype=torch.uint8))
-        self.register_buffer("scales", torch.zeros(out_features, dtype=torch.float32))
-        self.register_buffer("zero_points", torch.zeros(out_features, dtype=torch.float32))
+        sshape = (out_features,) if not group_size else (out_features, in_features // group_size)
+        self.register_buffer("scales", torch.zeros(sshape, dtype=torch.float32))
+        self.register_buffer("zero_points", torch.zeros(sshape, dtype=torch.float32))
         if bias:
             self.register_buffer("bias", torch.zeros(out_features, dtype=torch.float32))
         else:
@@ -42,12 +57,15 @@ class QuantizedLinear(nn.Module):
         return self
 
     @classmethod
-    def from_linear(cls, linear: nn.Linear) -> "QuantizedLinear":
+    def from_linear(cls, linear: nn.Linear, group_size: int = 0) -> "QuantizedLinear":
         # python/module.py:84 asserts `linear.bias is None`; here the bias is kept in fp32 and added by the kernel
-        module = cls(linear.in_features, linear.out_features, bias=linear.bias is not None)
+        module = cls(linear.in_features, linear.out_features, bias=linear.bias is not None, group_size=group_size)
         if linear.bias is not None:
             module.bias = linear.bias.data.detach().to(torch.float32).clone()
-        packed, scales, zp = quantize_weights(linear.weight.data)
+        if group_size:
+            packed, scales, zp = quantize_weights_grouped(linear.weight.data, group_size)
+        else:
+            packed, scales, zp = quantize_weights(linear.weight.data)
         module.packed_weights = packed
         module.scales = scales
         module.zero_points = zp
@@ -67,6 +85,18 @@ class QuantizedLinear(nn.Module):
         lead = x.shape[:-1]
         if x.shape[-1] != self.in_features:
             raise RuntimeError(f"expected last dim {self.in_features}, got {x.shape[-1]}")
+        if self.group_size:
+            # group-wise scales: the format's reference-speed kernel (the fast paths take per-row scales)
+            x2 = x.reshape(-1, self.in_features).contiguous()
+            y = _lib.linear_groupwise_fwd(x2, self.packed_weights, self.scales, self.zero_points, self.group_size)
+            if self.bias is not None:
+                y = y + self.bias.to(y.dtype)
+            return y.reshape(*lead, self.out_features)
+        if not self.packed_weights.is_contiguous():
+            # buffers that are strided views of an interleaved gate / up stack (QuantizedGatedMLP): compact them for this call
+            x2 = x.reshape(-1, self.in_features).contiguous()
+            y = _lib.linear_fwd(x2, self.packed_weights.contiguous(), self.scales.contiguous(), self.zero_points.contiguous(), bias=self.bias)
+            return y.reshape(*lead, self.out_features)
         ext = _lib.torch_ext()
         if ext is not None and x.is_contiguous():
             # compiled binding: checks, output / workspace allocation, stream lookup and the C-ABI call in one C++ function
@@ -110,7 +140,70 @@ class QuantizedLinear(nn.Module):
     def extra_repr(self) -> str:
         return (f"in_features={self.in_features}, "
                 f"out_features={self.out_features}, "
-                f"bits=4")
+                f"bits=4" + (f", group_size={self.group_size}" if self.group_size else ""))
+
+
+class QuantizedGatedMLP(nn.Module):
+    """`down(silu(gate(x)) * up(x))` -- a Llama-style MLP -- in TWO launches: the gate and up
+    projections are one fused dequantize-linear whose epilogue applies the SiLU-gate (b200q_linear_gated_fwd: decode
+    kernel for M <= 16, tcgen05 GEMM above), then the down projection.
+
+    `gate_proj`, `up_proj`, `down_proj` are QuantizedLinear modules with the reference's buffer names, so a state_dict of
+    three reference QuantizedLinear layers loads unchanged; the rows of gate and up live ONCE on the device, interleaved
+    (2f: gate, 2f+1: up), and the two modules' buffers are strided views of that stack."""
+
+    def __init__(self, hidden_dim: int, ffn_dim: int):
+        super().__init__()
+        self.hidden_dim, self.ffn_dim = hidden_dim, ffn_dim
+        self.gate_proj = QuantizedLinear(hidden_dim, ffn_dim)
+        self.up_proj = QuantizedLinear(hidden_dim, ffn_dim)
+        self.down_proj = QuantizedLinear(ffn_dim, hidden_dim)
+        self._stack = None
+        self._stamp = None
+
+    @classmethod
+    def from_linears(cls, gate: nn.Linear, up: nn.Linear, down: nn.Linear) -> "QuantizedGatedMLP":
+        assert gate.bias is None and up.bias is None, "the fused gate / up pair takes no bias"
+        mlp = cls(gate.in_features, gate.out_features)
+        mlp.gate_proj = QuantizedLinear.from_linear(gate)
+        mlp.up_proj = QuantizedLinear.from_linear(up)
+        mlp.down_proj = QuantizedLinear.from_linear(down)
+        return mlp
+
+    def _views(self, st):
+        out = []
+        for j, name in enumerate(("packed_weights", "scales", "zero_points")):
+            out.append((self.gate_proj, name, st[j][0::2]))
+            out.append((self.up_proj, name, st[j][1::2]))
+        return out
+
+    def stacked(self):
+        stamp = (id(self.gate_proj), self.gate_proj._gen, id(self.up_proj), self.up_proj._gen)
+        if self._stack is None or self._stamp != stamp:
+            st = self._stack
+            ok = st is not None and all(m._buffers[n].data_ptr() == v.data_ptr() and m._buffers[n].stride() == v.stride()
+                                        and m._buffers[n].device == v.device for m, n, v in self._views(st))
+            if not ok:
+                dev = self.gate_proj.packed_weights.device
+                F, d = self.ffn_dim, self.hidden_dim
+                st = (torch.empty((2 * F, d // 2), dtype=torch.uint8, device=dev),
+                      torch.empty((2 * F,), dtype=torch.float32, device=dev), torch.empty((2 * F,), dtype=torch.float32, device=dev))
+                for m, n, v in self._views(st):
+                    v.copy_(m._buffers[n].to(dev))
+                    m._buffers[n] = v
+                self._stack = st
+            self._stamp = stamp
+        return self._stack
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        _lib.require_cuda(x, "x")
+        lead = x.shape[:-1]
+        x2 = x.reshape(-1, self.hidden_dim)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        p13, s13, z13 = self.stacked()
+        h = _lib.linear_gated_fwd(x2, p13, s13, z13, flags=_lib.FLAG_STATIC_WEIGHTS, next_packed=self.down_proj.packed_weights)
+        return self.down_proj(h).reshape(*lead, self.hidden_dim)
 
 
 def link_decode_order(layers, cyclic: bool = True):

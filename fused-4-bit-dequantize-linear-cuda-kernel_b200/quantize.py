@@ -56,3 +56,21 @@ def reference_quantized_linear(input: torch.Tensor, packed_weights: torch.Tensor
     w = dequantize_weights(packed_weights.to(x.device), scales.to(x.device), zero_points.to(x.device))
     y = torch.nn.functional.linear(x, w)
     return y.to(home) if home is not None else y
+
+
+def quantize_weights_grouped(weight_fp32: torch.Tensor, group_size: int = 128):
+    """Group-wise variant: the reference's per-row formulas (python/quantize.py:73-109) applied to every
+    `group_size` consecutive columns.  [N,K] float32 -> (packed uint8 [N,K/2], scales f32 [N,K/G], zero_points f32 [N,K/G]).
+    The nibble order inside a row is unchanged, so `packed` differs from the per-row result only through the codes."""
+    assert weight_fp32.ndim == 2 and group_size % 8 == 0 and weight_fp32.shape[1] % group_size == 0
+    N, K = weight_fp32.shape
+    packed, scales, zps = quantize_weights(weight_fp32.reshape(N * (K // group_size), group_size))
+    return packed.reshape(N, K // 2), scales.reshape(N, K // group_size), zps.reshape(N, K // group_size)
+
+
+def dequantize_weights_grouped(packed_uint8: torch.Tensor, scales: torch.Tensor, zero_points: torch.Tensor):
+    """Inverse of quantize_weights_grouped: (q - zp[n, k // G]) * scale[n, k // G] -> [N,K] float32."""
+    N, Kh = packed_uint8.shape
+    ngrp = scales.shape[1]
+    out = dequantize_weights(packed_uint8.reshape(N * ngrp, Kh // ngrp), scales.reshape(-1), zero_points.reshape(-1))
+    return out.reshape(N, 2 * Kh)

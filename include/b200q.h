@@ -137,6 +137,25 @@ int b200q_linear_bias_fwd(const void* x, int x_dtype, const uint8_t* packed, con
                           void* ws, size_t ws_bytes, unsigned flags, void* stream,
                           const uint8_t* next_packed, size_t next_bytes);
 
+/* Group-wise scales (the reference's format is per-row only, python/quantize.py:73-80): one scale / zero
+ * point per `group_size` consecutive columns, scales / zps [N, K/group_size] f32 row-major, packed as above.  The groups are
+ * quantised with the per-row formulas on W viewed as [N K / group_size, group_size] (b200q_quantize_rows on that view gives
+ * exactly this layout; b200q_dequantize_rows inverts it).  This entry point is the format's reference-speed kernel
+ * (w = (q - zp) * s, fp32 multiply-add, the reference's arithmetic order); the decode / tcgen05 fast paths take per-row
+ * scales only.  group_size: a multiple of 8 that divides K. */
+int b200q_linear_groupwise_fwd(const void* x, int x_dtype, const uint8_t* packed, const float* scales, const float* zps,
+                               int64_t group_size, void* y, int y_dtype, int64_t M, int64_t N, int64_t K, void* stream);
+
+/* Fused gate + up pair of a gated MLP (`down(silu(gate(x)) * up(x))` in two launches):
+ *   h[m,f] = silu(x[m,:] . W[2f,:]) * (x[m,:] . W[2f+1,:])
+ * packed13 [2F,K/2], scales13 / zps13 [2F]: the rows of the gate and the up projection INTERLEAVED (2f: gate, 2f+1: up),
+ * h [M,F].  M <= 16: the decode kernel with the gate in its epilogue (both rows of a column live in one CTA); larger M:
+ * the tcgen05 GEMM with the gated epilogue.  Needs K % 128 == 0 and 16-byte aligned buffers.
+ * ws: >= b200q_linear_ws_bytes(M, 2F, K). */
+int b200q_linear_gated_fwd(const void* x, int x_dtype, const uint8_t* packed13, const float* scales13, const float* zps13,
+                           void* h, int h_dtype, int64_t M, int64_t F, int64_t K, void* ws, size_t ws_bytes, unsigned flags,
+                           void* stream, const uint8_t* next_packed, size_t next_bytes);
+
 /* Same with HOST activations: enqueues H2D copy of x (h_x -> the caller's device staging buffer d_x), the
  * fused dequantize-linear, and the D2H copy of the result (d_y -> h_y) on `stream`; h_x / h_y should be
  * pinned.  This is the call a host-resident caller of the reference's QuantizedLinear.forward maps to

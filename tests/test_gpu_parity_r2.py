@@ -190,3 +190,81 @@ def test_stacked_weight_cache_follows_load_state_dict_and_expert_replacement(ora
     for i in range(E):
         b.experts[i] = c.experts[i]
     assert torch.equal(b.forward_routed(x, logits), yc)
+
+
+# ---- fused gate + up pair; 8(f)4: group-wise scales ---------------------------------------------------
+@pytest.mark.parametrize("M", [1, 2, 5, 16, 40, 300])
+@pytest.mark.parametrize("d,F", [(256, 512), (1024, 2816), (4096, 11008)])
+def test_fused_gate_up_mlp(oracle, pkg, M, d, F):
+    """QuantizedGatedMLP = down(silu(gate(x)) * up(x)) in two launches, against the float64 oracle composed from the
+    reference's primitives, and against the three layers run one by one; state_dict compatible with three reference
+    QuantizedLinear modules."""
+    if (d, F) == (4096, 11008) and M not in (1, 16, 300):
+        pytest.skip("full Llama size: three batch sizes are enough")
+    torch.manual_seed(d + F)
+    gate, up, down = (torch.nn.Linear(d, F, bias=False), torch.nn.Linear(d, F, bias=False), torch.nn.Linear(F, d, bias=False))
+    mlp = pkg.QuantizedGatedMLP.from_linears(gate.cuda(), up.cuda(), down.cuda())
+    x = torch.randn(M, d)
+    q = lambda lin: oracle.quantize_weights(lin.weight.detach().cpu().numpy())
+    qg, qu, qd = q(gate), q(up), q(down)
+    g = oracle.reference_quantized_linear(x.numpy(), *qg, acc=np.float64)
+    u = oracle.reference_quantized_linear(x.numpy(), *qu, acc=np.float64)
+    h = (oracle.silu(g) * u).astype(np.float32)                     # the product keeps h in fp32 (the activations' dtype)
+    ref = oracle.reference_quantized_linear(h, *qd, acc=np.float64)
+    y = mlp(x.cuda()).cpu().numpy()
+    assert np.abs(y - ref).max() <= 2e-4 * np.abs(ref).max() + 1e-6
+    # the sub-modules still work on their own (strided views of the interleaved stack) and carry the reference's keys
+    y3 = mlp.down_proj(torch.nn.functional.silu(mlp.gate_proj(x.cuda())) * mlp.up_proj(x.cuda())).cpu().numpy()
+    assert np.abs(y3 - ref).max() <= 2e-4 * np.abs(ref).max() + 1e-6
+    assert sorted(mlp.state_dict()) == sorted(f"{m}.{b}" for m in ("gate_proj", "up_proj", "down_proj")
+                                                for b in ("packed_weights", "scales", "zero_points"))
+    assert np.array_equal(mlp.gate_proj.packed_weights.cpu().numpy(), qg[0]) and np.array_equal(mlp.up_proj.scales.cpu().numpy(), qu[1])
+    mlp2 = pkg.QuantizedGatedMLP(d, F).cuda()
+    mlp2.load_state_dict(mlp.state_dict())
+    assert torch.equal(mlp2(x.cuda()), mlp(x.cuda()))
+
+
+def test_fused_gate_up_nonfinite(oracle, pkg):
+    """NaN / Inf rows of x through the gated decode kernel: same pattern as the three separate layers."""
+    torch.manual_seed(0)
+    d, F = 512, 1024
+    mlp = pkg.QuantizedGatedMLP.from_linears(torch.nn.Linear(d, F, bias=False).cuda(), torch.nn.Linear(d, F, bias=False).cuda(),
+                                             torch.nn.Linear(F, d, bias=False).cuda())
+    x = torch.randn(4, d)
+    x[1, 3] = float("nan")
+    x[2, 7] = float("inf")
+    y = mlp(x.cuda()).cpu().numpy()
+    y3 = mlp.down_proj(torch.nn.functional.silu(mlp.gate_proj(x.cuda())) * mlp.up_proj(x.cuda())).cpu().numpy()
+    assert np.isnan(y[1]).all() and np.array_equal(np.isnan(y), np.isnan(y3)) and np.isfinite(y[[0, 3]]).all()
+
+
+@pytest.mark.parametrize("G", [32, 128])
+@pytest.mark.parametrize("M", [1, 8, 40])
+def test_groupwise_scales(oracle, pkg, G, M):
+    """One scale / zero point per G columns: packing / scales / zero points bit-exact with the reference's formulas
+    applied per group (the oracle's quantize_weights on W viewed as [N K/G, G]); forward against the float64 oracle;
+    finer groups follow an outlier-heavy weight matrix better than per-row scales."""
+    rng = np.random.default_rng(G + M)
+    N, K = 192, 1024
+    w = rng.standard_normal((N, K)).astype(np.float32)
+    w[:, ::97] *= 20.0                                              # outliers: what group-wise scales are for
+    p0, s0, z0 = oracle.quantize_weights(w.reshape(N * (K // G), G))
+    p, s, z = pkg.quantize_weights_grouped(torch.from_numpy(w).cuda(), G)
+    assert np.array_equal(p.cpu().numpy(), p0.reshape(N, K // 2))
+    assert np.array_equal(s.cpu().numpy(), s0.reshape(N, K // G)) and np.array_equal(z.cpu().numpy(), z0.reshape(N, K // G))
+    wd = oracle.dequantize_weights(p0, s0, z0).reshape(N, K)
+    assert np.array_equal(pkg.dequantize_weights_grouped(p, s, z).cpu().numpy(), wd)
+    lin = torch.nn.Linear(K, N, bias=True)
+    lin.weight.data = torch.from_numpy(w)
+    ql = pkg.QuantizedLinear.from_linear(lin.cuda(), group_size=G)
+    assert ql.scales.shape == (N, K // G) and "group_size" in repr(ql)
+    x = rng.standard_normal((M, K)).astype(np.float32)
+    ref = x.astype(np.float64) @ wd.astype(np.float64).T + lin.bias.detach().cpu().numpy().astype(np.float64)
+    y = ql(torch.from_numpy(x).cuda()).cpu().numpy()
+    assert np.abs(y - ref).max() <= 1e-4 * np.abs(ref).max()
+    ql2 = pkg.QuantizedLinear(K, N, bias=True, group_size=G).cuda()
+    ql2.load_state_dict(ql.state_dict())
+    assert torch.equal(ql2(torch.from_numpy(x).cuda()), ql(torch.from_numpy(x).cuda()))
+    # accuracy: group-wise error is well below the per-row error on this matrix
+    wr = oracle.dequantize_weights(*oracle.quantize_weights(w))
+    assert np.abs(wd - w).mean() < 0.5 * np.abs(wr - w).mean()
