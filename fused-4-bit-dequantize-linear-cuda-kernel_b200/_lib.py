@@ -59,6 +59,8 @@ SIGNATURES = {
     "b200q_ep_comm_destroy": (_i32, [_vp]),
     "b200q_ep_allgather_i32": (_i32, [_vp, _vp, _vp, _i64, _vp]),
     "b200q_ep_exchange": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "b200q_moe_decode_ws_bytes": (_sz, [_i64, _i32, _i32, _i64, _i64]),
+    "b200q_moe_decode_fwd": (_i32, [_vp, _i32, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _sz, _vp]),
     "b200q_moe_silu_mul": (_i32, [_vp, _i32, _i64, _i64, _vp, _vp]),
     "b200q_moe_combine": (_i32, [_vp, _i32, _vp, _vp, _i64, _i32, _i64, _vp, _i32, _vp]),
 }
@@ -416,6 +418,23 @@ def moe_grouped_fwd_mapped(xs: torch.Tensor, packed: torch.Tensor, scales: torch
                                                ws.numel() if ws is not None else 0, stream_ptr(xs.device)),
               "b200q_moe_grouped_fwd_mapped")
     return y
+
+
+def moe_decode_fwd(x: torch.Tensor, logits: torch.Tensor, k: int, w13, w2) -> torch.Tensor:
+    """Whole routed gated layer for T <= 16 tokens in one C call: w13 = (packed [E,2F,d/2] interleaved, scales, zps),
+    w2 = (packed [E,d,F/2], scales, zps) -> out [T,d] f32."""
+    lib = load()
+    T, d = x.shape
+    E, F = w13[0].shape[0], w13[0].shape[1] // 2
+    dev = x.device
+    with torch.cuda.device(dev):
+        out = torch.empty((T, d), dtype=torch.float32, device=dev)
+        nb = lib.b200q_moe_decode_ws_bytes(T, E, k, d, F)
+        ws = workspace(dev, nb, "moe_decode")
+        check(lib.b200q_moe_decode_fwd(x.data_ptr(), dtype_code(x), logits.data_ptr(), T, E, k, w13[0].data_ptr(), w13[1].data_ptr(),
+                                       w13[2].data_ptr(), w2[0].data_ptr(), w2[1].data_ptr(), w2[2].data_ptr(), d, F,
+                                       out.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr(dev)), "b200q_moe_decode_fwd")
+    return out
 
 
 def moe_silu_mul(gu: torch.Tensor) -> torch.Tensor:

@@ -155,6 +155,72 @@ int b200q_linear_gated_fwd(const void* x, int x_dtype, const uint8_t* packed13, 
     return set_error(B200Q_EINVAL, "linear_gated_fwd: needs K %% 128 == 0 (otherwise: b200q_linear_fwd on the concatenated rows, then b200q_moe_silu_mul)");
 }
 
+// ---- MoE decode (T <= 16 tokens): the whole routed gated layer behind one C call --------------------------------
+namespace {
+inline size_t up256(size_t v) { return (v + 255) / 256 * 256; }
+struct DecodeWs {
+    size_t idx, wts, counts, offsets, sorted_slot, inv_perm, perm_ws, xs, h, y, total;
+};
+DecodeWs decode_ws(int64_t T, int E, int k, int64_t d, int64_t F, int esz) {
+    DecodeWs w{};
+    const size_t A = (size_t)T * k;
+    size_t o = 0;
+    w.idx = o; o += up256(A * 4);
+    w.wts = o; o += up256(A * 4);
+    w.counts = o; o += up256((size_t)E * 4);
+    w.offsets = o; o += up256((size_t)(E + 1) * 4);
+    w.sorted_slot = o; o += up256(A * 4);
+    w.inv_perm = o; o += up256(A * 4);
+    w.perm_ws = o; o += up256(b200q_moe_permute_ws_bytes(T, E, k));
+    w.xs = o; o += up256(A * d * esz);
+    w.h = o; o += up256(A * F * esz);
+    w.y = o; o += up256(A * d * esz);
+    w.total = o;
+    return w;
+}
+}  // namespace
+
+size_t b200q_moe_decode_ws_bytes(int64_t T, int E, int k, int64_t d, int64_t F) {
+    if (T <= 0 || E <= 0 || k <= 0 || d <= 0 || F <= 0) return 0;
+    return decode_ws(T, E, k, d, F, 4).total;
+}
+
+int b200q_moe_decode_fwd(const void* x, int x_dtype, const float* logits, int64_t T, int E, int k,
+                         const uint8_t* packed13, const float* scales13, const float* zps13,
+                         const uint8_t* packed2, const float* scales2, const float* zps2, int64_t d, int64_t F,
+                         float* out, void* ws, size_t ws_bytes, void* stream) {
+    if (T <= 0 || T > 16 || E <= 0 || k <= 0 || k > E || d <= 0 || F <= 0) return set_error(B200Q_EINVAL, "moe_decode_fwd: need 1 <= T <= 16, 1 <= k <= E, d, F > 0");
+    if (!elem_size(x_dtype)) return set_error(B200Q_EINVAL, "moe_decode_fwd: unsupported dtype");
+    if (!x || !logits || !packed13 || !scales13 || !zps13 || !packed2 || !scales2 || !zps2 || !out || !ws) return set_error(B200Q_EINVAL, "moe_decode_fwd: null pointer");
+    const DecodeWs w = decode_ws(T, E, k, d, F, elem_size(x_dtype));
+    if (ws_bytes < w.total) return set_error(B200Q_EWORKSPACE, "moe_decode_fwd: workspace too small (%zu < %zu)", ws_bytes, w.total);
+    if (!aligned(x, 16) || !aligned(ws, 256) || !aligned(packed13, 16) || !aligned(packed2, 16)) return set_error(B200Q_EALIGN, "moe_decode_fwd: x / packed must be 16-byte, ws 256-byte aligned");
+    DeviceInfo dv;
+    if (int rc = current_device(&dv)) return rc;
+    // both expert GEMVs run on the resident decode kernel, grouped over the experts (device-side row offsets)
+    if (!gemv_dec_supported(dv, T, 2 * F, d, 1) || !gemv_dec_supported(dv, T, d, F, 0))
+        return set_error(B200Q_EINVAL, "moe_decode_fwd: shape not supported by the decode kernel (d, F multiples of 256, <= 16384)");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    uint8_t* base = static_cast<uint8_t*>(ws);
+    int32_t* idx = reinterpret_cast<int32_t*>(base + w.idx);
+    float* wts = reinterpret_cast<float*>(base + w.wts);
+    int32_t* counts = reinterpret_cast<int32_t*>(base + w.counts);
+    int32_t* offsets = reinterpret_cast<int32_t*>(base + w.offsets);
+    int32_t* sorted_slot = reinterpret_cast<int32_t*>(base + w.sorted_slot);
+    int32_t* inv_perm = reinterpret_cast<int32_t*>(base + w.inv_perm);
+    void* xs = base + w.xs;
+    void* h = base + w.h;
+    void* y = base + w.y;
+    if (int rc = b200q_moe_route(logits, nullptr, T, E, k, idx, wts, counts, offsets, sorted_slot, inv_perm, base + w.perm_ws,
+                                 b200q_moe_permute_ws_bytes(T, E, k), stream)) return rc;
+    if (int rc = b200q_moe_gather_rows(x, x_dtype, sorted_slot, T * k, k, d, xs, stream)) return rc;
+    if (int rc = launch_gemv_dec(dv, xs, x_dtype, packed13, scales13, zps13, nullptr, h, x_dtype, T, 2 * F, d, B200Q_FLAG_STATIC_WEIGHTS, st,
+                                 nullptr, 0, 1, offsets, E)) return rc;
+    if (int rc = launch_gemv_dec(dv, h, x_dtype, packed2, scales2, zps2, nullptr, y, x_dtype, T, d, F, B200Q_FLAG_STATIC_WEIGHTS, st,
+                                 nullptr, 0, 0, offsets, E)) return rc;
+    return b200q_moe_combine(y, x_dtype, inv_perm, wts, T, k, d, out, B200Q_F32, stream);
+}
+
 int b200q_linear_fwd_host(const void* h_x, int x_dtype, void* d_x, const uint8_t* packed, const float* scales,
                           const float* zps, void* d_y, void* h_y, int y_dtype, int64_t M, int64_t N, int64_t K,
                           void* ws, size_t ws_bytes, unsigned flags, void* stream) {

@@ -81,7 +81,6 @@ struct DecParams {
     unsigned int next_chunk;         // next_bytes / gridDim.x
     int x_dtype, y_dtype;
     int M, N, K;
-    int rows_q, rows_rem;            // CTA b owns rows_q (+1 if b < rows_rem) rows
     int npairs;                      // ceil(K / 256)
     int nbars;                       // pair groups (barriers) per tile
     int chunk;                       // pairs per group
@@ -95,6 +94,11 @@ struct DecParams {
     int early_tiles;                 // a + 10 b: a tiles requested before griddepcontrol.wait, b more behind the x loads
     int pf_mode;                     // next-layer L2 prefetch: 1 behind the last own request, 2 before the own requests, 3 after the operand build
     int gated;                       // 1: rows 2f / 2f+1 are the gate / up projection of column f; y is h [M, N/2] = silu(gate) * up
+    // work items: blockIdx.x = (expert e, row chunk c, CTA b of the chunk).  Row chunks let shapes whose rows do not fit
+    // in the shared memory of ONE wave of CTAs (Mixtral's 14336-wide projections) run as a few waves of the same kernel.
+    int grid_g, nchunks, chunk_rows; // CTAs per chunk, chunks per expert, weight rows per chunk (a multiple of the row unit)
+    const int32_t* offsets;          // grouped (MoE decode): rows [offsets[e], offsets[e+1]) of x / y belong to expert e of
+                                     //   packed [E, N, K/2] (device memory; experts without rows exit at once); else nullptr
     int debug;                       // B200Q_PROF builds: record phase stamps
 };
 
@@ -204,11 +208,28 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_dec_kernel(const __grid_constant
     const int g = lane >> 2, t = lane & 3;
 
     B200Q_STAMP(0);
-    const int b = (int)blockIdx.x;
+    // work item -> (expert, row chunk, CTA of the chunk)
+    const int b = (int)(blockIdx.x % (unsigned)p.grid_g);
+    const int chunk_i = (int)((blockIdx.x / (unsigned)p.grid_g) % (unsigned)p.nchunks);
+    const int expert = (int)(blockIdx.x / (unsigned)(p.grid_g * p.nchunks));
+    int Mrows = p.M;                                          // batch rows of this work item
+    int64_t xrow0 = 0;                                        // ... and where they start in x / y
+    if (p.offsets) {
+        const int lo = p.offsets[expert], hi = p.offsets[expert + 1];
+        Mrows = min(hi - lo, 16);
+        xrow0 = lo;
+        if (Mrows <= 0) return;                               // uniform: this expert has no tokens
+    }
     // (gated: rows are dealt out in gate / up pairs, so both projections of an output column meet in one CTA)
     const int unit = p.gated ? 2 : 1;
-    const int r0 = unit * (b * p.rows_q + min(b, p.rows_rem));
-    const int nrows = unit * (p.rows_q + (b < p.rows_rem ? 1 : 0));
+    const int chunk_start = chunk_i * p.chunk_rows;
+    const int chunk_units = (min(p.chunk_rows, p.N - chunk_start)) / unit;
+    const int cq = chunk_units / p.grid_g, crem = chunk_units % p.grid_g;
+    const int orow0 = chunk_start + unit * (b * cq + min(b, crem));      // first row of this CTA inside the expert's N rows
+    const int nrows = unit * (cq + (b < crem ? 1 : 0));
+    if (nrows <= 0) return;                                   // uniform
+    const int r0 = expert * p.N + orow0;                      // ... and in the stacked weight tensor [E N, K/2]
+    const int npasses = (Mrows + 2 * NT - 1) / (2 * NT);
     const int ntma = (nrows + TILE_ROWS - 1) / TILE_ROWS;    // tiles with weight rows
     // One more row: a row of bytes 0x11 (q_lo = q_hi = 1) behind the last weight row makes the tensor cores deliver
     // sum_k X (the zero-point term) as one more output row -- no extra arithmetic in the operand build.
@@ -229,7 +250,7 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_dec_kernel(const __grid_constant
         *s_flag = 0u;
     }
     if (!p.slots)                                            // pipelined reduction: integer atomics into a zeroed accumulator
-        for (int i = tid; i < p.npasses * p.ntiles_max * NT * 128; i += NTHR) fin[i] = 0;
+        for (int i = tid; i < npasses * p.ntiles_max * NT * 128; i += NTHR) fin[i] = 0;
     __syncthreads();
     pdl_launch_dependents();
     B200Q_STAMP(1);
@@ -299,7 +320,7 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_dec_kernel(const __grid_constant
     float xv[GPW2][MB][8];
     uint32_t bf[GPW2][4][NT][4];                              // per 32-byte step: {e-word b0, e-word b1, z-word b0, z-word b1}
 #pragma unroll 1
-    for (int pass = 0; pass < p.npasses; ++pass) {
+    for (int pass = 0; pass < npasses; ++pass) {
         const int m0 = pass * MB;
         // ---- x of this pass: this warp's columns only, all loads in flight at once
 #pragma unroll
@@ -309,7 +330,7 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_dec_kernel(const __grid_constant
             for (int hr = 0; hr < MB; ++hr) {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) xv[q][hr][e] = 0.0f;
-                if (col < p.K && m0 + hr < p.M) load8f(p.x, p.x_dtype, (int64_t)(m0 + hr) * p.K + col, xv[q][hr]);
+                if (col < p.K && m0 + hr < Mrows) load8f(p.x, p.x_dtype, (xrow0 + m0 + hr) * p.K + col, xv[q][hr]);
             }
         }
         if (pass == 0 && issuer && early < mid) {
@@ -323,7 +344,7 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_dec_kernel(const __grid_constant
         // as an exponent field of 0xff
 #pragma unroll
         for (int hr = 0; hr < MB; ++hr) {
-            if (m0 + hr < p.M) {                              // uniform
+            if (m0 + hr < Mrows) {                            // uniform
                 unsigned int u = 0u;
 #pragma unroll
                 for (int q = 0; q < GPW2; ++q)
@@ -337,7 +358,7 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_dec_kernel(const __grid_constant
         if (pass == 0) B200Q_STAMP(4);
 #pragma unroll
         for (int hr = 0; hr < MB; ++hr) {
-            if (m0 + hr < p.M) {                              // uniform
+            if (m0 + hr < Mrows) {                            // uniform
                 const unsigned int u = __reduce_max_sync(0xffffffffu, lane < NW ? s_amax[((pass & 1) * 4 + hr) * NW + lane] : 0u);
                 if (u >= 0x7f800000u) {
                     if (tid == 0) atomicOr(s_flag, 1u << (m0 + hr));
@@ -360,7 +381,7 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_dec_kernel(const __grid_constant
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {                  // the two batch rows of this n-tile: independent chains
                     const int hr = 2 * nt + hh;
-                    if (m0 + hr >= p.M) continue;                 // uniform: no such batch row (odd M)
+                    if (m0 + hr >= Mrows) continue;               // uniform: no such batch row (odd M)
                     const float up = __uint_as_float((uint32_t)(127 + ex[hr]) << 23), up16 = up * 0.0625f;
                     uint32_t D[8];
 #pragma unroll
@@ -383,7 +404,7 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_dec_kernel(const __grid_constant
                     sts32(d23 + 256, __byte_perm(e2, e3, 0x7632)); sts32(d23 + 264, __byte_perm(o2, o3, 0x7632));
                 }
                 __syncwarp();
-                if (m0 + 2 * nt + hsel < p.M) {                   // this lane's mma column belongs to a batch row that exists
+                if (m0 + 2 * nt + hsel < Mrows) {                 // this lane's mma column belongs to a batch row that exists
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         const uint4 v = lds128(ssrc + (uint32_t)(c * 64));
@@ -470,10 +491,10 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_dec_kernel(const __grid_constant
     if (p.slots) {
         // fold the 16 warp slots of every tile (integer adds: exact, order independent)
         // (M = 1: only mma columns 0..3 are live, i.e. the words of lane quads t = 0, 1)
-        const int sh = p.M == 1 ? 6 : 7;
+        const int sh = Mrows == 1 ? 6 : 7;
         for (int v = tid; v < (ntl << sh); v += NTHR) {
             const int tile = v >> sh, rem = v & ((1 << sh) - 1);
-            const int word = p.M == 1 ? ((rem >> 3) * 16 + (rem & 7)) : rem;
+            const int word = Mrows == 1 ? ((rem >> 3) * 16 + (rem & 7)) : rem;
             const uint32_t src = red + (uint32_t)((tile * NW) * 512 + word * 4);
             int s = 0;
 #pragma unroll
@@ -491,12 +512,12 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_dec_kernel(const __grid_constant
     auto word_of = [](int r, int col) { return (((r & 7) * 4 + (col >> 1)) * 4) + ((r >> 3) * 2 + (col & 1)); };
     {
         const bool mine = tid < nrows;
-        const int ti = tid >> 4, r = tid & 15, row = r0 + tid;
+        const int ti = tid >> 4, r = tid & 15, row = orow0 + tid;      // output column (row of the expert's weight matrix)
         const float sc = pre_sc, zp = pre_zp;
         const float bias = (mine && p.bias) ? __ldg(p.bias + row) : 0.0f;
         const int zi = __float2int_rn(zp);
         const bool zint = (float)zi == zp && zi >= -32768 && zi <= 32767;
-        for (int m = 0; m < p.M; ++m) {
+        for (int m = 0; m < Mrows; ++m) {
             if ((flagged >> m) & 1u) continue;               // uniform
             float v = 0.0f;
             if (mine) {
@@ -522,9 +543,9 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_dec_kernel(const __grid_constant
             if (p.gated) {
                 // fused gate + up pair: the even row (gate) fetches its neighbour's value (up) and writes silu(gate) * up
                 const float u = __shfl_down_sync(0xffffffffu, v, 1);
-                if (mine && !(tid & 1)) store_out(p.y, p.y_dtype, (int64_t)m * (p.N >> 1) + (row >> 1), v / (1.0f + __expf(-v)) * u);
+                if (mine && !(tid & 1)) store_out(p.y, p.y_dtype, (xrow0 + m) * (p.N >> 1) + (row >> 1), v / (1.0f + __expf(-v)) * u);
             } else if (mine) {
-                store_out(p.y, p.y_dtype, (int64_t)m * p.N + row, v + bias);
+                store_out(p.y, p.y_dtype, (xrow0 + m) * p.N + row, v + bias);
             }
         }
     }
@@ -532,31 +553,31 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_dec_kernel(const __grid_constant
     // non-finite values propagate as in F.linear; one warp per output, weights re-read from global memory
     if (flagged) {
         const int64_t row_bytes = p.K >> 1;
-        for (int m = 0; m < p.M; ++m) {
+        for (int m = 0; m < Mrows; ++m) {
             if (!((flagged >> m) & 1u)) continue;
-            auto ref_row = [&](int row) {
+            auto ref_row = [&](int row) {                     // row: index in the stacked weight tensor
                 const float sc = __ldg(p.scales + row), zp = __ldg(p.zps + row);
                 const uint8_t* wr = p.packed + (int64_t)row * row_bytes;
                 float acc = 0.0f;
                 for (int kb = lane; kb < row_bytes; kb += 32) {
                     const unsigned int byte = wr[kb];
                     const float w0 = ((float)(byte & 15u) - zp) * sc, w1 = ((float)(byte >> 4) - zp) * sc;
-                    acc = fmaf(w0, load1f(p.x, p.x_dtype, (int64_t)m * p.K + 2 * kb), acc);
-                    acc = fmaf(w1, load1f(p.x, p.x_dtype, (int64_t)m * p.K + 2 * kb + 1), acc);
+                    acc = fmaf(w0, load1f(p.x, p.x_dtype, (xrow0 + m) * p.K + 2 * kb), acc);
+                    acc = fmaf(w1, load1f(p.x, p.x_dtype, (xrow0 + m) * p.K + 2 * kb + 1), acc);
                 }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
                 return acc;
             };
             for (int rc = unit * warp; rc < nrows; rc += unit * NW) {
-                const int row = r0 + rc;
-                float acc = ref_row(row);
+                const int row = orow0 + rc;
+                float acc = ref_row(r0 + rc);
                 if (p.gated) {
-                    const float up = ref_row(row + 1);
-                    if (lane == 0) store_out(p.y, p.y_dtype, (int64_t)m * (p.N >> 1) + (row >> 1), acc / (1.0f + __expf(-acc)) * up);
+                    const float up = ref_row(r0 + rc + 1);
+                    if (lane == 0) store_out(p.y, p.y_dtype, (xrow0 + m) * (p.N >> 1) + (row >> 1), acc / (1.0f + __expf(-acc)) * up);
                 } else if (lane == 0) {
                     if (p.bias) acc += __ldg(p.bias + row);
-                    store_out(p.y, p.y_dtype, (int64_t)m * p.N + row, acc);
+                    store_out(p.y, p.y_dtype, (xrow0 + m) * p.N + row, acc);
                 }
             }
         }
@@ -565,45 +586,49 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_dec_kernel(const __grid_constant
 }
 
 struct DecPlan {
-    int grid, gpw2, nt, npasses, ntiles, npairs, nbars, chunk, tile_bytes, tile_off, rows_q, rows_rem;
+    int grid_g, nchunks, chunk_rows, gpw2, nt, npasses, ntiles, npairs, nbars, chunk, tile_bytes, tile_off;
     int red_off, fin_off, slots;
     size_t smem;
 };
 
+// M: (largest) number of batch rows of a work item; N: weight rows (per expert)
 bool plan_dec(int sm_count, int max_smem, int64_t M, int64_t N, int64_t K, DecPlan* c, int gated = 0) {
     if (M < 1 || M > 16 || K < 256 || K % 256 != 0 || K > 16384 || N < 1 || N > 0x7fffffff) return false;
     if (gated && (N & 1)) return false;
     const int unit = gated ? 2 : 1;                                // rows are dealt out in gate / up pairs
-    N /= unit;
     c->npairs = (int)(K / 256);
     c->gpw2 = (c->npairs + NW - 1) / NW;                          // <= 4
     c->nt = (M >= 3 && c->gpw2 <= 2) ? 2 : 1;                     // B fragments: 16 gpw2 nt registers
     const int mb = 2 * c->nt;
     c->npasses = (int)((M + mb - 1) / mb);
-    int cap = tuning().gemv_ctas > 0 ? tuning().gemv_ctas : sm_count;
-    if (cap > sm_count) cap = sm_count;
-    int64_t grid = (N * unit + TILE_ROWS - 2 - (unit - 1)) / (TILE_ROWS - unit);       // few rows: at most 15 (14) per CTA (+ the 0x11 row = one tile)
-    if (grid > cap) grid = cap;
-    c->grid = (int)grid;
-    c->rows_q = (int)(N / grid); c->rows_rem = (int)(N % grid);
-    const int br = unit * (c->rows_q + (c->rows_rem ? 1 : 0));
-    if (br > 256) return false;                                    // one output row per thread in the epilogue
-    c->ntiles = (br + 1 + TILE_ROWS - 1) / TILE_ROWS;             // one more row: the 0x11 row that yields sum_k X
     c->nbars = c->gpw2;
     c->chunk = (c->npairs + c->nbars - 1) / c->nbars;
-    if (c->ntiles * c->nbars > MAX_BARS) return false;
     c->tile_bytes = c->nbars * c->chunk * PAIR_BYTES;             // >= npairs * 2 KB: a 3-D box always has room
-    const int fin_bytes = c->npasses * c->ntiles * c->nt * 512;
-    const int red_bytes = 2 * NW * WARP_RED;
-    const int slot_bytes = (c->ntiles > 4 ? c->ntiles : 4) * NW * 512;      // >= 4 slots per warp: its exchange space
-    // (1) single pass of <= 2 batch rows: one slot per (tile, warp); (2) double-buffered pipelined reduction
-    for (int form = (c->nt == 1 && c->npasses == 1 && tuning().gemv_slots != 0) ? 0 : 1; form < 2; ++form) {
-        c->slots = form == 0;
-        c->red_off = OFF_DYN;
-        c->fin_off = c->red_off + (c->slots ? slot_bytes : red_bytes);
-        c->tile_off = (c->fin_off + fin_bytes + 1023) / 1024 * 1024;
-        c->smem = (size_t)c->tile_off + (size_t)c->ntiles * c->tile_bytes;
-        if (c->smem <= (size_t)max_smem) return true;
+    int cap = tuning().gemv_ctas > 0 ? tuning().gemv_ctas : sm_count;
+    if (cap > sm_count) cap = sm_count;
+    // row chunks: the fewest waves of CTAs whose rows fit in shared memory (one for the Llama shapes)
+    for (int nch = 1; nch <= 16; ++nch) {
+        const int64_t units = (N / unit + nch - 1) / nch;        // row units per chunk
+        int64_t g = (units * unit + TILE_ROWS - 2 - (unit - 1)) / (TILE_ROWS - unit);       // few rows: at most 15 (14) per CTA (+ the 0x11 row = one tile)
+        if (g > cap) g = cap;
+        if (g < 1) g = 1;
+        const int br = unit * (int)((units + g - 1) / g);         // most rows of a CTA
+        if (br > 256) continue;                                    // one output row per thread in the epilogue
+        c->grid_g = (int)g; c->nchunks = nch; c->chunk_rows = (int)(units * unit);
+        c->ntiles = (br + 1 + TILE_ROWS - 1) / TILE_ROWS;         // one more row: the 0x11 row that yields sum_k X
+        if (c->ntiles * c->nbars > MAX_BARS) continue;
+        const int fin_bytes = c->npasses * c->ntiles * c->nt * 512;
+        const int red_bytes = 2 * NW * WARP_RED;
+        const int slot_bytes = (c->ntiles > 4 ? c->ntiles : 4) * NW * 512;      // >= 4 slots per warp: its exchange space
+        // (1) single pass of <= 2 batch rows: one slot per (tile, warp); (2) double-buffered pipelined reduction
+        for (int form = (c->nt == 1 && c->npasses == 1 && tuning().gemv_slots != 0) ? 0 : 1; form < 2; ++form) {
+            c->slots = form == 0;
+            c->red_off = OFF_DYN;
+            c->fin_off = c->red_off + (c->slots ? slot_bytes : red_bytes);
+            c->tile_off = (c->fin_off + fin_bytes + 1023) / 1024 * 1024;
+            c->smem = (size_t)c->tile_off + (size_t)c->ntiles * c->tile_bytes;
+            if (c->smem <= (size_t)max_smem) return true;
+        }
     }
     return false;
 }
@@ -656,7 +681,7 @@ int weight_map(const uint8_t* packed, int64_t N, int64_t K, int chunk, CUtensorM
 }
 
 template <int GPW2, int NT>
-int launch_dec_inst(const DecPlan& c, const CUtensorMap& map, const DecParams& p, bool pdl, cudaStream_t st) {
+int launch_dec_inst(const DecPlan& c, int grid_total, const CUtensorMap& map, const DecParams& p, bool pdl, cudaStream_t st) {
     auto kfn = gemv_dec_kernel<GPW2, NT>;
     static thread_local int attr_dev_smem[64] = {0};
     int dev = 0;
@@ -666,7 +691,7 @@ int launch_dec_inst(const DecPlan& c, const CUtensorMap& map, const DecParams& p
         attr_dev_smem[dev] = (int)c.smem;
     }
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)c.grid);
+    cfg.gridDim = dim3((unsigned)grid_total);
     cfg.blockDim = dim3(NTHR);
     cfg.dynamicSmemBytes = c.smem;
     cfg.stream = st;
@@ -691,8 +716,10 @@ bool gemv_dec_supported(const DeviceInfo& dev, int64_t M, int64_t N, int64_t K, 
 
 int launch_gemv_dec(const DeviceInfo& dev, const void* x, int x_dtype, const uint8_t* packed, const float* scales,
                     const float* zps, const float* bias, void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
-                    unsigned flags, cudaStream_t st, const uint8_t* next_packed, size_t next_bytes, int gated) {
+                    unsigned flags, cudaStream_t st, const uint8_t* next_packed, size_t next_bytes, int gated,
+                    const int32_t* offsets, int n_experts) {
     DecPlan c;
+    if (n_experts < 1) n_experts = 1;
     if (!plan_dec(dev.sm_count, dev.max_smem_optin, M, N, K, &c, gated))
         return set_error(B200Q_EINVAL, "gemv_dec: unsupported shape M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
     if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(packed) & 15))
@@ -702,7 +729,8 @@ int launch_gemv_dec(const DeviceInfo& dev, const void* x, int x_dtype, const uin
     p.gated = gated;
     p.x_dtype = x_dtype; p.y_dtype = y_dtype;
     p.M = (int)M; p.N = (int)N; p.K = (int)K;
-    p.rows_q = c.rows_q; p.rows_rem = c.rows_rem;
+    p.grid_g = c.grid_g; p.nchunks = c.nchunks; p.chunk_rows = c.chunk_rows;
+    p.offsets = offsets;
     p.npairs = c.npairs; p.nbars = c.nbars; p.chunk = c.chunk;
     p.ntiles_max = c.ntiles; p.tile_bytes = c.tile_bytes; p.tile_off = c.tile_off; p.npasses = c.npasses;
     p.red_off = c.red_off; p.fin_off = c.fin_off; p.slots = c.slots;
@@ -711,13 +739,15 @@ int launch_gemv_dec(const DeviceInfo& dev, const void* x, int x_dtype, const uin
     p.next_packed = next_packed;
     p.pf_mode = tuning().gemv_pf;
     p.next_bytes = (tuning().gemv_pf != 0 && next_packed && (reinterpret_cast<uintptr_t>(next_packed) & 15) == 0) ? next_bytes : 0;
-    p.next_chunk = (unsigned int)(p.next_bytes / (unsigned long long)c.grid);
+    const int grid_total = c.grid_g * c.nchunks * n_experts;
+    if (offsets) p.next_bytes = 0;
+    p.next_chunk = (unsigned int)(p.next_bytes / (unsigned long long)grid_total);
     p.debug = tuning().gemv_debug > 0 ? tuning().gemv_debug : 0;
     CUtensorMap map;
-    if (int rc = weight_map(packed, N, K, c.chunk, &map)) return rc;
+    if (int rc = weight_map(packed, N * n_experts, K, c.chunk, &map)) return rc;
     const bool pdl = tuning().gemv_pdl != 0;
 #define B200Q_DEC_CASE(GPW2_, NT_) \
-    if (c.gpw2 == GPW2_ && c.nt == NT_) return launch_dec_inst<GPW2_, NT_>(c, map, p, pdl, st);
+    if (c.gpw2 == GPW2_ && c.nt == NT_) return launch_dec_inst<GPW2_, NT_>(c, grid_total, map, p, pdl, st);
     B200Q_DEC_CASE(1, 1) B200Q_DEC_CASE(2, 1) B200Q_DEC_CASE(3, 1) B200Q_DEC_CASE(4, 1)
     B200Q_DEC_CASE(1, 2) B200Q_DEC_CASE(2, 2)
 #undef B200Q_DEC_CASE

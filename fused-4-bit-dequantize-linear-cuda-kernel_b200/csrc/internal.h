@@ -94,12 +94,14 @@ int launch_zero_rows_outside(void* y, int y_dtype, int64_t R, int64_t N, const i
 // device-addressable pinned host memory -> device buffer, `bytes` % 16 == 0 (one small kernel instead of a copy node)
 int launch_stage_host(const void* src_mapped, void* dst, size_t bytes, cudaStream_t st);
 
-// decode GEMV with the CTA's rows resident in shared memory (gemv_dec.cu): M <= 16, K % 128 == 0, K <= 16384 and
-// ceil(N / SMs) rows x K / 2 bytes fit in shared memory; no workspace; optional bias [N] f32
+// decode GEMV with the CTA's rows resident in shared memory (gemv_dec.cu): M <= 16, K % 256 == 0, K <= 16384; rows that do not
+// fit in one wave of CTAs run as a few waves (row chunks); no workspace; optional bias [N] f32; gated: fused SiLU-gate of
+// interleaved gate / up rows; offsets != nullptr: grouped over n_experts experts (M = the largest group, <= 16)
 bool gemv_dec_supported(const DeviceInfo& dev, int64_t M, int64_t N, int64_t K, int gated = 0);
 int launch_gemv_dec(const DeviceInfo& dev, const void* x, int x_dtype, const uint8_t* packed, const float* scales,
                     const float* zps, const float* bias, void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
-                    unsigned flags, cudaStream_t st, const uint8_t* next_packed, size_t next_bytes, int gated = 0);
+                    unsigned flags, cudaStream_t st, const uint8_t* next_packed, size_t next_bytes, int gated = 0,
+                    const int32_t* offsets = nullptr, int n_experts = 1);
 
 // prefill / grouped path on tcgen05 tensor cores (M >= 17 rows, K % 128 == 0, N % 16 == 0).
 // starts == nullptr: plain linear; else grouped over E experts (packed [E,N,K/2]).

@@ -199,6 +199,11 @@ class QuantizedMoE(nn.Module):
         reference's combine (routing.py:186-187 multiplies by fp32 routing weights).
         """
         _lib.require_cuda(x, "x")
+        if (routing is None and self.fused_gate and x.shape[0] <= 16 and self.hidden_dim % 256 == 0
+                and self.ffn_dim % 256 == 0 and max(self.hidden_dim, self.ffn_dim) <= 16384):
+            # decode-sized call: the whole layer behind one C call, both expert GEMVs grouped on the resident decode kernel
+            w13, w2 = self.stacked_weights()
+            return _lib.moe_decode_fwd(x.contiguous(), router_logits.to(torch.float32).contiguous(), top_k, w13, w2)
         dr = routing if routing is not None else route(router_logits, top_k)
         return self.forward_dispatched(x, dr)
 

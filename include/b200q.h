@@ -251,6 +251,19 @@ int b200q_moe_grouped_fwd_mapped(const void* xs, int x_dtype, const uint8_t* pac
                                  const int32_t* range_expert, int n_ranges, int n_experts, int gated, void* y, int y_dtype,
                                  int64_t R, int64_t N, int64_t K, void* ws, size_t ws_bytes, void* stream);
 
+/* The whole routed gated layer for DECODE-sized calls (T <= 16 tokens) behind one C call:
+ *   out[t,:] = sum_s p[t,s] * w2_e( silu(w1_e x[t,:]) * (w3_e x[t,:]) ),  e = expert of slot s of token t  (fp32)
+ * = b200q_moe_route, b200q_moe_gather_rows, the fused gate / up GEMV and the down GEMV -- both grouped over the experts
+ * with device-side row offsets on the resident decode kernel (experts without tokens exit at once; HBM-bound: only
+ * the experts that were hit are read) -- and b200q_moe_combine.  packed13 [E,2F,d/2] (w1 / w3 interleaved), packed2
+ * [E,d,F/2]; d and F multiples of 256.  ws: >= b200q_moe_decode_ws_bytes, 256-byte aligned (no zero-fill needed).
+ * B200Q_EINVAL when the shape does not fit the decode kernel (use the grouped tcgen05 path then). */
+size_t b200q_moe_decode_ws_bytes(int64_t T, int E, int k, int64_t d, int64_t F);
+int b200q_moe_decode_fwd(const void* x, int x_dtype, const float* logits, int64_t T, int E, int k,
+                         const uint8_t* packed13, const float* scales13, const float* zps13,
+                         const uint8_t* packed2, const float* scales2, const float* zps2, int64_t d, int64_t F,
+                         float* out, void* ws, size_t ws_bytes, void* stream);
+
 /* out[t,:] = sum_s weights[t,s] * y[inv_perm[t*k+s], :]   (routing.py:175-187). */
 int b200q_moe_combine(const void* y, int dtype, const int32_t* inv_perm, const float* weights,
                       int64_t T, int k, int64_t F, void* out, int out_dtype, void* stream);

@@ -99,7 +99,7 @@ def test_llama_mixtral_decode_shapes(oracle, K, N, M):
     scale = np.abs(ref).max()
     print(f"K={K} N={N} M={M}: max abs err {err:.3e}, |y|max {scale:.2f}, rel {err / scale:.2e}")
     # exact-integer IMMA path (error = final fp32 rounding) for M <= 16 on the Llama shapes and M <= 8 on Mixtral's
-    # (ring kernel); Mixtral M = 16: tcgen05 path, fp16 hi/lo split of x, fp32 accumulation over up to 14336 terms
+    # (resident decode kernel, row chunks); Mixtral M = 16: tcgen05 path, fp16 hi/lo split of x, fp32 accumulation over up to 14336 terms
     assert err < 1e-2 and err / scale < (2e-5 if (M <= 8 or 14336 not in (K, N)) else 1e-4)
     # linearity: f(2x) == 2 f(x) exactly (power-of-two scaling commutes with every rounding step)
     y2 = ext.forward(cuda(2 * x), P, S, Z).cpu().numpy()
@@ -230,11 +230,13 @@ def test_forward_host_pinned(oracle, pkg):
 # ---- decode kernels: CTA-resident (gemv_dec.cu, force_path 6) and ring (gemv.cu, force_path 2, M <= 8) ----------
 @pytest.mark.parametrize("M", [1, 2, 3, 4, 5, 8, 9, 13, 16])
 @pytest.mark.parametrize("N,K", [(1, 128), (7, 128), (9, 256), (16, 384), (200, 1024), (2371, 2048), (11008, 4096),
-                                 (3000, 6144), (4096, 11008), (1500, 8192), (600, 16384)])
+                                 (3000, 6144), (4096, 11008), (1500, 8192), (600, 16384), (14336, 4096), (4096, 14336),
+                                 (5000, 8192)])
 def test_resident_decode_kernel_edge_shapes(oracle, pkg, M, N, K):
     """Ragged row counts (fewer tiles than SMs, last tile partly foreign / out of bounds), every batch size of the
     decode path (passes of two or four batch rows), one to four column pairs per warp, K = 128 mod 256 (half-empty
-    last TMA box); the resident kernel against the float64 oracle and, for M <= 8, against the ring kernel."""
+    last TMA box), shapes whose rows do not fit one wave of CTAs (row chunks: several waves in one launch); the
+    resident kernel against the float64 oracle and, for M <= 8, against the ring kernel."""
     rng = np.random.default_rng(1000 * M + N + K)
     packed = rng.integers(0, 256, size=(N, K // 2), dtype=np.uint8)
     scales = (rng.random(N, dtype=np.float32) * 0.01 + 0.001).astype(np.float32)

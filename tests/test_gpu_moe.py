@@ -237,3 +237,101 @@ def test_fused_silu_gate_epilogue_matches_unfused(oracle, pkg):
     assert np.abs(h_fused - ref).max() <= 2e-4 * scale
     assert np.abs(h_two - ref).max() <= 2e-4 * scale
     assert np.abs(h_fused - h_two).max() <= 2e-4 * scale
+
+
+# ---- MoE decode (T <= 16): one C call, both expert GEMVs grouped on the resident decode kernel -------------------
+def _gated_experts(oracle, rng, E, d, F, scale=0.05):
+    mk = lambda n, k: [(rng.standard_normal((n, k)) * scale).astype(np.float32) for _ in range(E)]
+    w1, w3, w2 = mk(F, d), mk(F, d), mk(d, F)
+    q = lambda ws: [oracle.quantize_weights(w) for w in ws]
+    return (w1, w3, w2), (q(w1), q(w3), q(w2))
+
+
+@pytest.mark.parametrize("T", [1, 2, 3, 5, 8, 16])
+@pytest.mark.parametrize("E,k,d,F", [(4, 2, 256, 512), (8, 2, 1024, 3584), (8, 1, 512, 256), (16, 4, 256, 768)])
+def test_moe_decode_call_matches_oracle_and_grouped_path(oracle, pkg, T, E, k, d, F):
+    """b200q_moe_decode_fwd (route + gather + grouped gate/up GEMV + grouped down GEMV + combine) against the float64
+    oracle composed from the reference's primitives and against the prefill-sized path (tcgen05 grouped GEMMs) on the
+    same layer; experts that receive no token contribute nothing and cost nothing."""
+    rng = np.random.default_rng(T * 131 + E + d)
+    (w1, w3, w2), (q1, q3, q2) = _gated_experts(oracle, rng, E, d, F)
+    f = lambda a: [torch.from_numpy(w).cuda() for w in a]
+    moe = pkg.QuantizedMoE.from_gated_fp16_weights(f(w1), f(w3), f(w2))
+    x = rng.standard_normal((T, d), dtype=np.float32)
+    logits = rng.standard_normal((T, E), dtype=np.float32)
+    ref = oracle.moe_gated(x, logits, q1, q3, q2, k, acc=np.float64)
+    y = moe.forward_routed(cuda(x), cuda(logits), top_k=k)
+    assert y.dtype == torch.float32 and y.shape == (T, d)
+    scale = np.abs(ref).max()
+    assert np.abs(y.cpu().numpy() - ref).max() <= 2e-5 * scale + 1e-7
+    yg = moe.forward_dispatched(cuda(x), pkg.route(cuda(logits), k)).cpu().numpy()
+    assert np.abs(yg - ref).max() <= 3e-4 * scale + 1e-7
+    assert torch.equal(moe.forward_routed(cuda(x), cuda(logits), top_k=k), y)          # deterministic
+
+
+def test_moe_decode_all_tokens_on_one_expert_and_half_precision(oracle, pkg):
+    """Skew at its worst (every token picks the same two experts: groups of 16 rows, the others empty) and bf16 / fp16
+    activations (16-bit h and expert outputs, fp32 combine, as moe_int4_module.py:71-72 keeps the input dtype)."""
+    rng = np.random.default_rng(7)
+    E, k, d, F, T = 8, 2, 512, 1024, 16
+    (w1, w3, w2), (q1, q3, q2) = _gated_experts(oracle, rng, E, d, F)
+    f = lambda a: [torch.from_numpy(w).cuda() for w in a]
+    moe = pkg.QuantizedMoE.from_gated_fp16_weights(f(w1), f(w3), f(w2))
+    x = rng.standard_normal((T, d), dtype=np.float32)
+    logits = rng.standard_normal((T, E), dtype=np.float32) * 0.1
+    logits[:, 3] += 9.0
+    logits[:, 6] += 7.0
+    ref = oracle.moe_gated(x, logits, q1, q3, q2, k, acc=np.float64)
+    y = moe.forward_routed(cuda(x), cuda(logits), top_k=k).cpu().numpy()
+    assert np.abs(y - ref).max() <= 2e-5 * np.abs(ref).max()
+    for dt, tol in ((torch.bfloat16, 3e-2), (torch.float16, 4e-3)):
+        xh = torch.from_numpy(x).to(dt)
+        refh = oracle.moe_gated(xh.float().numpy(), logits, q1, q3, q2, k, acc=np.float64)
+        yh = moe.forward_routed(xh.cuda(), cuda(logits), top_k=k).cpu().numpy()
+        assert np.abs(yh - refh).max() <= tol * np.abs(refh).max()
+
+
+def test_moe_decode_nonfinite_token_poisons_only_its_row(oracle, pkg):
+    rng = np.random.default_rng(11)
+    E, k, d, F, T = 4, 2, 256, 512, 6
+    (w1, w3, w2), _ = _gated_experts(oracle, rng, E, d, F)
+    f = lambda a: [torch.from_numpy(w).cuda() for w in a]
+    moe = pkg.QuantizedMoE.from_gated_fp16_weights(f(w1), f(w3), f(w2))
+    x = rng.standard_normal((T, d), dtype=np.float32)
+    x[2, 5] = np.nan
+    x[4, 9] = np.inf
+    logits = rng.standard_normal((T, E), dtype=np.float32)
+    y = moe.forward_routed(cuda(x), cuda(logits), top_k=k).cpu().numpy()
+    assert np.isnan(y[2]).all() and not np.isfinite(y[4]).any() and np.isfinite(y[[0, 1, 3, 5]]).all()
+
+
+def test_moe_decode_mixtral_size_sampled(oracle, pkg):
+    """Mixtral-8x7B layer (E=8, d=4096, F=14336, k=2) at T = 1 and 4: the full layer against the float64 oracle on
+    the experts that were hit (the oracle only dequantises those)."""
+    torch.manual_seed(0)
+    E, k, d, F = 8, 2, 4096, 14336
+    g = torch.Generator(device="cuda").manual_seed(1)
+    rnd = lambda *s: torch.randint(0, 256, s, dtype=torch.uint8, device="cuda", generator=g)
+    moe = pkg.QuantizedMoE(E, d, F, gated=True).cuda()
+    w13, w2 = moe.stacked_weights()
+    w13[0].copy_(rnd(*w13[0].shape)); w2[0].copy_(rnd(*w2[0].shape))
+    for t in (w13, w2):
+        t[1].copy_(torch.rand(t[1].shape, device="cuda", generator=g) * 0.002 + 0.0005)
+        t[2].copy_(torch.randint(0, 16, t[2].shape, device="cuda", generator=g).float())
+    for T in (1, 4):
+        x = torch.randn(T, d, device="cuda", generator=g)
+        logits = torch.randn(T, E, device="cuda", generator=g)
+        y = moe.forward_routed(x, logits, top_k=k).cpu().numpy()
+        idx, wts = oracle.softmax_topk(logits.cpu().numpy(), k)
+        ref = np.zeros((T, d))
+        xn = x.cpu().numpy()
+        bufs = lambda m: tuple(getattr(m, b).cpu().numpy() for b in ("packed_weights", "scales", "zero_points"))
+        for t in range(T):
+            for s in range(k):
+                e = int(idx[t, s])
+                q1, q3, q2 = bufs(moe.experts[e]), bufs(moe.experts_up[e]), bufs(moe.experts_down[e])
+                gg = oracle.reference_quantized_linear(xn[t:t + 1], *q1, acc=np.float64)
+                uu = oracle.reference_quantized_linear(xn[t:t + 1], *q3, acc=np.float64)
+                h = (oracle.silu(gg) * uu).astype(np.float32)
+                ref[t] += wts[t, s] * oracle.reference_quantized_linear(h, *q2, acc=np.float64)[0].astype(np.float32)
+        assert np.abs(y - ref).max() <= 3e-5 * np.abs(ref).max()

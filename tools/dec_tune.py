@@ -12,11 +12,14 @@ KEYS = ["gemv_early", "gemv_pf", "gemv_slots", "gemv_pdl", "gemv_ctas", "force_p
 pools = {}
 
 
+POOL_LAYERS = int(os.environ.get("POOL_LAYERS", "24"))
+
+
 def pool(N, K):
     if (N, K) not in pools:
         pools.clear()
         out = []
-        for i in range(24):
+        for i in range(POOL_LAYERS):
             g = torch.Generator(device=dev); g.manual_seed(i)
             out.append((torch.randint(0, 256, (N, K // 2), generator=g, device=dev, dtype=torch.uint8),
                         torch.rand(N, generator=g, device=dev) * 0.01 + 0.001, torch.randint(0, 16, (N,), generator=g, device=dev).float()))
@@ -30,10 +33,11 @@ def measure(M, K, N, tune, hint=True, reps=8):
     for k, v in tune.items(): _lib.tune(k, v)
     x = torch.randn(M, K, device=dev); y = torch.empty(M, N, device=dev)
     ws = torch.zeros(max(lib.b200q_linear_ws_bytes(M, N, K), 16), dtype=torch.uint8, device=dev)
+    reps = reps * 24 // len(layers)
     def launch_all(sp):
         for r in range(reps):
             for i, (p, s, z) in enumerate(layers):
-                nxt = layers[(i + 1) % 24][0]
+                nxt = layers[(i + 1) % len(layers)][0]
                 _lib.check(lib.b200q_linear_fwd_next(x.data_ptr(), 0, p.data_ptr(), s.data_ptr(), z.data_ptr(), y.data_ptr(), 0, M, N, K,
                                                      ws.data_ptr(), ws.numel(), 1, sp, nxt.data_ptr() if hint else None, nxt.numel() if hint else 0), "fwd")
     side = torch.cuda.Stream(dev); side.wait_stream(torch.cuda.current_stream(dev))
@@ -51,7 +55,7 @@ def measure(M, K, N, tune, hint=True, reps=8):
         e0.record()
         for _ in range(10): g.replay()
         e1.record(); torch.cuda.synchronize()
-        best = min(best, e0.elapsed_time(e1) * 1e3 / (10 * 24 * reps))
+        best = min(best, e0.elapsed_time(e1) * 1e3 / (10 * len(layers) * reps))
     for k in KEYS: _lib.tune(k, -1)
     return best
 
