@@ -101,7 +101,10 @@ int b200q_linear_bias_fwd(const void* x, int x_dtype, const uint8_t* packed, con
     const bool vec_ok = aligned(x, 16) && aligned(packed, 16) && aligned(y, 16);
     // decode (M <= 16): the CTA-resident IMMA kernel (gemv_dec.cu) whenever ceil(N / SMs) rows fit in shared memory
     // (wide K with many batch rows would need > 4 passes of two rows: the tcgen05 GEMM is faster there)
-    if ((force <= 0 || force == 6) && vec_ok && gemv_dec_supported(d, M, N, K) && (force == 6 || M <= 8 || K <= 8192))
+    // (K > 8192 with M >= 3 and fewer tile buffers than tiles -- Mixtral's down projection -- refills only in the last
+    // pass over a buffer: measured slower than the ring kernel below, 32 vs 28 us at M = 4)
+    if ((force <= 0 || force == 6) && vec_ok && gemv_dec_supported(d, M, N, K) &&
+        (force == 6 || ((M <= 8 || K <= 8192) && (M <= 2 || K <= 8192 || gemv_dec_resident(d, M, N, K)))))
         return launch_gemv_dec(d, x, x_dtype, packed, scales, zps, bias, y, y_dtype, M, N, K, flags, st, next_packed, next_bytes);
     int rc = 0;
     bool done = false;
@@ -159,7 +162,7 @@ int b200q_linear_gated_fwd(const void* x, int x_dtype, const uint8_t* packed13, 
 namespace {
 inline size_t up256(size_t v) { return (v + 255) / 256 * 256; }
 struct DecodeWs {
-    size_t idx, wts, counts, offsets, sorted_slot, inv_perm, perm_ws, xs, h, y, total;
+    size_t idx, wts, counts, offsets, sorted_slot, inv_perm, perm_ws, h, y, total;
 };
 DecodeWs decode_ws(int64_t T, int E, int k, int64_t d, int64_t F, int esz) {
     DecodeWs w{};
@@ -171,8 +174,7 @@ DecodeWs decode_ws(int64_t T, int E, int k, int64_t d, int64_t F, int esz) {
     w.offsets = o; o += up256((size_t)(E + 1) * 4);
     w.sorted_slot = o; o += up256(A * 4);
     w.inv_perm = o; o += up256(A * 4);
-    w.perm_ws = o; o += up256(b200q_moe_permute_ws_bytes(T, E, k));
-    w.xs = o; o += up256(A * d * esz);
+    w.perm_ws = o; o += up256(A * 4);                         // token of every sorted position
     w.h = o; o += up256(A * F * esz);
     w.y = o; o += up256(A * d * esz);
     w.total = o;
@@ -189,7 +191,8 @@ int b200q_moe_decode_fwd(const void* x, int x_dtype, const float* logits, int64_
                          const uint8_t* packed13, const float* scales13, const float* zps13,
                          const uint8_t* packed2, const float* scales2, const float* zps2, int64_t d, int64_t F,
                          float* out, void* ws, size_t ws_bytes, void* stream) {
-    if (T <= 0 || T > 16 || E <= 0 || k <= 0 || k > E || d <= 0 || F <= 0) return set_error(B200Q_EINVAL, "moe_decode_fwd: need 1 <= T <= 16, 1 <= k <= E, d, F > 0");
+    if (T <= 0 || T > 16 || E <= 0 || E > 256 || k <= 0 || k > 8 || k > E || d <= 0 || F <= 0)
+        return set_error(B200Q_EINVAL, "moe_decode_fwd: need 1 <= T <= 16, 1 <= k <= min(8, E), E <= 256, d, F > 0");
     if (!elem_size(x_dtype)) return set_error(B200Q_EINVAL, "moe_decode_fwd: unsupported dtype");
     if (!x || !logits || !packed13 || !scales13 || !zps13 || !packed2 || !scales2 || !zps2 || !out || !ws) return set_error(B200Q_EINVAL, "moe_decode_fwd: null pointer");
     const DecodeWs w = decode_ws(T, E, k, d, F, elem_size(x_dtype));
@@ -208,14 +211,13 @@ int b200q_moe_decode_fwd(const void* x, int x_dtype, const float* logits, int64_
     int32_t* offsets = reinterpret_cast<int32_t*>(base + w.offsets);
     int32_t* sorted_slot = reinterpret_cast<int32_t*>(base + w.sorted_slot);
     int32_t* inv_perm = reinterpret_cast<int32_t*>(base + w.inv_perm);
-    void* xs = base + w.xs;
+    int32_t* src_token = reinterpret_cast<int32_t*>(base + w.perm_ws);
     void* h = base + w.h;
     void* y = base + w.y;
-    if (int rc = b200q_moe_route(logits, nullptr, T, E, k, idx, wts, counts, offsets, sorted_slot, inv_perm, base + w.perm_ws,
-                                 b200q_moe_permute_ws_bytes(T, E, k), stream)) return rc;
-    if (int rc = b200q_moe_gather_rows(x, x_dtype, sorted_slot, T * k, k, d, xs, stream)) return rc;
-    if (int rc = launch_gemv_dec(dv, xs, x_dtype, packed13, scales13, zps13, nullptr, h, x_dtype, T, 2 * F, d, B200Q_FLAG_STATIC_WEIGHTS, st,
-                                 nullptr, 0, 1, offsets, E)) return rc;
+    // three launches + the combine: routing (one CTA), gate / up GEMV reading x in place through the token map, down GEMV
+    if (int rc = moe_route_small(logits, T, E, k, idx, wts, counts, offsets, sorted_slot, inv_perm, src_token, st)) return rc;
+    if (int rc = launch_gemv_dec(dv, x, x_dtype, packed13, scales13, zps13, nullptr, h, x_dtype, T, 2 * F, d, B200Q_FLAG_STATIC_WEIGHTS, st,
+                                 nullptr, 0, 1, offsets, E, src_token)) return rc;
     if (int rc = launch_gemv_dec(dv, h, x_dtype, packed2, scales2, zps2, nullptr, y, x_dtype, T, d, F, B200Q_FLAG_STATIC_WEIGHTS, st,
                                  nullptr, 0, 0, offsets, E)) return rc;
     return b200q_moe_combine(y, x_dtype, inv_perm, wts, T, k, d, out, B200Q_F32, stream);

@@ -64,8 +64,10 @@ constexpr int OFF_BARS = 0;          // [MAX_BARS] tile barriers
 constexpr int OFF_FULL = 512;        // [2]
 constexpr int OFF_EMPTY = 528;       // [2]
 constexpr int OFF_FLAG = 544;        // bit m: batch row m holds NaN / Inf
+constexpr int OFF_SUMX = 576;        // [16 batch rows][4 digits] s32: sum_k X of every batch row (kept for the later windows)
 constexpr int OFF_EX = 832;          // [16] exponent of every batch row
 constexpr int OFF_AMAX = 1024;       // [2 (pass parity)][4 rows][16 warps] u32
+constexpr int OFF_CONS = 1536;       // [MAX_BARS] "consumed" barriers of the tile buffers (ring mode)
 constexpr int OFF_DYN = 2048;        // partial-tile buffers (their owner's slots double as its operand exchange space), accumulator, tiles
 constexpr int WARP_RED = 1024;       // bytes of a warp in one partial-tile buffer (pipelined reduction)
 
@@ -81,10 +83,11 @@ struct DecParams {
     unsigned int next_chunk;         // next_bytes / gridDim.x
     int x_dtype, y_dtype;
     int M, N, K;
+    int rows_q, rows_rem;            // CTA b owns rows_q (+1 if b < rows_rem) row units (host-computed: no division in the kernel)
     int npairs;                      // ceil(K / 256)
     int nbars;                       // pair groups (barriers) per tile
     int chunk;                       // pairs per group
-    int ntiles_max;
+    int ntiles_max;                  // tile buffers W = tiles per window
     int tile_bytes;
     int tile_off;                    // byte offset of tile 0 in dynamic shared memory (1024-aligned)
     int red_off, fin_off;            // partial-tile buffers, accumulator
@@ -94,11 +97,15 @@ struct DecParams {
     int early_tiles;                 // a + 10 b: a tiles requested before griddepcontrol.wait, b more behind the x loads
     int pf_mode;                     // next-layer L2 prefetch: 1 behind the last own request, 2 before the own requests, 3 after the operand build
     int gated;                       // 1: rows 2f / 2f+1 are the gate / up projection of column f; y is h [M, N/2] = silu(gate) * up
-    // work items: blockIdx.x = (expert e, row chunk c, CTA b of the chunk).  Row chunks let shapes whose rows do not fit
-    // in the shared memory of ONE wave of CTAs (Mixtral's 14336-wide projections) run as a few waves of the same kernel.
-    int grid_g, nchunks, chunk_rows; // CTAs per chunk, chunks per expert, weight rows per chunk (a multiple of the row unit)
+    // work items: blockIdx.x = (expert e, CTA b of the expert).  A CTA whose rows do not fit in its W tile buffers
+    // (Mixtral's 14336-wide projections) runs them as a ring: a buffer is requested again as soon as all warps are
+    // done with it, and the outputs are produced window by window (W tiles each).
+    // (GEN instances only; the plain instances -- one expert, every tile resident -- carry none of this code)
+    int win_hi[2], win_lo[2];        // {R windows, T0 tiles of the first one} for CTAs with rows_q + 1 / rows_q row units
     const int32_t* offsets;          // grouped (MoE decode): rows [offsets[e], offsets[e+1]) of x / y belong to expert e of
                                      //   packed [E, N, K/2] (device memory; experts without rows exit at once); else nullptr
+    const int32_t* row_map;          // grouped: batch row r of the group reads x[row_map[offsets[e] + r]] (the token of that
+                                     //   sorted position: x is read in place, no gathered copy); y rows stay in sorted order
     int debug;                       // B200Q_PROF builds: record phase stamps
 };
 
@@ -184,21 +191,46 @@ __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
-// weight requests [from, to) (request = (tile, pair group), ~32 KB): one 3-D box [16 rows][chunk pairs][128 B] per (tile, pair group), one elected
-// thread.  Not inlined: three call sites (before griddepcontrol.wait, behind the x loads, after the operand build),
-// and code that runs once costs ~10 clk per instruction whatever it does (profiles/r02_decode_notes.md).
+// weight requests [from, to) (request = (tile, pair group), ~32 KB): one 3-D box [16 rows][chunk pairs][128 B] each,
+// one elected thread.  Not inlined: three call sites (before griddepcontrol.wait, behind the x loads, after the operand
+// build), and code that runs once costs ~10 clk per instruction whatever it does (profiles/r02_decode_notes.md).
 __device__ __noinline__ void dec_issue_tiles(const CUtensorMap* tmap, uint32_t bar0, uint32_t dst0, int row0, int from, int to,
                                              int nbars, int chunk, int tile_bytes) {
     const uint64_t pol = policy_evict_first();
+    int i = nbars == 1 ? from : from / nbars, grp = from - i * nbars;
     for (int op = from; op < to; ++op) {                      // op = tile * nbars + pair group
-        const int i = op / nbars, grp = op - i * nbars;
         const uint32_t bar = bar0 + 8u * (uint32_t)op;
         mbar_arrive_expect_tx(bar, (uint32_t)(chunk * PAIR_BYTES));
         tma_box_3d(dst0 + (uint32_t)(i * tile_bytes + grp * chunk * PAIR_BYTES), tmap, 0, row0 + i * TILE_ROWS, grp * chunk, bar, pol);
+        if (++grp == nbars) { grp = 0; ++i; }
     }
 }
 
-template <int GPW2, int NT>          // pairs per warp, n-tiles (two batch rows each) per pass
+// Tile order of the GEN instances.  The CTA's positions (weight rows + one more: the row of 0x11 bytes) form S tiles
+// of 16, grouped into R windows of W tiles (W = tile buffers).  The windows are processed from the LAST one (partial,
+// T0 tiles; it holds the 0x11 row, whose result every epilogue needs) to the first; s counts tiles in processing order
+// and tile s lives in buffer s % W.
+__device__ __forceinline__ int ring_row_tile(int s, int W, int T0, int R) {      // tile index in row order, s <= W (windows 0 and 1)
+    return s < T0 ? (R - 1) * W + s : (R - 2) * W + (s - T0);
+}
+// first fill of the ring: tiles [0, min(S, W)) -- buffer = tile
+__device__ __noinline__ void dec_issue_ring(const CUtensorMap* tmap, uint32_t bar0, uint32_t dst0, int row0, int from, int to,
+                                            int nbars, int chunk, int tile_bytes, int W, int T0, int R) {
+    const uint64_t pol = policy_evict_first();
+    int s = nbars == 1 ? from : from / nbars, grp = from - s * nbars;
+    for (int op = from; op < to; ++op) {
+        const uint32_t bar = bar0 + 8u * (uint32_t)op;
+        mbar_arrive_expect_tx(bar, (uint32_t)(chunk * PAIR_BYTES));
+        tma_box_3d(dst0 + (uint32_t)(s * tile_bytes + grp * chunk * PAIR_BYTES), tmap, 0, row0 + ring_row_tile(s, W, T0, R) * TILE_ROWS,
+                   grp * chunk, bar, pol);
+        if (++grp == nbars) { grp = 0; ++s; }
+    }
+}
+
+// GPW2: pairs per warp; NT: n-tiles (two batch rows each) per pass; GEN: grouped (MoE decode: blockIdx.y = expert,
+// device-side row offsets) and / or more tiles than tile buffers (ring).  GEN = false is the Llama-shape kernel: every
+// GEN feature is compiled out of it.
+template <int GPW2, int NT, bool GEN>
 __global__ void __launch_bounds__(NTHR, 1) gemv_dec_kernel(const __grid_constant__ CUtensorMap tmap, const DecParams p) {
     constexpr int MB = 2 * NT;       // batch rows per pass
     constexpr int RB = NW * WARP_RED;   // bytes of one partial-tile buffer
@@ -208,49 +240,61 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_dec_kernel(const __grid_constant
     const int g = lane >> 2, t = lane & 3;
 
     B200Q_STAMP(0);
-    // work item -> (expert, row chunk, CTA of the chunk)
-    const int b = (int)(blockIdx.x % (unsigned)p.grid_g);
-    const int chunk_i = (int)((blockIdx.x / (unsigned)p.grid_g) % (unsigned)p.nchunks);
-    const int expert = (int)(blockIdx.x / (unsigned)(p.grid_g * p.nchunks));
+    // work item -> (expert, CTA of the expert)
+    const int b = (int)blockIdx.x;
+    const int expert = GEN ? (int)blockIdx.y : 0;
     int Mrows = p.M;                                          // batch rows of this work item
     int64_t xrow0 = 0;                                        // ... and where they start in x / y
-    if (p.offsets) {
-        const int lo = p.offsets[expert], hi = p.offsets[expert + 1];
-        Mrows = min(hi - lo, 16);
-        xrow0 = lo;
-        if (Mrows <= 0) return;                               // uniform: this expert has no tokens
+    if constexpr (GEN) {
+        if (p.offsets) {
+            const int lo = p.offsets[expert], hi = p.offsets[expert + 1];
+            Mrows = min(hi - lo, 16);
+            xrow0 = lo;
+            if (Mrows <= 0) return;                           // uniform: this expert has no tokens
+        }
     }
+    auto x_row = [&](int m) -> int64_t {                      // row of x that batch row m of this work item reads
+        if constexpr (GEN) { if (p.row_map) return p.row_map[xrow0 + m]; }
+        return xrow0 + m;
+    };
     // (gated: rows are dealt out in gate / up pairs, so both projections of an output column meet in one CTA)
     const int unit = p.gated ? 2 : 1;
-    const int chunk_start = chunk_i * p.chunk_rows;
-    const int chunk_units = (min(p.chunk_rows, p.N - chunk_start)) / unit;
-    const int cq = chunk_units / p.grid_g, crem = chunk_units % p.grid_g;
-    const int orow0 = chunk_start + unit * (b * cq + min(b, crem));      // first row of this CTA inside the expert's N rows
-    const int nrows = unit * (cq + (b < crem ? 1 : 0));
-    if (nrows <= 0) return;                                   // uniform
-    const int r0 = expert * p.N + orow0;                      // ... and in the stacked weight tensor [E N, K/2]
-    const int npasses = (Mrows + 2 * NT - 1) / (2 * NT);
-    const int ntma = (nrows + TILE_ROWS - 1) / TILE_ROWS;    // tiles with weight rows
+    const int orow0 = unit * (b * p.rows_q + min(b, p.rows_rem));    // first row of this CTA inside the expert's N rows
+    const int nrows = unit * (p.rows_q + (b < p.rows_rem ? 1 : 0));
+    if constexpr (GEN) { if (nrows <= 0) return; }            // uniform
+    const int r0 = GEN ? expert * p.N + orow0 : orow0;        // ... and in the stacked weight tensor [E N, K/2]
+    const int npasses = GEN ? (Mrows + MB - 1) / MB : p.npasses;
     // One more row: a row of bytes 0x11 (q_lo = q_hi = 1) behind the last weight row makes the tensor cores deliver
     // sum_k X (the zero-point term) as one more output row -- no extra arithmetic in the operand build.
-    const int tf = nrows >> 4, rf = nrows & 15;              // tile / row of that row
-    const int ntl = tf + 1;                                  // tiles of the main loop (= ntma unless nrows % 16 == 0)
+    const int S = (nrows + 1 + TILE_ROWS - 1) / TILE_ROWS;   // tiles of this CTA
+    const int W = p.ntiles_max;                               // tile buffers = tiles per window (plain instances: >= S)
+    const int R = GEN ? (b < p.rows_rem ? p.win_hi[0] : p.win_lo[0]) : 1;       // windows
+    const int T0 = GEN ? (b < p.rows_rem ? p.win_hi[1] : p.win_lo[1]) : S;      // tiles of the window processed first (the last rows)
+    const bool ring = GEN && S > W;
+    const int tf = (nrows >> 4) - (R - 1) * W, rf = nrows & 15;      // tile (of the first window) / row of the 0x11 row
     int* s_ex = reinterpret_cast<int*>(smem + OFF_EX);
     unsigned int* s_flag = reinterpret_cast<unsigned int*>(smem + OFF_FLAG);
     unsigned int* s_amax = reinterpret_cast<unsigned int*>(smem + OFF_AMAX);
     int* fin = reinterpret_cast<int*>(smem + p.fin_off);
-    auto tile_bar = [&](int i, int grp) { return sbase + OFF_BARS + 8u * (uint32_t)(i * p.nbars + grp); };
+    int* s_sumx = reinterpret_cast<int*>(smem + OFF_SUMX);
+    auto tile_bar = [&](int buf, int grp) { return sbase + OFF_BARS + 8u * (uint32_t)(buf * p.nbars + grp); };
+    auto cons_bar = [&](int buf, int grp) { return sbase + OFF_CONS + 8u * (uint32_t)(buf * p.nbars + grp); };
     auto full_bar = [&](int bb) { return sbase + OFF_FULL + 8u * (uint32_t)bb; };
     auto empty_bar = [&](int bb) { return sbase + OFF_EMPTY + 8u * (uint32_t)bb; };
 
     if (tid == 0) {
-        for (int i = 0; i < ntma * p.nbars; ++i) mbar_init(sbase + OFF_BARS + 8u * i, 1);
+        const int nb = min(S, W) * p.nbars;
+        for (int i = 0; i < nb; ++i) mbar_init(sbase + OFF_BARS + 8u * i, 1);
+        if constexpr (GEN) {
+            if (ring)                                        // one arrival per pair of the group (by the warp that owns the pair)
+                for (int i = 0; i < nb; ++i) mbar_init(sbase + OFF_CONS + 8u * i, (uint32_t)min(p.chunk, p.npairs - (i % p.nbars) * p.chunk));
+        }
         for (int i = 0; i < 2; ++i) { mbar_init(full_bar(i), NW); mbar_init(empty_bar(i), NW); }
         fence_mbar_init();
         *s_flag = 0u;
     }
     if (!p.slots)                                            // pipelined reduction: integer atomics into a zeroed accumulator
-        for (int i = tid; i < npasses * p.ntiles_max * NT * 128; i += NTHR) fin[i] = 0;
+        for (int i = tid; i < npasses * W * NT * 128; i += NTHR) fin[i] = 0;
     __syncthreads();
     pdl_launch_dependents();
     B200Q_STAMP(1);
@@ -259,7 +303,16 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_dec_kernel(const __grid_constant
     // Staged (tuning key gemv_early = a + 10 * b): a tiles before griddepcontrol.wait, b more once the x loads are
     // in flight, the rest when the x operand is built -- bounds what queues ahead of the x loads.
     const bool issuer = warp == NW - 1 && lane == 0 && !B200Q_ABL(4);
-    const int nops = ntma * p.nbars;                         // requests of ~32 KB: (tile, pair group)
+    const int nops = min(S, W) * p.nbars;                    // first fill: requests of ~32 KB, (tile, pair group)
+    auto issue = [&](int from, int to) {
+        if constexpr (GEN) dec_issue_ring(&tmap, sbase + OFF_BARS, sbase + p.tile_off, r0, from, to, p.nbars, p.chunk, p.tile_bytes, W, T0, R);
+        else dec_issue_tiles(&tmap, sbase + OFF_BARS, sbase + p.tile_off, r0, from, to, p.nbars, p.chunk, p.tile_bytes);
+    };
+    // (GEN, issuer) next refill: request (tile nx_s = processing order, pair group nx_grp) into buffer nx_buf once the
+    // tile that is there now has been consumed (parity nx_par of its barrier); nx_rt: its tile index in row order
+    int nx_s = W, nx_grp = 0, nx_buf = 0, nx_rt = 0;
+    uint32_t nx_par = 0u;
+    if constexpr (GEN) { if (ring) nx_rt = ring_row_tile(W, W, T0, R); }
     const int early = min(p.early_tiles % 10, nops);
     const int mid = min(early + p.early_tiles / 10, nops);
     auto prefetch_next = [&]() {
@@ -275,7 +328,7 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_dec_kernel(const __grid_constant
     if (issuer) {
         tma_prefetch_desc(&tmap);
         if (p.pf_mode == 2) prefetch_next();
-        dec_issue_tiles(&tmap, sbase + OFF_BARS, sbase + p.tile_off, r0, 0, early, p.nbars, p.chunk, p.tile_bytes);
+        issue(0, early);
         if (early == nops && p.pf_mode == 1) prefetch_next();
     }
     B200Q_STAMP(2);
@@ -295,11 +348,31 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_dec_kernel(const __grid_constant
     const uint32_t xs1 = p.slots ? (uint32_t)(NW * 512) : 512u, xs2 = p.slots ? (uint32_t)(2 * NW * 512) : (uint32_t)RB;
     auto xpart = [&](int k) { return xbase + (uint32_t)(k & 1) * xs1 + (uint32_t)(k >> 1) * xs2; };
     const int hsel = g >> 2, lsel = g & 3;                   // lane (g, t) holds mma column g: digit lsel of batch row 2 nt + hsel
-    // scale / zero point of this thread's output row (one row per thread: at most 256 rows per CTA), fetched early
-    // (latency hidden by the main loop)
-    float pre_sc = 0.0f, pre_zp = 0.0f;
-    if (tid < nrows) { pre_sc = __ldg(p.scales + r0 + tid); pre_zp = __ldg(p.zps + r0 + tid); }
+    // ring refills (issuer only): request tile s + W as soon as every warp is done with tile s; lim: first tile (processing
+    // order) that must not be requested yet
+    auto advance = [&](int lim_s, bool block) {
+        while (nx_s < lim_s) {
+            const uint32_t cb = cons_bar(nx_buf, nx_grp);
+            if (block) mbar_wait(cb, nx_par);
+            else if (!mbar_try_wait(cb, nx_par)) break;
+            const uint32_t bar = tile_bar(nx_buf, nx_grp);
+            mbar_arrive_expect_tx(bar, (uint32_t)(p.chunk * PAIR_BYTES));
+            tma_box_3d(sbase + p.tile_off + (uint32_t)(nx_buf * p.tile_bytes + nx_grp * p.chunk * PAIR_BYTES), &tmap, 0,
+                       r0 + nx_rt * TILE_ROWS, nx_grp * p.chunk, bar, policy_evict_first());
+            if (++nx_grp == p.nbars) {
+                nx_grp = 0;
+                ++nx_s;
+                if (++nx_buf == W) { nx_buf = 0; nx_par ^= 1u; }
+                nx_rt += (nx_buf == (T0 == W ? 0 : T0)) ? 1 - 2 * W : 1;     // a new window starts one window further up
+            }
+        }
+    };
 
+    // pair group (= barrier) of each of this warp's pairs: computed here, not in the loop (an integer division costs
+    // ~150 clk on the critical path of every tile)
+    int grp_of[GPW2];
+#pragma unroll
+    for (int q = 0; q < GPW2; ++q) grp_of[q] = GPW2 == 1 ? 0 : (warp + NW * q) / p.chunk;
     int it = 0;                                              // partial tiles handed over so far (all passes)
     auto reduce_tile = [&](int itx, int pass, int tile) {
         const int bb = itx & 1;
@@ -310,18 +383,29 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_dec_kernel(const __grid_constant
         int s = 0;
 #pragma unroll
         for (int w = 0; w < PER; ++w) s += lds32(src + (uint32_t)(w * WARP_RED));
-        red_add_s32(sbase + p.fin_off + (uint32_t)((((pass * p.ntiles_max + tile) * NT) * 128 + rho) * 4), s);
+        red_add_s32(sbase + p.fin_off + (uint32_t)((((pass * W + tile) * NT) * 128 + rho) * 4), s);
         __syncwarp();
         if (lane == 0) mbar_arrive(empty_bar(bb));
     };
 
     pdl_wait();              // x (and y) belong to the stream-ordered predecessor
     B200Q_STAMP(3);
-    float xv[GPW2][MB][8];
     uint32_t bf[GPW2][4][NT][4];                              // per 32-byte step: {e-word b0, e-word b1, z-word b0, z-word b1}
+#pragma unroll 1
+  for (int k = 0; k < R; ++k) {                               // windows of W tiles, last rows first (plain instances: one)
+    const int Tk = k == 0 ? T0 : W;                           // tiles of this window
+    const int pos0 = (R - 1 - k) * W * TILE_ROWS;             // ... and its first row (relative to the CTA's rows)
+    // scale / zero point of this thread's output row (one row per thread and window), fetched early (latency hidden
+    // by the main loop)
+    const bool mine = tid < Tk * TILE_ROWS && pos0 + tid < nrows;
+    float pre_sc = 0.0f, pre_zp = 0.0f;
+    if (mine) { pre_sc = __ldg(p.scales + r0 + pos0 + tid); pre_zp = __ldg(p.zps + r0 + pos0 + tid); }
 #pragma unroll 1
     for (int pass = 0; pass < npasses; ++pass) {
         const int m0 = pass * MB;
+        const bool first = k == 0 && pass == 0;
+      if (k == 0 || npasses > 1) {                            // (one pass: the operand stays in registers for every window)
+        float xv[GPW2][MB][8];
         // ---- x of this pass: this warp's columns only, all loads in flight at once
 #pragma unroll
         for (int q = 0; q < GPW2; ++q) {
@@ -330,11 +414,11 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_dec_kernel(const __grid_constant
             for (int hr = 0; hr < MB; ++hr) {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) xv[q][hr][e] = 0.0f;
-                if (col < p.K && m0 + hr < Mrows) load8f(p.x, p.x_dtype, (xrow0 + m0 + hr) * p.K + col, xv[q][hr]);
+                if (col < p.K && m0 + hr < Mrows) load8f(p.x, p.x_dtype, x_row(m0 + hr) * p.K + col, xv[q][hr]);
             }
         }
-        if (pass == 0 && issuer && early < mid) {
-            dec_issue_tiles(&tmap, sbase + OFF_BARS, sbase + p.tile_off, r0, early, mid, p.nbars, p.chunk, p.tile_bytes);
+        if (first && issuer && early < mid) {
+            issue(early, mid);
             if (mid == nops && p.pf_mode == 1) prefetch_next();
         }
         int ex[MB];
@@ -355,7 +439,7 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_dec_kernel(const __grid_constant
             }
         }
         __syncthreads();
-        if (pass == 0) B200Q_STAMP(4);
+        if (first) B200Q_STAMP(4);
 #pragma unroll
         for (int hr = 0; hr < MB; ++hr) {
             if (m0 + hr < Mrows) {                            // uniform
@@ -419,28 +503,39 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_dec_kernel(const __grid_constant
                 __syncwarp();
             }
         }
-        if (pass == 0 && issuer) {
-            if (mid < nops) dec_issue_tiles(&tmap, sbase + OFF_BARS, sbase + p.tile_off, r0, mid, nops, p.nbars, p.chunk, p.tile_bytes);
+      }
+        if (first && issuer) {
+            if (mid < nops) issue(mid, nops);
             if (p.pf_mode == 3 || (p.pf_mode == 1 && mid < nops)) prefetch_next();
         }
-        if (pass == 0) B200Q_STAMP(5);
+        if (first) B200Q_STAMP(5);
 
         // ---- main loop: one 16-row tile per iteration, this warp's pairs of it
-        for (int i = 0; i < ntl; ++i) {
+        for (int i = 0; i < Tk; ++i) {
+            // (GEN) buffer of the tile and parity of its barriers: tile s = T0 + (k - 1) W + i of the processing order
+            int buf = i;
+            uint32_t par = 0u;
+            if constexpr (GEN) {
+                if (k > 0) {
+                    const int tq = T0 + i, wrap = tq >= W ? 1 : 0;
+                    buf = tq - wrap * W;
+                    par = (uint32_t)((k - 1 + wrap) & 1);
+                }
+            }
             // raw bytes x digits of Xe, masked bytes x digits of Z (two chains of dependent IMMAs; four were not faster)
             int c0[NT][4], c1[NT][4];
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
                 for (int r = 0; r < 4; ++r) { c0[nt][r] = 0; c1[nt][r] = 0; }
-            const uint32_t tb = sbase + p.tile_off + (uint32_t)(i * p.tile_bytes);
+            const uint32_t tb = sbase + p.tile_off + (uint32_t)(buf * p.tile_bytes);
 #pragma unroll
             for (int q = 0; q < GPW2; ++q) {
                 const int P = warp + NW * q;
                 if (P < p.npairs) {                           // uniform
-                    if (pass == 0 && i < ntma && !B200Q_ABL(4)) mbar_wait(tile_bar(i, P / p.chunk), 0);
+                    if (pass == 0 && !B200Q_ABL(4)) mbar_wait(tile_bar(buf, grp_of[q]), par);
                     const uint32_t pb = tb + (uint32_t)(P * PAIR_BYTES);
-                    if (pass == 0 && i == tf) {               // the row of 0x11 bytes behind the last weight row
+                    if (first && i == tf) {                   // the row of 0x11 bytes behind the last weight row
                         if (lane < 8) sts128(pb + (uint32_t)(rf * 128 + lane * 16), make_uint4(0x11111111u, 0x11111111u, 0x11111111u, 0x11111111u));
                         __syncwarp();
                     }
@@ -456,6 +551,15 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_dec_kernel(const __grid_constant
 #pragma unroll
                         for (int nt = 0; nt < NT; ++nt) imma(c1[nt], a[0], a[1], a[2], a[3], bf[q][c][nt][2], bf[q][c][nt][3]);
                     }
+                    if constexpr (GEN) {
+                        if (ring && pass == npasses - 1) {    // uniform: hand the buffer back, refill what is free
+                            if (k + 1 < R) {                  // (a tile of the last window is never refilled... its successor is)
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive(cons_bar(buf, grp_of[q]));
+                            }
+                            if (issuer) advance(S, false);
+                        }
+                    }
                 }
             }
             if (p.slots) {
@@ -463,7 +567,7 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_dec_kernel(const __grid_constant
                 sts128(red + (uint32_t)((i * NW + warp) * 512 + lane * 16),
                        make_uint4((uint32_t)(c0[0][0] + c1[0][0]), (uint32_t)(c0[0][1] + c1[0][1]),
                                   (uint32_t)(c0[0][2] + c1[0][2]), (uint32_t)(c0[0][3] + c1[0][3])));
-                if (i < 6) B200Q_STAMP(6 + i);
+                if (first && i < 6) B200Q_STAMP(6 + i);
                 continue;
             }
             // hand the partial tile over (double buffer; the buffer was last read for tile it - 2)
@@ -477,22 +581,25 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_dec_kernel(const __grid_constant
             __syncwarp();
             if (lane == 0) mbar_arrive(full_bar(bb));
             if (i >= 1) reduce_tile(it - 1, pass, i - 1);
-            if (pass == 0 && i < 6) B200Q_STAMP(6 + i);
+            if (first && i < 6) B200Q_STAMP(6 + i);
             ++it;
         }
-        if (!p.slots) reduce_tile(it - 1, pass, ntl - 1);
-        if (pass == 0) B200Q_STAMP(12);
+        if (!p.slots) reduce_tile(it - 1, pass, Tk - 1);
+        if (first) B200Q_STAMP(12);
         // (the exchange space of the next pass is the warp's own partial-tile slots: the amax barrier of that pass comes
         // after every warp has folded the last tile of this one, so they are free again)
     }
 
-    // ======== after the last pass: fold, epilogue
+    // ======== after the last pass of the window: fold, epilogue
     __syncthreads();
+    if constexpr (GEN) {
+        if (ring && issuer) advance(min(S, T0 + k * W + W), true);      // every buffer of this window is free
+    }
     if (p.slots) {
         // fold the 16 warp slots of every tile (integer adds: exact, order independent)
         // (M = 1: only mma columns 0..3 are live, i.e. the words of lane quads t = 0, 1)
         const int sh = Mrows == 1 ? 6 : 7;
-        for (int v = tid; v < (ntl << sh); v += NTHR) {
+        for (int v = tid; v < (Tk << sh); v += NTHR) {
             const int tile = v >> sh, rem = v & ((1 << sh) - 1);
             const int word = Mrows == 1 ? ((rem >> 3) * 16 + (rem & 7)) : rem;
             const uint32_t src = red + (uint32_t)((tile * NW) * 512 + word * 4);
@@ -503,7 +610,7 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_dec_kernel(const __grid_constant
         }
         __syncthreads();
     }
-    B200Q_STAMP(13);
+    if (k == 0) B200Q_STAMP(13);
 
     // ---- epilogue: one thread per output (tile, batch row, row): digits -> sum_k q*X (exact s64),
     // y = s * 2^-e * (sum_k q*X - zp * sum_k X) (+ bias)
@@ -511,8 +618,11 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_dec_kernel(const __grid_constant
     // word of (mma row r, column col) in a 16 x 8 tile stored as [lane = 4 (r & 7) + col / 2][reg = 2 (r >> 3) + (col & 1)]
     auto word_of = [](int r, int col) { return (((r & 7) * 4 + (col >> 1)) * 4) + ((r >> 3) * 2 + (col & 1)); };
     {
-        const bool mine = tid < nrows;
-        const int ti = tid >> 4, r = tid & 15, row = orow0 + tid;      // output column (row of the expert's weight matrix)
+        if (k == 0 && R > 1 && tid < 4 * Mrows) {            // sum_k X of every batch row, for the epilogues of the later windows
+            const int m = tid >> 2, pass = m / MB, mm = m - pass * MB;
+            s_sumx[tid] = fin[((pass * W + tf) * NT + (mm >> 1)) * 128 + word_of(rf, 4 * (mm & 1) + (tid & 3))];
+        }
+        const int ti = tid >> 4, r = tid & 15, row = orow0 + pos0 + tid;      // output column (row of the expert's weight matrix)
         const float sc = pre_sc, zp = pre_zp;
         const float bias = (mine && p.bias) ? __ldg(p.bias + row) : 0.0f;
         const int zi = __float2int_rn(zp);
@@ -522,13 +632,13 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_dec_kernel(const __grid_constant
             float v = 0.0f;
             if (mine) {
                 const int pass = m / MB, mm = m - pass * MB, nt = mm >> 1, h = mm & 1;
-                const int* f = fin + ((pass * p.ntiles_max + ti) * NT + nt) * 128;
-                const int* ft = fin + ((pass * p.ntiles_max + tf) * NT + nt) * 128;     // the 0x11 row: sum_k X
+                const int* f = fin + ((pass * W + ti) * NT + nt) * 128;
+                const int* ft = fin + ((pass * W + tf) * NT + nt) * 128;     // the 0x11 row: sum_k X
                 long long a = 0, txl = 0;
 #pragma unroll
                 for (int l = 0; l < 4; ++l) {
                     a += (long long)f[word_of(r, 4 * h + l)] << (8 * l);
-                    txl += (long long)ft[word_of(rf, 4 * h + l)] << (8 * l);
+                    txl += (long long)(k == 0 ? ft[word_of(rf, 4 * h + l)] : s_sumx[4 * m + l]) << (8 * l);
                 }
                 const int ex = s_ex[m];
                 if (zint && ex >= -126) {
@@ -549,9 +659,15 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_dec_kernel(const __grid_constant
             }
         }
     }
+    if (k + 1 < R && !p.slots) {                              // the accumulator of the next window starts from zero
+        __syncthreads();
+        for (int i = tid; i < npasses * W * NT * 128; i += NTHR) fin[i] = 0;
+        __syncthreads();
+    }
+  }
     // ---- batch rows with NaN / Inf: the reference's arithmetic (dequantise, then fp32 multiply-add), so that
     // non-finite values propagate as in F.linear; one warp per output, weights re-read from global memory
-    if (flagged) {
+    if (const unsigned int flagged = *s_flag) {
         const int64_t row_bytes = p.K >> 1;
         for (int m = 0; m < Mrows; ++m) {
             if (!((flagged >> m) & 1u)) continue;
@@ -562,8 +678,8 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_dec_kernel(const __grid_constant
                 for (int kb = lane; kb < row_bytes; kb += 32) {
                     const unsigned int byte = wr[kb];
                     const float w0 = ((float)(byte & 15u) - zp) * sc, w1 = ((float)(byte >> 4) - zp) * sc;
-                    acc = fmaf(w0, load1f(p.x, p.x_dtype, (xrow0 + m) * p.K + 2 * kb), acc);
-                    acc = fmaf(w1, load1f(p.x, p.x_dtype, (xrow0 + m) * p.K + 2 * kb + 1), acc);
+                    acc = fmaf(w0, load1f(p.x, p.x_dtype, x_row(m) * p.K + 2 * kb), acc);
+                    acc = fmaf(w1, load1f(p.x, p.x_dtype, x_row(m) * p.K + 2 * kb + 1), acc);
                 }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -586,7 +702,7 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_dec_kernel(const __grid_constant
 }
 
 struct DecPlan {
-    int grid_g, nchunks, chunk_rows, gpw2, nt, npasses, ntiles, npairs, nbars, chunk, tile_bytes, tile_off;
+    int grid_g, rows_q, rows_rem, s_max, gpw2, nt, npasses, ntiles, npairs, nbars, chunk, tile_bytes, tile_off;
     int red_off, fin_off, slots;
     size_t smem;
 };
@@ -606,27 +722,33 @@ bool plan_dec(int sm_count, int max_smem, int64_t M, int64_t N, int64_t K, DecPl
     c->tile_bytes = c->nbars * c->chunk * PAIR_BYTES;             // >= npairs * 2 KB: a 3-D box always has room
     int cap = tuning().gemv_ctas > 0 ? tuning().gemv_ctas : sm_count;
     if (cap > sm_count) cap = sm_count;
-    // row chunks: the fewest waves of CTAs whose rows fit in shared memory (one for the Llama shapes)
-    for (int nch = 1; nch <= 16; ++nch) {
-        const int64_t units = (N / unit + nch - 1) / nch;        // row units per chunk
-        int64_t g = (units * unit + TILE_ROWS - 2 - (unit - 1)) / (TILE_ROWS - unit);       // few rows: at most 15 (14) per CTA (+ the 0x11 row = one tile)
-        if (g > cap) g = cap;
-        if (g < 1) g = 1;
-        const int br = unit * (int)((units + g - 1) / g);         // most rows of a CTA
-        if (br > 256) continue;                                    // one output row per thread in the epilogue
-        c->grid_g = (int)g; c->nchunks = nch; c->chunk_rows = (int)(units * unit);
-        c->ntiles = (br + 1 + TILE_ROWS - 1) / TILE_ROWS;         // one more row: the 0x11 row that yields sum_k X
-        if (c->ntiles * c->nbars > MAX_BARS) continue;
-        const int fin_bytes = c->npasses * c->ntiles * c->nt * 512;
+    const int64_t units = N / unit;
+    int64_t g = (N + TILE_ROWS - 2 - (unit - 1)) / (TILE_ROWS - unit);       // few rows: at most 15 (14) per CTA (+ the 0x11 row = one tile)
+    if (g > cap) g = cap;
+    if (g > units) g = units;
+    if (g < 1) g = 1;
+    c->grid_g = (int)g;
+    c->rows_q = (int)(units / g); c->rows_rem = (int)(units % g);
+    const int64_t br = unit * ((units + g - 1) / g);              // most rows of a CTA
+    if (br > 0x3fffffff) return false;
+    const int S = (int)((br + 1 + TILE_ROWS - 1) / TILE_ROWS);    // one more row: the 0x11 row that yields sum_k X
+    c->s_max = S;
+    // as many tile buffers as fit (all S tiles for the Llama shapes: no refills); 16 rows x 16 tiles = one output row
+    // per thread in the epilogue of a window
+    const int wmax = tuning().gemv_bufs > 0 ? tuning().gemv_bufs : 16;
+    for (int w = S < wmax ? S : wmax; w >= 1; --w) {
+        if (w * c->nbars > MAX_BARS) continue;
+        c->ntiles = w;
+        const int fin_bytes = c->npasses * w * c->nt * 512;
         const int red_bytes = 2 * NW * WARP_RED;
-        const int slot_bytes = (c->ntiles > 4 ? c->ntiles : 4) * NW * 512;      // >= 4 slots per warp: its exchange space
+        const int slot_bytes = (w > 4 ? w : 4) * NW * 512;        // >= 4 slots per warp: its exchange space
         // (1) single pass of <= 2 batch rows: one slot per (tile, warp); (2) double-buffered pipelined reduction
         for (int form = (c->nt == 1 && c->npasses == 1 && tuning().gemv_slots != 0) ? 0 : 1; form < 2; ++form) {
             c->slots = form == 0;
             c->red_off = OFF_DYN;
             c->fin_off = c->red_off + (c->slots ? slot_bytes : red_bytes);
             c->tile_off = (c->fin_off + fin_bytes + 1023) / 1024 * 1024;
-            c->smem = (size_t)c->tile_off + (size_t)c->ntiles * c->tile_bytes;
+            c->smem = (size_t)c->tile_off + (size_t)w * c->tile_bytes;
             if (c->smem <= (size_t)max_smem) return true;
         }
     }
@@ -680,9 +802,9 @@ int weight_map(const uint8_t* packed, int64_t N, int64_t K, int chunk, CUtensorM
     return 0;
 }
 
-template <int GPW2, int NT>
-int launch_dec_inst(const DecPlan& c, int grid_total, const CUtensorMap& map, const DecParams& p, bool pdl, cudaStream_t st) {
-    auto kfn = gemv_dec_kernel<GPW2, NT>;
+template <int GPW2, int NT, bool GEN>
+int launch_dec_inst(const DecPlan& c, dim3 grid, const CUtensorMap& map, const DecParams& p, bool pdl, cudaStream_t st) {
+    auto kfn = gemv_dec_kernel<GPW2, NT, GEN>;
     static thread_local int attr_dev_smem[64] = {0};
     int dev = 0;
     B200Q_CUDA(cudaGetDevice(&dev));
@@ -691,7 +813,7 @@ int launch_dec_inst(const DecPlan& c, int grid_total, const CUtensorMap& map, co
         attr_dev_smem[dev] = (int)c.smem;
     }
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)grid_total);
+    cfg.gridDim = grid;
     cfg.blockDim = dim3(NTHR);
     cfg.dynamicSmemBytes = c.smem;
     cfg.stream = st;
@@ -714,10 +836,15 @@ bool gemv_dec_supported(const DeviceInfo& dev, int64_t M, int64_t N, int64_t K, 
     return plan_dec(dev.sm_count, dev.max_smem_optin, M, N, K, &c, gated);
 }
 
+bool gemv_dec_resident(const DeviceInfo& dev, int64_t M, int64_t N, int64_t K, int gated) {
+    DecPlan c;
+    return plan_dec(dev.sm_count, dev.max_smem_optin, M, N, K, &c, gated) && c.s_max <= c.ntiles;
+}
+
 int launch_gemv_dec(const DeviceInfo& dev, const void* x, int x_dtype, const uint8_t* packed, const float* scales,
                     const float* zps, const float* bias, void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
                     unsigned flags, cudaStream_t st, const uint8_t* next_packed, size_t next_bytes, int gated,
-                    const int32_t* offsets, int n_experts) {
+                    const int32_t* offsets, int n_experts, const int32_t* row_map) {
     DecPlan c;
     if (n_experts < 1) n_experts = 1;
     if (!plan_dec(dev.sm_count, dev.max_smem_optin, M, N, K, &c, gated))
@@ -729,8 +856,18 @@ int launch_gemv_dec(const DeviceInfo& dev, const void* x, int x_dtype, const uin
     p.gated = gated;
     p.x_dtype = x_dtype; p.y_dtype = y_dtype;
     p.M = (int)M; p.N = (int)N; p.K = (int)K;
-    p.grid_g = c.grid_g; p.nchunks = c.nchunks; p.chunk_rows = c.chunk_rows;
+    p.rows_q = c.rows_q; p.rows_rem = c.rows_rem;
+    const int unit = gated ? 2 : 1;
+    auto windows = [&](int units, int* out) {                 // {R, T0} of a CTA with that many row units
+        const int S = (units * unit + 1 + TILE_ROWS - 1) / TILE_ROWS;
+        out[0] = (S + c.ntiles - 1) / c.ntiles;
+        out[1] = S - (out[0] - 1) * c.ntiles;
+    };
+    windows(c.rows_q + 1, p.win_hi);
+    windows(c.rows_q, p.win_lo);
+    const bool gen = offsets != nullptr || n_experts > 1 || c.s_max > c.ntiles;
     p.offsets = offsets;
+    p.row_map = offsets ? row_map : nullptr;
     p.npairs = c.npairs; p.nbars = c.nbars; p.chunk = c.chunk;
     p.ntiles_max = c.ntiles; p.tile_bytes = c.tile_bytes; p.tile_off = c.tile_off; p.npasses = c.npasses;
     p.red_off = c.red_off; p.fin_off = c.fin_off; p.slots = c.slots;
@@ -739,15 +876,17 @@ int launch_gemv_dec(const DeviceInfo& dev, const void* x, int x_dtype, const uin
     p.next_packed = next_packed;
     p.pf_mode = tuning().gemv_pf;
     p.next_bytes = (tuning().gemv_pf != 0 && next_packed && (reinterpret_cast<uintptr_t>(next_packed) & 15) == 0) ? next_bytes : 0;
-    const int grid_total = c.grid_g * c.nchunks * n_experts;
-    if (offsets) p.next_bytes = 0;
+    const int grid_total = c.grid_g * n_experts;
+    if (gen && n_experts > 1) p.next_bytes = 0;
     p.next_chunk = (unsigned int)(p.next_bytes / (unsigned long long)grid_total);
     p.debug = tuning().gemv_debug > 0 ? tuning().gemv_debug : 0;
     CUtensorMap map;
     if (int rc = weight_map(packed, N * n_experts, K, c.chunk, &map)) return rc;
     const bool pdl = tuning().gemv_pdl != 0;
-#define B200Q_DEC_CASE(GPW2_, NT_) \
-    if (c.gpw2 == GPW2_ && c.nt == NT_) return launch_dec_inst<GPW2_, NT_>(c, grid_total, map, p, pdl, st);
+    const dim3 grid((unsigned)c.grid_g, (unsigned)n_experts);
+#define B200Q_DEC_CASE(GPW2_, NT_)                                                                                  \
+    if (c.gpw2 == GPW2_ && c.nt == NT_)                                                                             \
+        return gen ? launch_dec_inst<GPW2_, NT_, true>(c, grid, map, p, pdl, st) : launch_dec_inst<GPW2_, NT_, false>(c, grid, map, p, pdl, st);
     B200Q_DEC_CASE(1, 1) B200Q_DEC_CASE(2, 1) B200Q_DEC_CASE(3, 1) B200Q_DEC_CASE(4, 1)
     B200Q_DEC_CASE(1, 2) B200Q_DEC_CASE(2, 2)
 #undef B200Q_DEC_CASE

@@ -46,6 +46,7 @@ struct Tuning {
     int gemv_occ2 = 0;      // 1: 8-warp CTAs sized so that two launches share an SM (cross-layer prefetch)
     int gemv_debug = -1;    // bench-only ablations: 1 = skip the mma work, 2 = skip the weight loads
     int force_path = -1;    // 0 auto, 1 generic SIMT, 2 ring decode kernel, 3 tcgen05 gemm, 6 resident decode kernel (gemv_dec)
+    int gemv_bufs = 0;      // resident decode kernel: cap on the tile buffers of a CTA (0 = as many as fit; tests force the ring with it)
     int gemv_slots = 1;     // resident decode kernel, M <= 2: 0 = pipelined cross-warp reduction instead of per-warp slots
 };
 const Tuning& tuning();
@@ -94,14 +95,18 @@ int launch_zero_rows_outside(void* y, int y_dtype, int64_t R, int64_t N, const i
 // device-addressable pinned host memory -> device buffer, `bytes` % 16 == 0 (one small kernel instead of a copy node)
 int launch_stage_host(const void* src_mapped, void* dst, size_t bytes, cudaStream_t st);
 
-// decode GEMV with the CTA's rows resident in shared memory (gemv_dec.cu): M <= 16, K % 256 == 0, K <= 16384; rows that do not
-// fit in one wave of CTAs run as a few waves (row chunks); no workspace; optional bias [N] f32; gated: fused SiLU-gate of
+// decode GEMV with the CTA's rows resident in shared memory (gemv_dec.cu): M <= 16, K % 256 == 0, K <= 16384; a CTA whose rows do not
+// fit in its tile buffers refills them as a ring; no workspace; optional bias [N] f32; gated: fused SiLU-gate of
 // interleaved gate / up rows; offsets != nullptr: grouped over n_experts experts (M = the largest group, <= 16)
 bool gemv_dec_supported(const DeviceInfo& dev, int64_t M, int64_t N, int64_t K, int gated = 0);
+bool gemv_dec_resident(const DeviceInfo& dev, int64_t M, int64_t N, int64_t K, int gated = 0);     // every tile of a CTA has its own buffer
 int launch_gemv_dec(const DeviceInfo& dev, const void* x, int x_dtype, const uint8_t* packed, const float* scales,
                     const float* zps, const float* bias, void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
                     unsigned flags, cudaStream_t st, const uint8_t* next_packed, size_t next_bytes, int gated = 0,
-                    const int32_t* offsets = nullptr, int n_experts = 1);
+                    const int32_t* offsets = nullptr, int n_experts = 1, const int32_t* row_map = nullptr);
+// decode-sized routing in one launch (moe.cu): T <= 16, E <= 256, k <= 8; src_token (optional): token of every sorted position
+int moe_route_small(const float* logits, int64_t T, int E, int k, int32_t* idx, float* weights, int32_t* counts, int32_t* offsets,
+                    int32_t* sorted_slot, int32_t* inv_perm, int32_t* src_token, cudaStream_t st);
 
 // prefill / grouped path on tcgen05 tensor cores (M >= 17 rows, K % 128 == 0, N % 16 == 0).
 // starts == nullptr: plain linear; else grouped over E experts (packed [E,N,K/2]).

@@ -17,13 +17,8 @@ namespace {
 constexpr int TOPK_WARPS = 8;
 constexpr int MAX_E_PER_LANE = 8;
 
-__global__ void __launch_bounds__(TOPK_WARPS * 32)
-moe_topk_kernel(const float* __restrict__ logits, int64_t T, int E, int k,
-                int32_t* __restrict__ idx, float* __restrict__ weights) {
-    const int lane = threadIdx.x & 31;
-    const int64_t t = (int64_t)blockIdx.x * TOPK_WARPS + (threadIdx.x >> 5);
-    if (t >= T) return;
-    const float* lr = logits + t * E;
+// one warp: softmax over the E logits of a token, top-k, renormalise; lane s < k returns slot s in (isel, wsel)
+__device__ __forceinline__ void topk_token(const float* __restrict__ lr, int E, int k, int lane, int& isel_out, float& wsel_out) {
     float v[MAX_E_PER_LANE];
     float mx = -INFINITY;
 #pragma unroll
@@ -82,9 +77,86 @@ moe_topk_kernel(const float* __restrict__ logits, int64_t T, int E, int k,
         wsum += best;
         if (lane == s) { wsel = best; isel = besti; }
     }
+    isel_out = isel;
+    wsel_out = bad ? __int_as_float(0x7fc00000) : wsel / wsum;
+}
+
+__global__ void __launch_bounds__(TOPK_WARPS * 32)
+moe_topk_kernel(const float* __restrict__ logits, int64_t T, int E, int k,
+                int32_t* __restrict__ idx, float* __restrict__ weights) {
+    const int lane = threadIdx.x & 31;
+    const int64_t t = (int64_t)blockIdx.x * TOPK_WARPS + (threadIdx.x >> 5);
+    if (t >= T) return;
+    int isel;
+    float wsel;
+    topk_token(logits + t * E, E, k, lane, isel, wsel);
     if (lane < k) {
         idx[t * k + lane] = isel;
-        weights[t * k + lane] = bad ? __int_as_float(0x7fc00000) : wsel / wsum;
+        weights[t * k + lane] = wsel;
+    }
+}
+
+// Decode-sized routing (T <= 16 tokens) in ONE launch of one CTA: warp t routes token t, then the T k assignments are
+// counting-sorted by expert (stable: equal experts keep token order) -- the same outputs as the four kernels above.
+// src_token (optional): token of every sorted position, so a consumer can read x in place instead of a gathered copy.
+constexpr int ROUTE_SMALL_T = 16;
+__global__ void __launch_bounds__(ROUTE_SMALL_T * 32)
+moe_route_small_kernel(const float* __restrict__ logits, int T, int E, int k, int32_t* __restrict__ idx,
+                       float* __restrict__ weights, int32_t* __restrict__ counts, int32_t* __restrict__ offsets,
+                       int32_t* __restrict__ sorted_slot, int32_t* __restrict__ inv_perm, int32_t* __restrict__ src_token) {
+    __shared__ int32_t s_idx[ROUTE_SMALL_T * 8];
+    __shared__ int32_t s_off[32 * MAX_E_PER_LANE + 1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int A = T * k;
+    if (warp < T) {
+        int isel;
+        float wsel;
+        topk_token(logits + (int64_t)warp * E, E, k, lane, isel, wsel);
+        if (lane < k) {
+            idx[warp * k + lane] = isel;
+            weights[warp * k + lane] = wsel;
+            s_idx[warp * k + lane] = isel;
+        }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < E; e += blockDim.x) {
+        int c = 0;
+        for (int a = 0; a < A; ++a) c += s_idx[a] == e ? 1 : 0;
+        counts[e] = c;
+        s_off[e] = c;
+    }
+    __syncthreads();
+    if (warp == 0) {                                         // exclusive scan of the E <= 256 counts
+        int v[MAX_E_PER_LANE], tot = 0;
+#pragma unroll
+        for (int j = 0; j < MAX_E_PER_LANE; ++j) {
+            const int e = lane * MAX_E_PER_LANE + j;
+            v[j] = e < E ? s_off[e] : 0;
+            tot += v[j];
+        }
+        int incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += n;
+        }
+        int run = incl - tot;
+#pragma unroll
+        for (int j = 0; j < MAX_E_PER_LANE; ++j) {
+            const int e = lane * MAX_E_PER_LANE + j;
+            if (e < E) { s_off[e] = run; offsets[e] = run; }
+            run += v[j];
+        }
+        if (lane == 31) offsets[E] = incl;
+    }
+    __syncthreads();
+    for (int a = threadIdx.x; a < A; a += blockDim.x) {
+        const int e = s_idx[a];
+        int pos = s_off[e];
+        for (int b = 0; b < a; ++b) pos += s_idx[b] == e ? 1 : 0;
+        sorted_slot[pos] = a;
+        inv_perm[a] = pos;
+        if (src_token) src_token[pos] = a / k;
     }
 }
 
@@ -262,7 +334,7 @@ __global__ void __launch_bounds__(256)
 combine_kernel(const YT* __restrict__ y, const int32_t* __restrict__ inv_perm,
                const float* __restrict__ weights, int k, int64_t F, OT* __restrict__ out) {
     const int64_t t = blockIdx.x;
-    for (int64_t f = threadIdx.x; f < F; f += blockDim.x) {
+    for (int64_t f = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; f < F; f += (int64_t)gridDim.y * blockDim.x) {
         float acc = 0.0f;
         for (int s = 0; s < k; ++s) {
             const int64_t p = inv_perm[t * k + s];
@@ -276,7 +348,10 @@ combine_kernel(const YT* __restrict__ y, const int32_t* __restrict__ inv_perm,
 template <typename YT>
 int combine_out(const void* y, const int32_t* inv_perm, const float* weights, int64_t T, int k,
                 int64_t F, void* out, int out_dtype, cudaStream_t st) {
-    dim3 grid(static_cast<unsigned>(T));
+    // few tokens (decode): spread the columns of a token over several CTAs as well
+    int64_t ny = T >= 256 ? 1 : (256 + T - 1) / T;
+    if (ny > (F + 255) / 256) ny = (F + 255) / 256;
+    dim3 grid(static_cast<unsigned>(T), static_cast<unsigned>(ny));
     switch (out_dtype) {
         case B200Q_F32:
             combine_kernel<YT, float><<<grid, 256, 0, st>>>(static_cast<const YT*>(y), inv_perm, weights, k, F, static_cast<float*>(out));
@@ -293,6 +368,15 @@ int combine_out(const void* y, const int32_t* inv_perm, const float* weights, in
 }
 
 }  // namespace
+
+int moe_route_small(const float* logits, int64_t T, int E, int k, int32_t* idx, float* weights, int32_t* counts, int32_t* offsets,
+                    int32_t* sorted_slot, int32_t* inv_perm, int32_t* src_token, cudaStream_t st) {
+    if (T < 1 || T > ROUTE_SMALL_T || E < 1 || E > 32 * MAX_E_PER_LANE || k < 1 || k > 8 || k > E)
+        return set_error(B200Q_EINVAL, "moe_route_small: need 1<=T<=16, 1<=E<=256, 1<=k<=min(8,E) (T=%lld E=%d k=%d)", (long long)T, E, k);
+    moe_route_small_kernel<<<1, ROUTE_SMALL_T * 32, 0, st>>>(logits, (int)T, E, k, idx, weights, counts, offsets, sorted_slot, inv_perm, src_token);
+    return check_cuda(cudaGetLastError(), "moe_route_small launch");
+}
+
 }  // namespace b200q
 
 using namespace b200q;
@@ -328,6 +412,9 @@ int b200q_moe_permute(const int32_t* idx, int64_t T, int E, int k, int32_t* coun
 int b200q_moe_route(const float* logits, const int32_t* remap, int64_t T, int E, int k, int32_t* idx, float* weights,
                     int32_t* counts, int32_t* offsets, int32_t* sorted_slot, int32_t* inv_perm, void* ws, size_t ws_bytes,
                     void* stream) {
+    if (!remap && T >= 1 && T <= ROUTE_SMALL_T && E >= 1 && E <= 32 * MAX_E_PER_LANE && k >= 1 && k <= 8 && k <= E && logits && idx &&
+        weights && counts && offsets && sorted_slot && inv_perm)
+        return moe_route_small(logits, T, E, k, idx, weights, counts, offsets, sorted_slot, inv_perm, nullptr, static_cast<cudaStream_t>(stream));
     if (int rc = b200q_moe_topk(logits, T, E, k, idx, weights, stream)) return rc;
     return b200q_moe_permute_mapped(idx, remap, T, E, k, counts, offsets, sorted_slot, inv_perm, ws, ws_bytes, stream);
 }

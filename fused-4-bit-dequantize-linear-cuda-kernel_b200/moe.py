@@ -200,7 +200,8 @@ class QuantizedMoE(nn.Module):
         """
         _lib.require_cuda(x, "x")
         if (routing is None and self.fused_gate and x.shape[0] <= 16 and self.hidden_dim % 256 == 0
-                and self.ffn_dim % 256 == 0 and max(self.hidden_dim, self.ffn_dim) <= 16384):
+                and self.ffn_dim % 256 == 0 and max(self.hidden_dim, self.ffn_dim) <= 16384
+                and self.num_experts <= 256 and top_k <= 8):
             # decode-sized call: the whole layer behind one C call, both expert GEMVs grouped on the resident decode kernel
             w13, w2 = self.stacked_weights()
             return _lib.moe_decode_fwd(x.contiguous(), router_logits.to(torch.float32).contiguous(), top_k, w13, w2)

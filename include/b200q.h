@@ -253,9 +253,10 @@ int b200q_moe_grouped_fwd_mapped(const void* xs, int x_dtype, const uint8_t* pac
 
 /* The whole routed gated layer for DECODE-sized calls (T <= 16 tokens) behind one C call:
  *   out[t,:] = sum_s p[t,s] * w2_e( silu(w1_e x[t,:]) * (w3_e x[t,:]) ),  e = expert of slot s of token t  (fp32)
- * = b200q_moe_route, b200q_moe_gather_rows, the fused gate / up GEMV and the down GEMV -- both grouped over the experts
- * with device-side row offsets on the resident decode kernel (experts without tokens exit at once; HBM-bound: only
- * the experts that were hit are read) -- and b200q_moe_combine.  packed13 [E,2F,d/2] (w1 / w3 interleaved), packed2
+ * Four launches: routing (softmax / top-k / counting sort in one CTA), the fused gate / up GEMV (reads x in place through
+ * the token map) and the down GEMV -- both grouped over the experts with device-side row offsets on the resident decode
+ * kernel (experts without tokens exit at once; HBM-bound: only the experts that were hit are read) -- and
+ * b200q_moe_combine.  E <= 256, k <= 8.  packed13 [E,2F,d/2] (w1 / w3 interleaved), packed2
  * [E,d,F/2]; d and F multiples of 256.  ws: >= b200q_moe_decode_ws_bytes, 256-byte aligned (no zero-fill needed).
  * B200Q_EINVAL when the shape does not fit the decode kernel (use the grouped tcgen05 path then). */
 size_t b200q_moe_decode_ws_bytes(int64_t T, int E, int k, int64_t d, int64_t F);

@@ -266,10 +266,43 @@ def test_resident_decode_kernel_edge_shapes(oracle, pkg, M, N, K):
     # default dispatch (resident kernel when K % 256 == 0, else ring kernel / tcgen05): deterministic, within the bar
     y = pkg._lib.linear_fwd(X, P, S, Z).cpu().numpy()
     assert np.array_equal(pkg._lib.linear_fwd(X, P, S, Z).cpu().numpy(), y)
-    if 6 in outs and (M <= 8 or K <= 8192):          # (wide K with M > 8 goes to the tcgen05 GEMM by default)
+    # (wide K goes to the tcgen05 GEMM by default with M > 8, and to the ring kernel with M >= 3 when the CTA has fewer
+    # tile buffers than tiles)
+    if 6 in outs and (M <= 8 or K <= 8192) and (M <= 2 or (N, K) != (4096, 14336)):
         assert np.array_equal(y, outs[6])
     for m in range(M):
         assert np.abs(ref[m] - y[m, rows]).max() <= 1e-4 * np.abs(ref[m]).max() + 1e-30
+
+
+@pytest.mark.parametrize("M", [1, 2, 3, 4, 7, 16])
+@pytest.mark.parametrize("N,K", [(2371, 2048), (11008, 4096), (4096, 11008), (4736, 1024), (4737, 1024), (9000, 256), (600, 16384)])
+@pytest.mark.parametrize("bufs", [1, 2, 3])
+def test_resident_decode_kernel_ring_of_tile_buffers(oracle, pkg, M, N, K, bufs):
+    """A CTA with fewer tile buffers than tiles (Mixtral's 14336-wide projections; forced here on smaller shapes with
+    the tuning key gemv_bufs) refills a buffer as soon as every warp is done with it and produces its outputs window by
+    window.  Integer partial sums: bit-identical to the all-resident form, whatever the number of buffers; plain and
+    gated (silu(gate) * up) outputs."""
+    rng = np.random.default_rng(M * 7 + N + K + bufs)
+    packed = rng.integers(0, 256, size=(N - (N & 1), K // 2), dtype=np.uint8)
+    N = packed.shape[0]
+    scales = (rng.random(N, dtype=np.float32) * 0.01 + 0.001).astype(np.float32)
+    zps = rng.integers(0, 16, size=N).astype(np.float32)
+    x = rng.standard_normal((M, K), dtype=np.float32)
+    P, S, Z, X = cuda(packed), cuda(scales), cuda(zps), cuda(x)
+    pkg._lib.tune("force_path", 6)
+    try:
+        y0 = pkg._lib.linear_fwd(X, P, S, Z).cpu().numpy()
+        g0 = pkg._lib.linear_gated_fwd(X, P, S, Z).cpu().numpy()
+        pkg._lib.tune("gemv_bufs", bufs)
+        y1 = pkg._lib.linear_fwd(X, P, S, Z).cpu().numpy()
+        g1 = pkg._lib.linear_gated_fwd(X, P, S, Z).cpu().numpy()
+    finally:
+        pkg._lib.tune("gemv_bufs", -1)
+        pkg._lib.tune("force_path", -1)
+    assert np.array_equal(y0, y1) and np.array_equal(g0, g1)
+    rows = rng.choice(N, size=min(N, 256), replace=False)
+    ref = oracle.reference_quantized_linear(x, packed[rows], scales[rows], zps[rows], acc=np.float64)
+    assert np.abs(ref - y1[:, rows]).max() <= 1e-6 * np.abs(ref).max()
 
 
 @pytest.mark.parametrize("M,N,K", [(1, 11008, 4096), (2, 4096, 11008), (2, 700, 2048), (1, 2368, 4096), (1, 2369, 4096)])

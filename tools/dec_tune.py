@@ -8,7 +8,7 @@ from b200q_pkg import pkg
 _lib = pkg._lib
 lib = _lib.load()
 dev = torch.device("cuda", 0)
-KEYS = ["gemv_early", "gemv_pf", "gemv_slots", "gemv_pdl", "gemv_ctas", "force_path"]
+KEYS = ["gemv_early", "gemv_pf", "gemv_slots", "gemv_bufs", "gemv_pdl", "gemv_ctas", "force_path"]
 pools = {}
 
 
@@ -29,7 +29,11 @@ def pool(N, K):
 
 def measure(M, K, N, tune, hint=True, reps=8):
     layers = pool(N, K)
-    for k in KEYS: _lib.tune(k, -1)
+    for k in KEYS:
+        try:
+            _lib.tune(k, -1)
+        except RuntimeError:
+            pass                                            # an older build (B200Q_LIB) without the key
     for k, v in tune.items(): _lib.tune(k, v)
     x = torch.randn(M, K, device=dev); y = torch.empty(M, N, device=dev)
     ws = torch.zeros(max(lib.b200q_linear_ws_bytes(M, N, K), 16), dtype=torch.uint8, device=dev)
@@ -56,7 +60,11 @@ def measure(M, K, N, tune, hint=True, reps=8):
         for _ in range(10): g.replay()
         e1.record(); torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1) * 1e3 / (10 * len(layers) * reps))
-    for k in KEYS: _lib.tune(k, -1)
+    for k in KEYS:
+        try:
+            _lib.tune(k, -1)
+        except RuntimeError:
+            pass                                            # an older build (B200Q_LIB) without the key
     return best
 
 
