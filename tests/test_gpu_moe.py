@@ -335,3 +335,42 @@ def test_moe_decode_mixtral_size_sampled(oracle, pkg):
                 h = (oracle.silu(gg) * uu).astype(np.float32)
                 ref[t] += wts[t, s] * oracle.reference_quantized_linear(h, *q2, acc=np.float64)[0].astype(np.float32)
         assert np.abs(y - ref).max() <= 3e-5 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_mixtral_size_grouped_gemm_prefill_rows_vs_oracle(oracle, pkg, dtype):
+    """Mixtral-8x7B expert shapes (E=8, d=4096, F=14336) at a prefill token count (2048 tokens x top-2 = 4096 rows,
+    ragged groups, one expert empty): rows of the grouped tcgen05 path (fused SiLU-gate GEMM, then the down GEMM)
+    against the float64 oracle composed from the reference's primitives -- first, middle and last row of two experts,
+    all d outputs of each."""
+    E, d, F = 8, 4096, 14336
+    g = torch.Generator(device="cuda").manual_seed(3)
+    moe = pkg.QuantizedMoE(E, d, F, gated=True).cuda()
+    w13, w2 = moe.stacked_weights()
+    for t in (w13, w2):
+        t[0].copy_(torch.randint(0, 256, t[0].shape, dtype=torch.uint8, device="cuda", generator=g))
+        t[1].copy_(torch.rand(t[1].shape, device="cuda", generator=g) * 0.002 + 0.0005)
+        t[2].copy_(torch.randint(0, 16, t[2].shape, device="cuda", generator=g).float())
+    counts = [700, 0, 1111, 300, 517, 64, 1403, 1]
+    R = sum(counts)
+    assert R == 4096
+    offs = torch.tensor(np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)).cuda()
+    xs = (torch.randn(R, d, device="cuda", generator=g) * 0.5).to(dtype)
+    y = moe.forward_grouped(xs, offs)
+    assert y.shape == (R, d)
+    yn, xn = y.float().cpu().numpy(), xs.float().cpu().numpy()
+    bufs = lambda m: tuple(getattr(m, b).cpu().numpy() for b in ("packed_weights", "scales", "zero_points"))
+    lo16 = (lambda a: torch.from_numpy(a.astype(np.float32)).to(dtype).float().numpy().astype(np.float64)) if dtype != torch.float32 else (lambda a: a)
+    for e in (2, 7):
+        lo, hi = int(offs[e]), int(offs[e + 1])
+        rows = sorted({lo, (lo + hi) // 2, hi - 1})
+        q1, q3, q2 = bufs(moe.experts[e]), bufs(moe.experts_up[e]), bufs(moe.experts_down[e])
+        gg = oracle.reference_quantized_linear(xn[rows], *q1, acc=np.float64)
+        uu = oracle.reference_quantized_linear(xn[rows], *q3, acc=np.float64)
+        h = lo16(oracle.silu(gg) * uu)                              # the layer keeps h in the activations' dtype
+        ref = oracle.reference_quantized_linear(h.astype(np.float32), *q2, acc=np.float64)
+        err = np.abs(yn[rows] - ref).max() / np.abs(ref).max()
+        print(f"expert {e} rows {rows}: rel err {err:.2e}")
+        # fp32: fp16 hi / lo split of the activations, fp32 accumulation over 4096 / 14336 terms; bf16: plus the rounding of
+        # h and y to bf16
+        assert err <= (3e-4 if dtype == torch.float32 else 1.5e-2)

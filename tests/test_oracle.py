@@ -1,6 +1,7 @@
 """The numpy oracle (oracle/int4_oracle.py) against the golden outputs of the REAL reference
 (tests/golden/*.npz, made by tests/golden/make_golden.py).  Runs on CPU."""
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -137,3 +138,44 @@ def test_quantize_weights_moe(oracle):
     assert np.array_equal(p, MI["packed"])
     assert np.array_equal(s, MI["scales"])
     assert np.array_equal(z, MI["zp"])
+
+
+# ---- oracle/oracle.c (the timed CPU arm of bench.py when oracle/_ref is absent): pinned on the same golden vectors --
+@pytest.fixture(scope="module")
+def c_oracle():
+    import subprocess
+    sys_path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle")
+    if not os.path.exists(os.path.join(sys_path, "_build", "liboracle.so")):
+        subprocess.check_call(["make", "-C", sys_path, "-s"])
+    import sys
+    sys.path.insert(0, sys_path)
+    import c_oracle as c
+    return c
+
+
+@pytest.mark.parametrize("name", ["s42_16x32", "s123_256x512", "s42_64x128", "s42_256x512", "edge"])
+def test_c_oracle_quantize_dequantize_bit_exact(c_oracle, name):
+    p, s, z = c_oracle.quantize_weights(Q[f"{name}_w"])
+    assert np.array_equal(p, Q[f"{name}_packed"])
+    assert np.array_equal(s.view(np.uint32), Q[f"{name}_scales"].view(np.uint32))
+    assert np.array_equal(z, Q[f"{name}_zp"])
+    d = c_oracle.dequantize_weights(Q[f"{name}_packed"], Q[f"{name}_scales"], Q[f"{name}_zp"])
+    assert np.array_equal(d.view(np.uint32), Q[f"{name}_deq"].view(np.uint32))
+
+
+def test_c_oracle_linear_vectors_and_numpy_oracle(c_oracle, oracle):
+    """The C restatement against the reference's own linear vectors and, on a Llama-sized slice, against the numpy
+    oracle (fp32 accumulation in a different order: tolerance, as in the reference's tests)."""
+    y = c_oracle.Linear(Q["s42_64x128_packed"], Q["s42_64x128_scales"], Q["s42_64x128_zp"])(L["t1d_x"])
+    assert np.allclose(y[0], L["t1d_y"], atol=1e-5, rtol=0)
+    y = c_oracle.Linear(Q["s42_256x512_packed"], Q["s42_256x512_scales"], Q["s42_256x512_zp"])(L["tb_x"])
+    assert np.allclose(y, L["tb_y"], atol=1e-4, rtol=0)
+    rng = np.random.default_rng(0)
+    packed = rng.integers(0, 256, size=(512, 2048), dtype=np.uint8)
+    scales = (rng.random(512, dtype=np.float32) * 0.01 + 0.001).astype(np.float32)
+    zps = rng.integers(0, 16, size=512).astype(np.float32)
+    x = rng.standard_normal((3, 4096), dtype=np.float32)
+    ref = oracle.reference_quantized_linear(x, packed, scales, zps, acc=np.float64)
+    y = c_oracle.Linear(packed, scales, zps)(x)
+    assert np.abs(y - ref).max() <= 2e-5 * np.abs(ref).max()
+    assert c_oracle.max_threads() >= 1
