@@ -27,12 +27,17 @@
 
 namespace b200q {
 
-// phase timestamps (SM clock) of every CTA, written when the bench-only "gemv_debug" value has
-// bit 3 (8) set; read back with b200q_debug_read_prof
+// bench-only (-DB200Q_PROF build, tools/prof_gemv.py): ablation switches (tuning key gemv_debug: 1 = skip the mma work,
+// 2 = skip the weight loads), phase timestamps of every CTA (bit 8; 16 = globaltimer instead of the SM clock) and the
+// wall-clock of the first CTA start / last CTA end of the last 64 profiled launches.  The product build compiles all of
+// it out.
+#ifdef B200Q_PROF
 __device__ long long g_gemv_prof[256 * 16];
-// wall-clock (globaltimer, ns) of the first CTA start / last CTA end of the last 64 profiled launches
 __device__ unsigned long long g_gemv_wall[64 * 4];
-__device__ unsigned int g_gemv_launch_no;
+#define B200Q_GEMV_DBG(p) ((p).debug)
+#else
+#define B200Q_GEMV_DBG(p) 0
+#endif
 
 namespace {
 
@@ -130,12 +135,13 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) gemv_kernel(const Ge
     volatile int* flag = reinterpret_cast<volatile int*>(smem + MISC_OFF);
     const uint32_t ring = smem_base + p.ring_off;
     const int S = p.stages;
-    const int dbg = p.debug & 3;
+    const int dbg = B200Q_GEMV_DBG(p) & 3;
     auto full_bar = [&](int s) { return smem_base + 8u * s; };
     auto empty_bar = [&](int s) { return smem_base + 512u + 8u * s; };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ctid = threadIdx.x;
+#ifdef B200Q_PROF
     const bool prof = (p.debug & 8) && threadIdx.x == 0 && blockIdx.x < 256;
     auto stamp = [&](int i) {
         if (prof) {
@@ -145,9 +151,12 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) gemv_kernel(const Ge
             g_gemv_prof[blockIdx.x * 16 + i] = tnow;
         }
     };
-    stamp(0);
     unsigned long long wall0 = 0;
     if (prof) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(wall0));
+#else
+    auto stamp = [](int) {};
+#endif
+    stamp(0);
     const int slab = p.nslab == 1 ? 0 : (int)(blockIdx.x % p.nslab);
     const int rb = p.nslab == 1 ? (int)blockIdx.x : (int)(blockIdx.x / p.nslab);
     const int g0 = slab * p.gran_q + min(slab, p.gran_rem);
@@ -566,6 +575,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) gemv_kernel(const Ge
         }
     }
     stamp(9);
+#ifdef B200Q_PROF
     if (prof) {
         unsigned long long wall1;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(wall1));
@@ -575,6 +585,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) gemv_kernel(const Ge
         atomicMin(&g_gemv_wall[ln * 4 + 2], wall1);
         atomicMax(&g_gemv_wall[ln * 4 + 3], wall1);
     }
+#endif
 
     // ---- cross-slab reduction by the last CTA of the row block (deterministic slab order)
     if (p.nslab > 1) {
@@ -930,6 +941,7 @@ int launch_gemv(const DeviceInfo& dev, const void* x, int x_dtype, const uint8_t
 
 }  // namespace b200q
 
+#ifdef B200Q_PROF
 /* bench-only: wall-clock records (64 launches x {min start, max start, min end, max end}); reset = 1 re-arms them */
 extern "C" int b200q_debug_wall(unsigned long long* h_out, int reset) {
     if (reset) {
@@ -944,3 +956,4 @@ extern "C" int b200q_debug_wall(unsigned long long* h_out, int reset) {
 extern "C" int b200q_debug_read_prof(long long* h_out) {
     return b200q::check_cuda(cudaMemcpyFromSymbol(h_out, b200q::g_gemv_prof, sizeof(long long) * 256 * 16), "read prof");
 }
+#endif

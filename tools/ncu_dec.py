@@ -18,10 +18,12 @@ for i in range(24):
 x = torch.randn(M, K, device=dev); y = torch.empty(M, N, device=dev)
 ws = torch.zeros(max(lib.b200q_linear_ws_bytes(M, N, K), 16), dtype=torch.uint8, device=dev)
 sp = torch.cuda.current_stream(dev).cuda_stream
+HINT = os.environ.get("HINT", "1") != "0"        # the bench's timed configuration passes the next layer's weights as an L2 hint
 for r in range(2):
     for i, (p, s, z) in enumerate(layers):
         nxt = layers[(i + 1) % 24][0]
         _lib.check(lib.b200q_linear_fwd_next(x.data_ptr(), 0, p.data_ptr(), s.data_ptr(), z.data_ptr(), y.data_ptr(), 0, M, N, K,
-                                             ws.data_ptr(), ws.numel(), 1, sp, nxt.data_ptr(), nxt.numel()), "fwd")
+                                             ws.data_ptr(), ws.numel(), 1, sp, nxt.data_ptr() if HINT else None,
+                                             nxt.numel() if HINT else 0), "fwd")
 torch.cuda.synchronize()
 print("ok")
