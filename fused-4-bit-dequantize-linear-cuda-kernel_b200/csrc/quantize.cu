@@ -26,14 +26,26 @@ __device__ __forceinline__ uint32_t quant1(float w, float scale, float zp) {
     return static_cast<uint32_t>(q);
 }
 
+// torch.min / torch.max return NaN when the row holds one (python/quantize.py:74-75); fminf / fmaxf would drop it
+__device__ __forceinline__ float min_nan(float a, float b) {
+    float d;
+    asm("min.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+    return d;
+}
+__device__ __forceinline__ float max_nan(float a, float b) {
+    float d;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+    return d;
+}
+
 __device__ __forceinline__ float warp_min(float v) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    for (int o = 16; o > 0; o >>= 1) v = min_nan(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    for (int o = 16; o > 0; o >>= 1) v = max_nan(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
 
@@ -52,19 +64,19 @@ quantize_rows_kernel(const float* __restrict__ w, int64_t K, const float* __rest
                      ((reinterpret_cast<uintptr_t>(pr) & 3) == 0);
 
     if (!GIVEN) {
-        float mn = FLT_MAX, mx = -FLT_MAX;
+        float mn = INFINITY, mx = -INFINITY;       // (a row of +inf has min = +inf)
         if (vec) {
             const float4* w4 = reinterpret_cast<const float4*>(wr);
             for (int64_t i = threadIdx.x; i < K / 4; i += QTHREADS) {
                 float4 v = w4[i];
-                mn = fminf(fminf(mn, v.x), fminf(v.y, fminf(v.z, v.w)));
-                mx = fmaxf(fmaxf(mx, v.x), fmaxf(v.y, fmaxf(v.z, v.w)));
+                mn = min_nan(min_nan(mn, v.x), min_nan(v.y, min_nan(v.z, v.w)));
+                mx = max_nan(max_nan(mx, v.x), max_nan(v.y, max_nan(v.z, v.w)));
             }
         } else {
             for (int64_t i = threadIdx.x; i < K; i += QTHREADS) {
                 float v = wr[i];
-                mn = fminf(mn, v);
-                mx = fmaxf(mx, v);
+                mn = min_nan(mn, v);
+                mx = max_nan(mx, v);
             }
         }
         mn = warp_min(mn);
@@ -77,13 +89,13 @@ quantize_rows_kernel(const float* __restrict__ w, int64_t K, const float* __rest
         if (threadIdx.x == 0) {
 #pragma unroll
             for (int i = 1; i < QTHREADS / 32; ++i) {
-                mn = fminf(mn, s_min[i]);
-                mx = fmaxf(mx, s_max[i]);
+                mn = min_nan(mn, s_min[i]);
+                mx = max_nan(mx, s_max[i]);
             }
             // python/quantize.py:80-94
             float scale = __fdiv_rn(__fsub_rn(mx, mn), 15.0f);
             if (mx == mn) scale = __fdiv_rn(fmaxf(fabsf(mx), 1.0f), 15.0f);
-            scale = fmaxf(scale, 1e-8f);
+            scale = scale < 1e-8f ? 1e-8f : scale;          // torch.clamp(min=1e-8): NaN stays NaN (:94)
             // python/quantize.py:100-101
             float zp = rintf(__fdiv_rn(-mn, scale));
             zp = clamp_like_torch(zp, 0.0f, 15.0f);
@@ -164,12 +176,12 @@ minmax_kernel(const float* __restrict__ v, int64_t count, float* __restrict__ ou
     unsigned int* counter = reinterpret_cast<unsigned int*>(ws + 2 * MM_MAX_BLOCKS);
     __shared__ float s_min[QTHREADS / 32], s_max[QTHREADS / 32];
     __shared__ bool s_last;
-    float mn = FLT_MAX, mx = -FLT_MAX;
+    float mn = INFINITY, mx = -INFINITY;       // (a row of +inf has min = +inf)
     for (int64_t i = blockIdx.x * (int64_t)QTHREADS + threadIdx.x; i < count;
          i += (int64_t)gridDim.x * QTHREADS) {
         float x = v[i];
-        mn = fminf(mn, x);
-        mx = fmaxf(mx, x);
+        mn = min_nan(mn, x);
+        mx = max_nan(mx, x);
     }
     mn = warp_min(mn);
     mx = warp_max(mx);
@@ -180,8 +192,8 @@ minmax_kernel(const float* __restrict__ v, int64_t count, float* __restrict__ ou
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int i = 1; i < QTHREADS / 32; ++i) {
-            mn = fminf(mn, s_min[i]);
-            mx = fmaxf(mx, s_max[i]);
+            mn = min_nan(mn, s_min[i]);
+            mx = max_nan(mx, s_max[i]);
         }
         part_min[blockIdx.x] = mn;
         part_max[blockIdx.x] = mx;
@@ -192,11 +204,11 @@ minmax_kernel(const float* __restrict__ v, int64_t count, float* __restrict__ ou
     __syncthreads();
     if (s_last) {
         __threadfence();
-        mn = FLT_MAX;
-        mx = -FLT_MAX;
+        mn = INFINITY;
+        mx = -INFINITY;
         for (int i = threadIdx.x; i < (int)gridDim.x; i += QTHREADS) {
-            mn = fminf(mn, __ldcg(part_min + i));
-            mx = fmaxf(mx, __ldcg(part_max + i));
+            mn = min_nan(mn, __ldcg(part_min + i));
+            mx = max_nan(mx, __ldcg(part_max + i));
         }
         mn = warp_min(mn);
         mx = warp_max(mx);
@@ -207,8 +219,8 @@ minmax_kernel(const float* __restrict__ v, int64_t count, float* __restrict__ ou
         __syncthreads();
         if (threadIdx.x == 0) {
             for (int i = 1; i < QTHREADS / 32; ++i) {
-                mn = fminf(mn, s_min[i]);
-                mx = fmaxf(mx, s_max[i]);
+                mn = min_nan(mn, s_min[i]);
+                mx = max_nan(mx, s_max[i]);
             }
             out[0] = mn;
             out[1] = mx;

@@ -71,14 +71,39 @@ class QuantizedLinear(nn.Module):
         module.zero_points = zp
         return module
 
+    def _fast_state(self):
+        """(packed, scales, zero_points, bias, device, plain) of the buffers as they are now.  nn.Module resolves a buffer
+        name through __getattr__ (~0.4 us each, five per call: as much as the C call itself); this keeps the tensors in
+        a tuple that is rebuilt whenever one of them has been replaced (identity check against _buffers)."""
+        b = self._buffers
+        st = self.__dict__.get("_fast")
+        p = b["packed_weights"]
+        bias = b.get("bias")
+        if bias is None:
+            bias = self.__dict__.get("bias")
+        if st is None or st[0] is not p or st[1] is not b["scales"] or st[2] is not b["zero_points"] or st[3] is not bias:
+            st = (p, b["scales"], b["zero_points"], bias, p.device, p.is_contiguous() and not self.group_size)
+            self.__dict__["_fast"] = st
+        return st
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if not x.is_cuda:
             if self.packed_weights.is_cuda and x.is_pinned():
                 return self.forward_host(x)        # host-resident caller: copies + kernel enqueued by one C call
             raise RuntimeError("QuantizedLinear (b200) runs on CUDA only; move the module and the input to a B200 "
                                "(or pass a pinned host tensor to a module that lives on the GPU)")
-        if self.packed_weights.device != x.device:
-            raise RuntimeError(f"weights are on {self.packed_weights.device}, input on {x.device}")
+        st = self._fast_state()
+        if st[4] != x.device:
+            raise RuntimeError(f"weights are on {st[4]}, input on {x.device}")
+        ext = _lib.torch_ext()
+        if ext is not None and st[5] and x.is_contiguous() and x.shape[-1] == self.in_features:
+            # compiled binding: checks, output / workspace allocation, stream lookup and the C-ABI call in one C++ function
+            nxt = self._next
+            y = ext.linear_forward(x, st[0], st[1], st[2], st[3], None,
+                                   _lib.FLAG_STATIC_WEIGHTS if self._weights_settled else _lib.FLAG_NONE,
+                                   nxt._buffers["packed_weights"] if nxt is not None else None)
+            self._weights_settled = True
+            return y
         return self._forward_cuda(x)
 
     def _forward_cuda(self, x: torch.Tensor) -> torch.Tensor:

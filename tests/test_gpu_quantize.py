@@ -82,3 +82,24 @@ def test_quantize_weights_moe_bit_exact(pkg):
     assert np.array_equal(p.cpu().numpy(), MI["packed"])
     assert np.array_equal(s.cpu().numpy(), MI["scales"])
     assert np.array_equal(z.cpu().numpy(), MI["zp"])
+
+
+def test_quantize_rows_with_nan_and_inf_match_the_reference(pkg, oracle):
+    """torch.min / max propagate NaN and the formulas of python/quantize.py:80-109 then run on non-finite numbers: a row
+    with a NaN gets scale = zp = NaN, a row with +inf scale = inf and zp = 0, a row with -inf scale = inf and zp = NaN;
+    every byte of such rows is 0.  (Checked against the real reference when this test was written; the oracle restates it.)"""
+    import warnings
+    rng = np.random.default_rng(5)
+    w = rng.standard_normal((6, 64)).astype(np.float32)
+    w[1, 3] = np.nan
+    w[2, 5] = np.inf
+    w[3, 7] = -np.inf
+    w[4, :] = np.inf
+    w[5, 0], w[5, 9] = np.inf, -np.inf
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        p0, s0, z0 = oracle.quantize_weights(w)
+    p, s, z = (t.cpu().numpy() for t in pkg.quantize_weights(torch.from_numpy(w).cuda()))
+    assert np.array_equal(p, p0) and not p[1:].any()
+    assert np.array_equal(s, s0, equal_nan=True) and np.array_equal(z, z0, equal_nan=True)
+    assert np.isnan(s[1]) and np.isnan(z[1]) and np.isinf(s[2]) and z[2] == 0 and np.isnan(z[3])
