@@ -10,19 +10,26 @@
 // fp32 FMA), so non-finite inputs propagate exactly like dequantize + F.linear (python/quantize.py:172, 202).
 //
 // Structure:
-//   * weights: tile i = 16 rows x K/2 bytes arrives as TMA tensor boxes [16 rows x 128 bytes] with the 128-byte
-//     swizzle (one box per 256-column "pair", or one 3-D box per group of pairs), so that the 8-row LDS.128 of a
-//     warp is conflict-free for ANY row stride -- no K split, no skewed copies, K only has to be a multiple of 128.
-//     One single-use mbarrier per (tile, pair group);
-//   * warp w owns the column pairs w, w + 16, ... of every tile: it loads, converts and keeps the B fragments of
-//     exactly those columns (warp-private exchange buffer, __syncwarp only); the one block barrier of a pass is
-//     the row amax;
-//   * sum X for the zero-point term comes from the digit words (IDP4A), not from a second pass;
-//   * cross-warp reduction is pipelined: after tile i every warp parks its 16 x 8 partial tile in a double
-//     buffer (mbarrier full / empty), and all 512 threads fold the 16 partials of tile i - 1 into the
-//     accumulator (integer adds: exact, order independent) while the tensor cores work on tile i + 1;
-//   * M = 3..16: passes of up to four batch rows (two n-tiles) over the resident tiles -- the weights are read
-//     from HBM once whatever M is.
+//   * weights: tile i = 16 rows x K/2 bytes arrives as 3-D TMA tensor boxes [16 rows][chunk pairs][128 bytes] (pair =
+//     256 columns) with the 128-byte swizzle, one box and one mbarrier per (tile, pair group): shared memory holds
+//     [pair][row][128 B], which ldmatrix.x4 turns into IMMA A fragments without bank conflicts whatever K is.  K only
+//     has to be a multiple of 256; no K split, no repacked copy of the weights;
+//   * warp w owns the pairs w, w + 16, ... of every tile: it loads, converts and keeps the B fragments of exactly those
+//     columns (exchange through its own 2 KB of shared memory, __syncwarp only); the one block barrier of a pass is the
+//     row amax;
+//   * sum X for the zero-point term: a row of bytes 0x11 behind the CTA's last weight row makes the tensor cores
+//     deliver it as one more output row;
+//   * cross-warp reduction, one pass of <= 2 batch rows: every (tile, warp) parks its 16 x 8 partial tile in its own
+//     slot, folded once after the loop (integer adds: exact, order independent);
+//     otherwise pipelined: partial tiles go through a double buffer (mbarrier full / empty) and all 512 threads fold
+//     tile i - 1 into the accumulator with red.shared.add while the tensor cores work on tile i + 1;
+//   * M = 3..16: passes of up to four batch rows (two n-tiles) over the resident tiles -- the weights are read from
+//     HBM once whatever M is;
+//   * GEN instances (template flag): ring of tile buffers for CTAs whose rows do not fit (a buffer is requested again
+//     once all warps are done with it; outputs window by window), grouped mode over experts with device-side row
+//     offsets and a token map (MoE decode), gated epilogue silu(gate) * up.  The plain instances carry none of it:
+//     code that runs once per launch costs 5 - 12 clk per instruction and warp here (profiles/r02_decode_notes.md);
+//   * no integer division in the kernel: geometry comes from the host.
 //
 // Reference being replaced: csrc/quantized_linear_kernel.cu:90-279 (one thread per output, M x weight traffic).
 #include <cuda.h>

@@ -99,7 +99,7 @@ def test_llama_mixtral_decode_shapes(oracle, K, N, M):
     scale = np.abs(ref).max()
     print(f"K={K} N={N} M={M}: max abs err {err:.3e}, |y|max {scale:.2f}, rel {err / scale:.2e}")
     # exact-integer IMMA path (error = final fp32 rounding) for M <= 16 on the Llama shapes and M <= 8 on Mixtral's
-    # (resident decode kernel, row chunks); Mixtral M = 16: tcgen05 path, fp16 hi/lo split of x, fp32 accumulation over up to 14336 terms
+    # (resident decode kernel, ring of tile buffers); Mixtral M = 16: tcgen05 path, fp16 hi/lo split of x, fp32 accumulation over up to 14336 terms
     assert err < 1e-2 and err / scale < (2e-5 if (M <= 8 or 14336 not in (K, N)) else 1e-4)
     # linearity: f(2x) == 2 f(x) exactly (power-of-two scaling commutes with every rounding step)
     y2 = ext.forward(cuda(2 * x), P, S, Z).cpu().numpy()
@@ -235,7 +235,7 @@ def test_forward_host_pinned(oracle, pkg):
 def test_resident_decode_kernel_edge_shapes(oracle, pkg, M, N, K):
     """Ragged row counts (fewer tiles than SMs, last tile partly foreign / out of bounds), every batch size of the
     decode path (passes of two or four batch rows), one to four column pairs per warp, K = 128 mod 256 (half-empty
-    last TMA box), shapes whose rows do not fit one wave of CTAs (row chunks: several waves in one launch); the
+    last TMA box), shapes whose rows do not fit in a CTA's tile buffers (ring: buffers are refilled, outputs window by window); the
     resident kernel against the float64 oracle and, for M <= 8, against the ring kernel."""
     rng = np.random.default_rng(1000 * M + N + K)
     packed = rng.integers(0, 256, size=(N, K // 2), dtype=np.uint8)
