@@ -98,6 +98,38 @@ at::Tensor linear_forward(const at::Tensor& input, const at::Tensor& packed_weig
     return y;
 }
 
+// Host-resident caller (python/module.py:100-118 with x on the CPU and the module on the GPU): pinned x in, pinned y out;
+// the staging copies and the kernel are enqueued by one C call (b200q_linear_fwd_host).  x_stage / y_stage: the caller's
+// device staging buffers ([M, K] / [M, N] of the activations' dtype).
+at::Tensor linear_forward_host(const at::Tensor& x_host, const at::Tensor& x_stage, const at::Tensor& packed_weights,
+                               const at::Tensor& scales, const at::Tensor& zero_points, const at::Tensor& y_stage,
+                               const at::Tensor& y_host, int64_t flags) {
+    TORCH_CHECK(!x_host.is_cuda() && !y_host.is_cuda(), "x_host / y_host must be host tensors (pinned)");
+    TORCH_CHECK(x_host.is_contiguous() && y_host.is_contiguous() && x_stage.is_contiguous() && y_stage.is_contiguous(),
+                "activations must be contiguous");
+    TORCH_CHECK(packed_weights.is_cuda() && scales.is_cuda() && zero_points.is_cuda() && x_stage.is_cuda() && y_stage.is_cuda(),
+                "weights and staging buffers must be CUDA tensors");
+    TORCH_CHECK(packed_weights.is_contiguous() && scales.is_contiguous() && zero_points.is_contiguous(), "weights must be contiguous");
+    TORCH_CHECK(packed_weights.scalar_type() == at::kByte && scales.scalar_type() == at::kFloat && zero_points.scalar_type() == at::kFloat,
+                "packed_weights must be uint8, scales / zero_points float32");
+    TORCH_CHECK(x_host.dim() == 2 && packed_weights.dim() == 2, "x_host must be [M, K], packed_weights [N, K / 2]");
+    const int64_t M = x_host.size(0), K = x_host.size(1), N = packed_weights.size(0);
+    TORCH_CHECK(K % 2 == 0 && packed_weights.size(1) == K / 2, "packed_weights dim 1 must be input_dim / 2");
+    TORCH_CHECK(x_stage.numel() >= M * K && y_stage.numel() >= M * N && y_host.numel() == M * N, "staging / output buffers too small");
+    TORCH_CHECK(x_stage.scalar_type() == x_host.scalar_type() && y_stage.scalar_type() == y_host.scalar_type(), "staging dtypes must match");
+    const c10::cuda::CUDAGuard guard(packed_weights.device());
+    cudaStream_t stream = c10::cuda::getCurrentCUDAStream(packed_weights.device().index()).stream();
+    const size_t ws_bytes = b200q_linear_ws_bytes(M, N, K);
+    at::Tensor ws;
+    if (ws_bytes) ws = workspace(packed_weights.device(), stream, ws_bytes);
+    const int rc = b200q_linear_fwd_host(x_host.data_ptr(), dtype_code(x_host.scalar_type()), x_stage.data_ptr(),
+                                         packed_weights.data_ptr<uint8_t>(), scales.data_ptr<float>(), zero_points.data_ptr<float>(),
+                                         y_stage.data_ptr(), y_host.data_ptr(), dtype_code(y_host.scalar_type()), M, N, K,
+                                         ws_bytes ? ws.data_ptr() : nullptr, ws_bytes ? (size_t)ws.numel() : 0, (unsigned)flags, stream);
+    TORCH_CHECK(rc == 0, "b200q_linear_fwd_host failed (code ", rc, "): ", b200q_last_error_string());
+    return y_host;
+}
+
 // the reference's extension surface: forward(input [K] or [M,K] f32, packed, scales, zero_points) -> [N] or [M,N] f32
 at::Tensor forward(const at::Tensor& input, const at::Tensor& packed_weights, const at::Tensor& scales,
                    const at::Tensor& zero_points) {
@@ -115,5 +147,8 @@ PYBIND11_MODULE(b200q_torch, m) {
     m.def("linear_forward", &linear_forward, "fused INT4 dequantize + linear: any leading dims, f32 / f16 / bf16, bias, flags, next-layer hint",
           py::arg("input"), py::arg("packed_weights"), py::arg("scales"), py::arg("zero_points"), py::arg("bias") = py::none(),
           py::arg("out_dtype") = py::none(), py::arg("flags") = 0, py::arg("next_packed") = py::none());
+    m.def("linear_forward_host", &linear_forward_host, "pinned host activations in, pinned host result out (one C call enqueues copies + kernel)",
+          py::arg("x_host"), py::arg("x_stage"), py::arg("packed_weights"), py::arg("scales"), py::arg("zero_points"), py::arg("y_stage"),
+          py::arg("y_host"), py::arg("flags") = 0);
     m.def("version", []() { return b200q_version(); });
 }

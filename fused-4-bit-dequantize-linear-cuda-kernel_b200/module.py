@@ -146,6 +146,13 @@ class QuantizedLinear(nn.Module):
         x2 = x_host.reshape(-1, self.in_features)
         M = x2.shape[0]
         dev = self.packed_weights.device
+        if self.bias is not None or self.group_size or not self.packed_weights.is_contiguous():
+            # (bias / group-wise scales / strided views: the device path, with the two copies enqueued around it)
+            y = self.forward(x2.to(dev, non_blocking=True))
+            if out is None:
+                out = torch.empty((M, self.out_features), dtype=x2.dtype).pin_memory()
+            out.view(M, self.out_features).copy_(y, non_blocking=True)
+            return out.reshape(*x_host.shape[:-1], self.out_features)
         st = getattr(self, "_stage", None)
         if st is None or st[0].shape[0] != M or st[0].dtype != x2.dtype:
             st = (torch.empty((M, self.in_features), dtype=x2.dtype, device=dev),
@@ -154,7 +161,12 @@ class QuantizedLinear(nn.Module):
         if out is None:
             out = torch.empty((M, self.out_features), dtype=x2.dtype).pin_memory()
         flags = _lib.FLAG_STATIC_WEIGHTS if self._weights_settled else _lib.FLAG_NONE
-        _lib.linear_fwd_host(x2, st[0], self.packed_weights, self.scales, self.zero_points, st[1], out, flags=flags)
+        ext = _lib.torch_ext()
+        fs = self._fast_state()
+        if ext is not None and fs[5] and x2.is_contiguous() and out.is_contiguous() and out.dtype == x2.dtype:
+            ext.linear_forward_host(x2, st[0], fs[0], fs[1], fs[2], st[1], out.view(M, self.out_features), flags)
+        else:
+            _lib.linear_fwd_host(x2, st[0], self.packed_weights, self.scales, self.zero_points, st[1], out, flags=flags)
         self._weights_settled = True
         return out.reshape(*x_host.shape[:-1], self.out_features)
 

@@ -447,6 +447,25 @@ def test_wide_k_and_16bit_decode(oracle, pkg, dtype, M, N, K):
         assert np.array_equal(pkg._lib.linear_fwd(X, P, S, Z, out_dtype=torch.float32).cpu().numpy(), outs[6])
 
 
+def test_forward_host_with_bias_and_compiled_binding(oracle, pkg):
+    """Pinned host activations through a module with a bias (device path + copies) and without one (one C call through
+    the compiled binding when it is built): both against the float64 oracle."""
+    torch.manual_seed(3)
+    for bias in (False, True):
+        lin = torch.nn.Linear(1024, 384, bias=bias)
+        ql = pkg.QuantizedLinear.from_linear(lin.cuda())
+        p0, s0, z0 = oracle.quantize_weights(lin.weight.detach().cpu().numpy())
+        for M in (1, 5, 40):
+            x = torch.randn(M, 1024).pin_memory()
+            y = ql(x)
+            torch.cuda.synchronize()
+            assert not y.is_cuda and y.shape == (M, 384)
+            ref = oracle.reference_quantized_linear(x.numpy(), p0, s0, z0, acc=np.float64)
+            if bias:
+                ref = ref + lin.bias.detach().cpu().numpy().astype(np.float64)
+            assert np.abs(y.numpy() - ref).max() <= 1e-4 * np.abs(ref).max()
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_forward_host_direct_and_copy_paths_agree(oracle, pkg, dtype):
     """b200q_linear_fwd_host for decode-sized calls: staging kernel + stores straight into the pinned result buffer
