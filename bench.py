@@ -557,6 +557,9 @@ def run_gemv(args):
             if "cpu_baseline" in ml:
                 line["moe"]["cpu_baseline"] = ml["cpu_baseline"]
             line["moe_decode"] = moe_decode(torch, pkg, dev, peak)
+            if not args.no_sweeps:
+                from bench_moe import moe_prefill_sweep
+                line["moe_prefill"] = moe_prefill_sweep(torch, pkg, dev, float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])))
         except Exception as e:      # the headline line must not depend on the extra measurement
             line["moe"] = {"error": repr(e)[:200]}
     print(json.dumps(line))

@@ -183,7 +183,8 @@ def cpu_moe_reference(steps=2, tokens=512):
 
 
 def moe_decode(torch, pkg, dev, hbm_peak):
-    """BASELINE.json configs[3], decode: T = 1, 4, 16 tokens through QuantizedMoE.forward_routed (random routing).
+    """BASELINE.json configs[3], decode: T = 1, 4, 16 tokens through QuantizedMoE.forward_routed (random routing): the
+    decode call (grouped GEMVs) up to three rows per expert on average, the grouped tcgen05 GEMMs above (T = 16).
     HBM-bound: algorithmic bytes = (#distinct experts hit) x 88 MB of packed INT4 weights."""
     layer = build_local_moe(torch, pkg, list(range(E)), dev)
     out = []
@@ -194,6 +195,20 @@ def moe_decode(torch, pkg, dev, hbm_peak):
         nb = hit * EXPERT_BYTES
         out.append({"T": T, "experts_hit": hit, "ms": round(ms, 4), "tokens_per_s": round(T / (ms * 1e-3), 1),
                     "GBps": round(nb / ms / 1e6, 1), "frac_hbm_peak": round(nb / ms / 1e6 / hbm_peak, 4)})
+    return out
+
+
+def moe_prefill_sweep(torch, pkg, dev, tf_peak):
+    """BASELINE.json configs[3], prefill: T = 512, 2048, 8192 tokens through QuantizedMoE.forward_routed on one GPU
+    (random routing; T = 16384 is the `moe` headline).  Tensor-bound: FLOPs = T x 704,643,072."""
+    layer = build_local_moe(torch, pkg, list(range(E)), dev)
+    out = []
+    for T in (512, 2048, 8192):
+        x, logits = make_inputs(torch, 0, T, "random", dev)
+        ms = time_steps(torch, None, dev, lambda: layer.forward_routed(x, logits, top_k=TOPK), 10, 3)
+        tf = T * FLOPS_PER_TOKEN / (ms * 1e-3) / 1e12
+        out.append({"T": T, "ms": round(ms, 4), "tokens_per_s": round(T / (ms * 1e-3), 1), "TFLOPs": round(tf, 1),
+                    "frac_bf16_sustained_peak": round(tf / tf_peak, 4)})
     return out
 
 

@@ -1,0 +1,16 @@
+"""Mixtral layer, T = 1..16 tokens: the decode call (b200q_moe_decode_fwd: grouped GEMVs) against the prefill-shaped path
+(route -> gather -> grouped tcgen05 GEMMs -> combine), ms per layer call (CUDA events, eager)."""
+import os, sys, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from b200q_pkg import pkg
+from bench_moe import build_local_moe, make_inputs, time_steps, E, TOPK
+dev = torch.device("cuda", 0)
+layer = build_local_moe(torch, pkg, list(range(E)), dev)
+w13, w2 = layer.stacked_weights()
+for T in (1, 2, 4, 6, 8, 12, 16):
+    x, logits = make_inputs(torch, 0, T, "random", dev)
+    lg = logits.float().contiguous()
+    a = time_steps(torch, None, dev, lambda: pkg._lib.moe_decode_fwd(x, lg, TOPK, w13, w2), 30, 5)
+    b = time_steps(torch, None, dev, lambda: layer.forward_dispatched(x, pkg.route(logits, TOPK)), 30, 5)
+    print(json.dumps({"T": T, "decode_call_ms": round(a, 4), "grouped_gemm_ms": round(b, 4)}))
