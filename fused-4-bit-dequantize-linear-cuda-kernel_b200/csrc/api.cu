@@ -103,13 +103,17 @@ int b200q_linear_bias_fwd(const void* x, int x_dtype, const uint8_t* packed, con
     // (wide K with many batch rows would need > 4 passes of two rows: the tcgen05 GEMM is faster there)
     // (K > 8192 with M >= 3 and fewer tile buffers than tiles -- Mixtral's down projection -- refills only in the last
     // pass over a buffer: measured slower than the ring kernel below, 32 vs 28 us at M = 4)
+    // (measured crossovers with the tcgen05 GEMM, tools/dec_tune.py: 11008 -> 4096 M = 9 27.8 vs 31.9 us, M = 12 34.6 vs 32.1)
+    const bool dec_res = gemv_dec_resident(d, M, N, K);
     if ((force <= 0 || force == 6) && vec_ok && gemv_dec_supported(d, M, N, K) &&
-        (force == 6 || ((M <= 8 || K <= 8192) && (M <= 2 || K <= 8192 || gemv_dec_resident(d, M, N, K)))))
+        (force == 6 || ((M <= 8 || K <= 8192 || (M <= 10 && dec_res)) && (M <= 2 || K <= 8192 || dec_res))))
         return launch_gemv_dec(d, x, x_dtype, packed, scales, zps, bias, y, y_dtype, M, N, K, flags, st, next_packed, next_bytes);
     int rc = 0;
     bool done = false;
     // ... else the ring kernel (M <= 8: e.g. Mixtral's 14336-wide projections, 198 KB of weights per SM)
-    if (!done && (force <= 0 || force == 2) && vec_ok && gemv_supported(M, N, K, x_dtype)) {
+    // (14336 -> 4096: 24 / 28 / 40 / 49 us at M = 3 / 4 / 5 / 8 against 38 us for the 32-token tiles of the tcgen05 GEMM)
+    if (!done && (force <= 0 || force == 2) && vec_ok && gemv_supported(M, N, K, x_dtype) &&
+        (force == 2 || M <= 4 || K <= 8192 || !gemm_tc_supported(M, N, K, x_dtype, y_dtype))) {
         rc = launch_gemv(d, x, x_dtype, packed, scales, zps, y, y_dtype, M, N, K, ws, ws_bytes, flags, st, next_packed, next_bytes);
         if (!rc) rc = launch_nonfinite_fixup(x, x_dtype, packed, scales, zps, nullptr, y, y_dtype, M, N, K, nullptr, nullptr, 1, 0, st);
         done = true;
