@@ -366,7 +366,8 @@ def test_decode_non_integer_zero_points(oracle, pkg):
 
 
 # ---- tcgen05 GEMM: stream-K and small token tiles ----------------------------------------------------------
-@pytest.mark.parametrize("M,N,K", [(300, 4096, 11008), (70, 1000, 1024), (520, 2048, 2048), (1100, 640, 4096)])
+@pytest.mark.parametrize("M,N,K", [(300, 4096, 11008), (70, 1000, 1024), (520, 2048, 2048), (1100, 640, 4096),
+                                   (17, 11008, 4096), (33, 11008, 4096), (64, 14336, 4096), (24, 2000, 2048)])
 def test_stream_k_gemm_matches_whole_tiles_and_is_deterministic(oracle, pkg, M, N, K):
     """Stream-K (forced with gemm_sk=1, also on shapes the heuristic would leave alone: several contributors per
     tile, tiles finished by a CTA that also publishes) against the float64 oracle and against the whole-tile schedule;
