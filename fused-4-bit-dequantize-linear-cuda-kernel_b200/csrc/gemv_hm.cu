@@ -1,0 +1,538 @@
+// Decode path for batches of 3..16 tokens: y[M,N] = x[M,K] @ dequant(W)^T (+ bias), the CTA's whole share of W resident
+// in shared memory, nibbles turned into fp16 with one LOP3 per two weights and fed to mma.sync m16n8k16 (HMMA).
+//
+// Why a second decode kernel: the exact-integer kernel (gemv_dec.cu) spends four IMMA columns per batch row, so its
+// tensor and operand work grows linearly in M (M = 8: 15 us, M = 16: 28 us at 4096 -> 11008).  Here a weight fragment
+// of 16 rows x 16 columns meets EIGHT tokens in one HMMA: per 256 weights one instruction for 16-bit activations, two
+// for fp32 ones (fp16 hi + lo parts) -- 16 times fewer tensor instructions per token, HBM-bound up to M = 8.
+//
+// Arithmetic:
+//   * weights: a 32-bit word of a row = nibbles n0..n7 = columns 8j..8j+7 (python/quantize.py:120-122).  w & 0x000f000f
+//     is the fp16 pair (n0, n4) * 2^-24 (subnormals), w & 0x00f000f0 = (n1, n5) * 2^-20, the same of w >> 8 = (n2, n6),
+//     (n3, n7): four A registers from one SHF + four LOP3, no arithmetic.  The K order inside an MMA is whatever this
+//     yields; the B operand (x) is built in the same order, odd columns pre-multiplied by 2^-4;
+//   * x: every (warp, pair, token) has its own power-of-two scale 2^e (amax of its 256 columns -> [2^14, 2^15)), fp16
+//     hi = rn(x 2^e), and for fp32 inputs lo = rn(x 2^e - hi) in a second n-tile: q * hi and q * lo are exact in the
+//     fp32 accumulator, x is represented to 2^-22 relative (2^-39 of the amax for the smallest elements);
+//   * y = s * (sum_k q x - zp * sum_k x) + bias, sum_k x in fp32 from the loaded values; partial sums of the 16 warps
+//     are folded in a fixed order: results are deterministic (not bit-identical to gemv_dec.cu: fp32 accumulation,
+//     max error ~1e-6 relative vs the float64 oracle);
+//   * a token whose amax is NaN / Inf is recomputed in the reference's order (w = (q - zp) * s, fp32 FMA), so
+//     non-finite inputs propagate exactly like dequantize + F.linear (python/quantize.py:172, 202).
+//
+// Structure (one CTA per SM, 16 warps):
+//   * weights: tile i = 16 rows x K/2 bytes, 3-D TMA boxes [16 rows][chunk pairs][128 B] (pair = 256 columns), 128-byte
+//     swizzle, one single-use mbarrier per (pair group, tile), all requested up front (staged around the x loads);
+//     ldmatrix.x4 delivers the words of rows g / g + 8 every lane needs;
+//   * warp w owns the pairs w, w + 16, ...: lane (g, t) loads the 64 values of token g its B fragments are made of
+//     straight from global memory (no exchange through shared memory), the amax / sum of the token's 256 columns is a
+//     two-step quad reduction: NO block barrier before the main loop;
+//   * per (pair, tile): 4 x (ldmatrix.x4, 4 SHF, 16 LOP3, 4 NT HMMA); the partial tile 16 rows x 8 tokens is descaled
+//     and accumulated into the warp's OWN slot of the tile; one barrier, then all threads fold the 16 slots of every
+//     output and write y;
+//   * M > 8: a second pass over the resident tiles (weights come from HBM once).
+//
+// Reference being replaced: csrc/quantized_linear_kernel.cu:90-279 (one thread per output, M x weight traffic).
+#include <cuda.h>
+#include <cmath>
+#include "internal.h"
+#include "ptx.cuh"
+#include "tc.cuh"
+#include "dec.cuh"
+
+namespace b200q {
+
+// bench-only (-DB200Q_PROF build, tools/prof_hm.py): per-CTA wall-clock stamps of the phases of the last launch
+#ifdef B200Q_PROF
+__device__ long long g_hm_prof[256 * 16];
+#define HM_STAMP(i)                                                                  \
+    do {                                                                             \
+        if (p.debug && tid == 0 && blockIdx.x < 256) {                               \
+            long long t_;                                                            \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                   \
+            g_hm_prof[blockIdx.x * 16 + (i)] = t_;                                   \
+        }                                                                            \
+    } while (0)
+#else
+#define HM_STAMP(i) ((void)0)
+#endif
+#ifdef B200Q_PROF
+#define HM_ABL(bit) ((p.debug & (bit)) != 0)     // 2: no HMMA, 8: no LDSM
+#else
+#define HM_ABL(bit) false
+#endif
+
+namespace {
+
+constexpr int NW = 16;               // warps per CTA
+constexpr int NTHR = NW * 32;
+constexpr int TILE_ROWS = 16;
+constexpr int PAIR_BYTES = TILE_ROWS * 128;      // one pair (256 columns) of one tile in shared memory
+constexpr int MAX_BARS = 64;                     // (pair group, tile) barriers
+constexpr int MB = 8;                            // tokens per pass (one n-tile)
+constexpr int MAX_TILES = 8;                     // 128 row positions: one per thread of a quarter of the CTA in the fold
+
+// shared memory map (bytes)
+constexpr int OFF_BARS = 0;          // [MAX_BARS]
+constexpr int OFF_FLAG = 512;        // bit m: token m holds NaN / Inf
+constexpr int OFF_SX = 1024;         // [NW][MB] f32: sum_k x of the warp's columns, per token of the pass
+constexpr int OFF_PAR = 2048;        // [3][128] f32: scale, zero point, bias of the CTA's rows (for the fold)
+constexpr int OFF_SLOTS = 4096;      // [tile][warp][row][token] f32 partial tiles (512 B each), then the tiles (1024-aligned)
+constexpr int SLOT_BYTES = MB * TILE_ROWS * 4;
+
+struct HmParams {
+    const void* x;
+    const uint8_t* packed;
+    const float* scales;
+    const float* zps;
+    const float* bias;               // may be null
+    void* y;
+    const uint8_t* next_packed;      // L2 prefetch hint (weights of the next fused linear), may be null
+    unsigned long long next_bytes;
+    unsigned int next_chunk;         // next_bytes / gridDim.x
+    int x_dtype, y_dtype;
+    int M, N, K;
+    int rows_q, rows_rem;            // CTA b owns rows_q (+1 if b < rows_rem) row units (host-computed: no division in the kernel)
+    int npairs;                      // K / 256
+    int gpw;                         // pairs per warp (ceil(npairs / 16))
+    int nbars;                       // pair groups (barriers) per tile
+    int chunk;                       // pairs per group
+    int tile_bytes;
+    int tile_off;                    // byte offset of tile 0 (1024-aligned)
+    int npasses;
+    int wait_weights;                // 1: weights may be written by the preceding kernel
+    int early_tiles;                 // a + 10 b: a requests before griddepcontrol.wait, b more behind the x loads
+    int pf_mode;                     // next-layer L2 prefetch: 0 off, 2 before the own requests, else after the first operand build
+    int gated;                       // 1: rows 2f / 2f+1 are the gate / up projection of column f; y is h [M, N/2] = silu(gate) * up
+    int debug;                       // B200Q_PROF builds: record phase stamps
+};
+
+// weight requests [from, to): request op = (pair group, tile) in that order (the main loop walks pairs outside, tiles
+// inside), one 3-D box [16 rows][chunk pairs][128 B] each, barrier index = op.  One elected thread; not inlined (three
+// call sites).
+__device__ __noinline__ void hm_issue(const CUtensorMap* tmap, uint32_t bar0, uint32_t dst0, int row0, int from, int to, int S,
+                                      int nbars, int chunk, int tile_bytes) {
+    const uint64_t pol = policy_evict_first();
+    int grp = nbars == 1 ? 0 : from / S, i = from - grp * S;
+    for (int op = from; op < to; ++op) {
+        const uint32_t bar = bar0 + 8u * (uint32_t)op;
+        mbar_arrive_expect_tx(bar, (uint32_t)(chunk * PAIR_BYTES));
+        tma_box_3d(dst0 + (uint32_t)(i * tile_bytes + grp * chunk * PAIR_BYTES), tmap, 0, row0 + i * TILE_ROWS, grp * chunk, bar, pol);
+        if (++i == S) { i = 0; ++grp; }
+    }
+}
+
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+    const __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack_h2(uint32_t v) { return __half22float2(*reinterpret_cast<const __half2*>(&v)); }
+
+// eight consecutive activations as floats; the dtype is a template parameter so that the 8 (16) loads of an operand
+// build are straight-line code, all in flight at once (a run-time dtype switch serialises them: one L2 round trip each)
+template <int XT>
+__device__ __forceinline__ void hm_load8(const void* x, int64_t idx, float (&v)[8]) {
+    if constexpr (XT == B200Q_F32) {
+        const float4 a = *reinterpret_cast<const float4*>(static_cast<const float*>(x) + idx);
+        const float4 b = *reinterpret_cast<const float4*>(static_cast<const float*>(x) + idx + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+        const uint4 r = *reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(x) + idx);
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float2 f;
+            if constexpr (XT == B200Q_F16) f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+            else f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+            v[2 * i] = f.x; v[2 * i + 1] = f.y;
+        }
+    }
+}
+
+// XT: activation dtype.  fp32 -> two n-tiles per pass (hi parts, lo parts); else one
+template <int XT>
+__global__ void __launch_bounds__(NTHR, 1) gemv_hm_kernel(const __grid_constant__ CUtensorMap tmap, const HmParams p) {
+    constexpr bool F32 = XT == B200Q_F32;
+    constexpr int NT = F32 ? 2 : 1;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t sbase = smem_u32(smem);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+
+    HM_STAMP(0);
+    const int b = (int)blockIdx.x;
+    // (gated: rows are dealt out in gate / up pairs, so both projections of an output column meet in one CTA)
+    const int unit = p.gated ? 2 : 1;
+    const int r0 = unit * (b * p.rows_q + min(b, p.rows_rem));           // first weight row of this CTA
+    const int nrows = unit * (p.rows_q + (b < p.rows_rem ? 1 : 0));
+    const int S = (nrows + TILE_ROWS - 1) / TILE_ROWS;                   // tiles of this CTA (all resident)
+    unsigned int* s_flag = reinterpret_cast<unsigned int*>(smem + OFF_FLAG);
+    float* s_sx = reinterpret_cast<float*>(smem + OFF_SX);
+    float* s_par = reinterpret_cast<float*>(smem + OFF_PAR);
+    const int nops = S * p.nbars;
+
+    if (tid == 0) {
+        for (int i = 0; i < nops; ++i) mbar_init(sbase + OFF_BARS + 8u * i, 1);
+        fence_mbar_init();
+        *s_flag = 0u;
+    }
+    __syncthreads();
+    pdl_launch_dependents();
+    HM_STAMP(1);
+
+    // ---- weight requests (lane 0 of the last warp), staged: a requests before griddepcontrol.wait, b more once the x
+    // loads are in flight, the rest when the first operand is built
+    const int nwa = min(NW, p.npairs);                        // warps that own at least one pair
+    const bool issuer = warp == nwa - 1 && lane == 0;
+    auto issue = [&](int from, int to) {
+        hm_issue(&tmap, sbase + OFF_BARS, sbase + p.tile_off, r0, from, to, S, p.nbars, p.chunk, p.tile_bytes);
+    };
+    const int early = min(p.early_tiles % 10, nops);
+    const int mid = min(early + p.early_tiles / 10, nops);
+    auto prefetch_next = [&]() {
+        if (!p.next_bytes) return;
+        const unsigned long long per = (((unsigned long long)p.next_chunk) + 127ull) & ~127ull;
+        const unsigned long long beg = min(per * blockIdx.x, p.next_bytes), end = min(beg + per, p.next_bytes);
+        for (unsigned long long off = beg; off < end; off += 32768ull) {
+            const unsigned int n = (unsigned int)min(32768ull, end - off) & ~15u;
+            if (n) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.next_packed + off), "r"(n) : "memory");
+        }
+    };
+    if (p.wait_weights) pdl_wait();
+    if (issuer) {
+        tma_prefetch_desc(&tmap);
+        if (p.pf_mode == 2) prefetch_next();
+        issue(0, early);
+    }
+
+    // ldmatrix row address of this lane for the four 32-byte steps of a pair (lane i supplies row (i & 7) + 8 ((i >> 3) & 1)
+    // of the 16-byte column 2 c + (i >> 4); 128-byte swizzle: column ^ row)
+    uint32_t offc[4];
+    {
+        const int ri = lane & 7, mi = lane >> 3;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) offc[c] = (uint32_t)((ri + 8 * (mi & 1)) * 128 + (((2 * c + (mi >> 1)) ^ ri) << 4));
+    }
+    // scale / zero point / bias of the CTA's rows: fetched early by the first 128 threads, parked in shared memory for the fold
+    float sc = 0.0f, zp = 0.0f, bias = 0.0f;
+    if (tid < nrows) {                                        // nrows <= 128
+        sc = __ldg(p.scales + r0 + tid);
+        zp = __ldg(p.zps + r0 + tid);
+        if (p.bias) bias = __ldg(p.bias + r0 + tid);
+    }
+    if (warp >= nwa) {                                        // K < 4096: a warp without pairs contributes zeros to the fold
+        for (int i = 0; i < S; ++i) sts128(sbase + OFF_SLOTS + (uint32_t)((i * NW + warp) * SLOT_BYTES + lane * 16), make_uint4(0u, 0u, 0u, 0u));
+    }
+    pdl_wait();              // x (and y) belong to the stream-ordered predecessor
+    HM_STAMP(2);
+    constexpr uint32_t M0 = 0x000f000fu, M1 = 0x00f000f0u;
+#pragma unroll 1
+    for (int pass = 0; pass < p.npasses; ++pass) {
+        const int m0 = pass * MB;
+        if (pass > 0) __syncthreads();                        // the fold of the previous pass has read every slot
+        const bool tok = m0 + g < p.M;                        // token of this lane's B column exists
+        float sxacc = 0.0f;                                   // sum_k x of token g over this warp's pairs (quad-uniform)
+#pragma unroll 1
+        for (int q = 0; q < p.gpw; ++q) {
+            const int P = warp + NW * q;
+            if (P >= p.npairs) break;                         // uniform
+            const bool first = pass == 0 && q == 0;
+            // ---- x of token g, columns 256 P + 64 c + 32 h + 8 t + (0..7): exactly what this lane's B fragments hold
+            float xv[8][8];
+            {
+                const int64_t base = (int64_t)(m0 + g) * p.K + P * 256 + t * 8;
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) xv[ch][e] = 0.0f;
+                    if (tok) hm_load8<XT>(p.x, base + ch * 32, xv[ch]);
+                }
+            }
+            if (first && issuer && early < mid) issue(early, mid);
+            // ---- amax and sum of the token's 256 columns: the four lanes of a quad hold them all
+            unsigned int u = 0u;
+            float s = 0.0f;
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    u = max(u, __float_as_uint(xv[ch][e]) & 0x7fffffffu);
+                    s += xv[ch][e];
+                }
+            u = max(u, __shfl_xor_sync(0xffffffffu, u, 1));
+            u = max(u, __shfl_xor_sync(0xffffffffu, u, 2));
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            sxacc += s;
+            if (first) HM_STAMP(3);
+            const int E = (int)(u >> 23);
+            if (E == 255 && t == 0) atomicOr(s_flag, 1u << (m0 + g));
+            const int ex = min(126, 141 - E);                 // amax * 2^ex in [2^14, 2^15)
+            const float up = __uint_as_float((uint32_t)(127 + ex) << 23), up16 = up * 0.0625f;
+            // descale of the accumulator columns 2t, 2t + 1 (tokens 2t, 2t + 1 of the pass): 2^24 (subnormal nibbles) * 2^-ex
+            const float dn = __uint_as_float((uint32_t)(127 - ex) << 23);
+            const float d0 = __shfl_sync(0xffffffffu, dn, 8 * t), d1 = __shfl_sync(0xffffffffu, dn, 8 * t + 4);
+
+            // ---- B fragments: per 32-byte step c, half h: MMA alpha = nibbles (0,4 | 1,5), beta = (2,6 | 3,7) of every word
+            uint32_t bf[8][2][NT][2];                         // [2 c + h][alpha / beta][hi / lo][b0, b1]
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) {
+                float a[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) a[e] = xv[ch][e] * ((e & 1) ? up16 : up);
+                bf[ch][0][0][0] = pack_h2(a[0], a[4]); bf[ch][0][0][1] = pack_h2(a[1], a[5]);
+                bf[ch][1][0][0] = pack_h2(a[2], a[6]); bf[ch][1][0][1] = pack_h2(a[3], a[7]);
+                if constexpr (F32) {
+                    const float2 h04 = unpack_h2(bf[ch][0][0][0]), h15 = unpack_h2(bf[ch][0][0][1]);
+                    const float2 h26 = unpack_h2(bf[ch][1][0][0]), h37 = unpack_h2(bf[ch][1][0][1]);
+                    bf[ch][0][1][0] = pack_h2(a[0] - h04.x, a[4] - h04.y); bf[ch][0][1][1] = pack_h2(a[1] - h15.x, a[5] - h15.y);
+                    bf[ch][1][1][0] = pack_h2(a[2] - h26.x, a[6] - h26.y); bf[ch][1][1][1] = pack_h2(a[3] - h37.x, a[7] - h37.y);
+                }
+            }
+            if (first && issuer) {
+                if (mid < nops) issue(mid, nops);
+                if (p.pf_mode != 0 && p.pf_mode != 2) prefetch_next();
+            }
+            if (first) HM_STAMP(4);
+            int grp = 0;
+            if (p.nbars > 1) grp = P / p.chunk;
+
+            // ---- this pair of every tile
+#pragma unroll 1
+            for (int i = 0; i < S; ++i) {
+                if (pass == 0) mbar_wait(sbase + OFF_BARS + 8u * (uint32_t)(grp * S + i), 0u);
+                const uint32_t pb = sbase + p.tile_off + (uint32_t)(i * p.tile_bytes + P * PAIR_BYTES);
+                float acc[2][NT][4];                          // two chains (alpha, beta) per n-tile
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) acc[j][nt][r] = 0.0f;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t a[4];
+                    if (!HM_ABL(8)) ldsm_x4(a, pb + offc[c]); else { a[0] = c; a[1] = lane; a[2] = i; a[3] = 7; }                // a0 / a1: rows g / g + 8, bytes 32 c + 4 t ..; a2 / a3: + 16 bytes
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const uint32_t w0 = a[2 * h], w1 = a[2 * h + 1];
+                        const uint32_t v0 = w0 >> 8, v1 = w1 >> 8;
+#pragma unroll
+                        if (!HM_ABL(2)) for (int nt = 0; nt < NT; ++nt) {
+                            mma_m16n8k16_f16(acc[0][nt], w0 & M0, w1 & M0, w0 & M1, w1 & M1, bf[2 * c + h][0][nt][0], bf[2 * c + h][0][nt][1]);
+                            mma_m16n8k16_f16(acc[1][nt], v0 & M0, v1 & M0, v0 & M1, v1 & M1, bf[2 * c + h][1][nt][0], bf[2 * c + h][1][nt][1]);
+                        }
+                        else { acc[0][0][0] += __uint_as_float((w0 & M0) ^ (w1 & M1) ^ (v0 & M0) ^ (v1 & M1) ^ (w0 & M1) ^ (w1 & M0) ^ (v0 & M1) ^ (v1 & M0)); }
+                    }
+                }
+                // partial tile -> this warp's own slot of the tile, descaled: q was 2^-24 too small
+                float v[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    float a = acc[0][0][r] + acc[1][0][r];
+                    if constexpr (F32) a += acc[0][1][r] + acc[1][1][r];
+                    v[r] = (a * 16777216.0f) * ((r & 1) ? d1 : d0);
+                }
+                // slot layout [row][token]: lane (g, t) owns tokens 2t, 2t + 1 of rows g and g + 8 -- two conflict-free 8-byte stores
+                float2* slot = reinterpret_cast<float2*>(smem + OFF_SLOTS + (i * NW + warp) * SLOT_BYTES);
+                float2 lo2 = make_float2(v[0], v[1]), hi2 = make_float2(v[2], v[3]);
+                if (q > 0) {
+                    const float2 o0 = slot[g * 4 + t], o1 = slot[(g + 8) * 4 + t];
+                    lo2.x += o0.x; lo2.y += o0.y; hi2.x += o1.x; hi2.y += o1.y;
+                }
+                slot[g * 4 + t] = lo2;
+                slot[(g + 8) * 4 + t] = hi2;
+                if (first && i < 5) HM_STAMP(5 + i);
+            }
+        }
+        if (pass == 0) HM_STAMP(10);
+        if (t == 0) s_sx[warp * MB + g] = sxacc;
+        if (pass == 0 && tid < 128) { s_par[tid] = sc; s_par[128 + tid] = zp; s_par[256 + tid] = bias; }
+        __syncthreads();
+        if (pass == 0) HM_STAMP(11);
+
+        // ---- fold the 16 warps and write y.  Thread = (tile, row, token quad tq, half of the warps): 8 x (16-byte load
+        // of 4 tokens of its row + 16-byte load of their sum_k x), the two halves meet in one shuffle step -- a fixed
+        // order: deterministic.  Lanes 0..7 of a quarter warp read 128 consecutive bytes: no bank conflicts.
+        // (the whole fold is 80 + 80 vector loads per SM; one 4-byte load per (output, warp) was 1 us of LSU time)
+        {
+            const unsigned int flagged = *s_flag;
+            const int tq = tid & 1, half = (tid >> 3) & 1, tile = tid >> 6;
+            const int row = ((tid >> 1) & 3) + 4 * ((tid >> 4) & 3);
+            const int rowpos = tile * TILE_ROWS + row;
+            if (tile < S) {                                   // uniform per warp
+                const float4* src = reinterpret_cast<const float4*>(smem + OFF_SLOTS + ((tile * NW + half * 8) * SLOT_BYTES)) + row * 2 + tq;
+                const float4* ssx = reinterpret_cast<const float4*>(s_sx + half * 8 * MB) + tq;
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f), s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int w = 0; w < 8; ++w) {                 // (idle warps hold zeros)
+                    const float4 av = src[w * (SLOT_BYTES / 16)], sv = ssx[w * (MB / 4)];
+                    a.x += av.x; a.y += av.y; a.z += av.z; a.w += av.w;
+                    s.x += sv.x; s.y += sv.y; s.z += sv.z; s.w += sv.w;
+                }
+                a.x += __shfl_xor_sync(0xffffffffu, a.x, 8); a.y += __shfl_xor_sync(0xffffffffu, a.y, 8);
+                a.z += __shfl_xor_sync(0xffffffffu, a.z, 8); a.w += __shfl_xor_sync(0xffffffffu, a.w, 8);
+                s.x += __shfl_xor_sync(0xffffffffu, s.x, 8); s.y += __shfl_xor_sync(0xffffffffu, s.y, 8);
+                s.z += __shfl_xor_sync(0xffffffffu, s.z, 8); s.w += __shfl_xor_sync(0xffffffffu, s.w, 8);
+                if (pass == 0) HM_STAMP(13);
+                const bool mine = rowpos < nrows;
+                const float rsc = s_par[rowpos], rzp = s_par[128 + rowpos], rbias = s_par[256 + rowpos];
+                float vv[4] = {rsc * fmaf(-rzp, s.x, a.x), rsc * fmaf(-rzp, s.y, a.y), rsc * fmaf(-rzp, s.z, a.z), rsc * fmaf(-rzp, s.w, a.w)};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int m = m0 + tq * 4 + j;
+                    if (p.gated) {
+                        // fused gate + up pair: the even row (gate) fetches its neighbour's value (up, lane ^ 2) and writes silu(gate) * up
+                        const float uu = __shfl_xor_sync(0xffffffffu, vv[j], 2);
+                        if (mine && half == 0 && !(row & 1) && m < p.M && !((flagged >> m) & 1u))
+                            store_out(p.y, p.y_dtype, (int64_t)m * (p.N >> 1) + ((r0 + rowpos) >> 1), vv[j] / (1.0f + __expf(-vv[j])) * uu);
+                    } else if (mine && half == 0 && m < p.M && !((flagged >> m) & 1u)) {
+                        store_out(p.y, p.y_dtype, (int64_t)m * p.N + r0 + rowpos, vv[j] + rbias);
+                    }
+                }
+            }
+        }
+        if (pass < 1) HM_STAMP(12 + pass);
+    }
+
+    HM_STAMP(14);
+    // ---- tokens with NaN / Inf: the reference's arithmetic (dequantise, then fp32 multiply-add), so that non-finite
+    // values propagate as in F.linear; one warp per output, weights re-read from global memory
+    if (const unsigned int flagged = *s_flag) {
+        const int64_t row_bytes = p.K >> 1;
+        for (int m = 0; m < p.M; ++m) {
+            if (!((flagged >> m) & 1u)) continue;
+            auto ref_row = [&](int row) {
+                const float rs = __ldg(p.scales + row), rz = __ldg(p.zps + row);
+                const uint8_t* wr = p.packed + (int64_t)row * row_bytes;
+                float acc = 0.0f;
+                for (int kb = lane; kb < row_bytes; kb += 32) {
+                    const unsigned int byte = wr[kb];
+                    const float w0 = ((float)(byte & 15u) - rz) * rs, w1 = ((float)(byte >> 4) - rz) * rs;
+                    acc = fmaf(w0, load1f(p.x, p.x_dtype, (int64_t)m * p.K + 2 * kb), acc);
+                    acc = fmaf(w1, load1f(p.x, p.x_dtype, (int64_t)m * p.K + 2 * kb + 1), acc);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                return acc;
+            };
+            for (int rc = unit * warp; rc < nrows; rc += unit * NW) {
+                const int row = r0 + rc;
+                float acc = ref_row(row);
+                if (p.gated) {
+                    const float upv = ref_row(row + 1);
+                    if (lane == 0) store_out(p.y, p.y_dtype, (int64_t)m * (p.N >> 1) + (row >> 1), acc / (1.0f + __expf(-acc)) * upv);
+                } else if (lane == 0) {
+                    if (p.bias) acc += __ldg(p.bias + row);
+                    store_out(p.y, p.y_dtype, (int64_t)m * p.N + row, acc);
+                }
+            }
+        }
+    }
+}
+
+struct HmPlan {
+    int grid, rows_q, rows_rem, s_max, npairs, gpw, nbars, chunk, tile_bytes, tile_off, npasses;
+    size_t smem;
+};
+
+bool plan_hm(int sm_count, int max_smem, int64_t M, int64_t N, int64_t K, int gated, HmPlan* c) {
+    if (M < 1 || M > 16 || K < 256 || K % 256 != 0 || K > 16384 || N < 1 || N > 0x3fffffff) return false;
+    if (gated && (N & 1)) return false;
+    const int unit = gated ? 2 : 1;
+    c->npairs = (int)(K / 256);
+    c->gpw = (c->npairs + NW - 1) / NW;                          // <= 4
+    c->nbars = c->gpw;
+    c->chunk = (c->npairs + c->nbars - 1) / c->nbars;
+    c->tile_bytes = c->nbars * c->chunk * PAIR_BYTES;            // >= npairs * 2 KB: a 3-D box always has room
+    c->npasses = (int)((M + MB - 1) / MB);
+    int cap = tuning().gemv_ctas > 0 ? tuning().gemv_ctas : sm_count;
+    if (cap > sm_count) cap = sm_count;
+    const int64_t units = N / unit;
+    int64_t g = (N + TILE_ROWS - 1) / TILE_ROWS;                 // few rows: one tile per CTA
+    if (g > cap) g = cap;
+    if (g > units) g = units;
+    if (g < 1) g = 1;
+    c->grid = (int)g;
+    c->rows_q = (int)(units / g); c->rows_rem = (int)(units % g);
+    const int64_t br = unit * ((units + g - 1) / g);             // most rows of a CTA
+    const int64_t S = (br + TILE_ROWS - 1) / TILE_ROWS;
+    if (S > MAX_TILES || S * c->nbars > MAX_BARS) return false;
+    c->s_max = (int)S;
+    c->tile_off = (OFF_SLOTS + (int)S * NW * SLOT_BYTES + 1023) / 1024 * 1024;
+    c->smem = (size_t)c->tile_off + (size_t)S * c->tile_bytes;
+    return c->smem <= (size_t)max_smem;
+}
+
+template <int XT>
+int launch_hm_inst(const HmPlan& c, const CUtensorMap& map, const HmParams& p, bool pdl, cudaStream_t st) {
+    auto kfn = gemv_hm_kernel<XT>;
+    static thread_local int attr_dev_smem[64] = {0};
+    int dev = 0;
+    B200Q_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && attr_dev_smem[dev] < (int)c.smem) {
+        B200Q_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
+        attr_dev_smem[dev] = (int)c.smem;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)c.grid);
+    cfg.blockDim = dim3(NTHR);
+    cfg.dynamicSmemBytes = c.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attrs[1];
+    int na = 0;
+    if (pdl) {
+        attrs[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attrs[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attrs;
+    cfg.numAttrs = na;
+    return check_cuda(cudaLaunchKernelEx(&cfg, kfn, map, p), "gemv_hm launch");
+}
+
+}  // namespace
+
+bool gemv_hm_supported(const DeviceInfo& dev, int64_t M, int64_t N, int64_t K, int gated) {
+    HmPlan c;
+    return plan_hm(dev.sm_count, dev.max_smem_optin, M, N, K, gated, &c);
+}
+
+int launch_gemv_hm(const DeviceInfo& dev, const void* x, int x_dtype, const uint8_t* packed, const float* scales,
+                   const float* zps, const float* bias, void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
+                   unsigned flags, cudaStream_t st, const uint8_t* next_packed, size_t next_bytes, int gated) {
+    HmPlan c;
+    if (!plan_hm(dev.sm_count, dev.max_smem_optin, M, N, K, gated, &c))
+        return set_error(B200Q_EINVAL, "gemv_hm: unsupported shape M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
+    if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(packed) & 15))
+        return set_error(B200Q_EALIGN, "gemv_hm: x and packed must be 16-byte aligned");
+    HmParams p{};
+    p.x = x; p.packed = packed; p.scales = scales; p.zps = zps; p.bias = gated ? nullptr : bias; p.y = y;
+    p.gated = gated;
+    p.x_dtype = x_dtype; p.y_dtype = y_dtype;
+    p.M = (int)M; p.N = (int)N; p.K = (int)K;
+    p.rows_q = c.rows_q; p.rows_rem = c.rows_rem;
+    p.npairs = c.npairs; p.gpw = c.gpw; p.nbars = c.nbars; p.chunk = c.chunk;
+    p.tile_bytes = c.tile_bytes; p.tile_off = c.tile_off; p.npasses = c.npasses;
+    p.wait_weights = (flags & B200Q_FLAG_STATIC_WEIGHTS) ? 0 : 1;
+    p.early_tiles = tuning().gemv_early >= 0 ? tuning().gemv_early : 92;
+    p.next_packed = next_packed;
+    p.pf_mode = tuning().gemv_pf;
+    p.next_bytes = (tuning().gemv_pf != 0 && next_packed && (reinterpret_cast<uintptr_t>(next_packed) & 15) == 0) ? next_bytes : 0;
+    p.next_chunk = (unsigned int)(p.next_bytes / (unsigned long long)c.grid);
+    p.debug = tuning().gemv_debug > 0 ? tuning().gemv_debug : 0;
+    CUtensorMap map;
+    if (int rc = dec_weight_map(packed, N, K, c.chunk, &map)) return rc;
+    const bool pdl = tuning().gemv_pdl != 0;
+    if (x_dtype == B200Q_F32) return launch_hm_inst<B200Q_F32>(c, map, p, pdl, st);
+    if (x_dtype == B200Q_F16) return launch_hm_inst<B200Q_F16>(c, map, p, pdl, st);
+    return launch_hm_inst<B200Q_BF16>(c, map, p, pdl, st);
+}
+
+}  // namespace b200q
+
+#ifdef B200Q_PROF
+extern "C" int b200q_debug_read_prof_hm(long long* h_out) {
+    return b200q::check_cuda(cudaMemcpyFromSymbol(h_out, b200q::g_hm_prof, sizeof(long long) * 256 * 16), "read prof");
+}
+#endif

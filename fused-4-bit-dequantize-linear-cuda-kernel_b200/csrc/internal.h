@@ -5,6 +5,8 @@
 #include <cstddef>
 #include "../../include/b200q.h"
 
+struct CUtensorMap_st;
+
 namespace b200q {
 
 // ---- error plumbing (thread-local message, C ABI never throws)
@@ -45,8 +47,9 @@ struct Tuning {
     int gemv_pf = 3;        // next-layer L2 prefetch: 0 off; resident kernel: 1 behind the last own request, 2 before the own requests, 3 after the operand build (default: the prologue is sensitive to memory traffic)
     int gemv_occ2 = 0;      // 1: 8-warp CTAs sized so that two launches share an SM (cross-layer prefetch)
     int gemv_debug = -1;    // bench-only ablations: 1 = skip the mma work, 2 = skip the weight loads
-    int force_path = -1;    // 0 auto, 1 generic SIMT, 2 ring decode kernel, 3 tcgen05 gemm, 6 resident decode kernel (gemv_dec)
+    int force_path = -1;    // 0 auto, 1 generic SIMT, 2 ring decode kernel, 3 tcgen05 gemm, 6 resident decode kernel (gemv_dec), 7 fp16 HMMA decode kernel (gemv_hm)
     int gemv_bufs = 0;      // resident decode kernel: cap on the tile buffers of a CTA (0 = as many as fit; tests force the ring with it)
+    int hm_min_m = 3;       // smallest batch that goes to the fp16 HMMA decode kernel (gemv_hm.cu)
     int gemv_slots = 1;     // resident decode kernel, M <= 2: 0 = pipelined cross-warp reduction instead of per-warp slots
 };
 const Tuning& tuning();
@@ -104,6 +107,15 @@ int launch_gemv_dec(const DeviceInfo& dev, const void* x, int x_dtype, const uin
                     const float* zps, const float* bias, void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
                     unsigned flags, cudaStream_t st, const uint8_t* next_packed, size_t next_bytes, int gated = 0,
                     const int32_t* offsets = nullptr, int n_experts = 1, const int32_t* row_map = nullptr);
+// 3-D tensor map over packed [N, K/2] viewed as [row][128-byte column][byte]: boxes of [16 rows][chunk columns][128 B]
+// land in shared memory as [column][row][128 B] with the 128-byte swizzle (cached per (pointer, shape, chunk))
+int dec_weight_map(const uint8_t* packed, int64_t N, int64_t K, int chunk, CUtensorMap_st* out);
+// decode GEMV on fp16 HMMA (gemv_hm.cu): M <= 16, every tile of a CTA resident in shared memory; tokens in passes of
+// eight; fp32 activations as fp16 hi + lo parts; optional bias; gated: fused SiLU-gate of interleaved gate / up rows
+bool gemv_hm_supported(const DeviceInfo& dev, int64_t M, int64_t N, int64_t K, int gated = 0);
+int launch_gemv_hm(const DeviceInfo& dev, const void* x, int x_dtype, const uint8_t* packed, const float* scales,
+                   const float* zps, const float* bias, void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
+                   unsigned flags, cudaStream_t st, const uint8_t* next_packed, size_t next_bytes, int gated = 0);
 // decode-sized routing in one launch (moe.cu): T <= 16, E <= 256, k <= 8; src_token (optional): token of every sorted position
 int moe_route_small(const float* logits, int64_t T, int E, int k, int32_t* idx, float* weights, int32_t* counts, int32_t* offsets,
                     int32_t* sorted_slot, int32_t* inv_perm, int32_t* src_token, cudaStream_t st);

@@ -268,8 +268,12 @@ def test_resident_decode_kernel_edge_shapes(oracle, pkg, M, N, K):
     assert np.array_equal(pkg._lib.linear_fwd(X, P, S, Z).cpu().numpy(), y)
     # (wide K goes to the tcgen05 GEMM by default with M > 8, and to the ring kernel with M >= 3 when the CTA has fewer
     # tile buffers than tiles)
-    if 6 in outs and (M <= 8 or K <= 8192) and (M <= 2 or (N, K) != (4096, 14336)):
+    # (3 <= M <= 16 with every tile resident: the HMMA kernel, tests/test_gpu_decode_hm.py -- equal to accumulation error)
+    if 6 in outs and M <= 2:
         assert np.array_equal(y, outs[6])
+    elif 6 in outs:
+        for m in range(M):
+            assert np.abs(y[m] - outs[6][m]).max() <= 1e-4 * np.abs(outs[6][m]).max() + 1e-30
     for m in range(M):
         assert np.abs(ref[m] - y[m, rows]).max() <= 1e-4 * np.abs(ref[m]).max() + 1e-30
 
@@ -444,7 +448,7 @@ def test_wide_k_and_16bit_decode(oracle, pkg, dtype, M, N, K):
         finally:
             pkg._lib.tune("force_path", -1)
         assert np.abs(outs[path] - ref).max() <= 1e-6 * np.abs(ref).max()
-    if M <= 8 or K <= 8192:
+    if M <= 2:                                           # (3 <= M <= 16: the default is the HMMA kernel, tests/test_gpu_decode_hm.py)
         assert np.array_equal(pkg._lib.linear_fwd(X, P, S, Z, out_dtype=torch.float32).cpu().numpy(), outs[6])
 
 
