@@ -131,29 +131,30 @@ __device__ __forceinline__ float2 unpack_h2(uint32_t v) { return __half22float2(
 // eight consecutive activations as floats; the dtype is a template parameter so that the 8 (16) loads of an operand
 // build are straight-line code, all in flight at once (a run-time dtype switch serialises them: one L2 round trip each)
 template <int XT>
-__device__ __forceinline__ void hm_load8(const void* x, int64_t idx, float (&v)[8]) {
-    if constexpr (XT == B200Q_F32) {
-        const float4 a = *reinterpret_cast<const float4*>(static_cast<const float*>(x) + idx);
-        const float4 b = *reinterpret_cast<const float4*>(static_cast<const float*>(x) + idx + 4);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+__device__ __forceinline__ void hm_load8(const void* x, int64_t idx, float2 (&v)[4]) {
+    if constexpr (XT == B200Q_F32) {                          // 32-byte aligned (the launcher checks x)
+        asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(v[0].x), "=f"(v[0].y), "=f"(v[1].x), "=f"(v[1].y), "=f"(v[2].x), "=f"(v[2].y), "=f"(v[3].x), "=f"(v[3].y)
+                     : "l"(static_cast<const float*>(x) + idx));
     } else {
         const uint4 r = *reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(x) + idx);
         const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            float2 f;
-            if constexpr (XT == B200Q_F16) f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
-            else f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
-            v[2 * i] = f.x; v[2 * i + 1] = f.y;
+            if constexpr (XT == B200Q_F16) v[i] = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+            else v[i] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
         }
     }
 }
 
-// XT: activation dtype.  fp32 -> two n-tiles per pass (hi parts, lo parts); else one
-template <int XT>
+// XT: activation dtype.  fp32 -> two n-tiles per pass (hi parts, lo parts); else one.
+// PK (fp32, M <= 4): ONE n-tile, column 2j = hi part, 2j + 1 = lo part of token j -- half the tensor work of the
+// eight-token form.
+template <int XT, bool PK>
 __global__ void __launch_bounds__(NTHR, 1) gemv_hm_kernel(const __grid_constant__ CUtensorMap tmap, const HmParams p) {
     constexpr bool F32 = XT == B200Q_F32;
-    constexpr int NT = F32 ? 2 : 1;
+    constexpr int NT = (F32 && !PK) ? 2 : 1;
+    static_assert(!PK || F32, "the packed form is for fp32 activations");
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -230,7 +231,8 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_hm_kernel(const __grid_constant_
     for (int pass = 0; pass < p.npasses; ++pass) {
         const int m0 = pass * MB;
         if (pass > 0) __syncthreads();                        // the fold of the previous pass has read every slot
-        const bool tok = m0 + g < p.M;                        // token of this lane's B column exists
+        const int tk = PK ? (g >> 1) : g;                     // token (of the pass) of this lane's B column
+        const bool tok = m0 + tk < p.M;                       // ... exists
         float sxacc = 0.0f;                                   // sum_k x of token g over this warp's pairs (quad-uniform)
 #pragma unroll 1
         for (int q = 0; q < p.gpw; ++q) {
@@ -238,55 +240,65 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_hm_kernel(const __grid_constant_
             if (P >= p.npairs) break;                         // uniform
             const bool first = pass == 0 && q == 0;
             // ---- x of token g, columns 256 P + 64 c + 32 h + 8 t + (0..7): exactly what this lane's B fragments hold
-            float xv[8][8];
+            // (fp32: one 32-byte load per step -- the four lanes of a quad read one whole 128-byte line per instruction)
+            float2 xv[8][4];
             {
-                const int64_t base = (int64_t)(m0 + g) * p.K + P * 256 + t * 8;
+                const int64_t base = (int64_t)(m0 + tk) * p.K + P * 256 + t * 8;
 #pragma unroll
                 for (int ch = 0; ch < 8; ++ch) {
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) xv[ch][e] = 0.0f;
+                    for (int e = 0; e < 4; ++e) xv[ch][e] = make_float2(0.0f, 0.0f);
                     if (tok) hm_load8<XT>(p.x, base + ch * 32, xv[ch]);
                 }
             }
             if (first && issuer && early < mid) issue(early, mid);
-            // ---- amax and sum of the token's 256 columns: the four lanes of a quad hold them all
-            unsigned int u = 0u;
-            float s = 0.0f;
+            // ---- amax and sum of the token's 256 columns: the four lanes of a quad hold them all.  (fmaxf drops NaN:
+            // a NaN shows up in the sum, Inf in the amax)
+            float am = 0.0f;
+            float2 s2 = make_float2(0.0f, 0.0f);
 #pragma unroll
             for (int ch = 0; ch < 8; ++ch)
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    u = max(u, __float_as_uint(xv[ch][e]) & 0x7fffffffu);
-                    s += xv[ch][e];
+                for (int e = 0; e < 4; ++e) {
+                    am = fmaxf(am, fmaxf(fabsf(xv[ch][e].x), fabsf(xv[ch][e].y)));
+                    s2 = __fadd2_rn(s2, xv[ch][e]);
                 }
-            u = max(u, __shfl_xor_sync(0xffffffffu, u, 1));
-            u = max(u, __shfl_xor_sync(0xffffffffu, u, 2));
+            float s = s2.x + s2.y;
+            am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, 1));
+            am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, 2));
             s += __shfl_xor_sync(0xffffffffu, s, 1);
             s += __shfl_xor_sync(0xffffffffu, s, 2);
             sxacc += s;
             if (first) HM_STAMP(3);
-            const int E = (int)(u >> 23);
-            if (E == 255 && t == 0) atomicOr(s_flag, 1u << (m0 + g));
+            const int E = (int)(__float_as_uint(am) >> 23);
+            if ((E == 255 || s != s) && t == 0) atomicOr(s_flag, 1u << (m0 + tk));
             const int ex = min(126, 141 - E);                 // amax * 2^ex in [2^14, 2^15)
-            const float up = __uint_as_float((uint32_t)(127 + ex) << 23), up16 = up * 0.0625f;
+            const float up = __uint_as_float((uint32_t)(127 + ex) << 23);
+            const float2 up2 = make_float2(up, up * 0.0625f); // (even column, odd column: its nibble arrives 2^4 too large)
             // descale of the accumulator columns 2t, 2t + 1 (tokens 2t, 2t + 1 of the pass): 2^24 (subnormal nibbles) * 2^-ex
             const float dn = __uint_as_float((uint32_t)(127 - ex) << 23);
+            // (PK: columns 2t, 2t + 1 = hi / lo of token t, whose lanes are g = 2t, 2t + 1: the same scale)
             const float d0 = __shfl_sync(0xffffffffu, dn, 8 * t), d1 = __shfl_sync(0xffffffffu, dn, 8 * t + 4);
 
             // ---- B fragments: per 32-byte step c, half h: MMA alpha = nibbles (0,4 | 1,5), beta = (2,6 | 3,7) of every word
             uint32_t bf[8][2][NT][2];                         // [2 c + h][alpha / beta][hi / lo][b0, b1]
 #pragma unroll
             for (int ch = 0; ch < 8; ++ch) {
-                float a[8];
+                float2 a[4];                                  // (x0, x1 / 16) (x2, x3 / 16) (x4, x5 / 16) (x6, x7 / 16), scaled
 #pragma unroll
-                for (int e = 0; e < 8; ++e) a[e] = xv[ch][e] * ((e & 1) ? up16 : up);
-                bf[ch][0][0][0] = pack_h2(a[0], a[4]); bf[ch][0][0][1] = pack_h2(a[1], a[5]);
-                bf[ch][1][0][0] = pack_h2(a[2], a[6]); bf[ch][1][0][1] = pack_h2(a[3], a[7]);
+                for (int e = 0; e < 4; ++e) a[e] = __fmul2_rn(xv[ch][e], up2);
+                bf[ch][0][0][0] = pack_h2(a[0].x, a[2].x); bf[ch][0][0][1] = pack_h2(a[0].y, a[2].y);
+                bf[ch][1][0][0] = pack_h2(a[1].x, a[3].x); bf[ch][1][0][1] = pack_h2(a[1].y, a[3].y);
                 if constexpr (F32) {
                     const float2 h04 = unpack_h2(bf[ch][0][0][0]), h15 = unpack_h2(bf[ch][0][0][1]);
                     const float2 h26 = unpack_h2(bf[ch][1][0][0]), h37 = unpack_h2(bf[ch][1][0][1]);
-                    bf[ch][0][1][0] = pack_h2(a[0] - h04.x, a[4] - h04.y); bf[ch][0][1][1] = pack_h2(a[1] - h15.x, a[5] - h15.y);
-                    bf[ch][1][1][0] = pack_h2(a[2] - h26.x, a[6] - h26.y); bf[ch][1][1][1] = pack_h2(a[3] - h37.x, a[7] - h37.y);
+                    const uint32_t l0 = pack_h2(a[0].x - h04.x, a[2].x - h04.y), l1 = pack_h2(a[0].y - h15.x, a[2].y - h15.y);
+                    const uint32_t l2 = pack_h2(a[1].x - h26.x, a[3].x - h26.y), l3 = pack_h2(a[1].y - h37.x, a[3].y - h37.y);
+                    if constexpr (PK) {
+                        if (g & 1) { bf[ch][0][0][0] = l0; bf[ch][0][0][1] = l1; bf[ch][1][0][0] = l2; bf[ch][1][0][1] = l3; }
+                    } else {
+                        bf[ch][0][1][0] = l0; bf[ch][0][1][1] = l1; bf[ch][1][1][0] = l2; bf[ch][1][1][1] = l3;
+                    }
                 }
             }
             if (first && issuer) {
@@ -330,23 +342,31 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_hm_kernel(const __grid_constant_
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
                     float a = acc[0][0][r] + acc[1][0][r];
-                    if constexpr (F32) a += acc[0][1][r] + acc[1][1][r];
+                    if constexpr (NT == 2) a += acc[0][1][r] + acc[1][1][r];
                     v[r] = (a * 16777216.0f) * ((r & 1) ? d1 : d0);
                 }
+                if constexpr (PK) { v[0] += v[1]; v[2] += v[3]; }      // hi + lo column of token t
                 // slot layout [row][token]: lane (g, t) owns tokens 2t, 2t + 1 of rows g and g + 8 -- two conflict-free 8-byte stores
                 float2* slot = reinterpret_cast<float2*>(smem + OFF_SLOTS + (i * NW + warp) * SLOT_BYTES);
-                float2 lo2 = make_float2(v[0], v[1]), hi2 = make_float2(v[2], v[3]);
-                if (q > 0) {
-                    const float2 o0 = slot[g * 4 + t], o1 = slot[(g + 8) * 4 + t];
-                    lo2.x += o0.x; lo2.y += o0.y; hi2.x += o1.x; hi2.y += o1.y;
+                if constexpr (PK) {                           // token t of rows g, g + 8 (tokens 4..7 of the slot are never read for a result)
+                    float* s1 = reinterpret_cast<float*>(slot);
+                    if (q > 0) { v[0] += s1[g * 8 + t]; v[2] += s1[(g + 8) * 8 + t]; }
+                    s1[g * 8 + t] = v[0];
+                    s1[(g + 8) * 8 + t] = v[2];
+                } else {
+                    float2 lo2 = make_float2(v[0], v[1]), hi2 = make_float2(v[2], v[3]);
+                    if (q > 0) {
+                        const float2 o0 = slot[g * 4 + t], o1 = slot[(g + 8) * 4 + t];
+                        lo2.x += o0.x; lo2.y += o0.y; hi2.x += o1.x; hi2.y += o1.y;
+                    }
+                    slot[g * 4 + t] = lo2;
+                    slot[(g + 8) * 4 + t] = hi2;
                 }
-                slot[g * 4 + t] = lo2;
-                slot[(g + 8) * 4 + t] = hi2;
                 if (first && i < 5) HM_STAMP(5 + i);
             }
         }
         if (pass == 0) HM_STAMP(10);
-        if (t == 0) s_sx[warp * MB + g] = sxacc;
+        if (t == 0) s_sx[warp * MB + (PK ? 4 * (g & 1) + tk : g)] = (PK && (g & 1)) ? 0.0f : sxacc;
         if (pass == 0 && tid < 128) { s_par[tid] = sc; s_par[128 + tid] = zp; s_par[256 + tid] = bias; }
         __syncthreads();
         if (pass == 0) HM_STAMP(11);
@@ -464,9 +484,9 @@ bool plan_hm(int sm_count, int max_smem, int64_t M, int64_t N, int64_t K, int ga
     return c->smem <= (size_t)max_smem;
 }
 
-template <int XT>
+template <int XT, bool PK>
 int launch_hm_inst(const HmPlan& c, const CUtensorMap& map, const HmParams& p, bool pdl, cudaStream_t st) {
-    auto kfn = gemv_hm_kernel<XT>;
+    auto kfn = gemv_hm_kernel<XT, PK>;
     static thread_local int attr_dev_smem[64] = {0};
     int dev = 0;
     B200Q_CUDA(cudaGetDevice(&dev));
@@ -504,8 +524,8 @@ int launch_gemv_hm(const DeviceInfo& dev, const void* x, int x_dtype, const uint
     HmPlan c;
     if (!plan_hm(dev.sm_count, dev.max_smem_optin, M, N, K, gated, &c))
         return set_error(B200Q_EINVAL, "gemv_hm: unsupported shape M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
-    if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(packed) & 15))
-        return set_error(B200Q_EALIGN, "gemv_hm: x and packed must be 16-byte aligned");
+    if ((reinterpret_cast<uintptr_t>(x) & (x_dtype == B200Q_F32 ? 31 : 15)) || (reinterpret_cast<uintptr_t>(packed) & 15))
+        return set_error(B200Q_EALIGN, "gemv_hm: packed must be 16-byte aligned, x 32-byte (fp32) / 16-byte aligned");
     HmParams p{};
     p.x = x; p.packed = packed; p.scales = scales; p.zps = zps; p.bias = gated ? nullptr : bias; p.y = y;
     p.gated = gated;
@@ -524,9 +544,10 @@ int launch_gemv_hm(const DeviceInfo& dev, const void* x, int x_dtype, const uint
     CUtensorMap map;
     if (int rc = dec_weight_map(packed, N, K, c.chunk, &map)) return rc;
     const bool pdl = tuning().gemv_pdl != 0;
-    if (x_dtype == B200Q_F32) return launch_hm_inst<B200Q_F32>(c, map, p, pdl, st);
-    if (x_dtype == B200Q_F16) return launch_hm_inst<B200Q_F16>(c, map, p, pdl, st);
-    return launch_hm_inst<B200Q_BF16>(c, map, p, pdl, st);
+    if (x_dtype == B200Q_F32)
+        return (M <= 4 && tuning().hm_packed != 0) ? launch_hm_inst<B200Q_F32, true>(c, map, p, pdl, st) : launch_hm_inst<B200Q_F32, false>(c, map, p, pdl, st);
+    if (x_dtype == B200Q_F16) return launch_hm_inst<B200Q_F16, false>(c, map, p, pdl, st);
+    return launch_hm_inst<B200Q_BF16, false>(c, map, p, pdl, st);
 }
 
 }  // namespace b200q
