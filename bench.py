@@ -252,17 +252,18 @@ def time_decode(torch, _lib, lib, layers, M, K, N, dev, hint=True, graph=True, r
 
 
 def decode_sweep(torch, pkg, dev, peak, first_pool=None):
-    """BASELINE.json configs[1]: M = 1, 2, 4, 8, 16 on both Llama-7B MLP shapes, fp32 activations, next-layer hint on."""
+    """BASELINE.json configs[1]: M = 1 .. 16 on both Llama-7B MLP shapes, fp32 activations, next-layer hint on."""
     _lib = pkg._lib
     lib = _lib.load()
     out = []
     for (K, N) in ((4096, 11008), (11008, 4096)):
         layers = first_pool if (first_pool is not None and (K, N) == (K_IN, N_OUT)) else make_pool(torch, pkg, POOL, dev, K, N)
-        for M in (1, 2, 4, 8, 16):
+        for M in (1, 2, 3, 4, 8, 12, 16):
             us = time_decode(torch, _lib, lib, layers, M, K, N, dev)
             nb = gemv_bytes(M, N, K)
             out.append({"K": K, "N": N, "M": M, "us_per_launch": round(us, 3), "GBps": round(nb / us / 1e3, 1),
-                        "frac_hbm_peak": round(nb / us / 1e3 / peak, 4)})
+                        "frac_hbm_peak": round(nb / us / 1e3 / peak, 4),
+                        "kernel": "gemv_dec (exact-integer IMMA)" if M <= 2 else "gemv_hm (fp16 HMMA, hi + lo parts)"})
         if layers is not first_pool:
             del layers
             torch.cuda.empty_cache()
