@@ -469,19 +469,26 @@ bool plan_hm(int sm_count, int max_smem, int64_t M, int64_t N, int64_t K, int ga
     int cap = tuning().gemv_ctas > 0 ? tuning().gemv_ctas : sm_count;
     if (cap > sm_count) cap = sm_count;
     const int64_t units = N / unit;
-    int64_t g = (N + TILE_ROWS - 1) / TILE_ROWS;                 // few rows: one tile per CTA
-    if (g > cap) g = cap;
-    if (g > units) g = units;
-    if (g < 1) g = 1;
-    c->grid = (int)g;
-    c->rows_q = (int)(units / g); c->rows_rem = (int)(units % g);
-    const int64_t br = unit * ((units + g - 1) / g);             // most rows of a CTA
-    const int64_t S = (br + TILE_ROWS - 1) / TILE_ROWS;
-    if (S > MAX_TILES || S * c->nbars > MAX_BARS) return false;
-    c->s_max = (int)S;
-    c->tile_off = (OFF_SLOTS + (int)S * NW * SLOT_BYTES + 1023) / 1024 * 1024;
-    c->smem = (size_t)c->tile_off + (size_t)S * c->tile_bytes;
-    return c->smem <= (size_t)max_smem;
+    // One CTA per SM when its rows fit in shared memory; else 2, 3, ... waves of smaller CTAs (Llama's fused gate + up
+    // pair, Mixtral's 14336-wide projections): each wave pays the prologue again, the weights are still read once.
+    const int max_waves = tuning().hm_waves > 0 ? tuning().hm_waves : 4;
+    for (int waves = 1; waves <= max_waves; ++waves) {
+        int64_t g = (N + TILE_ROWS - 1) / TILE_ROWS;             // few rows: one tile per CTA
+        if (g > (int64_t)cap * waves) g = (int64_t)cap * waves;
+        if (g > units) g = units;
+        if (g < 1) g = 1;
+        c->grid = (int)g;
+        c->rows_q = (int)(units / g); c->rows_rem = (int)(units % g);
+        const int64_t br = unit * ((units + g - 1) / g);         // most rows of a CTA
+        const int64_t S = (br + TILE_ROWS - 1) / TILE_ROWS;
+        if (S > MAX_TILES || S * c->nbars > MAX_BARS) continue;
+        c->s_max = (int)S;
+        c->tile_off = (OFF_SLOTS + (int)S * NW * SLOT_BYTES + 1023) / 1024 * 1024;
+        c->smem = (size_t)c->tile_off + (size_t)S * c->tile_bytes;
+        if (c->smem <= (size_t)max_smem) return true;
+        if (g < (int64_t)cap * waves) break;                     // more waves would not make the CTAs smaller
+    }
+    return false;
 }
 
 template <int XT, bool PK>
@@ -515,7 +522,11 @@ int launch_hm_inst(const HmPlan& c, const CUtensorMap& map, const HmParams& p, b
 
 bool gemv_hm_supported(const DeviceInfo& dev, int64_t M, int64_t N, int64_t K, int gated) {
     HmPlan c;
-    return plan_hm(dev.sm_count, dev.max_smem_optin, M, N, K, gated, &c);
+    if (!plan_hm(dev.sm_count, dev.max_smem_optin, M, N, K, gated, &c)) return false;
+    // measured crossover with the tcgen05 GEMM (tools/dec_tune.py): K = 14336 needs several waves of one-tile CTAs with four
+    // pairs per warp; two passes over them (M > 8) are no faster than the GEMM (14336 -> 4096 M = 16: 39.2 vs 37.7 us)
+    if (tuning().force_path != 7 && M > MB && c.gpw >= 4 && c.grid > dev.sm_count) return false;
+    return true;
 }
 
 int launch_gemv_hm(const DeviceInfo& dev, const void* x, int x_dtype, const uint8_t* packed, const float* scales,

@@ -32,11 +32,12 @@ def _forced(pkg, path, fn):
 
 @pytest.mark.parametrize("M", [1, 2, 3, 4, 5, 8, 9, 13, 16])
 @pytest.mark.parametrize("N,K", [(1, 256), (7, 256), (9, 512), (16, 768), (200, 1024), (2371, 2048), (11008, 4096), (4096, 4096),
-                                 (3000, 6144), (4096, 11008), (1500, 8192), (600, 16384)])
+                                 (3000, 6144), (4096, 11008), (1500, 8192), (600, 16384), (14336, 4096), (4096, 14336), (22016, 4096)])
 def test_hm_kernel_edge_shapes(oracle, pkg, M, N, K):
     """Ragged row counts (fewer tiles than SMs, last tile partly foreign / out of bounds), one and two passes of eight
     tokens with a ragged last pass, one to four column pairs per warp, K < 4096 (warps without a pair), batch rows of
-    very different magnitude (every (warp, pair, token) has its own scale)."""
+    very different magnitude (every (warp, pair, token) has its own scale), shapes that need two or more waves of CTAs
+    (Mixtral's 14336-wide projections, Llama's gate + up rows in one matrix)."""
     rng = np.random.default_rng(1000 * M + N + K)
     packed, scales, zps = _weights(rng, N, K)
     x = (rng.standard_normal((M, K)) * rng.choice([1e-3, 1.0, 300.0], size=(M, 1))).astype(np.float32)
@@ -75,7 +76,7 @@ def test_hm_kernel_16bit_activations(oracle, pkg, dtype, M, N, K):
 
 
 @pytest.mark.parametrize("M", [3, 8, 12, 16])
-@pytest.mark.parametrize("F,K", [(150, 1024), (5504, 4096)])
+@pytest.mark.parametrize("F,K", [(150, 1024), (5504, 4096), (11008, 4096)])
 def test_hm_kernel_gated_and_bias(oracle, pkg, M, F, K):
     """Fused gate + up pair (rows 2f / 2f+1 interleaved, h = silu(gate) * up) and the bias epilogue."""
     rng = np.random.default_rng(M + F + K)
@@ -131,5 +132,5 @@ def test_hm_kernel_is_the_default_for_mid_batches_and_agrees_with_the_integer_ke
     y6 = _forced(pkg, 6, lambda: pkg._lib.linear_fwd(X, P, S, Z)).cpu().numpy()
     assert np.array_equal(y, y7)
     assert np.abs(y7 - y6).max() <= 2e-6 * np.abs(y6).max()
-    with pytest.raises(RuntimeError):                        # a CTA's rows must fit: Mixtral's 14336-wide projection does not
-        _forced(pkg, 7, lambda: pkg._lib.linear_fwd(X, cuda(np.zeros((14336, K // 2), np.uint8)), cuda(np.ones(14336, np.float32)), cuda(np.zeros(14336, np.float32))))
+    with pytest.raises(RuntimeError):                        # K must be a multiple of 256 (whole TMA boxes)
+        _forced(pkg, 7, lambda: pkg._lib.linear_fwd(X[:, :384].contiguous(), cuda(np.zeros((64, 192), np.uint8)), cuda(np.ones(64, np.float32)), cuda(np.zeros(64, np.float32))))
