@@ -147,14 +147,19 @@ __device__ __forceinline__ void hm_load8(const void* x, int64_t idx, float2 (&v)
     }
 }
 
-// XT: activation dtype.  fp32 -> two n-tiles per pass (hi parts, lo parts); else one.
-// PK (fp32, M <= 4): ONE n-tile, column 2j = hi part, 2j + 1 = lo part of token j -- half the tensor work of the
-// eight-token form.
-template <int XT, bool PK>
+// XT: activation dtype.
+// FORM 0 (HMMA): nibbles -> fp16 subnormals, x in fp16: one n-tile per pass for 16-bit activations, two (hi parts, lo
+// parts) for fp32 ones.
+// FORM 2 (I3, fp32; the default for fp32): x as a 22-bit fixed-point number per (warp, pair, token), cut into three
+// base-256 digits = three n-tiles of IMMA m16n8k32 (u8 x u8, top digit u8 x s8); the nibbles are widened to bytes
+// (w & 0x0f0f0f0f, (w >> 4) & 0x0f0f0f0f).  Three tensor + six ALU instructions per 512 weights against four + ten of
+// the hi / lo HMMA form: the main loop is bound by exactly those (M = 8: 8.8 -> 8.0 us, M = 16: 15.7 -> 13.6 us).
+template <int XT, int FORM>
 __global__ void __launch_bounds__(NTHR, 1) gemv_hm_kernel(const __grid_constant__ CUtensorMap tmap, const HmParams p) {
     constexpr bool F32 = XT == B200Q_F32;
-    constexpr int NT = (F32 && !PK) ? 2 : 1;
-    static_assert(!PK || F32, "the packed form is for fp32 activations");
+    constexpr bool I3 = FORM == 2;
+    constexpr int NT = F32 ? 2 : 1;
+    static_assert(FORM == 0 || (FORM == 2 && F32), "the integer form is for fp32 activations");
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -231,7 +236,7 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_hm_kernel(const __grid_constant_
     for (int pass = 0; pass < p.npasses; ++pass) {
         const int m0 = pass * MB;
         if (pass > 0) __syncthreads();                        // the fold of the previous pass has read every slot
-        const int tk = PK ? (g >> 1) : g;                     // token (of the pass) of this lane's B column
+        const int tk = g;                                     // token (of the pass) of this lane's B column
         const bool tok = m0 + tk < p.M;                       // ... exists
         float sxacc = 0.0f;                                   // sum_k x of token g over this warp's pairs (quad-uniform)
 #pragma unroll 1
@@ -272,16 +277,40 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_hm_kernel(const __grid_constant_
             if (first) HM_STAMP(3);
             const int E = (int)(__float_as_uint(am) >> 23);
             if ((E == 255 || s != s) && t == 0) atomicOr(s_flag, 1u << (m0 + tk));
-            const int ex = min(126, 141 - E);                 // amax * 2^ex in [2^14, 2^15)
+            const int ex = min(126, (I3 ? 148 : 141) - E);    // amax * 2^ex in [2^14, 2^15)   (I3: [2^21, 2^22))
             const float up = __uint_as_float((uint32_t)(127 + ex) << 23);
             const float2 up2 = make_float2(up, up * 0.0625f); // (even column, odd column: its nibble arrives 2^4 too large)
             // descale of the accumulator columns 2t, 2t + 1 (tokens 2t, 2t + 1 of the pass): 2^24 (subnormal nibbles) * 2^-ex
             const float dn = __uint_as_float((uint32_t)(127 - ex) << 23);
-            // (PK: columns 2t, 2t + 1 = hi / lo of token t, whose lanes are g = 2t, 2t + 1: the same scale)
             const float d0 = __shfl_sync(0xffffffffu, dn, 8 * t), d1 = __shfl_sync(0xffffffffu, dn, 8 * t + 4);
 
-            // ---- B fragments: per 32-byte step c, half h: MMA alpha = nibbles (0,4 | 1,5), beta = (2,6 | 3,7) of every word
-            uint32_t bf[8][2][NT][2];                         // [2 c + h][alpha / beta][hi / lo][b0, b1]
+            // ---- B fragments
+            uint32_t bi[I3 ? 8 : 1][3][2];                    // I3: [2 c + h][digit][even columns, odd columns]
+            uint32_t bf[I3 ? 1 : 8][2][NT][2];                // HMMA: [2 c + h][alpha / beta][hi / lo][b0, b1]
+            if constexpr (I3) {
+                // X = rn(x 2^ex) + 2^22 sits in the low 24 bits of fma(x, 2^ex, 1.5 * 2^23): bytes 0, 1 = unsigned digits,
+                // byte 2 - 64 = signed top digit.  Columns 2j (even) meet the low nibbles, 2j + 1 the high nibbles.
+                const float2 upi = make_float2(up, up), magic = make_float2(12582912.0f, 12582912.0f);
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch) {
+                    uint32_t ev[4], od[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 a = __ffma2_rn(xv[ch][e], upi, magic);
+                        ev[e] = __float_as_uint(a.x); od[e] = __float_as_uint(a.y);
+                    }
+#pragma unroll
+                    for (int par = 0; par < 2; ++par) {
+                        const uint32_t* v = par ? od : ev;
+                        const uint32_t t01 = __byte_perm(v[0], v[1], 0x5140), t23 = __byte_perm(v[2], v[3], 0x5140);
+                        const uint32_t u01 = __byte_perm(v[0], v[1], 0x0062), u23 = __byte_perm(v[2], v[3], 0x0062);
+                        bi[ch][0][par] = __byte_perm(t01, t23, 0x5410);
+                        bi[ch][1][par] = __byte_perm(t01, t23, 0x7632);
+                        bi[ch][2][par] = (__byte_perm(u01, u23, 0x5410) + 0x40404040u) ^ 0x80808080u;       // byte - 64 as s8
+                    }
+                }
+            } else {
+            // per 32-byte step c, half h: MMA alpha = nibbles (0,4 | 1,5), beta = (2,6 | 3,7) of every word
 #pragma unroll
             for (int ch = 0; ch < 8; ++ch) {
                 float2 a[4];                                  // (x0, x1 / 16) (x2, x3 / 16) (x4, x5 / 16) (x6, x7 / 16), scaled
@@ -294,12 +323,9 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_hm_kernel(const __grid_constant_
                     const float2 h26 = unpack_h2(bf[ch][1][0][0]), h37 = unpack_h2(bf[ch][1][0][1]);
                     const uint32_t l0 = pack_h2(a[0].x - h04.x, a[2].x - h04.y), l1 = pack_h2(a[0].y - h15.x, a[2].y - h15.y);
                     const uint32_t l2 = pack_h2(a[1].x - h26.x, a[3].x - h26.y), l3 = pack_h2(a[1].y - h37.x, a[3].y - h37.y);
-                    if constexpr (PK) {
-                        if (g & 1) { bf[ch][0][0][0] = l0; bf[ch][0][0][1] = l1; bf[ch][1][0][0] = l2; bf[ch][1][0][1] = l3; }
-                    } else {
-                        bf[ch][0][1][0] = l0; bf[ch][0][1][1] = l1; bf[ch][1][1][0] = l2; bf[ch][1][1][1] = l3;
-                    }
+                    bf[ch][0][1][0] = l0; bf[ch][0][1][1] = l1; bf[ch][1][1][0] = l2; bf[ch][1][1][1] = l3;
                 }
+            }
             }
             if (first && issuer) {
                 if (mid < nops) issue(mid, nops);
@@ -314,6 +340,30 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_hm_kernel(const __grid_constant_
             for (int i = 0; i < S; ++i) {
                 if (pass == 0) mbar_wait(sbase + OFF_BARS + 8u * (uint32_t)(grp * S + i), 0u);
                 const uint32_t pb = sbase + p.tile_off + (uint32_t)(i * p.tile_bytes + P * PAIR_BYTES);
+                float v[4];
+                if constexpr (I3) {
+                    int ac[3][4];                             // one chain per digit
+#pragma unroll
+                    for (int d = 0; d < 3; ++d)
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) ac[d][r] = 0;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        uint32_t a[4];
+                        ldsm_x4(a, pb + offc[c]);
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const uint32_t w0 = a[2 * h], w1 = a[2 * h + 1];
+                            const uint32_t e0 = w0 & 0x0f0f0f0fu, e1 = w1 & 0x0f0f0f0fu, o0 = (w0 >> 4) & 0x0f0f0f0fu, o1 = (w1 >> 4) & 0x0f0f0f0fu;
+                            imma_uu(ac[0], e0, e1, o0, o1, bi[2 * c + h][0][0], bi[2 * c + h][0][1]);
+                            imma_uu(ac[1], e0, e1, o0, o1, bi[2 * c + h][1][0], bi[2 * c + h][1][1]);
+                            imma(ac[2], e0, e1, o0, o1, bi[2 * c + h][2][0], bi[2 * c + h][2][1]);
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)               // digits -> value (|sum| < 2^38: the low part is exact in s32, one rounding each)
+                        v[r] = fmaf((float)ac[2][r], 65536.0f, (float)(ac[0][r] + (ac[1][r] << 8))) * ((r & 1) ? d1 : d0);
+                } else {
                 float acc[2][NT][4];                          // two chains (alpha, beta) per n-tile
 #pragma unroll
                 for (int j = 0; j < 2; ++j)
@@ -338,35 +388,27 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_hm_kernel(const __grid_constant_
                     }
                 }
                 // partial tile -> this warp's own slot of the tile, descaled: q was 2^-24 too small
-                float v[4];
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
                     float a = acc[0][0][r] + acc[1][0][r];
                     if constexpr (NT == 2) a += acc[0][1][r] + acc[1][1][r];
                     v[r] = (a * 16777216.0f) * ((r & 1) ? d1 : d0);
                 }
-                if constexpr (PK) { v[0] += v[1]; v[2] += v[3]; }      // hi + lo column of token t
+                }
                 // slot layout [row][token]: lane (g, t) owns tokens 2t, 2t + 1 of rows g and g + 8 -- two conflict-free 8-byte stores
                 float2* slot = reinterpret_cast<float2*>(smem + OFF_SLOTS + (i * NW + warp) * SLOT_BYTES);
-                if constexpr (PK) {                           // token t of rows g, g + 8 (tokens 4..7 of the slot are never read for a result)
-                    float* s1 = reinterpret_cast<float*>(slot);
-                    if (q > 0) { v[0] += s1[g * 8 + t]; v[2] += s1[(g + 8) * 8 + t]; }
-                    s1[g * 8 + t] = v[0];
-                    s1[(g + 8) * 8 + t] = v[2];
-                } else {
-                    float2 lo2 = make_float2(v[0], v[1]), hi2 = make_float2(v[2], v[3]);
-                    if (q > 0) {
-                        const float2 o0 = slot[g * 4 + t], o1 = slot[(g + 8) * 4 + t];
-                        lo2.x += o0.x; lo2.y += o0.y; hi2.x += o1.x; hi2.y += o1.y;
-                    }
-                    slot[g * 4 + t] = lo2;
-                    slot[(g + 8) * 4 + t] = hi2;
+                float2 lo2 = make_float2(v[0], v[1]), hi2 = make_float2(v[2], v[3]);
+                if (q > 0) {
+                    const float2 o0 = slot[g * 4 + t], o1 = slot[(g + 8) * 4 + t];
+                    lo2.x += o0.x; lo2.y += o0.y; hi2.x += o1.x; hi2.y += o1.y;
                 }
+                slot[g * 4 + t] = lo2;
+                slot[(g + 8) * 4 + t] = hi2;
                 if (first && i < 5) HM_STAMP(5 + i);
             }
         }
         if (pass == 0) HM_STAMP(10);
-        if (t == 0) s_sx[warp * MB + (PK ? 4 * (g & 1) + tk : g)] = (PK && (g & 1)) ? 0.0f : sxacc;
+        if (t == 0) s_sx[warp * MB + g] = sxacc;
         if (pass == 0 && tid < 128) { s_par[tid] = sc; s_par[128 + tid] = zp; s_par[256 + tid] = bias; }
         __syncthreads();
         if (pass == 0) HM_STAMP(11);
@@ -491,9 +533,9 @@ bool plan_hm(int sm_count, int max_smem, int64_t M, int64_t N, int64_t K, int ga
     return false;
 }
 
-template <int XT, bool PK>
+template <int XT, int FORM>
 int launch_hm_inst(const HmPlan& c, const CUtensorMap& map, const HmParams& p, bool pdl, cudaStream_t st) {
-    auto kfn = gemv_hm_kernel<XT, PK>;
+    auto kfn = gemv_hm_kernel<XT, FORM>;
     static thread_local int attr_dev_smem[64] = {0};
     int dev = 0;
     B200Q_CUDA(cudaGetDevice(&dev));
@@ -556,9 +598,9 @@ int launch_gemv_hm(const DeviceInfo& dev, const void* x, int x_dtype, const uint
     if (int rc = dec_weight_map(packed, N, K, c.chunk, &map)) return rc;
     const bool pdl = tuning().gemv_pdl != 0;
     if (x_dtype == B200Q_F32)
-        return (M <= 4 && tuning().hm_packed != 0) ? launch_hm_inst<B200Q_F32, true>(c, map, p, pdl, st) : launch_hm_inst<B200Q_F32, false>(c, map, p, pdl, st);
-    if (x_dtype == B200Q_F16) return launch_hm_inst<B200Q_F16, false>(c, map, p, pdl, st);
-    return launch_hm_inst<B200Q_BF16, false>(c, map, p, pdl, st);
+        return tuning().hm_i3 != 0 ? launch_hm_inst<B200Q_F32, 2>(c, map, p, pdl, st) : launch_hm_inst<B200Q_F32, 0>(c, map, p, pdl, st);
+    if (x_dtype == B200Q_F16) return launch_hm_inst<B200Q_F16, 0>(c, map, p, pdl, st);
+    return launch_hm_inst<B200Q_BF16, 0>(c, map, p, pdl, st);
 }
 
 }  // namespace b200q

@@ -50,7 +50,7 @@ struct Tuning {
     int force_path = -1;    // 0 auto, 1 generic SIMT, 2 ring decode kernel, 3 tcgen05 gemm, 6 resident decode kernel (gemv_dec), 7 fp16 HMMA decode kernel (gemv_hm)
     int gemv_bufs = 0;      // resident decode kernel: cap on the tile buffers of a CTA (0 = as many as fit; tests force the ring with it)
     int hm_waves = 0;       // gemv_hm.cu: most waves of CTAs (0 = 4); 1 = only shapes whose rows fit with one CTA per SM
-    int hm_packed = 1;      // 0: fp32 batches of <= 4 tokens use the eight-token form of gemv_hm.cu too
+    int hm_i3 = 1;          // gemv_hm.cu, fp32 activations, 1 = three-digit IMMA form, 0 = fp16 hi / lo HMMA form
     int hm_min_m = 3;       // smallest batch that goes to the fp16 HMMA decode kernel (gemv_hm.cu)
     int gemv_slots = 1;     // resident decode kernel, M <= 2: 0 = pipelined cross-warp reduction instead of per-warp slots
 };

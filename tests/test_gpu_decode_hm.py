@@ -1,9 +1,10 @@
-"""fp16 HMMA decode kernel (csrc/gemv_hm.cu, force_path 7; the default for 3 <= M <= 16 when every tile of a CTA is
-resident in shared memory) against the float64 oracle, through the C ABI.
+"""Mid-batch decode kernel (csrc/gemv_hm.cu, force_path 7; the default for 3 <= M <= 16 when the rows of a CTA fit in
+shared memory) against the float64 oracle, through the C ABI.
 
-Tolerance: fp32 activations are carried as fp16 hi + lo parts (2^-22 relative) and accumulated in fp32 on the tensor
-cores; measured max error 1.0e-6 of the largest output of a batch row (tools/hm_check.py); the bar here is 4e-6 per
-batch row.  16-bit activations are exact in the operand (error = fp32 accumulation only)."""
+Tolerance: fp32 activations are carried as a 22-bit fixed-point number per (warp, 256 columns, token) in three IMMA
+digits (default, hm_i3 = 1) or as fp16 hi + lo parts on HMMA (hm_i3 = 0), partial sums in s32 / fp32; measured max
+error 0.8e-6 / 1.0e-6 of the largest output of a batch row (tools/hm_check.py); the bar here is 4e-6 per batch row.
+16-bit activations (HMMA form) are exact in the operand (error = fp32 accumulation only)."""
 import numpy as np
 import pytest
 import torch
@@ -22,12 +23,14 @@ def _weights(rng, N, K):
     return packed, scales, zps
 
 
-def _forced(pkg, path, fn):
+def _forced(pkg, path, fn, i3=-1):
     pkg._lib.tune("force_path", path)
+    pkg._lib.tune("hm_i3", i3)
     try:
         return fn()
     finally:
         pkg._lib.tune("force_path", -1)
+        pkg._lib.tune("hm_i3", -1)
 
 
 @pytest.mark.parametrize("M", [1, 2, 3, 4, 5, 8, 9, 13, 16])
@@ -45,11 +48,14 @@ def test_hm_kernel_edge_shapes(oracle, pkg, M, N, K):
     rows = np.arange(N) if N <= 512 else rng.choice(N, size=512, replace=False)
     ref = oracle.reference_quantized_linear(x, packed[rows], scales[rows], zps[rows], acc=np.float64)
     y = _forced(pkg, 7, lambda: pkg._lib.linear_fwd(X, P, S, Z)).cpu().numpy()
+    # the fp16 hi / lo HMMA form of the same kernel (what 16-bit activations always use) agrees to the same bar
+    yh = _forced(pkg, 7, lambda: pkg._lib.linear_fwd(X, P, S, Z), i3=0).cpu().numpy()
     # (few outputs: max |y| of a row is not a scale -- a single output may be small by cancellation; sum_k |w x| is)
     absdot = np.abs(x).astype(np.float64) @ np.abs(oracle.dequantize_weights(packed[rows], scales[rows], zps[rows]).astype(np.float64)).T
     for m in range(M):
-        err = np.abs(ref[m] - y[m, rows])
-        assert (err <= 4e-6 * np.abs(ref[m]).max() + 2e-7 * absdot[m]).all(), f"row {m}: {err.max()} vs |y|max {np.abs(ref[m]).max()}"
+        for out in (y, yh):
+            err = np.abs(ref[m] - out[m, rows])
+            assert (err <= 4e-6 * np.abs(ref[m]).max() + 2e-7 * absdot[m]).all(), f"row {m}: {err.max()} vs |y|max {np.abs(ref[m]).max()}"
     # deterministic (fixed fold order), and exactly linear under power-of-two scaling of x
     y2 = _forced(pkg, 7, lambda: pkg._lib.linear_fwd(X, P, S, Z)).cpu().numpy()
     assert np.array_equal(y, y2)
@@ -95,8 +101,8 @@ def test_hm_kernel_gated_and_bias(oracle, pkg, M, F, K):
 
 
 @pytest.mark.parametrize("M", [3, 4, 9, 16])
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-def test_hm_kernel_nonfinite_rows(oracle, pkg, M, dtype):
+@pytest.mark.parametrize("dtype,i3", [(torch.float32, 1), (torch.float32, 0), (torch.bfloat16, 1)])
+def test_hm_kernel_nonfinite_rows(oracle, pkg, M, dtype, i3):
     """python/quantize.py:172, 202: NaN / Inf in a row of x propagate as in dequantize + F.linear; the other rows of
     the batch are not disturbed."""
     rng = np.random.default_rng(M)
@@ -112,7 +118,7 @@ def test_hm_kernel_nonfinite_rows(oracle, pkg, M, dtype):
     xr = X.float().cpu().numpy()
     with np.errstate(all="ignore"):
         ref = oracle.reference_quantized_linear(xr, packed, scales, zps)
-    y = _forced(pkg, 7, lambda: pkg._lib.linear_fwd(X, cuda(packed), cuda(scales), cuda(zps), out_dtype=torch.float32)).cpu().numpy()
+    y = _forced(pkg, 7, lambda: pkg._lib.linear_fwd(X, cuda(packed), cuda(scales), cuda(zps), out_dtype=torch.float32), i3=i3).cpu().numpy()
     assert np.array_equal(np.isnan(y), np.isnan(ref))
     assert np.array_equal(np.isposinf(y), np.isposinf(ref)) and np.array_equal(np.isneginf(y), np.isneginf(ref))
     clean = [m for m in range(M) if np.isfinite(xr[m]).all()]

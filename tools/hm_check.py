@@ -51,7 +51,7 @@ if __name__ == "__main__":
     print(json.dumps({"worst_rel_err_vs_f64": worst}), flush=True)
     import dec_tune
     for (K, N) in [(4096, 11008), (11008, 4096)]:
-        for M in [int(v) for v in os.environ.get("HM_MS", "4,8,16").split(",")]:
+        for M in [int(v) for v in os.environ.get("HM_MS", "3,4,8,16").split(",")]:
             a = dec_tune.measure(M, K, N, {"force_path": 7})
             b = dec_tune.measure(M, K, N, {"hm_min_m": 99})
             nb = N * K // 2 + 8 * N + 4 * M * K + 4 * M * N
