@@ -263,7 +263,7 @@ def decode_sweep(torch, pkg, dev, peak, first_pool=None):
             nb = gemv_bytes(M, N, K)
             out.append({"K": K, "N": N, "M": M, "us_per_launch": round(us, 3), "GBps": round(nb / us / 1e3, 1),
                         "frac_hbm_peak": round(nb / us / 1e3 / peak, 4),
-                        "kernel": "gemv_dec (exact-integer IMMA)" if M <= 2 else "gemv_hm (fp16 HMMA, hi + lo parts)"})
+                        "kernel": "gemv_dec (exact-integer IMMA)" if M <= 2 else "gemv_hm (three-digit IMMA form, eight tokens per instruction)"})
         if layers is not first_pool:
             del layers
             torch.cuda.empty_cache()
