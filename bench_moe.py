@@ -183,12 +183,13 @@ def cpu_moe_reference(steps=2, tokens=512):
 
 
 def moe_decode(torch, pkg, dev, hbm_peak):
-    """BASELINE.json configs[3], decode: T = 1, 4, 16 tokens through QuantizedMoE.forward_routed (random routing): the
-    decode call (grouped GEMVs) up to three rows per expert on average, the grouped tcgen05 GEMMs above (T = 16).
-    HBM-bound: algorithmic bytes = (#distinct experts hit) x 88 MB of packed INT4 weights."""
+    """BASELINE.json configs[3], decode: T = 1, 4, 8, 16 tokens through QuantizedMoE.forward_routed (random routing): the
+    decode call (route + grouped gate/up GEMV + grouped down GEMV + combine; exact-integer kernel below 1.5 rows per
+    expert on average, mid-batch kernel above).  HBM-bound: algorithmic bytes = (#distinct experts hit) x 88 MB of packed
+    INT4 weights."""
     layer = build_local_moe(torch, pkg, list(range(E)), dev)
     out = []
-    for T in (1, 4, 16):
+    for T in (1, 4, 8, 16):
         x, logits = make_inputs(torch, 0, T, "random", dev)
         ms = time_steps(torch, None, dev, lambda: layer.forward_routed(x, logits, top_k=TOPK), 50, 5)
         hit = int(torch.unique(pkg.route(logits, TOPK).expert_indices).numel())

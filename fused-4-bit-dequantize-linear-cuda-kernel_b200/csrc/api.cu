@@ -225,6 +225,19 @@ int b200q_moe_decode_fwd(const void* x, int x_dtype, const float* logits, int64_
     void* y = base + w.y;
     // three launches + the combine: routing (one CTA), gate / up GEMV reading x in place through the token map, down GEMV
     if (int rc = moe_route_small(logits, T, E, k, idx, wts, counts, offsets, sorted_slot, inv_perm, src_token, st)) return rc;
+    // from 1.5 rows per expert on average the mid-batch kernel (eight tokens per tensor instruction, gemv_hm.cu) serves the
+    // groups; below that the exact-integer kernel (two rows per pass).  Mixtral layer, tools/moe_decode_crossover.py:
+    // T = 4: 0.219 / 0.216 ms, T = 6: 0.250 / 0.221, T = 8: 0.337 / 0.258, T = 16: 0.552 / 0.298 (grouped tcgen05 GEMMs: 0.488)
+    const int hm_mode = tuning().moe_dec_hm;
+    const bool use_hm = hm_mode != 0 && (hm_mode > 0 || 2 * T * k >= 3 * (int64_t)E) && (x_dtype != B200Q_F32 || aligned(x, 32)) &&
+                        gemv_hm_supported(dv, T < 8 ? T : 8, 2 * F, d, 1) && gemv_hm_supported(dv, T < 8 ? T : 8, d, F, 0);   // (the plan does not depend on the rows beyond the pass count)
+    if (use_hm) {
+        if (int rc = launch_gemv_hm(dv, x, x_dtype, packed13, scales13, zps13, nullptr, h, x_dtype, T, 2 * F, d, B200Q_FLAG_STATIC_WEIGHTS, st,
+                                    nullptr, 0, 1, offsets, E, src_token)) return rc;
+        if (int rc = launch_gemv_hm(dv, h, x_dtype, packed2, scales2, zps2, nullptr, y, x_dtype, T, d, F, B200Q_FLAG_STATIC_WEIGHTS, st,
+                                    nullptr, 0, 0, offsets, E, nullptr)) return rc;
+        return b200q_moe_combine(y, x_dtype, inv_perm, wts, T, k, d, out, B200Q_F32, stream);
+    }
     if (int rc = launch_gemv_dec(dv, x, x_dtype, packed13, scales13, zps13, nullptr, h, x_dtype, T, 2 * F, d, B200Q_FLAG_STATIC_WEIGHTS, st,
                                  nullptr, 0, 1, offsets, E, src_token)) return rc;
     if (int rc = launch_gemv_dec(dv, h, x_dtype, packed2, scales2, zps2, nullptr, y, x_dtype, T, d, F, B200Q_FLAG_STATIC_WEIGHTS, st,

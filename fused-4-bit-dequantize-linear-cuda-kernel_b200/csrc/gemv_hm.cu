@@ -104,6 +104,11 @@ struct HmParams {
     int early_tiles;                 // a + 10 b: a requests before griddepcontrol.wait, b more behind the x loads
     int pf_mode;                     // next-layer L2 prefetch: 0 off, 2 before the own requests, else after the first operand build
     int gated;                       // 1: rows 2f / 2f+1 are the gate / up projection of column f; y is h [M, N/2] = silu(gate) * up
+    // grouped (MoE decode, GRP instances): blockIdx.y = expert of packed [E, N, K/2]; rows [offsets[e], offsets[e+1]) of y
+    // belong to it (device memory, <= 16 rows; experts without rows exit at once); row r of the group reads
+    // x[row_map[offsets[e] + r]] (x is read in place, no gathered copy) or x[offsets[e] + r] when row_map is null
+    const int32_t* offsets;
+    const int32_t* row_map;
     int debug;                       // B200Q_PROF builds: record phase stamps
 };
 
@@ -154,7 +159,7 @@ __device__ __forceinline__ void hm_load8(const void* x, int64_t idx, float2 (&v)
 // base-256 digits = three n-tiles of IMMA m16n8k32 (u8 x u8, top digit u8 x s8); the nibbles are widened to bytes
 // (w & 0x0f0f0f0f, (w >> 4) & 0x0f0f0f0f).  Three tensor + six ALU instructions per 512 weights against four + ten of
 // the hi / lo HMMA form: the main loop is bound by exactly those (M = 8: 8.8 -> 8.0 us, M = 16: 15.7 -> 13.6 us).
-template <int XT, int FORM>
+template <int XT, int FORM, bool GRP>
 __global__ void __launch_bounds__(NTHR, 1) gemv_hm_kernel(const __grid_constant__ CUtensorMap tmap, const HmParams p) {
     constexpr bool F32 = XT == B200Q_F32;
     constexpr bool I3 = FORM == 2;
@@ -172,6 +177,21 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_hm_kernel(const __grid_constant_
     const int r0 = unit * (b * p.rows_q + min(b, p.rows_rem));           // first weight row of this CTA
     const int nrows = unit * (p.rows_q + (b < p.rows_rem ? 1 : 0));
     const int S = (nrows + TILE_ROWS - 1) / TILE_ROWS;                   // tiles of this CTA (all resident)
+    // grouped: this CTA's expert, its token rows and where they start in y (and in x, through the row map)
+    int Mrows = p.M, npasses = p.npasses, xrow0 = 0, wrow0 = r0;         // wrow0: first row in the stacked weight tensor
+    if constexpr (GRP) {
+        const int expert = (int)blockIdx.y;
+        const int lo = p.offsets[expert], hi = p.offsets[expert + 1];
+        Mrows = min(hi - lo, 2 * MB);
+        if (Mrows <= 0) return;                                          // uniform: this expert has no tokens
+        npasses = (Mrows + MB - 1) / MB;
+        xrow0 = lo;
+        wrow0 = expert * p.N + r0;
+    }
+    auto x_row = [&](int m) -> int64_t {                                 // row of x that token row m of this CTA reads
+        if constexpr (GRP) { return p.row_map ? (int64_t)p.row_map[xrow0 + m] : (int64_t)(xrow0 + m); }
+        return (int64_t)m;
+    };
     unsigned int* s_flag = reinterpret_cast<unsigned int*>(smem + OFF_FLAG);
     float* s_sx = reinterpret_cast<float*>(smem + OFF_SX);
     float* s_par = reinterpret_cast<float*>(smem + OFF_PAR);
@@ -191,7 +211,7 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_hm_kernel(const __grid_constant_
     const int nwa = min(NW, p.npairs);                        // warps that own at least one pair
     const bool issuer = warp == nwa - 1 && lane == 0;
     auto issue = [&](int from, int to) {
-        hm_issue(&tmap, sbase + OFF_BARS, sbase + p.tile_off, r0, from, to, S, p.nbars, p.chunk, p.tile_bytes);
+        hm_issue(&tmap, sbase + OFF_BARS, sbase + p.tile_off, wrow0, from, to, S, p.nbars, p.chunk, p.tile_bytes);
     };
     const int early = min(p.early_tiles % 10, nops);
     const int mid = min(early + p.early_tiles / 10, nops);
@@ -222,9 +242,9 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_hm_kernel(const __grid_constant_
     // scale / zero point / bias of the CTA's rows: fetched early by the first 128 threads, parked in shared memory for the fold
     float sc = 0.0f, zp = 0.0f, bias = 0.0f;
     if (tid < nrows) {                                        // nrows <= 128
-        sc = __ldg(p.scales + r0 + tid);
-        zp = __ldg(p.zps + r0 + tid);
-        if (p.bias) bias = __ldg(p.bias + r0 + tid);
+        sc = __ldg(p.scales + wrow0 + tid);
+        zp = __ldg(p.zps + wrow0 + tid);
+        if (p.bias) bias = __ldg(p.bias + wrow0 + tid);
     }
     if (warp >= nwa) {                                        // K < 4096: a warp without pairs contributes zeros to the fold
         for (int i = 0; i < S; ++i) sts128(sbase + OFF_SLOTS + (uint32_t)((i * NW + warp) * SLOT_BYTES + lane * 16), make_uint4(0u, 0u, 0u, 0u));
@@ -233,11 +253,11 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_hm_kernel(const __grid_constant_
     HM_STAMP(2);
     constexpr uint32_t M0 = 0x000f000fu, M1 = 0x00f000f0u;
 #pragma unroll 1
-    for (int pass = 0; pass < p.npasses; ++pass) {
+    for (int pass = 0; pass < npasses; ++pass) {
         const int m0 = pass * MB;
         if (pass > 0) __syncthreads();                        // the fold of the previous pass has read every slot
         const int tk = g;                                     // token (of the pass) of this lane's B column
-        const bool tok = m0 + tk < p.M;                       // ... exists
+        const bool tok = m0 + tk < Mrows;                     // ... exists
         float sxacc = 0.0f;                                   // sum_k x of token g over this warp's pairs (quad-uniform)
 #pragma unroll 1
         for (int q = 0; q < p.gpw; ++q) {
@@ -248,7 +268,7 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_hm_kernel(const __grid_constant_
             // (fp32: one 32-byte load per step -- the four lanes of a quad read one whole 128-byte line per instruction)
             float2 xv[8][4];
             {
-                const int64_t base = (int64_t)(m0 + tk) * p.K + P * 256 + t * 8;
+                const int64_t base = (tok ? x_row(m0 + tk) : 0) * p.K + P * 256 + t * 8;
 #pragma unroll
                 for (int ch = 0; ch < 8; ++ch) {
 #pragma unroll
@@ -446,10 +466,10 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_hm_kernel(const __grid_constant_
                     if (p.gated) {
                         // fused gate + up pair: the even row (gate) fetches its neighbour's value (up, lane ^ 2) and writes silu(gate) * up
                         const float uu = __shfl_xor_sync(0xffffffffu, vv[j], 2);
-                        if (mine && half == 0 && !(row & 1) && m < p.M && !((flagged >> m) & 1u))
-                            store_out(p.y, p.y_dtype, (int64_t)m * (p.N >> 1) + ((r0 + rowpos) >> 1), vv[j] / (1.0f + __expf(-vv[j])) * uu);
-                    } else if (mine && half == 0 && m < p.M && !((flagged >> m) & 1u)) {
-                        store_out(p.y, p.y_dtype, (int64_t)m * p.N + r0 + rowpos, vv[j] + rbias);
+                        if (mine && half == 0 && !(row & 1) && m < Mrows && !((flagged >> m) & 1u))
+                            store_out(p.y, p.y_dtype, (int64_t)(xrow0 + m) * (p.N >> 1) + ((r0 + rowpos) >> 1), vv[j] / (1.0f + __expf(-vv[j])) * uu);
+                    } else if (mine && half == 0 && m < Mrows && !((flagged >> m) & 1u)) {
+                        store_out(p.y, p.y_dtype, (int64_t)(xrow0 + m) * p.N + r0 + rowpos, vv[j] + rbias);
                     }
                 }
             }
@@ -462,7 +482,7 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_hm_kernel(const __grid_constant_
     // values propagate as in F.linear; one warp per output, weights re-read from global memory
     if (const unsigned int flagged = *s_flag) {
         const int64_t row_bytes = p.K >> 1;
-        for (int m = 0; m < p.M; ++m) {
+        for (int m = 0; m < Mrows; ++m) {
             if (!((flagged >> m) & 1u)) continue;
             auto ref_row = [&](int row) {
                 const float rs = __ldg(p.scales + row), rz = __ldg(p.zps + row);
@@ -471,22 +491,22 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_hm_kernel(const __grid_constant_
                 for (int kb = lane; kb < row_bytes; kb += 32) {
                     const unsigned int byte = wr[kb];
                     const float w0 = ((float)(byte & 15u) - rz) * rs, w1 = ((float)(byte >> 4) - rz) * rs;
-                    acc = fmaf(w0, load1f(p.x, p.x_dtype, (int64_t)m * p.K + 2 * kb), acc);
-                    acc = fmaf(w1, load1f(p.x, p.x_dtype, (int64_t)m * p.K + 2 * kb + 1), acc);
+                    acc = fmaf(w0, load1f(p.x, p.x_dtype, x_row(m) * p.K + 2 * kb), acc);
+                    acc = fmaf(w1, load1f(p.x, p.x_dtype, x_row(m) * p.K + 2 * kb + 1), acc);
                 }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
                 return acc;
             };
             for (int rc = unit * warp; rc < nrows; rc += unit * NW) {
-                const int row = r0 + rc;
-                float acc = ref_row(row);
+                const int row = r0 + rc, wrow = wrow0 + rc;   // output column / row of the stacked weight tensor
+                float acc = ref_row(wrow);
                 if (p.gated) {
-                    const float upv = ref_row(row + 1);
-                    if (lane == 0) store_out(p.y, p.y_dtype, (int64_t)m * (p.N >> 1) + (row >> 1), acc / (1.0f + __expf(-acc)) * upv);
+                    const float upv = ref_row(wrow + 1);
+                    if (lane == 0) store_out(p.y, p.y_dtype, (int64_t)(xrow0 + m) * (p.N >> 1) + (row >> 1), acc / (1.0f + __expf(-acc)) * upv);
                 } else if (lane == 0) {
-                    if (p.bias) acc += __ldg(p.bias + row);
-                    store_out(p.y, p.y_dtype, (int64_t)m * p.N + row, acc);
+                    if (p.bias) acc += __ldg(p.bias + wrow);
+                    store_out(p.y, p.y_dtype, (int64_t)(xrow0 + m) * p.N + row, acc);
                 }
             }
         }
@@ -533,9 +553,9 @@ bool plan_hm(int sm_count, int max_smem, int64_t M, int64_t N, int64_t K, int ga
     return false;
 }
 
-template <int XT, int FORM>
-int launch_hm_inst(const HmPlan& c, const CUtensorMap& map, const HmParams& p, bool pdl, cudaStream_t st) {
-    auto kfn = gemv_hm_kernel<XT, FORM>;
+template <int XT, int FORM, bool GRP>
+int launch_hm_inst(const HmPlan& c, int n_experts, const CUtensorMap& map, const HmParams& p, bool pdl, cudaStream_t st) {
+    auto kfn = gemv_hm_kernel<XT, FORM, GRP>;
     static thread_local int attr_dev_smem[64] = {0};
     int dev = 0;
     B200Q_CUDA(cudaGetDevice(&dev));
@@ -544,7 +564,7 @@ int launch_hm_inst(const HmPlan& c, const CUtensorMap& map, const HmParams& p, b
         attr_dev_smem[dev] = (int)c.smem;
     }
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)c.grid);
+    cfg.gridDim = dim3((unsigned)c.grid, (unsigned)n_experts);
     cfg.blockDim = dim3(NTHR);
     cfg.dynamicSmemBytes = c.smem;
     cfg.stream = st;
@@ -573,8 +593,11 @@ bool gemv_hm_supported(const DeviceInfo& dev, int64_t M, int64_t N, int64_t K, i
 
 int launch_gemv_hm(const DeviceInfo& dev, const void* x, int x_dtype, const uint8_t* packed, const float* scales,
                    const float* zps, const float* bias, void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
-                   unsigned flags, cudaStream_t st, const uint8_t* next_packed, size_t next_bytes, int gated) {
+                   unsigned flags, cudaStream_t st, const uint8_t* next_packed, size_t next_bytes, int gated,
+                   const int32_t* offsets, int n_experts, const int32_t* row_map) {
     HmPlan c;
+    if (n_experts < 1) n_experts = 1;
+    const bool grp = offsets != nullptr;
     if (!plan_hm(dev.sm_count, dev.max_smem_optin, M, N, K, gated, &c))
         return set_error(B200Q_EINVAL, "gemv_hm: unsupported shape M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
     if ((reinterpret_cast<uintptr_t>(x) & (x_dtype == B200Q_F32 ? 31 : 15)) || (reinterpret_cast<uintptr_t>(packed) & 15))
@@ -594,13 +617,20 @@ int launch_gemv_hm(const DeviceInfo& dev, const void* x, int x_dtype, const uint
     p.next_bytes = (tuning().gemv_pf != 0 && next_packed && (reinterpret_cast<uintptr_t>(next_packed) & 15) == 0) ? next_bytes : 0;
     p.next_chunk = (unsigned int)(p.next_bytes / (unsigned long long)c.grid);
     p.debug = tuning().gemv_debug > 0 ? tuning().gemv_debug : 0;
+    p.offsets = offsets; p.row_map = grp ? row_map : nullptr;
+    if (grp) p.next_bytes = 0;
     CUtensorMap map;
-    if (int rc = dec_weight_map(packed, N, K, c.chunk, &map)) return rc;
+    if (int rc = dec_weight_map(packed, N * n_experts, K, c.chunk, &map)) return rc;
     const bool pdl = tuning().gemv_pdl != 0;
+    if (grp) {
+        if (x_dtype == B200Q_F32) return launch_hm_inst<B200Q_F32, 2, true>(c, n_experts, map, p, pdl, st);
+        if (x_dtype == B200Q_F16) return launch_hm_inst<B200Q_F16, 0, true>(c, n_experts, map, p, pdl, st);
+        return launch_hm_inst<B200Q_BF16, 0, true>(c, n_experts, map, p, pdl, st);
+    }
     if (x_dtype == B200Q_F32)
-        return tuning().hm_i3 != 0 ? launch_hm_inst<B200Q_F32, 2>(c, map, p, pdl, st) : launch_hm_inst<B200Q_F32, 0>(c, map, p, pdl, st);
-    if (x_dtype == B200Q_F16) return launch_hm_inst<B200Q_F16, 0>(c, map, p, pdl, st);
-    return launch_hm_inst<B200Q_BF16, 0>(c, map, p, pdl, st);
+        return tuning().hm_i3 != 0 ? launch_hm_inst<B200Q_F32, 2, false>(c, 1, map, p, pdl, st) : launch_hm_inst<B200Q_F32, 0, false>(c, 1, map, p, pdl, st);
+    if (x_dtype == B200Q_F16) return launch_hm_inst<B200Q_F16, 0, false>(c, 1, map, p, pdl, st);
+    return launch_hm_inst<B200Q_BF16, 0, false>(c, 1, map, p, pdl, st);
 }
 
 }  // namespace b200q

@@ -50,6 +50,7 @@ struct Tuning {
     int force_path = -1;    // 0 auto, 1 generic SIMT, 2 ring decode kernel, 3 tcgen05 gemm, 6 resident decode kernel (gemv_dec), 7 fp16 HMMA decode kernel (gemv_hm)
     int gemv_bufs = 0;      // resident decode kernel: cap on the tile buffers of a CTA (0 = as many as fit; tests force the ring with it)
     int hm_waves = 0;       // gemv_hm.cu: most waves of CTAs (0 = 4); 1 = only shapes whose rows fit with one CTA per SM
+    int moe_dec_hm = -1;    // b200q_moe_decode_fwd: -1 the mid-batch kernel from 1.5 rows per expert on average, 0 never, 1 always
     int hm_i3 = 1;          // gemv_hm.cu, fp32 activations, 1 = three-digit IMMA form, 0 = fp16 hi / lo HMMA form
     int hm_min_m = 3;       // smallest batch that goes to the fp16 HMMA decode kernel (gemv_hm.cu)
     int gemv_slots = 1;     // resident decode kernel, M <= 2: 0 = pipelined cross-warp reduction instead of per-warp slots
@@ -117,7 +118,8 @@ int dec_weight_map(const uint8_t* packed, int64_t N, int64_t K, int chunk, CUten
 bool gemv_hm_supported(const DeviceInfo& dev, int64_t M, int64_t N, int64_t K, int gated = 0);
 int launch_gemv_hm(const DeviceInfo& dev, const void* x, int x_dtype, const uint8_t* packed, const float* scales,
                    const float* zps, const float* bias, void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
-                   unsigned flags, cudaStream_t st, const uint8_t* next_packed, size_t next_bytes, int gated = 0);
+                   unsigned flags, cudaStream_t st, const uint8_t* next_packed, size_t next_bytes, int gated = 0,
+                   const int32_t* offsets = nullptr, int n_experts = 1, const int32_t* row_map = nullptr);
 // decode-sized routing in one launch (moe.cu): T <= 16, E <= 256, k <= 8; src_token (optional): token of every sorted position
 int moe_route_small(const float* logits, int64_t T, int E, int k, int32_t* idx, float* weights, int32_t* counts, int32_t* offsets,
                     int32_t* sorted_slot, int32_t* inv_perm, int32_t* src_token, cudaStream_t st);

@@ -199,9 +199,9 @@ class QuantizedMoE(nn.Module):
         reference's combine (routing.py:186-187 multiplies by fp32 routing weights).
         """
         _lib.require_cuda(x, "x")
-        # (decode call vs grouped tcgen05 GEMMs, Mixtral layer: 0.069 / 0.22 ms at T = 1, 0.46 / 0.49 at T = 12, 0.55 / 0.49 at
-        # T = 16 -- the GEMVs need one pass per two to four rows of an expert: tools/moe_decode_crossover.py)
-        if (routing is None and self.fused_gate and x.shape[0] <= 16 and x.shape[0] * top_k <= 3 * self.num_experts
+        # (decode call vs grouped tcgen05 GEMMs, Mixtral layer: 0.069 / 0.22 ms at T = 1, 0.26 / 0.47 at T = 8, 0.30 / 0.49 at
+        # T = 16 -- groups of three and more rows run on the mid-batch kernel: tools/moe_decode_crossover.py)
+        if (routing is None and self.fused_gate and x.shape[0] <= 16
                 and self.hidden_dim % 256 == 0
                 and self.ffn_dim % 256 == 0 and max(self.hidden_dim, self.ffn_dim) <= 16384
                 and self.num_experts <= 256 and top_k <= 8):

@@ -268,9 +268,9 @@ def test_moe_decode_call_matches_oracle_and_grouped_path(oracle, pkg, T, E, k, d
     yg = moe.forward_dispatched(cuda(x), pkg.route(cuda(logits), k)).cpu().numpy()
     assert np.abs(yg - ref).max() <= 3e-4 * scale + 1e-7
     assert torch.equal(decode(), y)                                                    # deterministic
-    # the module picks one of the two by the number of rows per expert (decode call up to three on average)
+    # the module takes the decode call for every T <= 16
     yr = moe.forward_routed(cuda(x), cuda(logits), top_k=k)
-    assert torch.equal(yr, y) if T * k <= 3 * E else np.abs(yr.cpu().numpy() - ref).max() <= 3e-4 * scale + 1e-7
+    assert torch.equal(yr, y)
 
 
 def test_moe_decode_all_tokens_on_one_expert_and_half_precision(oracle, pkg):
@@ -308,6 +308,46 @@ def test_moe_decode_nonfinite_token_poisons_only_its_row(oracle, pkg):
     logits = rng.standard_normal((T, E), dtype=np.float32)
     y = pkg._lib.moe_decode_fwd(cuda(x), cuda(logits), k, *moe.stacked_weights()).cpu().numpy()
     assert np.isnan(y[2]).all() and not np.isfinite(y[4]).any() and np.isfinite(y[[0, 1, 3, 5]]).all()
+
+
+@pytest.mark.parametrize("T", [1, 3, 5, 8, 12, 16])
+@pytest.mark.parametrize("E,k,d,F", [(4, 2, 256, 512), (8, 2, 1024, 3584), (16, 4, 256, 768)])
+def test_moe_decode_call_on_the_mid_batch_kernel(oracle, pkg, T, E, k, d, F):
+    """The same call with both expert GEMVs on the grouped form of gemv_hm.cu (eight tokens per tensor instruction; the
+    default from three rows per expert on average, forced here with moe_dec_hm = 1 for every T): against the float64 oracle,
+    against the exact-integer kernel (moe_dec_hm = 0), fp32 and bf16 activations, a group of 16 rows (two passes),
+    NaN / Inf confined to their token."""
+    rng = np.random.default_rng(T * 17 + E + d)
+    (w1, w3, w2), (q1, q3, q2) = _gated_experts(oracle, rng, E, d, F)
+    f = lambda a: [torch.from_numpy(w).cuda() for w in a]
+    moe = pkg.QuantizedMoE.from_gated_fp16_weights(f(w1), f(w3), f(w2))
+    x = rng.standard_normal((T, d), dtype=np.float32)
+    logits = rng.standard_normal((T, E), dtype=np.float32)
+    if T == 16:
+        logits[:, 1] += 9.0                                  # every token picks expert 1: a group of 16 rows
+    ref = oracle.moe_gated(x, logits, q1, q3, q2, k, acc=np.float64)
+    def decode(xx, mode):
+        pkg._lib.tune("moe_dec_hm", mode)
+        try:
+            return pkg._lib.moe_decode_fwd(xx, cuda(logits), k, *moe.stacked_weights())
+        finally:
+            pkg._lib.tune("moe_dec_hm", -1)
+    y = decode(cuda(x), 1)
+    scale = np.abs(ref).max()
+    assert np.abs(y.cpu().numpy() - ref).max() <= 2e-5 * scale + 1e-7
+    assert np.abs(y.cpu().numpy() - decode(cuda(x), 0).cpu().numpy()).max() <= 2e-5 * scale + 1e-7
+    assert torch.equal(decode(cuda(x), 1), y)                # deterministic
+    xh = torch.from_numpy(x).to(torch.bfloat16)
+    refh = oracle.moe_gated(xh.float().numpy(), logits, q1, q3, q2, k, acc=np.float64)
+    assert np.abs(decode(xh.cuda(), 1).cpu().numpy() - refh).max() <= 3e-2 * np.abs(refh).max()
+    if T >= 5:
+        xn = x.copy()
+        xn[2, 5] = np.nan
+        xn[4, 9] = np.inf
+        yn = decode(cuda(xn), 1).cpu().numpy()
+        ok = [m for m in range(T) if m not in (2, 4)]
+        assert np.isnan(yn[2]).all() and not np.isfinite(yn[4]).any() and np.isfinite(yn[ok]).all()
+        assert np.abs(yn[ok] - ref[ok]).max() <= 2e-5 * scale + 1e-7
 
 
 def test_moe_decode_mixtral_size_sampled(oracle, pkg):
