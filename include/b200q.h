@@ -109,9 +109,11 @@ int b200q_dequantize_rows(const uint8_t* packed, const float* scales, const floa
 /* y[M,N] = x[M,K] @ dequant(packed[N,K/2], scales[N], zps[N])^T
  *   x_dtype / y_dtype: B200Q_F32 | B200Q_F16 | B200Q_BF16 (the reference API is f32/f32).
  *   x, y row-major and contiguous; x 16-byte aligned, packed 16-byte aligned, K even.
- *   M may be any value >= 0.  K % 128 == 0 with 16-byte aligned pointers: M <= 16 takes the decode
- *   kernel (TMA tensor boxes, exact-integer IMMA) whenever ceil(N / SMs) weight rows fit in shared memory,
- *   larger batches the tcgen05 GEMM; anything else a generic SIMT kernel.
+ *   M may be any value >= 0.  K % 256 == 0 with 16-byte aligned pointers: M <= 2 takes the exact-integer decode
+ *   kernel (TMA tensor boxes, IMMA over the raw packed bytes), 3 <= M <= 16 the mid-batch decode kernel (eight tokens per
+ *   tensor instruction: three-digit IMMA form for fp32 activations -- wants x 32-byte aligned --, fp16 HMMA form for 16-bit
+ *   ones), both with the CTA's weight rows resident in shared memory; larger batches the tcgen05 GEMM; anything else a
+ *   generic SIMT kernel.
  *   Rows of x that contain NaN / Inf give the values dequantize + F.linear gives (python/quantize.py:172, 202).
  *   ws: >= b200q_linear_ws_bytes(M,N,K) bytes (may be NULL when that is 0). */
 size_t b200q_linear_ws_bytes(int64_t M, int64_t N, int64_t K);
@@ -167,7 +169,8 @@ int b200q_linear_fwd_host(const void* h_x, int x_dtype, void* d_x, const uint8_t
                           void* ws, size_t ws_bytes, unsigned flags, void* stream);
 
 /* Bench / tuning hook: override a launch heuristic process-wide; value < 0 restores the default.  Keys:
- *   force_path (1 generic SIMT, 2 ring decode kernel, 3 tcgen05 GEMM, 6 resident decode kernel), gemv_early, gemv_pf,
+ *   force_path (1 generic SIMT, 2 ring decode kernel, 3 tcgen05 GEMM, 6 exact-integer decode kernel, 7 mid-batch decode
+ *   kernel), hm_min_m, hm_i3, hm_waves, moe_dec_hm, gemv_early, gemv_pf,
  *   gemv_tma3d, gemv_xprep, gemv_warps, gemv_slabs, gemv_stages, gemv_pdl, gemv_ctas, gemv_occ2, gemv_debug,
  *   gemm_bn (32 / 64 / 128 / 192 / 256), gemm_sk, gemm_debug (needs a -DB200Q_PROF build), host_direct.
  * Their meaning is documented next to the Tuning struct in csrc/internal.h.  Not needed by callers. */
@@ -254,8 +257,9 @@ int b200q_moe_grouped_fwd_mapped(const void* xs, int x_dtype, const uint8_t* pac
 /* The whole routed gated layer for DECODE-sized calls (T <= 16 tokens) behind one C call:
  *   out[t,:] = sum_s p[t,s] * w2_e( silu(w1_e x[t,:]) * (w3_e x[t,:]) ),  e = expert of slot s of token t  (fp32)
  * Four launches: routing (softmax / top-k / counting sort in one CTA), the fused gate / up GEMV (reads x in place through
- * the token map) and the down GEMV -- both grouped over the experts with device-side row offsets on the resident decode
- * kernel (experts without tokens exit at once; HBM-bound: only the experts that were hit are read) -- and
+ * the token map) and the down GEMV -- both grouped over the experts with device-side row offsets on the decode kernels
+ * (exact-integer kernel below 1.5 rows per expert on average, mid-batch kernel above; experts without tokens exit at
+ * once; HBM-bound: only the experts that were hit are read) -- and
  * b200q_moe_combine.  E <= 256, k <= 8.  packed13 [E,2F,d/2] (w1 / w3 interleaved), packed2
  * [E,d,F/2]; d and F multiples of 256.  ws: >= b200q_moe_decode_ws_bytes, 256-byte aligned (no zero-fill needed).
  * B200Q_EINVAL when the shape does not fit the decode kernel (use the grouped tcgen05 path then). */
