@@ -105,7 +105,7 @@ int b200q_linear_bias_fwd(const void* x, int x_dtype, const uint8_t* packed, con
     // pass over a buffer: measured slower than the ring kernel below, 32 vs 28 us at M = 4)
     // (measured crossovers with the tcgen05 GEMM, tools/dec_tune.py: 11008 -> 4096 M = 9 27.8 vs 31.9 us, M = 12 34.6 vs 32.1)
     // 3 <= M <= 16 with every tile resident: the fp16 HMMA decode kernel (gemv_hm.cu; tuning key hm_min_m moves the crossover)
-    if ((force <= 0 || force == 7) && vec_ok && (x_dtype != B200Q_F32 || aligned(x, 32)) && M <= 16 && (force == 7 || M >= tuning().hm_min_m) && gemv_hm_supported(d, M, N, K))
+    if ((force <= 0 || force == 7) && vec_ok && (x_dtype != B200Q_F32 || aligned(x, 32)) && M <= tuning().hm_max_m && (force == 7 || M >= tuning().hm_min_m) && gemv_hm_supported(d, M, N, K))
         return launch_gemv_hm(d, x, x_dtype, packed, scales, zps, bias, y, y_dtype, M, N, K, flags, st, next_packed, next_bytes);
     const bool dec_res = gemv_dec_resident(d, M, N, K);
     if ((force <= 0 || force == 6) && vec_ok && gemv_dec_supported(d, M, N, K) &&
@@ -158,7 +158,7 @@ int b200q_linear_gated_fwd(const void* x, int x_dtype, const uint8_t* packed13, 
     if (!(aligned(x, 16) && aligned(packed13, 16) && aligned(h, 16)))
         return set_error(B200Q_EALIGN, "linear_gated_fwd: x, packed13 and h must be 16-byte aligned");
     const int force = tuning().force_path;
-    if ((force <= 0 || force == 7) && (x_dtype != B200Q_F32 || aligned(x, 32)) && M <= 16 && (force == 7 || M >= tuning().hm_min_m) && gemv_hm_supported(d, M, 2 * F, K, 1))
+    if ((force <= 0 || force == 7) && (x_dtype != B200Q_F32 || aligned(x, 32)) && M <= tuning().hm_max_m && (force == 7 || M >= tuning().hm_min_m) && gemv_hm_supported(d, M, 2 * F, K, 1))
         return launch_gemv_hm(d, x, x_dtype, packed13, scales13, zps13, nullptr, h, h_dtype, M, 2 * F, K, flags, st, next_packed, next_bytes, 1);
     if ((force <= 0 || force == 6) && gemv_dec_supported(d, M, 2 * F, K, 1) && (force == 6 || M <= 8 || K <= 8192))
         return launch_gemv_dec(d, x, x_dtype, packed13, scales13, zps13, nullptr, h, h_dtype, M, 2 * F, K, flags, st, next_packed, next_bytes, 1);

@@ -70,6 +70,7 @@ constexpr int TILE_ROWS = 16;
 constexpr int PAIR_BYTES = TILE_ROWS * 128;      // one pair (256 columns) of one tile in shared memory
 constexpr int MAX_BARS = 64;                     // (pair group, tile) barriers
 constexpr int MB = 8;                            // tokens per pass (one n-tile)
+constexpr int HM_MAX_M = 32;                     // four passes (the non-finite flags are one 32-bit word); grouped: 16 rows per expert
 constexpr int MAX_TILES = 8;                     // 128 row positions: one per thread of a quarter of the CTA in the fold
 
 // shared memory map (bytes)
@@ -519,7 +520,7 @@ struct HmPlan {
 };
 
 bool plan_hm(int sm_count, int max_smem, int64_t M, int64_t N, int64_t K, int gated, HmPlan* c) {
-    if (M < 1 || M > 16 || K < 256 || K % 256 != 0 || K > 16384 || N < 1 || N > 0x3fffffff) return false;
+    if (M < 1 || M > HM_MAX_M || K < 256 || K % 256 != 0 || K > 16384 || N < 1 || N > 0x3fffffff) return false;
     if (gated && (N & 1)) return false;
     const int unit = gated ? 2 : 1;
     c->npairs = (int)(K / 256);
@@ -588,6 +589,10 @@ bool gemv_hm_supported(const DeviceInfo& dev, int64_t M, int64_t N, int64_t K, i
     // measured crossover with the tcgen05 GEMM (tools/dec_tune.py): K = 14336 needs several waves of one-tile CTAs with four
     // pairs per warp; two passes over them (M > 8) are no faster than the GEMM (14336 -> 4096 M = 16: 39.2 vs 37.7 us)
     if (tuning().force_path != 7 && M > MB && c.gpw >= 4 && c.grid > dev.sm_count) return false;
+    // 25 .. 32 tokens (four passes): ahead of the 32-token tiles of the GEMM only for one wave of CTAs and K <= 8192
+    // (4096 -> 11008 M = 32: 24.1 vs 30.8 us; 11008 -> 4096: 36.0 vs 33.7; 4096 -> 14336: 37.2 vs 35.9; up to M = 24 always:
+    // 18.5 vs 30.7, 27.3 vs 33.4, 28.6 vs 35.7 us)
+    if (tuning().force_path != 7 && M > 3 * MB && (c.gpw > 2 || c.grid > dev.sm_count)) return false;
     return true;
 }
 

@@ -52,6 +52,7 @@ struct Tuning {
     int hm_waves = 0;       // gemv_hm.cu: most waves of CTAs (0 = 4); 1 = only shapes whose rows fit with one CTA per SM
     int moe_dec_hm = -1;    // b200q_moe_decode_fwd: -1 the mid-batch kernel from 1.5 rows per expert on average, 0 never, 1 always
     int hm_i3 = 1;          // gemv_hm.cu, fp32 activations, 1 = three-digit IMMA form, 0 = fp16 hi / lo HMMA form
+    int hm_max_m = 32;      // largest batch on the mid-batch decode kernel (<= 32: four passes of eight tokens)
     int hm_min_m = 3;       // smallest batch that goes to the fp16 HMMA decode kernel (gemv_hm.cu)
     int gemv_slots = 1;     // resident decode kernel, M <= 2: 0 = pipelined cross-warp reduction instead of per-warp slots
 };

@@ -110,7 +110,7 @@ int b200q_dequantize_rows(const uint8_t* packed, const float* scales, const floa
  *   x_dtype / y_dtype: B200Q_F32 | B200Q_F16 | B200Q_BF16 (the reference API is f32/f32).
  *   x, y row-major and contiguous; x 16-byte aligned, packed 16-byte aligned, K even.
  *   M may be any value >= 0.  K % 256 == 0 with 16-byte aligned pointers: M <= 2 takes the exact-integer decode
- *   kernel (TMA tensor boxes, IMMA over the raw packed bytes), 3 <= M <= 16 the mid-batch decode kernel (eight tokens per
+ *   kernel (TMA tensor boxes, IMMA over the raw packed bytes), 3 <= M <= 24 (32 for K <= 8192 when one wave of CTAs holds the rows) the mid-batch decode kernel (eight tokens per
  *   tensor instruction: three-digit IMMA form for fp32 activations -- wants x 32-byte aligned --, fp16 HMMA form for 16-bit
  *   ones), both with the CTA's weight rows resident in shared memory; larger batches the tcgen05 GEMM; anything else a
  *   generic SIMT kernel.
@@ -170,7 +170,7 @@ int b200q_linear_fwd_host(const void* h_x, int x_dtype, void* d_x, const uint8_t
 
 /* Bench / tuning hook: override a launch heuristic process-wide; value < 0 restores the default.  Keys:
  *   force_path (1 generic SIMT, 2 ring decode kernel, 3 tcgen05 GEMM, 6 exact-integer decode kernel, 7 mid-batch decode
- *   kernel), hm_min_m, hm_i3, hm_waves, moe_dec_hm, gemv_early, gemv_pf,
+ *   kernel), hm_min_m, hm_max_m, hm_i3, hm_waves, moe_dec_hm, gemv_early, gemv_pf,
  *   gemv_tma3d, gemv_xprep, gemv_warps, gemv_slabs, gemv_stages, gemv_pdl, gemv_ctas, gemv_occ2, gemv_debug,
  *   gemm_bn (32 / 64 / 128 / 192 / 256), gemm_sk, gemm_debug (needs a -DB200Q_PROF build), host_direct.
  * Their meaning is documented next to the Tuning struct in csrc/internal.h.  Not needed by callers. */

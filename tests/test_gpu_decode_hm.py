@@ -33,13 +33,14 @@ def _forced(pkg, path, fn, i3=-1):
         pkg._lib.tune("hm_i3", -1)
 
 
-@pytest.mark.parametrize("M", [1, 2, 3, 4, 5, 8, 9, 13, 16])
+@pytest.mark.parametrize("M", [1, 2, 3, 4, 5, 8, 9, 13, 16, 17, 24, 32])
 @pytest.mark.parametrize("N,K", [(1, 256), (7, 256), (9, 512), (16, 768), (200, 1024), (2371, 2048), (11008, 4096), (4096, 4096),
                                  (3000, 6144), (4096, 11008), (1500, 8192), (600, 16384), (14336, 4096), (4096, 14336), (22016, 4096)])
 def test_hm_kernel_edge_shapes(oracle, pkg, M, N, K):
     """Ragged row counts (fewer tiles than SMs, last tile partly foreign / out of bounds), one and two passes of eight
     tokens with a ragged last pass, one to four column pairs per warp, K < 4096 (warps without a pair), batch rows of
-    very different magnitude (every (warp, pair, token) has its own scale), shapes that need two or more waves of CTAs
+    one to four passes of eight tokens, very different magnitude (every (warp, pair, token) has its own scale), shapes that
+    need two or more waves of CTAs
     (Mixtral's 14336-wide projections, Llama's gate + up rows in one matrix)."""
     rng = np.random.default_rng(1000 * M + N + K)
     packed, scales, zps = _weights(rng, N, K)
@@ -65,7 +66,7 @@ def test_hm_kernel_edge_shapes(oracle, pkg, M, N, K):
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
-@pytest.mark.parametrize("M,N,K", [(3, 300, 1024), (8, 11008, 4096), (16, 4096, 11008), (11, 1000, 2048)])
+@pytest.mark.parametrize("M,N,K", [(3, 300, 1024), (8, 11008, 4096), (16, 4096, 11008), (11, 1000, 2048), (27, 11008, 4096)])
 def test_hm_kernel_16bit_activations(oracle, pkg, dtype, M, N, K):
     rng = np.random.default_rng(N + K + M)
     packed, scales, zps = _weights(rng, N, K)
@@ -81,7 +82,7 @@ def test_hm_kernel_16bit_activations(oracle, pkg, dtype, M, N, K):
     assert np.abs(yh[:, rows] - ref).max() <= eps * np.abs(ref).max()
 
 
-@pytest.mark.parametrize("M", [3, 8, 12, 16])
+@pytest.mark.parametrize("M", [3, 8, 12, 16, 21])
 @pytest.mark.parametrize("F,K", [(150, 1024), (5504, 4096), (11008, 4096)])
 def test_hm_kernel_gated_and_bias(oracle, pkg, M, F, K):
     """Fused gate + up pair (rows 2f / 2f+1 interleaved, h = silu(gate) * up) and the bias epilogue."""
@@ -100,7 +101,7 @@ def test_hm_kernel_gated_and_bias(oracle, pkg, M, F, K):
     assert np.abs(y - (full + bias)).max() <= 4e-6 * np.abs(full).max()
 
 
-@pytest.mark.parametrize("M", [3, 4, 9, 16])
+@pytest.mark.parametrize("M", [3, 4, 9, 16, 29])
 @pytest.mark.parametrize("dtype,i3", [(torch.float32, 1), (torch.float32, 0), (torch.bfloat16, 1)])
 def test_hm_kernel_nonfinite_rows(oracle, pkg, M, dtype, i3):
     """python/quantize.py:172, 202: NaN / Inf in a row of x propagate as in dequantize + F.linear; the other rows of

@@ -8,7 +8,7 @@ from b200q_pkg import pkg
 _lib = pkg._lib
 lib = _lib.load()
 dev = torch.device("cuda", 0)
-KEYS = ["hm_min_m", "hm_i3", "hm_waves", "gemm_sk", "gemm_bn", "gemv_early", "gemv_pf", "gemv_slots", "gemv_bufs", "gemv_pdl", "gemv_ctas", "force_path"]
+KEYS = ["hm_min_m", "hm_max_m", "hm_i3", "hm_waves", "gemm_sk", "gemm_bn", "gemv_early", "gemv_pf", "gemv_slots", "gemv_bufs", "gemv_pdl", "gemv_ctas", "force_path"]
 pools = {}
 
 
