@@ -35,14 +35,15 @@ def measure(M, K, N, tune, hint=True, reps=8):
         except RuntimeError:
             pass                                            # an older build (B200Q_LIB) without the key
     for k, v in tune.items(): _lib.tune(k, v)
-    x = torch.randn(M, K, device=dev); y = torch.empty(M, N, device=dev)
+    XD = int(os.environ.get("XD", "0")); TD = [torch.float32, torch.float16, torch.bfloat16][XD]
+    x = torch.randn(M, K, device=dev).to(TD); y = torch.empty(M, N, device=dev, dtype=TD)
     ws = torch.zeros(max(lib.b200q_linear_ws_bytes(M, N, K), 16), dtype=torch.uint8, device=dev)
     reps = reps * 24 // len(layers)
     def launch_all(sp):
         for r in range(reps):
             for i, (p, s, z) in enumerate(layers):
                 nxt = layers[(i + 1) % len(layers)][0]
-                _lib.check(lib.b200q_linear_fwd_next(x.data_ptr(), 0, p.data_ptr(), s.data_ptr(), z.data_ptr(), y.data_ptr(), 0, M, N, K,
+                _lib.check(lib.b200q_linear_fwd_next(x.data_ptr(), XD, p.data_ptr(), s.data_ptr(), z.data_ptr(), y.data_ptr(), XD, M, N, K,
                                                      ws.data_ptr(), ws.numel(), 1, sp, nxt.data_ptr() if hint else None, nxt.numel() if hint else 0), "fwd")
     side = torch.cuda.Stream(dev); side.wait_stream(torch.cuda.current_stream(dev))
     with torch.cuda.stream(side):
