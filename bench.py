@@ -589,6 +589,13 @@ def main():
     ap.add_argument("--no-moe", action="store_true", help="skip the MoE-layer sub-measurement of the N=1 gemv line")
     ap.add_argument("--no-sweeps", action="store_true", help="skip decode_sweep / prefill / ref_gpu_kernel of the N=1 gemv line")
     args = ap.parse_args()
+    # The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints its version banner when the
+    # library's own communicator comes up): send file descriptor 1 to stderr for the duration of the run and give
+    # sys.stdout the real one back -- the only writer left on it is the final print of the line.
+    sys.stdout.flush()
+    real_out = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_out, "w", buffering=1)
     if args.impl == "reference":
         return run_reference(args)
     workload = args.workload or default_workload(args)
