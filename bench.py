@@ -270,6 +270,46 @@ def decode_sweep(torch, pkg, dev, peak, first_pool=None):
     return out
 
 
+def groupwise_decode(torch, pkg, dev, peak):
+    """group-wise scales (one scale / zero point per 128 columns) on the decode path, 4096 -> 11008, fp32
+    activations: us per b200q_linear_groupwise_fwd call over the 24-layer pool (CUDA graph; the entry point has no
+    static-weights flag and no next-layer hint)."""
+    _lib = pkg._lib
+    lib = _lib.load()
+    K, N, G = K_IN, N_OUT, 128
+    layers = []
+    for i in range(POOL):
+        g = torch.Generator(device=dev); g.manual_seed(100 + i)
+        layers.append((torch.randint(0, 256, (N, K // 2), generator=g, device=dev, dtype=torch.uint8),
+                       torch.rand(N, K // G, generator=g, device=dev) * 0.01 + 0.001,
+                       torch.randint(0, 16, (N, K // G), generator=g, device=dev).float()))
+    out = []
+    for M in (1, 4, 8, 16):
+        x = torch.randn(M, K, device=dev); y = torch.empty(M, N, device=dev)
+        def launch_all(sp):
+            for (p, s, z) in layers:
+                _lib.check(lib.b200q_linear_groupwise_fwd(x.data_ptr(), 0, p.data_ptr(), s.data_ptr(), z.data_ptr(), G, y.data_ptr(), 0,
+                                                          M, N, K, sp), "groupwise")
+        side = torch.cuda.Stream(dev); side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            launch_all(side.cuda_stream)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            launch_all(torch.cuda.current_stream(dev).cuda_stream)
+        for _ in range(3): gr.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10): gr.replay()
+        e1.record(); torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / (10 * POOL)
+        nb = N * K // 2 + 8 * N * (K // G) + 4 * M * K + 4 * M * N
+        out.append({"K": K, "N": N, "group_size": G, "M": M, "us_per_launch": round(us, 3), "GBps": round(nb / us / 1e3, 1),
+                    "frac_hbm_peak": round(nb / us / 1e3 / peak, 4)})
+    return out
+
+
 def prefill_sweep(torch, pkg, dev, peak_tf):
     """BASELINE.json configs[2]: M = 512 .. 4096 through the tcgen05 GEMM, bf16 and fp32 activations (the reference API's
     dtype; hi + lo split = twice the MMAs).  FLOPs = 2 M N K (dequantisation not counted); includes the activation
@@ -534,6 +574,7 @@ def run_gemv(args):
             line["ref_gpu_kernel"] = ref_gpu_kernel(torch, dev, layers)
             line["decode_sweep"] = decode_sweep(torch, pkg, dev, peak, first_pool=layers)
             del mods, graph, e2e_graph
+            line["groupwise_decode"] = groupwise_decode(torch, pkg, dev, peak)
             line["prefill"] = prefill_sweep(torch, pkg, dev, float(peaks["bf16_tflops"]))
         except Exception as e:
             line["sweep_error"] = repr(e)[:300]

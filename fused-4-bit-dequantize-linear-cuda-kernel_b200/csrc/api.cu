@@ -141,6 +141,12 @@ int b200q_linear_groupwise_fwd(const void* x, int x_dtype, const uint8_t* packed
     if (!y || !scales || !zps || !x || !packed) return set_error(B200Q_EINVAL, "linear_groupwise_fwd: null pointer");
     DeviceInfo d;
     if (int rc = current_device(&d)) return rc;
+    // decode-sized batches with groups of 128, 256, ... columns: the mid-batch decode kernel (the two halves of every
+    // 256-column pair meet their own scale / zero point); everything else the reference-speed SIMT kernel
+    if (tuning().force_path != 1 && M <= 32 && group_size % 128 == 0 && aligned(x, x_dtype == B200Q_F32 ? 32 : 16) && aligned(packed, 16) &&
+        gemv_hm_supported(d, M <= 8 ? M : 8, N, K))
+        return launch_gemv_hm(d, x, x_dtype, packed, scales, zps, nullptr, y, y_dtype, M, N, K, 0u,
+                              static_cast<cudaStream_t>(stream), nullptr, 0, 0, nullptr, 1, nullptr, (int)group_size);
     return launch_linear_generic(x, x_dtype, packed, scales, zps, y, y_dtype, M, N, K, nullptr, nullptr, 1, 0,
                                  static_cast<cudaStream_t>(stream), nullptr, (int)group_size);
 }

@@ -110,6 +110,7 @@ struct HmParams {
     // x[row_map[offsets[e] + r]] (x is read in place, no gathered copy) or x[offsets[e] + r] when row_map is null
     const int32_t* offsets;
     const int32_t* row_map;
+    int kgroup, ngroups;             // group-wise scales (GS instances): scales / zps are [N][K / kgroup], kgroup % 128 == 0
     int debug;                       // B200Q_PROF builds: record phase stamps
 };
 
@@ -160,7 +161,9 @@ __device__ __forceinline__ void hm_load8(const void* x, int64_t idx, float2 (&v)
 // base-256 digits = three n-tiles of IMMA m16n8k32 (u8 x u8, top digit u8 x s8); the nibbles are widened to bytes
 // (w & 0x0f0f0f0f, (w >> 4) & 0x0f0f0f0f).  Three tensor + six ALU instructions per 512 weights against four + ten of
 // the hi / lo HMMA form: the main loop is bound by exactly those (M = 8: 8.8 -> 8.0 us, M = 16: 15.7 -> 13.6 us).
-template <int XT, int FORM, bool GRP>
+// GS: group-wise scales.  The two 128-column halves of a pair are accumulated separately and meet their own scale / zero
+// point of every row in the main-loop epilogue; the slots then hold finished partial outputs and the fold only adds.
+template <int XT, int FORM, bool GRP, bool GS>
 __global__ void __launch_bounds__(NTHR, 1) gemv_hm_kernel(const __grid_constant__ CUtensorMap tmap, const HmParams p) {
     constexpr bool F32 = XT == B200Q_F32;
     constexpr bool I3 = FORM == 2;
@@ -243,8 +246,11 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_hm_kernel(const __grid_constant_
     // scale / zero point / bias of the CTA's rows: fetched early by the first 128 threads, parked in shared memory for the fold
     float sc = 0.0f, zp = 0.0f, bias = 0.0f;
     if (tid < nrows) {                                        // nrows <= 128
-        sc = __ldg(p.scales + wrow0 + tid);
-        zp = __ldg(p.zps + wrow0 + tid);
+        if constexpr (GS) { sc = 1.0f; }                      // (applied per group in the main loop)
+        else {
+            sc = __ldg(p.scales + wrow0 + tid);
+            zp = __ldg(p.zps + wrow0 + tid);
+        }
         if (p.bias) bias = __ldg(p.bias + wrow0 + tid);
     }
     if (warp >= nwa) {                                        // K < 4096: a warp without pairs contributes zeros to the fold
@@ -281,20 +287,30 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_hm_kernel(const __grid_constant_
             // ---- amax and sum of the token's 256 columns: the four lanes of a quad hold them all.  (fmaxf drops NaN:
             // a NaN shows up in the sum, Inf in the amax)
             float am = 0.0f;
-            float2 s2 = make_float2(0.0f, 0.0f);
+            float2 s2 = make_float2(0.0f, 0.0f), s2b = make_float2(0.0f, 0.0f);      // (GS: columns 0..127 / 128..255 apart)
 #pragma unroll
             for (int ch = 0; ch < 8; ++ch)
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     am = fmaxf(am, fmaxf(fabsf(xv[ch][e].x), fabsf(xv[ch][e].y)));
-                    s2 = __fadd2_rn(s2, xv[ch][e]);
+                    if (GS && ch >= 4) s2b = __fadd2_rn(s2b, xv[ch][e]);
+                    else s2 = __fadd2_rn(s2, xv[ch][e]);
                 }
-            float s = s2.x + s2.y;
+            float s = s2.x + s2.y, sb = s2b.x + s2b.y;
             am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, 1));
             am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, 2));
             s += __shfl_xor_sync(0xffffffffu, s, 1);
             s += __shfl_xor_sync(0xffffffffu, s, 2);
-            sxacc += s;
+            float sxg[2][2] = {{0.0f, 0.0f}, {0.0f, 0.0f}};   // GS: sum_k x of tokens 2t, 2t + 1 over the two halves of the pair
+            if constexpr (GS) {
+                sb += __shfl_xor_sync(0xffffffffu, sb, 1);
+                sb += __shfl_xor_sync(0xffffffffu, sb, 2);
+                sxg[0][0] = __shfl_sync(0xffffffffu, s, 8 * t);  sxg[0][1] = __shfl_sync(0xffffffffu, s, 8 * t + 4);
+                sxg[1][0] = __shfl_sync(0xffffffffu, sb, 8 * t); sxg[1][1] = __shfl_sync(0xffffffffu, sb, 8 * t + 4);
+                s += sb;                                      // (NaN detection below)
+            } else {
+                sxacc += s;
+            }
             if (first) HM_STAMP(3);
             const int E = (int)(__float_as_uint(am) >> 23);
             if ((E == 255 || s != s) && t == 0) atomicOr(s_flag, 1u << (m0 + tk));
@@ -355,6 +371,8 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_hm_kernel(const __grid_constant_
             if (first) HM_STAMP(4);
             int grp = 0;
             if (p.nbars > 1) grp = P / p.chunk;
+            int gidx[2] = {0, 0};                             // GS: scale group of the two halves of this pair
+            if constexpr (GS) { gidx[0] = (P * 256) / p.kgroup; gidx[1] = (P * 256 + 128) / p.kgroup; }
 
             // ---- this pair of every tile
 #pragma unroll 1
@@ -362,6 +380,16 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_hm_kernel(const __grid_constant_
                 if (pass == 0) mbar_wait(sbase + OFF_BARS + 8u * (uint32_t)(grp * S + i), 0u);
                 const uint32_t pb = sbase + p.tile_off + (uint32_t)(i * p.tile_bytes + P * PAIR_BYTES);
                 float v[4];
+                float gsc[2][2], gzp[2][2];                   // GS: [half][row g / g + 8] scale, zero point (in flight during the MMAs)
+                float va[4];                                  // GS: the first half's values
+                if constexpr (GS) {
+                    const int64_t ra = (int64_t)min(wrow0 + i * TILE_ROWS + g, p.N - 1) * p.ngroups, rb = (int64_t)min(wrow0 + i * TILE_ROWS + g + 8, p.N - 1) * p.ngroups;
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        gsc[hh][0] = __ldg(p.scales + ra + gidx[hh]); gzp[hh][0] = __ldg(p.zps + ra + gidx[hh]);
+                        gsc[hh][1] = __ldg(p.scales + rb + gidx[hh]); gzp[hh][1] = __ldg(p.zps + rb + gidx[hh]);
+                    }
+                }
                 if constexpr (I3) {
                     int ac[3][4];                             // one chain per digit
 #pragma unroll
@@ -370,6 +398,13 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_hm_kernel(const __grid_constant_
                         for (int r = 0; r < 4; ++r) ac[d][r] = 0;
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
+                        if (GS && c == 2) {                   // the first 128 columns are done: keep their values, start over
+#pragma unroll
+                            for (int r = 0; r < 4; ++r) {
+                                va[r] = fmaf((float)ac[2][r], 65536.0f, (float)(ac[0][r] + (ac[1][r] << 8))) * ((r & 1) ? d1 : d0);
+                                ac[0][r] = 0; ac[1][r] = 0; ac[2][r] = 0;
+                            }
+                        }
                         uint32_t a[4];
                         ldsm_x4(a, pb + offc[c]);
 #pragma unroll
@@ -394,6 +429,18 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_hm_kernel(const __grid_constant_
                         for (int r = 0; r < 4; ++r) acc[j][nt][r] = 0.0f;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
+                    if (GS && c == 2) {
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            float a = acc[0][0][r] + acc[1][0][r];
+                            if constexpr (NT == 2) a += acc[0][1][r] + acc[1][1][r];
+                            va[r] = (a * 16777216.0f) * ((r & 1) ? d1 : d0);
+#pragma unroll
+                            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                                for (int nt = 0; nt < NT; ++nt) acc[j][nt][r] = 0.0f;
+                        }
+                    }
                     uint32_t a[4];
                     if (!HM_ABL(8)) ldsm_x4(a, pb + offc[c]); else { a[0] = c; a[1] = lane; a[2] = i; a[3] = 7; }                // a0 / a1: rows g / g + 8, bytes 32 c + 4 t ..; a2 / a3: + 16 bytes
 #pragma unroll
@@ -415,6 +462,11 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_hm_kernel(const __grid_constant_
                     if constexpr (NT == 2) a += acc[0][1][r] + acc[1][1][r];
                     v[r] = (a * 16777216.0f) * ((r & 1) ? d1 : d0);
                 }
+                }
+                if constexpr (GS) {                           // v = second half so far: scale both halves, subtract the zero-point terms
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+                        v[r] = gsc[0][r >> 1] * fmaf(-gzp[0][r >> 1], sxg[0][r & 1], va[r]) + gsc[1][r >> 1] * fmaf(-gzp[1][r >> 1], sxg[1][r & 1], v[r]);
                 }
                 // slot layout [row][token]: lane (g, t) owns tokens 2t, 2t + 1 of rows g and g + 8 -- two conflict-free 8-byte stores
                 float2* slot = reinterpret_cast<float2*>(smem + OFF_SLOTS + (i * NW + warp) * SLOT_BYTES);
@@ -486,10 +538,15 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_hm_kernel(const __grid_constant_
         for (int m = 0; m < Mrows; ++m) {
             if (!((flagged >> m) & 1u)) continue;
             auto ref_row = [&](int row) {
-                const float rs = __ldg(p.scales + row), rz = __ldg(p.zps + row);
+                float rs = 0.0f, rz = 0.0f;
+                if constexpr (!GS) { rs = __ldg(p.scales + row); rz = __ldg(p.zps + row); }
                 const uint8_t* wr = p.packed + (int64_t)row * row_bytes;
                 float acc = 0.0f;
                 for (int kb = lane; kb < row_bytes; kb += 32) {
+                    if constexpr (GS) {
+                        const int64_t gi = (int64_t)row * p.ngroups + (2 * kb) / p.kgroup;
+                        rs = __ldg(p.scales + gi); rz = __ldg(p.zps + gi);
+                    }
                     const unsigned int byte = wr[kb];
                     const float w0 = ((float)(byte & 15u) - rz) * rs, w1 = ((float)(byte >> 4) - rz) * rs;
                     acc = fmaf(w0, load1f(p.x, p.x_dtype, x_row(m) * p.K + 2 * kb), acc);
@@ -554,9 +611,9 @@ bool plan_hm(int sm_count, int max_smem, int64_t M, int64_t N, int64_t K, int ga
     return false;
 }
 
-template <int XT, int FORM, bool GRP>
+template <int XT, int FORM, bool GRP, bool GS>
 int launch_hm_inst(const HmPlan& c, int n_experts, const CUtensorMap& map, const HmParams& p, bool pdl, cudaStream_t st) {
-    auto kfn = gemv_hm_kernel<XT, FORM, GRP>;
+    auto kfn = gemv_hm_kernel<XT, FORM, GRP, GS>;
     static thread_local int attr_dev_smem[64] = {0};
     int dev = 0;
     B200Q_CUDA(cudaGetDevice(&dev));
@@ -599,7 +656,7 @@ bool gemv_hm_supported(const DeviceInfo& dev, int64_t M, int64_t N, int64_t K, i
 int launch_gemv_hm(const DeviceInfo& dev, const void* x, int x_dtype, const uint8_t* packed, const float* scales,
                    const float* zps, const float* bias, void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
                    unsigned flags, cudaStream_t st, const uint8_t* next_packed, size_t next_bytes, int gated,
-                   const int32_t* offsets, int n_experts, const int32_t* row_map) {
+                   const int32_t* offsets, int n_experts, const int32_t* row_map, int kgroup) {
     HmPlan c;
     if (n_experts < 1) n_experts = 1;
     const bool grp = offsets != nullptr;
@@ -624,18 +681,25 @@ int launch_gemv_hm(const DeviceInfo& dev, const void* x, int x_dtype, const uint
     p.debug = tuning().gemv_debug > 0 ? tuning().gemv_debug : 0;
     p.offsets = offsets; p.row_map = grp ? row_map : nullptr;
     if (grp) p.next_bytes = 0;
+    p.kgroup = kgroup; p.ngroups = kgroup > 0 ? (int)(K / kgroup) : 0;
     CUtensorMap map;
     if (int rc = dec_weight_map(packed, N * n_experts, K, c.chunk, &map)) return rc;
     const bool pdl = tuning().gemv_pdl != 0;
+    if (kgroup > 0) {                                       // group-wise scales (plain linear only)
+        if (grp || gated || kgroup % 128 != 0 || K % kgroup != 0) return set_error(B200Q_EINVAL, "gemv_hm: group-wise scales need kgroup %% 128 == 0, K %% kgroup == 0, no grouping / gate");
+        if (x_dtype == B200Q_F32) return launch_hm_inst<B200Q_F32, 2, false, true>(c, 1, map, p, pdl, st);
+        if (x_dtype == B200Q_F16) return launch_hm_inst<B200Q_F16, 0, false, true>(c, 1, map, p, pdl, st);
+        return launch_hm_inst<B200Q_BF16, 0, false, true>(c, 1, map, p, pdl, st);
+    }
     if (grp) {
-        if (x_dtype == B200Q_F32) return launch_hm_inst<B200Q_F32, 2, true>(c, n_experts, map, p, pdl, st);
-        if (x_dtype == B200Q_F16) return launch_hm_inst<B200Q_F16, 0, true>(c, n_experts, map, p, pdl, st);
-        return launch_hm_inst<B200Q_BF16, 0, true>(c, n_experts, map, p, pdl, st);
+        if (x_dtype == B200Q_F32) return launch_hm_inst<B200Q_F32, 2, true, false>(c, n_experts, map, p, pdl, st);
+        if (x_dtype == B200Q_F16) return launch_hm_inst<B200Q_F16, 0, true, false>(c, n_experts, map, p, pdl, st);
+        return launch_hm_inst<B200Q_BF16, 0, true, false>(c, n_experts, map, p, pdl, st);
     }
     if (x_dtype == B200Q_F32)
-        return tuning().hm_i3 != 0 ? launch_hm_inst<B200Q_F32, 2, false>(c, 1, map, p, pdl, st) : launch_hm_inst<B200Q_F32, 0, false>(c, 1, map, p, pdl, st);
-    if (x_dtype == B200Q_F16) return launch_hm_inst<B200Q_F16, 0, false>(c, 1, map, p, pdl, st);
-    return launch_hm_inst<B200Q_BF16, 0, false>(c, 1, map, p, pdl, st);
+        return tuning().hm_i3 != 0 ? launch_hm_inst<B200Q_F32, 2, false, false>(c, 1, map, p, pdl, st) : launch_hm_inst<B200Q_F32, 0, false, false>(c, 1, map, p, pdl, st);
+    if (x_dtype == B200Q_F16) return launch_hm_inst<B200Q_F16, 0, false, false>(c, 1, map, p, pdl, st);
+    return launch_hm_inst<B200Q_BF16, 0, false, false>(c, 1, map, p, pdl, st);
 }
 
 }  // namespace b200q

@@ -120,7 +120,7 @@ bool gemv_hm_supported(const DeviceInfo& dev, int64_t M, int64_t N, int64_t K, i
 int launch_gemv_hm(const DeviceInfo& dev, const void* x, int x_dtype, const uint8_t* packed, const float* scales,
                    const float* zps, const float* bias, void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
                    unsigned flags, cudaStream_t st, const uint8_t* next_packed, size_t next_bytes, int gated = 0,
-                   const int32_t* offsets = nullptr, int n_experts = 1, const int32_t* row_map = nullptr);
+                   const int32_t* offsets = nullptr, int n_experts = 1, const int32_t* row_map = nullptr, int kgroup = 0);
 // decode-sized routing in one launch (moe.cu): T <= 16, E <= 256, k <= 8; src_token (optional): token of every sorted position
 int moe_route_small(const float* logits, int64_t T, int E, int k, int32_t* idx, float* weights, int32_t* counts, int32_t* offsets,
                     int32_t* sorted_slot, int32_t* inv_perm, int32_t* src_token, cudaStream_t st);
