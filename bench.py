@@ -272,8 +272,8 @@ def decode_sweep(torch, pkg, dev, peak, first_pool=None):
 
 def groupwise_decode(torch, pkg, dev, peak):
     """group-wise scales (one scale / zero point per 128 columns) on the decode path, 4096 -> 11008, fp32
-    activations: us per b200q_linear_groupwise_fwd call over the 24-layer pool (CUDA graph; the entry point has no
-    static-weights flag and no next-layer hint)."""
+    activations: us per b200q_linear_groupwise_bias_fwd call over the 24-layer pool (CUDA graph, static-weights flag and
+    next-layer hint as in the per-row sweep)."""
     _lib = pkg._lib
     lib = _lib.load()
     K, N, G = K_IN, N_OUT, 128
@@ -287,9 +287,10 @@ def groupwise_decode(torch, pkg, dev, peak):
     for M in (1, 4, 8, 16):
         x = torch.randn(M, K, device=dev); y = torch.empty(M, N, device=dev)
         def launch_all(sp):
-            for (p, s, z) in layers:
-                _lib.check(lib.b200q_linear_groupwise_fwd(x.data_ptr(), 0, p.data_ptr(), s.data_ptr(), z.data_ptr(), G, y.data_ptr(), 0,
-                                                          M, N, K, sp), "groupwise")
+            for i, (p, s, z) in enumerate(layers):
+                nxt = layers[(i + 1) % len(layers)][0]
+                _lib.check(lib.b200q_linear_groupwise_bias_fwd(x.data_ptr(), 0, p.data_ptr(), s.data_ptr(), z.data_ptr(), None, G, y.data_ptr(), 0,
+                                                               M, N, K, 1, sp, nxt.data_ptr(), nxt.numel()), "groupwise")
         side = torch.cuda.Stream(dev); side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             launch_all(side.cuda_stream)

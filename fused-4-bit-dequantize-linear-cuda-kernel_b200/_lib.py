@@ -39,6 +39,7 @@ SIGNATURES = {
     "b200q_linear_fwd_next": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _i32, _i64, _i64, _i64, _vp, _sz, _u32, _vp, _vp, _sz]),
     "b200q_linear_bias_fwd": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i64, _i64, _vp, _sz, _u32, _vp, _vp, _sz]),
     "b200q_linear_groupwise_fwd": (_i32, [_vp, _i32, _vp, _vp, _vp, _i64, _vp, _i32, _i64, _i64, _i64, _vp]),
+    "b200q_linear_groupwise_bias_fwd": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _i64, _i64, _i64, _u32, _vp, _vp, _sz]),
     "b200q_linear_gated_fwd": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _i32, _i64, _i64, _i64, _vp, _sz, _u32, _vp, _vp, _sz]),
     "b200q_linear_fwd_host": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i64, _i64, _vp, _sz, _u32, _vp]),
     "b200q_tune_set": (_i32, [_c.c_char_p, _i32]),
@@ -191,17 +192,22 @@ def linear_fwd(x: torch.Tensor, packed: torch.Tensor, scales: torch.Tensor, zps:
 
 
 def linear_groupwise_fwd(x: torch.Tensor, packed: torch.Tensor, scales: torch.Tensor, zps: torch.Tensor, group_size: int,
-                         out_dtype=None) -> torch.Tensor:
-    """y = x @ dequant(packed, scales [N, K/G], zps [N, K/G])^T with one scale / zero point per G columns."""
+                         out_dtype=None, flags: int = FLAG_NONE, bias: torch.Tensor | None = None,
+                         next_packed: torch.Tensor | None = None) -> torch.Tensor:
+    """y = x @ dequant(packed, scales [N, K/G], zps [N, K/G])^T (+ bias [N] f32) with one scale / zero point per G columns.
+    next_packed: packed weights of the fused linear that follows on this stream (L2 prefetch hint)."""
     lib = load()
     M, K = x.shape
     N = packed.shape[0]
     out_dtype = out_dtype or x.dtype
     with torch.cuda.device(x.device):
         y = torch.empty((M, N), dtype=out_dtype, device=x.device)
-        check(lib.b200q_linear_groupwise_fwd(x.data_ptr(), dtype_code(x), packed.data_ptr(), scales.data_ptr(), zps.data_ptr(),
-                                             group_size, y.data_ptr(), dtype_code(y), M, N, K, stream_ptr(x.device)),
-              "b200q_linear_groupwise_fwd")
+        check(lib.b200q_linear_groupwise_bias_fwd(x.data_ptr(), dtype_code(x), packed.data_ptr(), scales.data_ptr(), zps.data_ptr(),
+                                                  bias.data_ptr() if bias is not None else None, group_size, y.data_ptr(), dtype_code(y),
+                                                  M, N, K, flags, stream_ptr(x.device),
+                                                  next_packed.data_ptr() if next_packed is not None else None,
+                                                  next_packed.numel() if next_packed is not None else 0),
+              "b200q_linear_groupwise_bias_fwd")
     return y
 
 

@@ -134,21 +134,30 @@ int b200q_linear_bias_fwd(const void* x, int x_dtype, const uint8_t* packed, con
 
 int b200q_linear_groupwise_fwd(const void* x, int x_dtype, const uint8_t* packed, const float* scales, const float* zps,
                                int64_t group_size, void* y, int y_dtype, int64_t M, int64_t N, int64_t K, void* stream) {
+    return b200q_linear_groupwise_bias_fwd(x, x_dtype, packed, scales, zps, nullptr, group_size, y, y_dtype, M, N, K, 0u, stream, nullptr, 0);
+}
+
+int b200q_linear_groupwise_bias_fwd(const void* x, int x_dtype, const uint8_t* packed, const float* scales, const float* zps,
+                                    const float* bias, int64_t group_size, void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
+                                    unsigned flags, void* stream, const uint8_t* next_packed, size_t next_bytes) {
     if (M < 0 || N < 0 || K < 0 || (K & 1)) return set_error(B200Q_EINVAL, "linear_groupwise_fwd: need M,N >= 0 and even K >= 0");
     if (group_size <= 0 || (group_size & 7) || K % group_size) return set_error(B200Q_EINVAL, "linear_groupwise_fwd: group_size must be a multiple of 8 that divides K (got %lld, K=%lld)", (long long)group_size, (long long)K);
     if (!elem_size(x_dtype) || !elem_size(y_dtype)) return set_error(B200Q_EINVAL, "linear_groupwise_fwd: unsupported dtype");
     if (M == 0 || N == 0) return 0;
     if (!y || !scales || !zps || !x || !packed) return set_error(B200Q_EINVAL, "linear_groupwise_fwd: null pointer");
+    if (bias && !aligned(bias, 4)) return set_error(B200Q_EALIGN, "linear_groupwise_fwd: bias must be 4-byte aligned");
     DeviceInfo d;
     if (int rc = current_device(&d)) return rc;
     // decode-sized batches with groups of 128, 256, ... columns: the mid-batch decode kernel (the two halves of every
     // 256-column pair meet their own scale / zero point); everything else the reference-speed SIMT kernel
     if (tuning().force_path != 1 && M <= 32 && group_size % 128 == 0 && aligned(x, x_dtype == B200Q_F32 ? 32 : 16) && aligned(packed, 16) &&
         gemv_hm_supported(d, M <= 8 ? M : 8, N, K))
-        return launch_gemv_hm(d, x, x_dtype, packed, scales, zps, nullptr, y, y_dtype, M, N, K, 0u,
-                              static_cast<cudaStream_t>(stream), nullptr, 0, 0, nullptr, 1, nullptr, (int)group_size);
-    return launch_linear_generic(x, x_dtype, packed, scales, zps, y, y_dtype, M, N, K, nullptr, nullptr, 1, 0,
-                                 static_cast<cudaStream_t>(stream), nullptr, (int)group_size);
+        return launch_gemv_hm(d, x, x_dtype, packed, scales, zps, bias, y, y_dtype, M, N, K, flags,
+                              static_cast<cudaStream_t>(stream), next_packed, next_bytes, 0, nullptr, 1, nullptr, (int)group_size);
+    int rc = launch_linear_generic(x, x_dtype, packed, scales, zps, y, y_dtype, M, N, K, nullptr, nullptr, 1, 0,
+                                   static_cast<cudaStream_t>(stream), nullptr, (int)group_size);
+    if (!rc && bias) rc = launch_bias_add(y, y_dtype, bias, M, N, static_cast<cudaStream_t>(stream));
+    return rc;
 }
 
 int b200q_linear_gated_fwd(const void* x, int x_dtype, const uint8_t* packed13, const float* scales13, const float* zps13,

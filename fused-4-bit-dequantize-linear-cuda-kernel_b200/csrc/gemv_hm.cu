@@ -135,6 +135,15 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
 }
 __device__ __forceinline__ float2 unpack_h2(uint32_t v) { return __half22float2(*reinterpret_cast<const __half2*>(&v)); }
 
+// c0 + 256 c1 + 65536 c2 of three s32 digit sums (|c| < 2^22) as a float: every digit sum is converted exactly by the
+// magic-number add (int -> float on the integer and FMA pipes; I2F runs on the quarter-rate XU pipe, 12 per warp and tile)
+__device__ __forceinline__ float digits_to_float(int c0, int c1, int c2) {
+    const float f0 = __int_as_float(c0 + 0x4B400000) - 12582912.0f;
+    const float f1 = __int_as_float(c1 + 0x4B400000) - 12582912.0f;
+    const float f2 = __int_as_float(c2 + 0x4B400000) - 12582912.0f;
+    return fmaf(f2, 65536.0f, fmaf(f1, 256.0f, f0));
+}
+
 // eight consecutive activations as floats; the dtype is a template parameter so that the 8 (16) loads of an operand
 // build are straight-line code, all in flight at once (a run-time dtype switch serialises them: one L2 round trip each)
 template <int XT>
@@ -401,7 +410,7 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_hm_kernel(const __grid_constant_
                         if (GS && c == 2) {                   // the first 128 columns are done: keep their values, start over
 #pragma unroll
                             for (int r = 0; r < 4; ++r) {
-                                va[r] = fmaf((float)ac[2][r], 65536.0f, (float)(ac[0][r] + (ac[1][r] << 8))) * ((r & 1) ? d1 : d0);
+                                va[r] = digits_to_float(ac[0][r], ac[1][r], ac[2][r]) * ((r & 1) ? d1 : d0);
                                 ac[0][r] = 0; ac[1][r] = 0; ac[2][r] = 0;
                             }
                         }
@@ -417,8 +426,8 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_hm_kernel(const __grid_constant_
                         }
                     }
 #pragma unroll
-                    for (int r = 0; r < 4; ++r)               // digits -> value (|sum| < 2^38: the low part is exact in s32, one rounding each)
-                        v[r] = fmaf((float)ac[2][r], 65536.0f, (float)(ac[0][r] + (ac[1][r] << 8))) * ((r & 1) ? d1 : d0);
+                    for (int r = 0; r < 4; ++r)               // digits -> value
+                        v[r] = digits_to_float(ac[0][r], ac[1][r], ac[2][r]) * ((r & 1) ? d1 : d0);
                 } else {
                 float acc[2][NT][4];                          // two chains (alpha, beta) per n-tile
 #pragma unroll

@@ -111,11 +111,12 @@ class QuantizedLinear(nn.Module):
         if x.shape[-1] != self.in_features:
             raise RuntimeError(f"expected last dim {self.in_features}, got {x.shape[-1]}")
         if self.group_size:
-            # group-wise scales: the format's reference-speed kernel (the fast paths take per-row scales)
+            # group-wise scales: decode-sized batches with G % 128 == 0 on the mid-batch decode kernel, else the format's
+            # reference-speed kernel; the bias is fused / added by the library
             x2 = x.reshape(-1, self.in_features).contiguous()
-            y = _lib.linear_groupwise_fwd(x2, self.packed_weights, self.scales, self.zero_points, self.group_size)
-            if self.bias is not None:
-                y = y + self.bias.to(y.dtype)
+            y = _lib.linear_groupwise_fwd(x2, self.packed_weights, self.scales, self.zero_points, self.group_size,
+                                          flags=_lib.FLAG_STATIC_WEIGHTS if self._weights_settled else _lib.FLAG_NONE,
+                                          bias=self.bias, next_packed=self._next.packed_weights if self._next is not None else None)
             return y.reshape(*lead, self.out_features)
         if not self.packed_weights.is_contiguous():
             # buffers that are strided views of an interleaved gate / up stack (QuantizedGatedMLP): compact them for this call

@@ -142,11 +142,17 @@ int b200q_linear_bias_fwd(const void* x, int x_dtype, const uint8_t* packed, con
 /* Group-wise scales (the reference's format is per-row only, python/quantize.py:73-80): one scale / zero
  * point per `group_size` consecutive columns, scales / zps [N, K/group_size] f32 row-major, packed as above.  The groups are
  * quantised with the per-row formulas on W viewed as [N K / group_size, group_size] (b200q_quantize_rows on that view gives
- * exactly this layout; b200q_dequantize_rows inverts it).  This entry point is the format's reference-speed kernel
- * (w = (q - zp) * s, fp32 multiply-add, the reference's arithmetic order); the decode / tcgen05 fast paths take per-row
- * scales only.  group_size: a multiple of 8 that divides K. */
+ * exactly this layout; b200q_dequantize_rows inverts it).  group_size: a multiple of 8 that divides K.  Decode-sized
+ * batches (M <= 32) with group_size % 128 == 0 run on the mid-batch decode kernel (K % 256 == 0, x 32-byte (fp32) / 16-byte
+ * aligned); everything else on the format's reference-speed kernel (w = (q - zp) * s, fp32 multiply-add, the reference's
+ * arithmetic order).  The prefill GEMM takes per-row scales only. */
 int b200q_linear_groupwise_fwd(const void* x, int x_dtype, const uint8_t* packed, const float* scales, const float* zps,
                                int64_t group_size, void* y, int y_dtype, int64_t M, int64_t N, int64_t K, void* stream);
+/* Same with an optional bias [N] f32 (fused on the decode kernel), the B200Q_FLAG_* flags and the next-layer L2 hint of
+ * b200q_linear_bias_fwd. */
+int b200q_linear_groupwise_bias_fwd(const void* x, int x_dtype, const uint8_t* packed, const float* scales, const float* zps,
+                                    const float* bias, int64_t group_size, void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
+                                    unsigned flags, void* stream, const uint8_t* next_packed, size_t next_bytes);
 
 /* Fused gate + up pair of a gated MLP (`down(silu(gate(x)) * up(x))` in two launches):
  *   h[m,f] = silu(x[m,:] . W[2f,:]) * (x[m,:] . W[2f+1,:])

@@ -19,8 +19,10 @@ def measure(M, K, N, G, force):
     x = torch.randn(M, K, device=dev); y = torch.empty(M, N, device=dev)
     _lib.tune("force_path", force)
     def launch_all(sp):
-        for (p, s, z) in layers:
-            _lib.check(lib.b200q_linear_groupwise_fwd(x.data_ptr(), 0, p.data_ptr(), s.data_ptr(), z.data_ptr(), G, y.data_ptr(), 0, M, N, K, sp), "fwd")
+        for i, (p, s, z) in enumerate(layers):
+            nxt = layers[(i + 1) % len(layers)][0]
+            _lib.check(lib.b200q_linear_groupwise_bias_fwd(x.data_ptr(), 0, p.data_ptr(), s.data_ptr(), z.data_ptr(), None, G, y.data_ptr(), 0, M, N, K,
+                                                           1, sp, nxt.data_ptr(), nxt.numel()), "fwd")
     side = torch.cuda.Stream(dev); side.wait_stream(torch.cuda.current_stream(dev))
     with torch.cuda.stream(side):
         launch_all(side.cuda_stream)
