@@ -115,7 +115,7 @@ int b200q_linear_bias_fwd(const void* x, int x_dtype, const uint8_t* packed, con
     bool done = false;
     // ... else the ring kernel (M <= 8: e.g. Mixtral's 14336-wide projections, 198 KB of weights per SM)
     // (14336 -> 4096: 24 / 28 / 40 / 49 us at M = 3 / 4 / 5 / 8 against 38 us for the 32-token tiles of the tcgen05 GEMM)
-    if (!done && (force <= 0 || force == 2) && vec_ok && gemv_supported(M, N, K, x_dtype) &&
+    if (!done && (force <= 0 || force == 2) && vec_ok && gemv_supported(M, N, K, x_dtype, &d) &&
         (force == 2 || M <= 4 || K <= 8192 || !gemm_tc_supported(M, N, K, x_dtype, y_dtype))) {
         rc = launch_gemv(d, x, x_dtype, packed, scales, zps, y, y_dtype, M, N, K, ws, ws_bytes, flags, st, next_packed, next_bytes);
         if (!rc) rc = launch_nonfinite_fixup(x, x_dtype, packed, scales, zps, nullptr, y, y_dtype, M, N, K, nullptr, nullptr, 1, 0, st);

@@ -842,11 +842,14 @@ int launch_inst(const GemvConfig& c, const GemvParams& p, bool pdl, cudaStream_t
 
 }  // namespace
 
-bool gemv_supported(int64_t M, int64_t N, int64_t K, int x_dtype) {
+bool gemv_supported(int64_t M, int64_t N, int64_t K, int x_dtype, const DeviceInfo* dev) {
     (void)x_dtype;
     DeviceInfo d;
-    d.sm_count = 148;
-    d.max_smem_optin = 232448;
+    if (dev) d = *dev;
+    else if (current_device(&d)) {   // no device yet (workspace sizing before the first launch): a whole B200
+        d.sm_count = 148;
+        d.max_smem_optin = 232448;
+    }
     GemvConfig c;
     return plan(d, M, N, K, &c);
 }

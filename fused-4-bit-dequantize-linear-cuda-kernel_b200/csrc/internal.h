@@ -76,7 +76,7 @@ int launch_linear_generic(const void* x, int x_dtype, const uint8_t* packed, con
 
 // decode GEMV, M <= 16, K % 128 == 0.  Returns B200Q_EINVAL if the shape is not supported so
 // the dispatcher can fall through.
-bool gemv_supported(int64_t M, int64_t N, int64_t K, int x_dtype);
+bool gemv_supported(int64_t M, int64_t N, int64_t K, int x_dtype, const DeviceInfo* dev = nullptr);   // dev == nullptr: the current device
 size_t gemv_ws_bytes(int64_t M, int64_t N, int64_t K);
 int launch_gemv(const DeviceInfo& dev, const void* x, int x_dtype, const uint8_t* packed,
                 const float* scales, const float* zps, void* y, int y_dtype, int64_t M, int64_t N,
