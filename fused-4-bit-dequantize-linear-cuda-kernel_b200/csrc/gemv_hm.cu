@@ -238,6 +238,22 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_hm_kernel(const __grid_constant_
         }
     };
     if (p.wait_weights) pdl_wait();
+    if constexpr (GS) {
+        // the scales / zero points of this CTA's rows (one contiguous block of nrows * ngroups floats each) -> L2: the main
+        // loop asks for eight of them per (pair, tile) and needs them ~0.2 us later -- from DRAM, under the weight
+        // stream, every tile would wait for them
+        const size_t bytes = (size_t)nrows * (size_t)p.ngroups * 4;
+        const char* base[2] = {reinterpret_cast<const char*>(p.scales + (int64_t)wrow0 * p.ngroups),
+                               reinterpret_cast<const char*>(p.zps + (int64_t)wrow0 * p.ngroups)};
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            const size_t lead = reinterpret_cast<uintptr_t>(base[a]) & 127;          // first line starts `lead` bytes before the block
+            for (size_t off = (size_t)tid * 128; off < bytes + lead; off += (size_t)NTHR * 128) {
+                const char* q = base[a] + (off > lead ? off - lead : 0);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(q) : "memory");
+            }
+        }
+    }
     if (issuer) {
         tma_prefetch_desc(&tmap);
         if (p.pf_mode == 2) prefetch_next();
@@ -380,8 +396,19 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_hm_kernel(const __grid_constant_
             if (first) HM_STAMP(4);
             int grp = 0;
             if (p.nbars > 1) grp = P / p.chunk;
-            int gidx[2] = {0, 0};                             // GS: scale group of the two halves of this pair
-            if constexpr (GS) { gidx[0] = (P * 256) / p.kgroup; gidx[1] = (P * 256 + 128) / p.kgroup; }
+            // GS: lane (g, t) fetches the scale / zero point of ONE (half of the pair, row g / g + 8) combination -- half = t >> 1,
+            // row = g + 8 (t & 1) -- one tile ahead (the values come out of L2 while the previous tile's MMAs run) and the
+            // quad exchanges them by shuffle in the tile epilogue: 4 live registers instead of 8, no exposed load latency
+            float csc = 0.0f, czp = 0.0f;
+            int64_t gs_off = 0;                               // column of this lane's group in the [N][ngroups] arrays
+            auto gs_load = [&](int i, float& s_, float& z_) {
+                const int64_t r = (int64_t)min(wrow0 + i * TILE_ROWS + g + 8 * (t & 1), p.N - 1) * p.ngroups + gs_off;
+                s_ = __ldg(p.scales + r); z_ = __ldg(p.zps + r);
+            };
+            if constexpr (GS) {
+                gs_off = (P * 256 + 128 * (t >> 1)) / p.kgroup;
+                gs_load(0, csc, czp);
+            }
 
             // ---- this pair of every tile
 #pragma unroll 1
@@ -389,15 +416,10 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_hm_kernel(const __grid_constant_
                 if (pass == 0) mbar_wait(sbase + OFF_BARS + 8u * (uint32_t)(grp * S + i), 0u);
                 const uint32_t pb = sbase + p.tile_off + (uint32_t)(i * p.tile_bytes + P * PAIR_BYTES);
                 float v[4];
-                float gsc[2][2], gzp[2][2];                   // GS: [half][row g / g + 8] scale, zero point (in flight during the MMAs)
                 float va[4];                                  // GS: the first half's values
+                float nsc = 0.0f, nzp = 0.0f;                 // GS: this lane's scale / zero point of the next tile (in flight during the MMAs)
                 if constexpr (GS) {
-                    const int64_t ra = (int64_t)min(wrow0 + i * TILE_ROWS + g, p.N - 1) * p.ngroups, rb = (int64_t)min(wrow0 + i * TILE_ROWS + g + 8, p.N - 1) * p.ngroups;
-#pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
-                        gsc[hh][0] = __ldg(p.scales + ra + gidx[hh]); gzp[hh][0] = __ldg(p.zps + ra + gidx[hh]);
-                        gsc[hh][1] = __ldg(p.scales + rb + gidx[hh]); gzp[hh][1] = __ldg(p.zps + rb + gidx[hh]);
-                    }
+                    if (i + 1 < S) gs_load(i + 1, nsc, nzp);
                 }
                 if constexpr (I3) {
                     int ac[3][4];                             // one chain per digit
@@ -473,6 +495,15 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_hm_kernel(const __grid_constant_
                 }
                 }
                 if constexpr (GS) {                           // v = second half so far: scale both halves, subtract the zero-point terms
+                    float gsc[2][2], gzp[2][2];               // [half][row g / g + 8] from the quad's lanes 2 half + row
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+                        for (int rr = 0; rr < 2; ++rr) {
+                            gsc[hh][rr] = __shfl_sync(0xffffffffu, csc, (lane & ~3) | (2 * hh + rr));
+                            gzp[hh][rr] = __shfl_sync(0xffffffffu, czp, (lane & ~3) | (2 * hh + rr));
+                        }
+                    csc = nsc; czp = nzp;
 #pragma unroll
                     for (int r = 0; r < 4; ++r)
                         v[r] = gsc[0][r >> 1] * fmaf(-gzp[0][r >> 1], sxg[0][r & 1], va[r]) + gsc[1][r >> 1] * fmaf(-gzp[1][r >> 1], sxg[1][r & 1], v[r]);
