@@ -253,10 +253,12 @@ int b200q_moe_decode_fwd(const void* x, int x_dtype, const float* logits, int64_
                                     nullptr, 0, 0, offsets, E, nullptr)) return rc;
         return b200q_moe_combine(y, x_dtype, inv_perm, wts, T, k, d, out, B200Q_F32, stream);
     }
+    // (T k routed rows hit at most T k experts: the grid has that many rows of CTAs, not E)
+    const int max_groups = tuning().moe_dec_compact != 0 ? (int)std::min<int64_t>(E, T * k) : 0;
     if (int rc = launch_gemv_dec(dv, x, x_dtype, packed13, scales13, zps13, nullptr, h, x_dtype, T, 2 * F, d, B200Q_FLAG_STATIC_WEIGHTS, st,
-                                 nullptr, 0, 1, offsets, E, src_token)) return rc;
+                                 nullptr, 0, 1, offsets, E, src_token, max_groups)) return rc;
     if (int rc = launch_gemv_dec(dv, h, x_dtype, packed2, scales2, zps2, nullptr, y, x_dtype, T, d, F, B200Q_FLAG_STATIC_WEIGHTS, st,
-                                 nullptr, 0, 0, offsets, E)) return rc;
+                                 nullptr, 0, 0, offsets, E, nullptr, max_groups)) return rc;
     return b200q_moe_combine(y, x_dtype, inv_perm, wts, T, k, d, out, B200Q_F32, stream);
 }
 

@@ -139,6 +139,7 @@ int b200q_tune_set(const char* key, int value) {
     else if (!strcmp(key, "gemv_bufs")) g_tuning.gemv_bufs = value < 0 ? 0 : value;
     else if (!strcmp(key, "hm_waves")) g_tuning.hm_waves = value < 0 ? 0 : value;
     else if (!strcmp(key, "moe_dec_hm")) g_tuning.moe_dec_hm = value;
+    else if (!strcmp(key, "moe_dec_compact")) g_tuning.moe_dec_compact = value;
     else if (!strcmp(key, "hm_i3")) g_tuning.hm_i3 = value < 0 ? 1 : value;
     else if (!strcmp(key, "hm_max_m")) g_tuning.hm_max_m = (value < 0 || value > 32) ? 32 : value;
     else if (!strcmp(key, "hm_min_m")) g_tuning.hm_min_m = value < 0 ? 3 : value;

@@ -114,6 +114,9 @@ struct DecParams {
                                      //   packed [E, N, K/2] (device memory; experts without rows exit at once); else nullptr
     const int32_t* row_map;          // grouped: batch row r of the group reads x[row_map[offsets[e] + r]] (the token of that
                                      //   sorted position: x is read in place, no gathered copy); y rows stay in sorted order
+    int n_groups;                    // grouped: experts in the weight tensor; gridDim.y < n_groups: blockIdx.y is the RANK of the
+                                     // CTA's expert among the experts that have rows (a decode step hits few experts: the CTAs of
+                                     // the others would each take their turn on an SM -- shared memory for one CTA -- only to exit)
     int debug;                       // B200Q_PROF builds: record phase stamps
 };
 
@@ -168,12 +171,24 @@ __global__ void __launch_bounds__(NTHR, 1) gemv_dec_kernel(const __grid_constant
     B200Q_STAMP(0);
     // work item -> (expert, CTA of the expert)
     const int b = (int)blockIdx.x;
-    const int expert = GEN ? (int)blockIdx.y : 0;
+    int expert = GEN ? (int)blockIdx.y : 0;
     int Mrows = p.M;                                          // batch rows of this work item
     int64_t xrow0 = 0;                                        // ... and where they start in x / y
     if constexpr (GEN) {
         if (p.offsets) {
-            const int lo = p.offsets[expert], hi = p.offsets[expert + 1];
+            int lo, hi;
+            if ((int)gridDim.y < p.n_groups) {                // compact grid (n_groups <= 32): lane e looks at expert e, every warp alike
+                const int e = lane < p.n_groups ? lane : 0;
+                const int lo_e = p.offsets[e], hi_e = p.offsets[e + 1];
+                const bool has = lane < p.n_groups && hi_e > lo_e;
+                const unsigned act = __ballot_sync(0xffffffffu, has);
+                const unsigned sel = __ballot_sync(0xffffffffu, has && __popc(act & ((1u << lane) - 1u)) == (int)blockIdx.y);
+                if (!sel) return;                             // uniform: fewer experts with rows than grid rows
+                expert = __ffs(sel) - 1;
+                lo = __shfl_sync(0xffffffffu, lo_e, expert); hi = __shfl_sync(0xffffffffu, hi_e, expert);
+            } else {
+                lo = p.offsets[expert]; hi = p.offsets[expert + 1];
+            }
             Mrows = min(hi - lo, 16);
             xrow0 = lo;
             if (Mrows <= 0) return;                           // uniform: this expert has no tokens
@@ -774,9 +789,11 @@ bool gemv_dec_resident(const DeviceInfo& dev, int64_t M, int64_t N, int64_t K, i
 int launch_gemv_dec(const DeviceInfo& dev, const void* x, int x_dtype, const uint8_t* packed, const float* scales,
                     const float* zps, const float* bias, void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
                     unsigned flags, cudaStream_t st, const uint8_t* next_packed, size_t next_bytes, int gated,
-                    const int32_t* offsets, int n_experts, const int32_t* row_map) {
+                    const int32_t* offsets, int n_experts, const int32_t* row_map, int max_groups) {
     DecPlan c;
     if (n_experts < 1) n_experts = 1;
+    // grid rows: one per expert, or -- when the caller knows that at most max_groups experts can have rows -- one per possible group
+    const int grid_y = (offsets && max_groups >= 1 && max_groups < n_experts && n_experts <= 32) ? max_groups : n_experts;
     if (!plan_dec(dev.sm_count, dev.max_smem_optin, M, N, K, &c, gated))
         return set_error(B200Q_EINVAL, "gemv_dec: unsupported shape M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
     if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(packed) & 15))
@@ -798,6 +815,7 @@ int launch_gemv_dec(const DeviceInfo& dev, const void* x, int x_dtype, const uin
     const bool gen = offsets != nullptr || n_experts > 1 || c.s_max > c.ntiles;
     p.offsets = offsets;
     p.row_map = offsets ? row_map : nullptr;
+    p.n_groups = n_experts;
     p.npairs = c.npairs; p.nbars = c.nbars; p.chunk = c.chunk;
     p.ntiles_max = c.ntiles; p.tile_bytes = c.tile_bytes; p.tile_off = c.tile_off; p.npasses = c.npasses;
     p.red_off = c.red_off; p.fin_off = c.fin_off; p.slots = c.slots;
@@ -813,7 +831,7 @@ int launch_gemv_dec(const DeviceInfo& dev, const void* x, int x_dtype, const uin
     CUtensorMap map;
     if (int rc = dec_weight_map(packed, N * n_experts, K, c.chunk, &map)) return rc;
     const bool pdl = tuning().gemv_pdl != 0;
-    const dim3 grid((unsigned)c.grid_g, (unsigned)n_experts);
+    const dim3 grid((unsigned)c.grid_g, (unsigned)grid_y);
 #define B200Q_DEC_CASE(GPW2_, NT_)                                                                                  \
     if (c.gpw2 == GPW2_ && c.nt == NT_)                                                                             \
         return gen ? launch_dec_inst<GPW2_, NT_, true>(c, grid, map, p, pdl, st) : launch_dec_inst<GPW2_, NT_, false>(c, grid, map, p, pdl, st);

@@ -51,6 +51,7 @@ struct Tuning {
     int gemv_bufs = 0;      // resident decode kernel: cap on the tile buffers of a CTA (0 = as many as fit; tests force the ring with it)
     int hm_waves = 0;       // gemv_hm.cu: most waves of CTAs (0 = 4); 1 = only shapes whose rows fit with one CTA per SM
     int moe_dec_hm = -1;    // b200q_moe_decode_fwd: -1 the mid-batch kernel from 1.5 rows per expert on average, 0 never, 1 always
+    int moe_dec_compact = 1;   // b200q_moe_decode_fwd: grid rows = min(E, T k) with device-side expert ranks (0: one grid row per expert)
     int hm_i3 = 1;          // gemv_hm.cu, fp32 activations, 1 = three-digit IMMA form, 0 = fp16 hi / lo HMMA form
     int hm_max_m = 32;      // largest batch on the mid-batch decode kernel (<= 32: four passes of eight tokens)
     int hm_min_m = 3;       // smallest batch that goes to the fp16 HMMA decode kernel (gemv_hm.cu)
@@ -110,7 +111,7 @@ bool gemv_dec_resident(const DeviceInfo& dev, int64_t M, int64_t N, int64_t K, i
 int launch_gemv_dec(const DeviceInfo& dev, const void* x, int x_dtype, const uint8_t* packed, const float* scales,
                     const float* zps, const float* bias, void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
                     unsigned flags, cudaStream_t st, const uint8_t* next_packed, size_t next_bytes, int gated = 0,
-                    const int32_t* offsets = nullptr, int n_experts = 1, const int32_t* row_map = nullptr);
+                    const int32_t* offsets = nullptr, int n_experts = 1, const int32_t* row_map = nullptr, int max_groups = 0);
 // 3-D tensor map over packed [N, K/2] viewed as [row][128-byte column][byte]: boxes of [16 rows][chunk columns][128 B]
 // land in shared memory as [column][row][128 B] with the 128-byte swizzle (cached per (pointer, shape, chunk))
 int dec_weight_map(const uint8_t* packed, int64_t N, int64_t K, int chunk, CUtensorMap_st* out);
