@@ -310,6 +310,35 @@ def test_moe_decode_nonfinite_token_poisons_only_its_row(oracle, pkg):
     assert np.isnan(y[2]).all() and not np.isfinite(y[4]).any() and np.isfinite(y[[0, 1, 3, 5]]).all()
 
 
+@pytest.mark.parametrize("T", [1, 2, 3])
+@pytest.mark.parametrize("E,k,d,F", [(8, 2, 1024, 3584), (8, 1, 512, 256), (16, 4, 256, 768), (32, 2, 256, 512)])
+def test_moe_decode_compact_grid_is_bit_identical(oracle, pkg, T, E, k, d, F):
+    """T k < E: the grouped GEMVs run with min(E, T k) grid rows and find their expert by its rank among the experts that
+    have rows (tuning key moe_dec_compact, default on) -- bit-identical to one grid row per expert, also when all tokens
+    pick the same experts (fewer groups than grid rows) and when the last expert is hit."""
+    rng = np.random.default_rng(T * 7 + E + d)
+    (w1, w3, w2), (q1, q3, q2) = _gated_experts(oracle, rng, E, d, F)
+    f = lambda a: [torch.from_numpy(w).cuda() for w in a]
+    moe = pkg.QuantizedMoE.from_gated_fp16_weights(f(w1), f(w3), f(w2))
+    x = rng.standard_normal((T, d), dtype=np.float32)
+    for variant in range(3):
+        logits = rng.standard_normal((T, E), dtype=np.float32)
+        if variant == 1:
+            logits[:, E - 1] += 9.0                          # every token picks the last expert
+        if variant == 2:
+            logits[:] = logits[0]                            # all tokens pick the same k experts
+        ref = oracle.moe_gated(x, logits, q1, q3, q2, k, acc=np.float64)
+        def decode(mode):
+            pkg._lib.tune("moe_dec_compact", mode)
+            try:
+                return pkg._lib.moe_decode_fwd(cuda(x), cuda(logits), k, *moe.stacked_weights())
+            finally:
+                pkg._lib.tune("moe_dec_compact", -1)
+        y1, y0 = decode(1), decode(0)
+        assert torch.equal(y1, y0)
+        assert np.abs(y1.cpu().numpy() - ref).max() <= 2e-5 * np.abs(ref).max() + 1e-7
+
+
 @pytest.mark.parametrize("T", [1, 3, 5, 8, 12, 16])
 @pytest.mark.parametrize("E,k,d,F", [(4, 2, 256, 512), (8, 2, 1024, 3584), (16, 4, 256, 768)])
 def test_moe_decode_call_on_the_mid_batch_kernel(oracle, pkg, T, E, k, d, F):
