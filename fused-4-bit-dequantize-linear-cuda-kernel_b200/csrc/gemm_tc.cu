@@ -801,7 +801,12 @@ int launch_gemm_tc(const DeviceInfo& dev, const void* x, int x_dtype, const uint
     p.sk = sk; p.skq = skq; p.skr = skr;
     p.debug = tuning().gemm_debug > 0 ? tuning().gemm_debug : 0;
     p.gated = gated;
-    p.mt_major = tuning().gemm_mt_major >= 0 ? (tuning().gemm_mt_major != 0 && starts != nullptr) : ((starts && emap) ? 1 : 0);
+    // tile order.  Weight-tile-major (0) makes every weight tile stream ALL activation rows again: fine while they stay in L2
+    // (dense prefill: M K 2 bytes), ruinous for a MoE layer (Mixtral, 16384 tokens: 268 MB of x 224 times, 940 MB of h 32
+    // times -- the layer was DRAM-bound: 17.3 ms).  Token-tile-major (1): the CTAs of a wave share a few activation tiles
+    // and stream the expert's weights, which fit in L2 (13.97 ms; tools/tile_order.py).  Dense shapes gain <= 8 % and only
+    // when activations outgrow L2 while (wave's activation tiles + all weights) still fit: they keep order 0.
+    p.mt_major = tuning().gemm_mt_major >= 0 ? (tuning().gemm_mt_major != 0) : (starts ? 1 : 0);
     p.part = reinterpret_cast<float*>(w8 + 2 * xbytes + 3 * sbytes);
     p.flags = reinterpret_cast<unsigned int*>(ws);
     const size_t smem = (size_t)OFF_STAGES + (size_t)stages * p.stage_bytes;

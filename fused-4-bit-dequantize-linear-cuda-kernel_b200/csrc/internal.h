@@ -39,7 +39,7 @@ struct Tuning {
     int gemm_bn = -1;       // token-tile height of the tcgen05 GEMM (128 / 192 / 256), default: heuristic
     int host_direct = -1;   // 0: b200q_linear_fwd_host always copies the result back instead of storing into pinned memory
     int gemm_debug = -1;    // bench-only ablations of the tcgen05 GEMM (1: no weight loads, 2: no activation loads)
-    int gemm_mt_major = -1; // grouped tcgen05 GEMM tile order: -1 auto (token-tile-major for mapped ranges), 0 weight-tile-major, 1 token-tile-major
+    int gemm_mt_major = -1; // tcgen05 GEMM tile order: -1 auto (token-tile-major for grouped calls, weight-tile-major for the dense linear), 0 weight-tile-major, 1 token-tile-major
     int gemm_sk = -1;       // stream-K in the tcgen05 GEMM: -1 heuristic, 0 off, 1 whenever possible
     int gemv_res = 1;       // 0: never use the resident-slab decode kernel
     int gemv_early = -1;    // tiles requested before the x loads (-1: all)
