@@ -15,8 +15,10 @@ N = 1 (default workload "gemv"): BASELINE.json configs[1], the Llama-7B up-proje
 N > 1 (default workload "moe"): BASELINE.json configs[4], the Mixtral-8x7B INT4 MoE layer,
   expert-parallel over N GPUs (one process per GPU, NCCL all-to-all dispatch / combine).
 
---impl reference times the CPU restatement of the reference path (oracle/int4_oracle.py: dequantize
-to fp32 + matmul, python/quantize.py:127-202) on the host cores, one layer per step.
+--impl reference times the reference's own CPU path (the real reference staged under oracle/_ref by
+oracle/make_ref.py: python/module.py forward = quantize.py dequantize_weights + F.linear; the oracle port only
+when that staging is absent) on the host cores, one layer per step; for the MoE workload a bounded sample.
+The N = 1 line also carries decode_sweep, groupwise_decode, prefill, ref_gpu_kernel, moe, moe_decode, moe_prefill.
 """
 import argparse
 import json
