@@ -345,9 +345,64 @@ combine_kernel(const YT* __restrict__ y, const int32_t* __restrict__ inv_perm,
     }
 }
 
+// Same arithmetic, 16 bytes of y per thread and slot (V = 8 halves / 4 floats): the scalar form moves 2-byte elements and
+// runs at a third of the HBM rate on the 0.5 GB of a 16384-token Mixtral step.  k <= 8; F % V == 0; y / out 16-byte aligned.
+template <typename YT, typename OT>
+__global__ void __launch_bounds__(256)
+combine_vec_kernel(const YT* __restrict__ y, const int32_t* __restrict__ inv_perm,
+                   const float* __restrict__ weights, int k, int64_t F, OT* __restrict__ out) {
+    constexpr int V = 16 / (int)sizeof(YT);
+    const int64_t t = blockIdx.x;
+    int64_t row[8];
+    float w[8];
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+        row[s] = s < k ? (int64_t)inv_perm[t * k + s] : -1;
+        w[s] = s < k ? weights[t * k + s] : 0.0f;
+    }
+    for (int64_t f = ((int64_t)blockIdx.y * blockDim.x + threadIdx.x) * V; f < F; f += (int64_t)gridDim.y * blockDim.x * V) {
+        float acc[V];
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            if (s < k) {
+                uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+                if (row[s] >= 0) raw = __ldcs(reinterpret_cast<const uint4*>(y + row[s] * F + f));     // (read once)
+                const YT* e = reinterpret_cast<const YT*>(&raw);
+#pragma unroll
+                for (int i = 0; i < V; ++i) {
+                    const float prod = row[s] < 0 ? 0.0f : __fmul_rn(to_f32<YT>(e[i]), w[s]);
+                    acc[i] = s == 0 ? prod : __fadd_rn(acc[i], prod);
+                }
+            }
+        }
+        alignas(16) OT o[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) o[i] = from_f32<OT>(acc[i]);
+        OT* dst = out + t * F + f;
+        if constexpr (V * sizeof(OT) >= 16) {
+#pragma unroll
+            for (int c = 0; c < (int)(V * sizeof(OT) / 16); ++c) reinterpret_cast<uint4*>(dst)[c] = reinterpret_cast<const uint4*>(o)[c];
+        } else {
+            *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(o);                      // 4 floats -> 4 halves
+        }
+    }
+}
+
 template <typename YT>
 int combine_out(const void* y, const int32_t* inv_perm, const float* weights, int64_t T, int k,
                 int64_t F, void* out, int out_dtype, cudaStream_t st) {
+    constexpr int V = 16 / (int)sizeof(YT);
+    if (k <= 8 && F % V == 0 && !(reinterpret_cast<uintptr_t>(y) & 15) && !(reinterpret_cast<uintptr_t>(out) & 15) &&
+        (out_dtype == B200Q_F32 || out_dtype == B200Q_F16 || out_dtype == B200Q_BF16)) {
+        const int64_t per_block = 256 * V;
+        int64_t ny = T >= 256 ? 1 : (256 + T - 1) / T;      // few tokens (decode): spread the columns of a token over several CTAs as well
+        if (ny > (F + per_block - 1) / per_block) ny = (F + per_block - 1) / per_block;
+        dim3 grid(static_cast<unsigned>(T), static_cast<unsigned>(ny));
+        if (out_dtype == B200Q_F32) combine_vec_kernel<YT, float><<<grid, 256, 0, st>>>(static_cast<const YT*>(y), inv_perm, weights, k, F, static_cast<float*>(out));
+        else if (out_dtype == B200Q_F16) combine_vec_kernel<YT, __half><<<grid, 256, 0, st>>>(static_cast<const YT*>(y), inv_perm, weights, k, F, static_cast<__half*>(out));
+        else combine_vec_kernel<YT, __nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const YT*>(y), inv_perm, weights, k, F, static_cast<__nv_bfloat16*>(out));
+        return check_cuda(cudaGetLastError(), "moe_combine launch");
+    }
     // few tokens (decode): spread the columns of a token over several CTAs as well
     int64_t ny = T >= 256 ? 1 : (256 + T - 1) / T;
     if (ny > (F + 255) / 256) ny = (F + 255) / 256;
