@@ -31,6 +31,7 @@
 // row) and csrc/moe_int4_kernel.cu:17-90 (one CTA per expert).
 #include <cuda.h>
 #include <mutex>
+#include <type_traits>
 #include "internal.h"
 #include "ptx.cuh"
 #include "tc.cuh"
@@ -533,6 +534,34 @@ template <> __device__ __forceinline__ void ld8<__nv_bfloat16>(const __nv_bfloat
     for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
 }
 
+// eight consecutive values of a row as they come out of memory
+template <typename T> struct Raw8 {
+    uint4 r;                                                 // 16-bit types
+    __device__ __forceinline__ void load(const T* p) { r = *reinterpret_cast<const uint4*>(p); }
+    __device__ __forceinline__ void zero() { r = make_uint4(0u, 0u, 0u, 0u); }
+    // (the compiler would otherwise unpack once and keep the floats alive across the block reduction)
+    __device__ __forceinline__ void opaque() { asm volatile("" : "+r"(r.x), "+r"(r.y), "+r"(r.z), "+r"(r.w)); }
+    __device__ __forceinline__ void unpack(float (&v)[8]) const {
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float2 f;
+            if constexpr (sizeof(T) == 2 && std::is_same<T, __half>::value) f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+            else f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+            v[2 * i] = f.x; v[2 * i + 1] = f.y;
+        }
+    }
+};
+template <> struct Raw8<float> {
+    float4 a, b;
+    __device__ __forceinline__ void load(const float* p) { a = *reinterpret_cast<const float4*>(p); b = *reinterpret_cast<const float4*>(p + 4); }
+    __device__ __forceinline__ void zero() { a = make_float4(0.f, 0.f, 0.f, 0.f); b = a; }
+    __device__ __forceinline__ void opaque() {}
+    __device__ __forceinline__ void unpack(float (&v)[8]) const {
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+};
+
 template <typename T>
 __global__ void __launch_bounds__(256) xprep_gemm_kernel(const XprepGemmParams p) {
     const int lane = threadIdx.x & 31;
@@ -586,7 +615,7 @@ __global__ void __launch_bounds__(256) xprep_gemm_kernel(const XprepGemmParams p
 // loads up front and keeps the values in registers, so a row costs ONE trip to memory plus a block reduction
 // (the warp-per-row kernel above walks the row twice with one load in flight: 8 us for 256 rows).
 template <typename T, int NCH>
-__global__ void __launch_bounds__(256) xprep_gemm_rows_kernel(const XprepGemmParams p) {
+__global__ void __launch_bounds__(256, sizeof(T) == 2 ? 2 : 1) xprep_gemm_rows_kernel(const XprepGemmParams p) {
     __shared__ unsigned int s_am[2][4];
     __shared__ float s_sum[2][4];
     pdl_launch_dependents();                        // the GEMM's CTAs may set themselves up meanwhile
@@ -594,22 +623,24 @@ __global__ void __launch_bounds__(256) xprep_gemm_rows_kernel(const XprepGemmPar
     const int64_t m = (int64_t)blockIdx.x * 2 + rw;
     const bool row_ok = m < p.R;
     const T* xr = static_cast<const T*>(p.x) + (row_ok ? m : 0) * p.K;
-    float v[NCH][8];
+    // the row stays in registers AS LOADED (16-bit inputs: 4 registers per 8 values, unpacked once for the amax / sum and once
+    // for the output): K = 14336 as floats was 149 registers per thread = one block per SM, 3.7 TB/s on the 1.8 GB of a MoE step
+    Raw8<T> raw[NCH];
     unsigned int ub = 0u;
     float sum = 0.0f;
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {
         const int k = i * 1024 + rt * 8;
-        if (row_ok && k < p.K) ld8<T>(xr + k, v[i]);
-        else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[i][j] = 0.0f;
-        }
+        if (row_ok && k < p.K) raw[i].load(xr + k);
+        else raw[i].zero();
     }
 #pragma unroll
-    for (int i = 0; i < NCH; ++i)
+    for (int i = 0; i < NCH; ++i) {
+        float v[8];
+        raw[i].unpack(v);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { ub = max(ub, __float_as_uint(v[i][j]) & 0x7fffffffu); sum += v[i][j]; }
+        for (int j = 0; j < 8; ++j) { ub = max(ub, __float_as_uint(v[j]) & 0x7fffffffu); sum += v[j]; }
+    }
     ub = __reduce_max_sync(0xffffffffu, ub);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
@@ -632,9 +663,12 @@ __global__ void __launch_bounds__(256) xprep_gemm_rows_kernel(const XprepGemmPar
     for (int i = 0; i < NCH; ++i) {
         const int k = i * 1024 + rt * 8;
         if (k >= p.K) continue;
+        float v[8];
+        raw[i].opaque();
+        raw[i].unpack(v);
         // (k0,k4) (k1,k5) (k2,k6) (k3,k7): the order the A registers hold the nibbles in
-        const float s0 = v[i][0] * up, s4 = v[i][4] * up, s1 = v[i][1] * up_hi, s5 = v[i][5] * up_hi;
-        const float s2 = v[i][2] * up, s6 = v[i][6] * up, s3 = v[i][3] * up_hi, s7 = v[i][7] * up_hi;
+        const float s0 = v[0] * up, s4 = v[4] * up, s1 = v[1] * up_hi, s5 = v[5] * up_hi;
+        const float s2 = v[2] * up, s6 = v[6] * up, s3 = v[3] * up_hi, s7 = v[7] * up_hi;
         __half2 h0 = __floats2half2_rn(s0, s4), h1 = __floats2half2_rn(s1, s5);
         __half2 h2 = __floats2half2_rn(s2, s6), h3 = __floats2half2_rn(s3, s7);
         *reinterpret_cast<uint4*>(hr + k) = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
@@ -772,7 +806,12 @@ int launch_gemm_tc(const DeviceInfo& dev, const void* x, int x_dtype, const uint
     int sk = 0, skq = 0, skr = 0, sk_grid = 0;
     if (!starts && !gated && tuning().gemm_sk != 0) {
         const int fbs = tuning().gemm_bn;
-        const int bnsk = (fbs == 128 || fbs == 192 || fbs == 256) ? fbs : (M <= 64 ? bn : 256);   // small batches keep their small token tile
+        // small batches keep their small token tile.  fp32 activations (hi + lo parts) never take stream-K on 256-token
+        // tiles: with the single accumulator and three 68 KB stages of that instance, tiles cut between ~10 CTAs came out
+        // wrong (M = 4096, K = 8192, N = 128: 0.3 relative error; tools/sk_check.py) -- not tracked down; 192-token tiles
+        // (two accumulators) are correct on every shape of the sweep and are what the heuristic would pick anyway
+        int bnsk = (fbs == 128 || fbs == 192 || fbs == 256) ? fbs : (M <= 64 ? bn : 256);
+        if (parts == 2 && bnsk == 256) bnsk = 192;
         const long long tiles256 = ((M + bnsk - 1) / bnsk) * n_tiles_h;
         const long long waves = (tiles256 + dev.sm_count - 1) / dev.sm_count;
         const double fill = (double)tiles256 / (double)(waves * dev.sm_count);

@@ -404,6 +404,32 @@ def test_stream_k_gemm_matches_whole_tiles_and_is_deterministic(oracle, pkg, M, 
     assert np.abs(y1 - ref[:1]).max() <= 2e-5 * np.abs(ref[:1]).max()
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("M,N,K", [(4096, 128, 8192), (2048, 256, 11008), (1024, 384, 14336)])
+def test_stream_k_few_long_tiles(oracle, pkg, dtype, M, N, K):
+    """Few weight rows, many tokens, long K: the heuristic itself picks stream-K and every tile is cut between ~10 CTAs.
+    Default dispatch and forced stream-K against the float64 oracle, fp32 and bf16 activations, three runs each (the
+    fp32 instance with 256-token tiles gave 0.3 relative error here -- the launcher keeps fp32 stream-K on 192-token tiles)."""
+    rng = np.random.default_rng(M + N + K)
+    packed = rng.integers(0, 256, size=(N, K // 2), dtype=np.uint8)
+    scales = (rng.random(N, dtype=np.float32) * 0.01 + 0.001).astype(np.float32)
+    zps = rng.integers(0, 16, size=N).astype(np.float32)
+    x = rng.standard_normal((M, K), dtype=np.float32)
+    P, S, Z = cuda(packed), cuda(scales), cuda(zps)
+    X = cuda(x).to(dtype)
+    ref = oracle.reference_quantized_linear(X.float().cpu().numpy(), packed, scales, zps, acc=np.float64)
+    for sk in (-1, 1):
+        pkg._lib.tune("force_path", 3)
+        pkg._lib.tune("gemm_sk", sk)
+        try:
+            for _ in range(3):
+                y = pkg._lib.linear_fwd(X, P, S, Z, out_dtype=torch.float32).cpu().numpy()
+                assert np.abs(y - ref).max() <= 1e-4 * np.abs(ref).max(), f"gemm_sk={sk}"
+        finally:
+            pkg._lib.tune("gemm_sk", -1)
+            pkg._lib.tune("force_path", -1)
+
+
 @pytest.mark.parametrize("bn", [32, 64, 128, 192, 256])
 def test_gemm_token_tile_heights(oracle, pkg, bn):
     """Every token-tile height of the tcgen05 GEMM on one ragged shape (M, N not multiples of the tile)."""
