@@ -333,6 +333,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
         for_each_item(p, KB, total_tiles, [&](const Item& w) {
             for (int kb = w.kb0; kb < w.kb1; ++kb, ++ait) {
                 if ((ait & 1) != grp) {                             // the other group's k-block
+                    // Still observe its fill.  With an ODD number of stages (fp32 activations on 256-token tiles: three 68 KB
+                    // stages) a group meets a stage only every other phase, and a parity wait that is two phases behind
+                    // the barrier returns at once: the group then read a stage before its data had landed -- stream-K with
+                    // tiles cut between ~10 CTAs (short items, the groups run far ahead) gave 0.3 relative error on
+                    // M = 4096, K = 8192, N = 128 fp32 (tools/sk_check.py, tests/test_gpu_linear.py::test_stream_k_few_long_tiles)
+                    mbar_wait(full(s), ph);
                     if (++s == S) { s = 0; ph ^= 1; }
                     continue;
                 }
@@ -806,12 +812,7 @@ int launch_gemm_tc(const DeviceInfo& dev, const void* x, int x_dtype, const uint
     int sk = 0, skq = 0, skr = 0, sk_grid = 0;
     if (!starts && !gated && tuning().gemm_sk != 0) {
         const int fbs = tuning().gemm_bn;
-        // small batches keep their small token tile.  fp32 activations (hi + lo parts) never take stream-K on 256-token
-        // tiles: with the single accumulator and three 68 KB stages of that instance, tiles cut between ~10 CTAs came out
-        // wrong (M = 4096, K = 8192, N = 128: 0.3 relative error; tools/sk_check.py) -- not tracked down; 192-token tiles
-        // (two accumulators) are correct on every shape of the sweep and are what the heuristic would pick anyway
-        int bnsk = (fbs == 128 || fbs == 192 || fbs == 256) ? fbs : (M <= 64 ? bn : 256);
-        if (parts == 2 && bnsk == 256) bnsk = 192;
+        const int bnsk = (fbs == 128 || fbs == 192 || fbs == 256) ? fbs : (M <= 64 ? bn : 256);   // small batches keep their small token tile
         const long long tiles256 = ((M + bnsk - 1) / bnsk) * n_tiles_h;
         const long long waves = (tiles256 + dev.sm_count - 1) / dev.sm_count;
         const double fill = (double)tiles256 / (double)(waves * dev.sm_count);

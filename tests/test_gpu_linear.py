@@ -409,7 +409,8 @@ def test_stream_k_gemm_matches_whole_tiles_and_is_deterministic(oracle, pkg, M, 
 def test_stream_k_few_long_tiles(oracle, pkg, dtype, M, N, K):
     """Few weight rows, many tokens, long K: the heuristic itself picks stream-K and every tile is cut between ~10 CTAs.
     Default dispatch and forced stream-K against the float64 oracle, fp32 and bf16 activations, three runs each (the
-    fp32 instance with 256-token tiles gave 0.3 relative error here -- the launcher keeps fp32 stream-K on 192-token tiles)."""
+    fp32 instance with 256-token tiles -- three pipeline stages -- gave 0.3 relative error here: a dequant group skipped the
+    other group's k-blocks without observing their fills, and its parity wait fell two phases behind)."""
     rng = np.random.default_rng(M + N + K)
     packed = rng.integers(0, 256, size=(N, K // 2), dtype=np.uint8)
     scales = (rng.random(N, dtype=np.float32) * 0.01 + 0.001).astype(np.float32)
