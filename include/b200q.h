@@ -178,7 +178,8 @@ int b200q_linear_fwd_host(const void* h_x, int x_dtype, void* d_x, const uint8_t
  *   force_path (1 generic SIMT, 2 ring decode kernel, 3 tcgen05 GEMM, 6 exact-integer decode kernel, 7 mid-batch decode
  *   kernel), hm_min_m, hm_max_m, hm_i3, hm_waves, moe_dec_hm, moe_dec_compact, gemv_early, gemv_pf,
  *   gemv_tma3d, gemv_xprep, gemv_warps, gemv_slabs, gemv_stages, gemv_pdl, gemv_ctas, gemv_occ2, gemv_debug,
- *   gemm_bn (32 / 64 / 128 / 192 / 256), gemm_sk, gemm_debug (needs a -DB200Q_PROF build), host_direct.
+ *   gemm_bn (32 / 64 / 128 / 192 / 256), gemm_sk, gemm_mt_major (tile order: 0 weight-tile-major, 1 token-tile-major),
+ *   gemm_debug (needs a -DB200Q_PROF build), host_direct.
  * Their meaning is documented next to the Tuning struct in csrc/internal.h.  Not needed by callers. */
 int b200q_tune_set(const char* key, int value);
 
